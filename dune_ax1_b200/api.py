@@ -1,0 +1,514 @@
+"""ctypes binding of libax1gpu.so plus the host-side mirror of the reference's interface for the
+PNP Newton hot path (same names, argument meaning and error behaviour as the C++ concepts that
+Acme2CylSetup::setup instantiates, dune/ax1/acme2_cyl/common/acme2_cyl_setup.hh:226-1018):
+
+    GridOperator.residual / .jacobian          <- IGO            (acme2_cyl_setup.hh:700-708)
+    ISTLBackend_BCGS_ILU0.apply / .norm        <- LS             (acme2_cyl_setup.hh:727-811)
+    Ax1Newton.apply / .result                  <- PDESOLVER      (acme2_cyl_setup.hh:822-854)
+    MembraneFlux.updateState / .acceptTimeStep <- gfMembFlux     (acme2_cyl_simulation.hh:457,921-927)
+
+There is no CPU fallback: every compute entry point raises if libax1gpu.so or a CUDA device is
+missing. PyTorch is only used by callers for streams / torch.distributed rendezvous.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libax1gpu.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+c_ubyte_p = C.POINTER(C.c_ubyte)
+
+
+class Grid(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("x", c_double_p), ("y", c_double_p),
+                ("left_proc_boundary", C.c_int), ("right_proc_boundary", C.c_int)]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("temperature", C.c_double), ("eps_elec", C.c_double), ("length_scale", C.c_double),
+        ("time_scale", C.c_double), ("diff_water", C.c_double * 3), ("valence", C.c_int * 3),
+        ("pot_residual_scale", C.c_double), ("do_volume_scaling", C.c_int),
+        ("do_stimulation", C.c_int), ("tinj_start", C.c_double), ("tinj_end", C.c_double),
+        ("stim_x", C.c_double), ("stim_y", C.c_double), ("I_inj", C.c_double),
+        ("do_equilibration", C.c_int), ("t_equilibrium", C.c_double), ("dummy_value", C.c_double),
+        ("membrane_active", C.c_int), ("automatic_channel_init", C.c_int),
+        ("channel_resting_potential", C.c_double), ("use_rownorm_preconditioner", C.c_int),
+        ("leak_ratio_na", C.c_double), ("leak_ratio_k", C.c_double),
+    ]
+
+
+class NewtonOpts(C.Structure):
+    _fields_ = [
+        ("reduction", C.c_double), ("abs_limit", C.c_double), ("min_lin_reduction", C.c_double),
+        ("fixed_lin_reduction", C.c_int), ("maxit", C.c_int), ("line_search_maxit", C.c_int),
+        ("lin_maxit", C.c_int), ("force_iteration", C.c_int), ("disable_line_search", C.c_int),
+        ("slab_w", C.c_int), ("fixed_work", C.c_int),
+    ]
+
+
+class NewtonResult(C.Structure):
+    _fields_ = [
+        ("converged", C.c_int), ("iterations", C.c_int), ("lin_iterations", C.c_int),
+        ("status", C.c_int), ("residual_evals", C.c_int),
+        ("first_defect", C.c_double), ("defect", C.c_double), ("reduction", C.c_double),
+        ("conv_rate", C.c_double), ("t_assembler", C.c_double), ("t_lin_solv", C.c_double),
+        ("t_elapsed", C.c_double),
+    ]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class LinResult(C.Structure):
+    _fields_ = [("converged", C.c_int), ("iterations", C.c_int), ("reduction", C.c_double),
+                ("it_half", C.c_double)]
+
+
+class HostBC(C.Structure):
+    _fields_ = [("top", C.c_int * 2), ("bottom", C.c_int * 2), ("left_cytosol", C.c_int * 2),
+                ("right_cytosol", C.c_int * 2), ("left_debye", C.c_int * 2), ("right_debye", C.c_int * 2),
+                ("left_extra", C.c_int * 2), ("right_extra", C.c_int * 2), ("debye_layer_width", C.c_double)]
+
+
+# Newton status codes -> names of the Dune::PDELab::NewtonError subclasses the time loop catches
+NEWTON_ERRORS = {1: "NewtonNotConverged", 2: "NewtonLinearSolverError", 3: "NewtonDefectError",
+                 4: "NewtonLineSearchError"}
+
+
+class Ax1GpuError(RuntimeError):
+    pass
+
+
+class NewtonError(Ax1GpuError):
+    """Dune::PDELab::NewtonError family (acme2_cyl_simulation.hh:593-692 halves dt and retries)."""
+
+    def __init__(self, status, result):
+        super().__init__(NEWTON_ERRORS.get(status, "NewtonError(%d)" % status))
+        self.status = status
+        self.result = result
+
+
+_lib = None
+
+
+def lib():
+    """Load libax1gpu.so (built in-tree by dune_ax1_b200.build); fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIBPATH):
+        raise Ax1GpuError("libax1gpu.so not built: run python -c 'import __graft_entry__ as g; g.build()'")
+    L = C.CDLL(_LIBPATH)
+    L.ax1gpu_last_error.restype = C.c_char_p
+    H = C.c_void_p
+    L.ax1gpu_create.argtypes = [C.POINTER(Grid), c_ubyte_p, c_double_p, c_double_p, c_ubyte_p, C.POINTER(Params),
+                                c_double_p, c_double_p, c_double_p, C.c_int, C.c_void_p, C.POINTER(H)]
+    L.ax1gpu_destroy.argtypes = [H]
+    L.ax1gpu_pattern.argtypes = [H, c_int_p, c_int_p, c_int_p]
+    L.ax1gpu_set_time.argtypes = [H, C.c_double, C.c_double]
+    L.ax1gpu_set_uold.argtypes = [H, c_double_p]
+    L.ax1gpu_update_state.argtypes = [H, c_double_p]
+    L.ax1gpu_accept_state.argtypes = [H]
+    L.ax1gpu_get_channel_state.argtypes = [H, c_double_p, C.c_int, c_double_p]
+    L.ax1gpu_set_channel_state.argtypes = [H, c_double_p, C.c_double, C.c_int]
+    L.ax1gpu_membrane_potential.argtypes = [H, c_double_p, c_double_p]
+    L.ax1gpu_residual.argtypes = [H, c_double_p, c_double_p, c_double_p]
+    L.ax1gpu_jacobian.argtypes = [H, c_double_p, c_double_p]
+    L.ax1gpu_set_jacobian.argtypes = [H, c_double_p]
+    L.ax1gpu_get_jacobian.argtypes = [H, c_double_p]
+    L.ax1gpu_solve.argtypes = [H, c_double_p, C.c_double, C.c_int, C.c_int, c_double_p, C.POINTER(LinResult)]
+    L.ax1gpu_newton.argtypes = [H, C.POINTER(NewtonOpts), c_double_p, C.POINTER(NewtonResult)]
+    L.ax1gpu_upload_u.argtypes = [H, c_double_p]
+    L.ax1gpu_download_u.argtypes = [H, c_double_p]
+    L.ax1gpu_set_uold_dev.argtypes = [H]
+    L.ax1gpu_newton_dev.argtypes = [H, C.POINTER(NewtonOpts), C.POINTER(NewtonResult)]
+    L.ax1gpu_spmv.argtypes = [H, c_double_p, c_double_p]
+    L.ax1gpu_ilu_factor.argtypes = [H, C.c_int]
+    L.ax1gpu_ilu_apply.argtypes = [H, c_double_p, c_double_p]
+    L.ax1gpu_rownorm.argtypes = [H, c_double_p]
+    L.ax1gpu_time_kernel.argtypes = [H, C.c_char_p, C.c_int, c_double_p]
+    L.ax1gpu_launch_count.argtypes = [H]
+    L.ax1gpu_launch_count.restype = C.c_longlong
+    L.ax1gpu_stream.argtypes = [H]
+    L.ax1gpu_stream.restype = C.c_void_p
+    L.ax1gpu_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p]
+    L.ax1gpu_comm_init.argtypes = [H, C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+    L.ax1host_generate_y.argtypes = [C.c_double] * 6 + [C.c_int, C.c_double, C.c_double, C.c_int, c_double_p, C.c_int]
+    L.ax1host_physics_maps.argtypes = [C.POINTER(Grid), C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                       C.c_double, C.c_int, C.c_double, C.POINTER(HostBC), c_ubyte_p, c_double_p,
+                                       c_ubyte_p]
+    L.ax1host_slab.argtypes = [C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p]
+    assert L.ax1gpu_sizeof_params() == C.sizeof(Params), "ax1gpu_params layout mismatch"
+    _lib = L
+    return L
+
+
+def _err():
+    return lib().ax1gpu_last_error().decode()
+
+
+def _chk(rc):
+    if rc != 0:
+        raise Ax1GpuError("libax1gpu error %d: %s" % (rc, _err()))
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p) if a is not None else None
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def nccl_library_path():
+    """The libnccl.so.2 torch uses (pip package nvidia-nccl), so both share one NCCL instance."""
+    try:
+        import nvidia.nccl as n  # noqa
+        base = list(n.__path__)[0]
+        p = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(p):
+            return p
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
+# ------------------------------------------------------------------------------------------------
+# host model (no GPU needed)
+def generate_y(ymin=0.0, ymax=10.0e6, ymemb=500.0, dmemb=5.0, dy_cell=100.0, dy_cell_min=0.5,
+               n_dy_cell_min=10, dy=100.0e3, dy_min=0.5, n_dy_min=10):
+    """Radial grid vector; defaults = src/config/square10mm.config of the reference."""
+    L = lib()
+    n = L.ax1host_generate_y(ymin, ymax, ymemb, dmemb, dy_cell, dy_cell_min, n_dy_cell_min, dy, dy_min, n_dy_min,
+                             None, 0)
+    if n < 0:
+        raise Ax1GpuError(_err())
+    out = np.zeros(n)
+    L.ax1host_generate_y(ymin, ymax, ymemb, dmemb, dy_cell, dy_cell_min, n_dy_cell_min, dy, dy_min, n_dy_min,
+                         _dp(out), n)
+    return out
+
+
+def slab(nx_global, nranks, rank):
+    """z-slab partition: (c0, c1) interior cell columns, (l0, l1) local columns incl. overlap."""
+    v = [C.c_int() for _ in range(4)]
+    _chk(lib().ax1host_slab(nx_global, nranks, rank, *[C.byref(a) for a in v]))
+    return tuple(a.value for a in v)
+
+
+class BoundaryConfig:
+    """[boundary.concentration] / [boundary.potential] of the INI file; True = Dirichlet."""
+
+    def __init__(self, top=(True, True), bottom=(False, False), left_cytosol=(False, False),
+                 right_cytosol=(False, False), left_debye=(False, False), right_debye=(False, False),
+                 left_extra=(False, False), right_extra=(False, False), debye_layer_width=0.0):
+        self.c = HostBC()
+        for name, val in (("top", top), ("bottom", bottom), ("left_cytosol", left_cytosol),
+                          ("right_cytosol", right_cytosol), ("left_debye", left_debye),
+                          ("right_debye", right_debye), ("left_extra", left_extra), ("right_extra", right_extra)):
+            getattr(self.c, name)[0] = int(val[0])
+            getattr(self.c, name)[1] = int(val[1])
+        self.c.debye_layer_width = debye_layer_width
+
+
+def physics_maps(x, y, ymemb=500.0, dmemb=5.0, xmin_global=None, xmax_global=None, ymin=None, ymax=None,
+                 do_volume_scaling=True, volume_scaling_threshold=-1.0, bc=None, left_pb=False, right_pb=False):
+    """cell_subdomain, node_volume, dirichlet_mask of one rank's local grid (host model of Physics)."""
+    x = f64(x)
+    y = f64(y)
+    nx, ny = len(x) - 1, len(y) - 1
+    g = Grid(nx, ny, _dp(x), _dp(y), int(left_pb), int(right_pb))
+    bc = bc or BoundaryConfig()
+    cs = np.zeros(nx * ny, dtype=np.uint8)
+    nvol = np.zeros((nx + 1) * (ny + 1))
+    dm = np.zeros((nx + 1) * (ny + 1), dtype=np.uint8)
+    _chk(lib().ax1host_physics_maps(
+        C.byref(g), ymemb, dmemb, x[0] if xmin_global is None else xmin_global,
+        x[-1] if xmax_global is None else xmax_global, y[0] if ymin is None else ymin,
+        y[-1] if ymax is None else ymax, int(do_volume_scaling), volume_scaling_threshold, C.byref(bc.c),
+        cs.ctypes.data_as(c_ubyte_p), _dp(nvol), dm.ctypes.data_as(c_ubyte_p)))
+    return cs, nvol, dm
+
+
+def default_params(**kw):
+    p = Params()
+    lib().ax1gpu_params_default(C.byref(p))
+    for k, v in kw.items():
+        if isinstance(v, (list, tuple)):
+            for i, vi in enumerate(v):
+                getattr(p, k)[i] = vi
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def default_newton_opts(**kw):
+    o = NewtonOpts()
+    lib().ax1gpu_newton_opts_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+# ------------------------------------------------------------------------------------------------
+class Ax1Gpu:
+    """Device-resident PNP problem of one rank (thin wrapper over the C ABI)."""
+
+    def __init__(self, x, y, cell_subdomain, memb_perm, node_volume, dirichlet_mask, params, g_leak, g_nav,
+                 g_kv, left_pb=False, right_pb=False, device=0, stream=None):
+        L = lib()
+        self.x = f64(x)
+        self.y = f64(y)
+        self.nx, self.ny = len(self.x) - 1, len(self.y) - 1
+        self.nv = (self.nx + 1) * (self.ny + 1)
+        self.n = 4 * self.nv
+        self.params = params
+        g = Grid(self.nx, self.ny, _dp(self.x), _dp(self.y), int(left_pb), int(right_pb))
+        bcast = lambda a: f64(np.broadcast_to(a, (self.nx,)))  # noqa: E731
+        cs = np.ascontiguousarray(cell_subdomain, dtype=np.uint8)
+        dm = np.ascontiguousarray(dirichlet_mask, dtype=np.uint8)
+        self.h = C.c_void_p()
+        rc = L.ax1gpu_create(C.byref(g), cs.ctypes.data_as(c_ubyte_p), _dp(bcast(memb_perm)), _dp(f64(node_volume)),
+                             dm.ctypes.data_as(c_ubyte_p), C.byref(params), _dp(bcast(g_leak)), _dp(bcast(g_nav)),
+                             _dp(bcast(g_kv)), int(device), C.c_void_p(stream) if stream else None, C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise Ax1GpuError("ax1gpu_create failed (%d): %s" % (rc, _err()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ax1gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- pattern / time / state
+    def pattern(self):
+        nb = C.c_int()
+        _chk(lib().ax1gpu_pattern(self.h, None, None, C.byref(nb)))
+        rowptr = np.zeros(self.nv + 1, dtype=np.int32)
+        col = np.zeros(nb.value, dtype=np.int32)
+        _chk(lib().ax1gpu_pattern(self.h, rowptr.ctypes.data_as(c_int_p), col.ctypes.data_as(c_int_p), C.byref(nb)))
+        return rowptr, col
+
+    def set_time(self, t, dt):
+        _chk(lib().ax1gpu_set_time(self.h, float(t), float(dt)))
+
+    def set_uold(self, u):
+        _chk(lib().ax1gpu_set_uold(self.h, _dp(f64(u))))
+
+    def update_state(self, u=None):
+        _chk(lib().ax1gpu_update_state(self.h, _dp(f64(u)) if u is not None else None))
+
+    def accept_state(self):
+        _chk(lib().ax1gpu_accept_state(self.h))
+
+    def channel_state(self, new=False):
+        s = np.zeros(5 * self.nx)
+        v = C.c_double()
+        _chk(lib().ax1gpu_get_channel_state(self.h, _dp(s), int(new), C.byref(v)))
+        return s, v.value
+
+    def set_channel_state(self, s, v_rest, initialized=True):
+        _chk(lib().ax1gpu_set_channel_state(self.h, _dp(f64(s)), float(v_rest), int(initialized)))
+
+    def membrane_potential(self, u=None):
+        vm = np.zeros(self.nx)
+        _chk(lib().ax1gpu_membrane_potential(self.h, _dp(f64(u)) if u is not None else None, _dp(vm)))
+        return vm
+
+    # -- assembly
+    def residual(self, u=None, want_r=True):
+        r = np.zeros(self.n) if want_r else None
+        nrm = C.c_double()
+        _chk(lib().ax1gpu_residual(self.h, _dp(f64(u)) if u is not None else None, _dp(r), C.byref(nrm)))
+        return r, nrm.value
+
+    def jacobian(self, u=None, download=True):
+        blocks = None
+        if download:
+            nb = C.c_int()
+            _chk(lib().ax1gpu_pattern(self.h, None, None, C.byref(nb)))
+            blocks = np.zeros(nb.value * 16)
+        _chk(lib().ax1gpu_jacobian(self.h, _dp(f64(u)) if u is not None else None, _dp(blocks)))
+        return blocks
+
+    def set_jacobian(self, blocks):
+        _chk(lib().ax1gpu_set_jacobian(self.h, _dp(f64(blocks))))
+
+    def rownorm(self, r):
+        r = f64(r).copy()
+        _chk(lib().ax1gpu_rownorm(self.h, _dp(r)))
+        nb = C.c_int()
+        _chk(lib().ax1gpu_pattern(self.h, None, None, C.byref(nb)))
+        blocks = np.zeros(nb.value * 16)
+        _chk(lib().ax1gpu_get_jacobian(self.h, _dp(blocks)))
+        return blocks, r
+
+    # -- linear algebra
+    def spmv(self, x):
+        y = np.zeros(self.n)
+        _chk(lib().ax1gpu_spmv(self.h, _dp(f64(x)), _dp(y)))
+        return y
+
+    def ilu_factor(self, slab_w=0):
+        _chk(lib().ax1gpu_ilu_factor(self.h, int(slab_w)))
+
+    def ilu_apply(self, d):
+        v = np.zeros(self.n)
+        _chk(lib().ax1gpu_ilu_apply(self.h, _dp(f64(d)), _dp(v)))
+        return v
+
+    def solve(self, r, reduction, maxit=5000, slab_w=0):
+        r = f64(r).copy()
+        z = np.zeros(self.n)
+        res = LinResult()
+        _chk(lib().ax1gpu_solve(self.h, _dp(r), float(reduction), int(maxit), int(slab_w), _dp(z), C.byref(res)))
+        return z, r, res
+
+    # -- Newton
+    def newton(self, u, opts=None):
+        u = f64(u).copy()
+        opts = opts or default_newton_opts()
+        res = NewtonResult()
+        _chk(lib().ax1gpu_newton(self.h, C.byref(opts), _dp(u), C.byref(res)))
+        return u, res
+
+    def upload_u(self, u):
+        _chk(lib().ax1gpu_upload_u(self.h, _dp(f64(u))))
+
+    def download_u(self):
+        u = np.zeros(self.n)
+        _chk(lib().ax1gpu_download_u(self.h, _dp(u)))
+        return u
+
+    def set_uold_dev(self):
+        _chk(lib().ax1gpu_set_uold_dev(self.h))
+
+    def newton_dev(self, opts=None):
+        opts = opts or default_newton_opts()
+        res = NewtonResult()
+        _chk(lib().ax1gpu_newton_dev(self.h, C.byref(opts), C.byref(res)))
+        return res
+
+    def time_kernel(self, name, reps=10):
+        ms = C.c_double()
+        _chk(lib().ax1gpu_time_kernel(self.h, name.encode(), int(reps), C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(lib().ax1gpu_launch_count(self.h))
+
+    def stream(self):
+        return lib().ax1gpu_stream(self.h)
+
+    def comm_init(self, unique_id, rank, nranks, libnccl=None):
+        _chk(lib().ax1gpu_comm_init(self.h, (libnccl or nccl_library_path()).encode(), unique_id, rank, nranks))
+
+
+def nccl_unique_id(libnccl=None):
+    buf = C.create_string_buffer(128)
+    _chk(lib().ax1gpu_nccl_unique_id((libnccl or nccl_library_path()).encode(), buf))
+    return buf.raw
+
+
+# ------------------------------------------------------------------------------------------------
+# Mirror of the reference's operator / backend / solver concepts
+class GridOperator:
+    """IGO: OneStepGridOperator over (spatial GO0, temporal GO1), implicit Euler."""
+
+    def __init__(self, dev):
+        self.dev = dev
+
+    def preStep(self, time, dt, uold):
+        """OneStepMethod::apply prologue: stage setup, r0 = -M(uold), LOP time = time+dt."""
+        self.dev.set_time(time, dt)
+        self.dev.set_uold(uold)
+
+    def residual(self, x, r=None):
+        out, _ = self.dev.residual(x)
+        if r is not None:
+            r[:] = out
+            return r
+        return out
+
+    def jacobian(self, x, A=None):
+        blocks = self.dev.jacobian(x)
+        if A is not None:
+            A[:] = blocks
+            return A
+        return blocks
+
+
+class ISTLBackend_BCGS_ILU0:
+    """LS: BiCGStab + block ILU0 over x-sub-slabs (ISTLBackend_{SEQ,OVLP}_BCGS_ILUn stand-in)."""
+
+    def __init__(self, dev, maxiter=5000, slab_w=0, verbose=0):
+        self.dev, self.maxiter, self.slab_w = dev, maxiter, slab_w
+        self.res = LinResult()
+
+    def norm(self, v):
+        return float(np.sqrt(np.dot(v, v)))
+
+    def apply(self, A, z, r, reduction):
+        if A is not None:
+            self.dev.set_jacobian(A)
+        zz, rr, self.res = self.dev.solve(r, reduction, self.maxiter, self.slab_w)
+        z[:] = zz
+        r[:] = rr
+
+    def result(self):
+        return self.res
+
+
+class MembraneFlux:
+    """gfMembFlux: implicit membrane flux grid function state (channels)."""
+
+    def __init__(self, dev):
+        self.dev = dev
+
+    def updateState(self, time=None, dt=None, u=None):
+        if time is not None:
+            self.dev.set_time(time, dt)
+        self.dev.update_state(u)
+
+    def acceptTimeStep(self):
+        self.dev.accept_state()
+
+
+class Ax1Newton:
+    """PDESOLVER: damped Newton with the Hackbusch-Reusken line search of Ax1Newton."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.opts = default_newton_opts()
+        self.res = NewtonResult()
+
+    def setReduction(self, v): self.opts.reduction = v
+    def setAbsoluteLimit(self, v): self.opts.abs_limit = v
+    def setMinLinearReduction(self, v): self.opts.min_lin_reduction = v
+    def setFixedLinearReduction(self, v): self.opts.fixed_lin_reduction = int(v)
+    def setMaxIterations(self, v): self.opts.maxit = int(v)
+    def setForceIteration(self, v): self.opts.force_iteration = int(v)
+    def setLineSearchMaxIterations(self, v): self.opts.line_search_maxit = int(v)
+    def setLinearSolverMaxIterations(self, v): self.opts.lin_maxit = int(v)
+    def setSlabWidth(self, v): self.opts.slab_w = int(v)
+
+    def apply(self, u):
+        unew, self.res = self.dev.newton(u, self.opts)
+        u[:] = unew
+        if self.res.status != 0:
+            raise NewtonError(self.res.status, self.res)
+        return u
+
+    def result(self):
+        return self.res

@@ -1,0 +1,277 @@
+// assembly.cu -- residual, mass (r0) and Jacobian assembly kernels + HH channel kernels.
+//
+// Row-owner ("gather") assembly: thread(s) own one vertex row and visit the <=4 cells around it,
+// so every residual entry / Jacobian block is written exactly once, in a fixed order: atomic-free
+// and bitwise deterministic. Replaces the PDELab cell loop + scatter and the
+// BCRSMatrix backend (acme2_cyl_setup.hh:696-708).
+#include "kernels.h"
+#include "pnp_device.cuh"
+
+namespace ax1 {
+
+// ------------------------------------------------------------------------------------------
+// residual: one thread per vertex. mode 0: full residual r = r0 + M(u) + dt*A(u), constrained
+// rows zeroed.  mode 1: r0 = -M(uold) (const part of implicit Euler, no constraints applied).
+__global__ void __launch_bounds__(128) residual_kernel(Dev g, const double* __restrict__ u,
+                                                       const double* __restrict__ r0, double* __restrict__ r,
+                                                       int mode) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= g.nv) return;
+  const int i = v % g.nvx, j = v / g.nvx;
+  double out[4] = {0.0, 0.0, 0.0, 0.0};
+  const double vs = g.do_volume_scaling ? 1. / g.node_vol[v] : 1.0;
+  // cells in index order (x fastest): (i-1,j-1), (i,j-1), (i-1,j), (i,j)
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int ci = i - 1 + a, cj = j - 1 + b;
+      if (ci < 0 || ci >= g.nx || cj < 0 || cj >= g.ny) continue;
+      const int k = (1 - a) + 2 * (1 - b);  // our local vertex number in that cell
+      CellCtx c;
+      load_cell(g, u, ci, cj, c);
+      if (cj == g.jm) {
+        if (mode == 0) memb_volume_row(g, c, k, vs, out[3]);
+      } else {
+        elec_volume_row(g, c, k, vs, mode == 0 ? 1.0 : -1.0, mode == 0, out);
+        if (mode == 0 && g.membrane_active && ((cj == g.jm - 1 && b == 0) || (cj == g.jm + 1 && b == 1))) {
+          // our vertex lies on the membrane interface face of this cell
+          FaceCtx f;
+          make_face(g, u, c, f);
+          elec_boundary_row(g, f, ci, c.xl, k, vs, out);
+        }
+      }
+    }
+  if (mode == 0) {
+    double q0, q1_, q2, q3;
+    ld4(r0 + 4 * (size_t)v, q0, q1_, q2, q3);
+    out[0] += q0; out[1] += q1_; out[2] += q2; out[3] += q3;
+    const uint8_t m = g.dmask[v];
+    if (m & 1) out[0] = 0.0;
+    if (m & 2) out[1] = 0.0;
+    if (m & 4) out[2] = 0.0;
+    if (m & 8) out[3] = 0.0;
+  }
+  double2* dst = reinterpret_cast<double2*>(r + 4 * (size_t)v);
+  dst[0] = make_double2(out[0], out[1]);
+  dst[1] = make_double2(out[2], out[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Jacobian: 4 lanes per vertex row, lane ri owns scalar row ri of the 9 blocks of the block row.
+// Analytic volume blocks (the reference's use*OperatorJacobianVolume = yes mode) + mass blocks.
+// Constrained rows -> unit row, constrained columns dropped (PDELab Dirichlet constraints).
+__global__ void __launch_bounds__(128) jacobian_kernel(Dev g, const double* __restrict__ u, double* __restrict__ A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = t >> 2, ri = t & 3;
+  if (v >= g.nv) return;
+  const int i = v % g.nvx, j = v / g.nvx;
+  double acc[9][4];
+#pragma unroll
+  for (int s = 0; s < 9; ++s)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[s][c] = 0.0;
+  const double vs = g.do_volume_scaling ? 1. / g.node_vol[v] : 1.0;
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int ci = i - 1 + a, cj = j - 1 + b;
+      if (ci < 0 || ci >= g.nx || cj < 0 || cj >= g.ny) continue;
+      const int k = (1 - a) + 2 * (1 - b);
+      const int ka = 1 - a, kb = 1 - b;
+      CellCtx c;
+      load_cell(g, u, ci, cj, c);
+      const bool memb = (cj == g.jm);
+      const double eps = memb ? g.eps_memb[ci] : g.eps_elec;
+#pragma unroll
+      for (int qa = 0; qa < 2; ++qa)
+#pragma unroll
+        for (int qb = 0; qb < 2; ++qb) {
+          QP q;
+          make_qp(c, qa ? AX1_GP1 : AX1_GP0, qb ? AX1_GP1 : AX1_GP0, q);
+          double gpx = 0, gpy = 0;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) { gpx += c.xl[12 + m] * q.gx[m]; gpy += c.xl[12 + m] * q.gy[m]; }
+          double uk = 0.0, D = 0.0, bx = 0.0, by = 0.0;
+          int z = 0;
+          if (ri < 3 && !memb) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) uk += c.xl[4 * ri + m] * q.phi[m];
+            D = g.D[ri]; z = g.valence[ri];
+            bx = -D * z * gpx; by = -D * z * gpy;
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int ja = jj & 1, jb = jj >> 1;
+            const int s = (jb - kb + 1) * 3 + (ja - ka + 1);  // compile-time after unrolling
+            if (ri == 3) {
+              if (!memb) {
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                  const double dfPot_du = -g.valence[kk] * q.phi[jj] * g.PC;
+                  acc[s][kk] += g.dt * ((-dfPot_du * q.phi[k]) * q.factor * vs * g.S_pot);
+                }
+              }
+              const double val = (((-eps) * q.gx[jj]) * q.gx[k] + ((-eps) * q.gy[jj]) * q.gy[k]);
+              acc[s][3] += g.dt * (val * q.factor * vs * g.S_pot);
+            } else if (!memb) {
+              const double cc = ((D * q.gx[jj]) * q.gx[k] + (D * q.gy[jj]) * q.gy[k]) -
+                                q.phi[jj] * (bx * q.gx[k] + by * q.gy[k]);
+              double e = g.dt * (cc * q.factor * vs);
+              e += 1.0 * (q.phi[jj] * q.phi[k] * q.factor * vs);  // mass block (toperator.hh:251)
+              const double dbx = q.gx[jj] * (-D * z), dby = q.gy[jj] * (-D * z);
+              const double cp = g.dt * ((-uk * (dbx * q.gx[k] + dby * q.gy[k])) * q.factor * vs);
+              // scalar column ri of the block = own species, column 3 = potential
+              if (ri == 0) acc[s][0] += e;
+              if (ri == 1) acc[s][1] += e;
+              if (ri == 2) acc[s][2] += e;
+              acc[s][3] += cp;
+            }
+          }
+        }
+    }
+  // constraints
+  const bool row_con = (g.dmask[v] >> ri) & 1;
+#pragma unroll
+  for (int s = 0; s < 9; ++s) {
+    const int ii = i + slot_di(s), jj = j + slot_dj(s);
+    const bool inb = ii >= 0 && ii < g.nvx && jj >= 0 && jj < g.nvy;
+    uint8_t cm = inb ? g.dmask[ii + g.nvx * jj] : 0xF;
+    double o0 = acc[s][0], o1 = acc[s][1], o2 = acc[s][2], o3 = acc[s][3];
+    if (row_con || (cm & 1)) o0 = 0.0;
+    if (row_con || (cm & 2)) o1 = 0.0;
+    if (row_con || (cm & 4)) o2 = 0.0;
+    if (row_con || (cm & 8)) o3 = 0.0;
+    if (row_con && s == 4) {
+      if (ri == 0) o0 = 1.0;
+      if (ri == 1) o1 = 1.0;
+      if (ri == 2) o2 = 1.0;
+      if (ri == 3) o3 = 1.0;
+    }
+    double2* dst = reinterpret_cast<double2*>(A + ((size_t)v * 9 + s) * 16 + ri * 4);
+    dst[0] = make_double2(o0, o1);
+    dst[1] = make_double2(o2, o3);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// HH channels: one thread per membrane column (= ES-side membrane edge).
+__device__ __forceinline__ double v_trap(double x, double y) {  // channel.hh:185-194
+  if (fabs(x / y) < 1e-8) return y * (1 - x / y / 2);
+  return x / (exp(x / y) - 1);
+}
+__device__ __forceinline__ double alpha_gate(int gt, double v_) {  // channel.hh:606-618, 667-676
+  if (gt == 0) return 1.0 * (0.1 * v_trap((25 - v_), 10));
+  if (gt == 1) return 1.0 * (0.07 * exp(-v_ / 20));
+  return 1.0 * (0.01 * v_trap((10 - v_), 10));
+}
+__device__ __forceinline__ double beta_gate(int gt, double v_) {  // channel.hh:624-642, 679-687
+  if (gt == 0) return 1.0 * (4 * exp(-v_ / 18));
+  if (gt == 1) return 1.0 * (1. / (exp((30 - v_) / 10) + 1));
+  return 1.0 * (0.125 * exp(-v_ / 80));
+}
+
+__device__ __forceinline__ double memb_pot_mV(const Dev& g, const double* u, int i) {  // physics.hh:562-603
+  const double in = 0.5 * u[4 * (size_t)(i + g.nvx * g.jm) + 3] + 0.5 * u[4 * (size_t)(i + 1 + g.nvx * g.jm) + 3];
+  const double out = 0.5 * u[4 * (size_t)(i + g.nvx * (g.jm + 1)) + 3] + 0.5 * u[4 * (size_t)(i + 1 + g.nvx * (g.jm + 1)) + 3];
+  double membPot = in;
+  membPot -= out;
+  return membPot * con_k * g.temperature / con_e * 1.0e3;
+}
+
+__device__ __forceinline__ void write_geff(const ChannelDev& ch, int nx, int i) {
+  // getNewEffConductance: channel.hh:356-366 (voltage gated), :497-501 (leak)
+  ch.geff[0 * (size_t)nx + i] = ch.gbar[0][i] * ch.ratio[0][i];
+  ch.geff[1 * (size_t)nx + i] = ch.gbar[0][i] * ch.ratio[1][i];
+  double gn = ch.gbar[1][i];
+  gn *= pow(ch.gate_new[0][i], 3.0);
+  gn *= pow(ch.gate_new[1][i], 1.0);
+  ch.geff[2 * (size_t)nx + i] = gn;
+  double gk = ch.gbar[2][i];
+  gk *= pow(ch.gate_new[2][i], 4.0);
+  ch.geff[3 * (size_t)nx + i] = gk;
+}
+
+// mode 0: initChannels (steady state at v - v_rest = 0, leak re-balancing, channelset.hh:186-311)
+// mode 1: backward-Euler gating step from the accepted state (channel.hh:394-402)
+// mode 2: only refresh geff from the current state
+__global__ void channel_kernel(Dev g, ChannelDev ch, const double* u, int mode, double dt_ms, int automatic,
+                               double v_fixed, int* err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nx) return;
+  if (mode == 0) {
+    const double v = automatic ? memb_pot_mV(g, u, i) : v_fixed;
+    // v_rest of the shared channel objects ends up as the value of the LAST edge visited
+    if (i == g.nx - 1) *ch.v_rest = v;
+    for (int gt = 0; gt < 3; ++gt) {
+      const double a = alpha_gate(gt, v - v), b = beta_gate(gt, v - v);
+      ch.gate[gt][i] = a / (a + b);
+      ch.gate_new[gt][i] = ch.gate[gt][i];
+    }
+    // recalculateLeakConductances
+    double gnav = ch.gbar[1][i];
+    gnav *= pow(ch.gate_new[0][i], 3.0);
+    gnav *= pow(ch.gate_new[1][i], 1.0);
+    double gkv = ch.gbar[2][i];
+    gkv *= pow(ch.gate_new[2][i], 4.0);
+    const double total = ch.gbar[0][i];
+    if (total > 0.0) {
+      for (int k = 0; k < 2; ++k) {
+        const double sumThis = (k == 0) ? gnav : gkv;
+        const double sumOther = (k == 0) ? gkv : gnav;
+        const double ratio = ch.ratio[k][i];
+        double leak = (ratio / (1. - ratio)) * (total + (0.0 + sumOther)) - (0.0 + sumThis);
+        leak /= 1. + (ratio / (1. - ratio));
+        const double newRatio = leak / total;
+        if (newRatio < 0.0 || newRatio > 1.0) atomicExch(err, 1);
+        ch.ratio[k][i] = newRatio;
+      }
+    }
+  } else if (mode == 1) {
+    const double v_ = memb_pot_mV(g, u, i) - *ch.v_rest;
+    for (int gt = 0; gt < 3; ++gt) {
+      const double a = alpha_gate(gt, v_), b = beta_gate(gt, v_);
+      ch.gate_new[gt][i] = (dt_ms * a + ch.gate[gt][i]) / (1 + dt_ms * (a + b));
+    }
+  }
+  write_geff(ch, g.nx, i);
+}
+
+__global__ void channel_accept_kernel(int nx, ChannelDev ch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nx) return;
+  for (int gt = 0; gt < 3; ++gt) ch.gate[gt][i] = ch.gate_new[gt][i];
+}
+
+__global__ void memb_pot_kernel(Dev g, const double* u, double* vm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nx) return;
+  vm[i] = memb_pot_mV(g, u, i);
+}
+
+// ------------------------------------------------------------------------------------------
+void launch_residual(const Dev& g, const double* u, const double* r0, double* r, int mode, cudaStream_t st) {
+  const int bs = 128;
+  residual_kernel<<<(g.nv + bs - 1) / bs, bs, 0, st>>>(g, u, r0, r, mode);
+}
+void launch_jacobian_volume(const Dev& g, const double* u, double* A, cudaStream_t st) {
+  const int bs = 128;
+  const long long nt = 4LL * g.nv;
+  jacobian_kernel<<<(unsigned)((nt + bs - 1) / bs), bs, 0, st>>>(g, u, A);
+}
+void launch_channels(const Dev& g, const ChannelDev& ch, const double* u, int mode, double dt_ms, int automatic,
+                     double v_fixed, int* err, cudaStream_t st) {
+  const int bs = 128;
+  channel_kernel<<<(g.nx + bs - 1) / bs, bs, 0, st>>>(g, ch, u, mode, dt_ms, automatic, v_fixed, err);
+}
+void launch_channel_accept(int nx, const ChannelDev& ch, cudaStream_t st) {
+  const int bs = 128;
+  channel_accept_kernel<<<(nx + bs - 1) / bs, bs, 0, st>>>(nx, ch);
+}
+void launch_memb_pot(const Dev& g, const double* u, double* vm, cudaStream_t st) {
+  const int bs = 128;
+  memb_pot_kernel<<<(g.nx + bs - 1) / bs, bs, 0, st>>>(g, u, vm);
+}
+
+}  // namespace ax1

@@ -1,0 +1,64 @@
+// common.cuh -- shared device-side definitions of libax1gpu (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/ax1gpu.h"
+
+namespace ax1 {
+
+// dune/ax1/common/constants.hh:64-74
+constexpr double con_pi = 3.1415926535897932384626433;
+constexpr double con_e = 1.602176487e-19;
+constexpr double con_k = 1.380650e-23;
+constexpr double con_eps0 = 8.854187817e-12;
+constexpr double con_mol = 6.02214129e23;
+
+enum { NA = 0, KK = 1, CL = 2, NSPEC = 3, POT = 3 };
+enum { SD_CYTOSOL = 0, SD_ES = 1, SD_MEMBRANE = 2 };
+
+// 2-point Gauss-Legendre on [0,1] (quadrature order 2, operator_fully_coupled.hh:161)
+#define AX1_GP0 0.2113248654051871177454256097490212721762
+#define AX1_GP1 0.7886751345948128822545743902509787278238
+
+// Everything a kernel needs to know about the problem; passed by value.
+struct Dev {
+  int nx, ny, nvx, nvy, nv, jm;
+  const double* x;
+  const double* y;
+  const double* node_vol;     // nv
+  const uint8_t* dmask;       // nv
+  const double* eps_memb;     // nx
+  const double* geff;         // 4*nx: Na_leak, K_leak, Nav, Kv new effective conductances
+  double eps_elec, PC, D[3], S_pot, kT_e, temperature;
+  double time_scale, length_scale;
+  int valence[3];
+  int do_volume_scaling, membrane_active;
+  // stimulation
+  int stim_on;                // evaluated on host for the current LOP time
+  double stim_x, stim_y, I_inj;
+  // equilibration
+  int equil;                  // do_equilibration && time < t_equilibrium (host evaluated)
+  double dummy_value;
+  double dt;
+};
+
+// Matrix layout: 9 stencil slots per vertex row, slot s = (dj+1)*3 + (di+1), each a row-major 4x4
+// block: A[(v*9 + s)*16 + r*4 + c]. Missing neighbours (domain boundary) hold zero blocks.
+__host__ __device__ inline int slot_di(int s) { return s % 3 - 1; }
+__host__ __device__ inline int slot_dj(int s) { return s / 3 - 1; }
+
+#define AX1_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      ax1::set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+      return AX1GPU_ECUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+void set_error(const std::string& s);
+
+}  // namespace ax1

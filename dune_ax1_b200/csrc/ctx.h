@@ -1,0 +1,68 @@
+// ctx.h -- the device-resident problem behind an ax1gpu_handle.
+#pragma once
+#include "kernels.h"
+#include "nccl_dyn.h"
+
+struct ax1gpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  ax1::Dev g{};
+  ax1gpu_params prm{};
+  // host copies
+  std::vector<double> hx, hy;
+  std::vector<int> h_rowptr, h_col;
+  int nblocks = 0;
+  bool left_pb = false, right_pb = false;
+  int own_lo = 0, own_hi = 0;
+  // time
+  double time = 0.0, dt = 0.0;
+  // device arrays
+  double *d_x = nullptr, *d_y = nullptr, *d_nodevol = nullptr, *d_epsm = nullptr;
+  uint8_t* d_dmask = nullptr;
+  int* d_rowptr = nullptr;
+  double *d_u = nullptr, *d_uold = nullptr, *d_r0 = nullptr, *d_r = nullptr, *d_z = nullptr, *d_uprev = nullptr;
+  double *d_A = nullptr, *d_LU = nullptr;
+  double *d_rt = nullptr, *d_p = nullptr, *d_v = nullptr, *d_y2 = nullptr, *d_t = nullptr, *d_tmp = nullptr;
+  double* d_bcrs = nullptr;  // staging for Jacobian up/download (allocated lazily)
+  // channels
+  ax1::ChannelDev ch{};
+  double *d_gbar = nullptr, *d_chstate = nullptr, *d_geff = nullptr, *d_vrest = nullptr, *d_vm = nullptr;
+  int* d_err = nullptr;
+  bool channels_initialized = false, channels_partially_initialized = false;
+  // reductions / Krylov scalars
+  double* d_partials = nullptr;   // 2 * nred_blocks
+  double* d_sums = nullptr;       // [4]
+  ax1::Scalars* d_sc = nullptr;
+  ax1::Scalars* h_sc = nullptr;   // pinned
+  double* h_pin = nullptr;        // pinned scratch (8 doubles)
+  int nred_blocks = 0;
+  // ILU
+  int slab_w = 0;
+  bool factored = false;
+  // multi-GPU
+  ax1::NcclApi nccl;
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  double *d_halo_send = nullptr, *d_halo_recv = nullptr;  // 2 sides x 3 columns x nvy x 4
+  // accounting
+  long long launches = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace ax1 {
+// driver.cu
+int drv_refresh_dev(ax1gpu_ctx* c);
+int drv_set_uold(ax1gpu_ctx* c);                       // r0 = -M(d_uold)
+int drv_update_state(ax1gpu_ctx* c, const double* d_u);
+int drv_accept_state(ax1gpu_ctx* c);
+int drv_residual(ax1gpu_ctx* c, const double* d_u, double* d_r, double* norm_host);
+int drv_jacobian(ax1gpu_ctx* c, const double* d_u);
+int drv_factor(ax1gpu_ctx* c, int slab_w);
+int drv_prec_apply(ax1gpu_ctx* c, const double* d, double* v);
+int drv_op_apply(ax1gpu_ctx* c, const double* x, double* y);
+int drv_solve(ax1gpu_ctx* c, double* d_rhs, double* d_zout, double reduction, int maxit, ax1gpu_lin_result* res);
+int drv_newton(ax1gpu_ctx* c, const ax1gpu_newton_opts* o, ax1gpu_newton_result* res);
+int drv_norm(ax1gpu_ctx* c, const double* a, double* out_host);
+int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms);
+}  // namespace ax1

@@ -1,0 +1,593 @@
+// driver.cu -- host-side orchestration of the hot path: gating update, residual, Jacobian,
+// BiCGStab(block ILU0) and the damped Newton loop, all on device-resident data.
+//
+//   BiCGStab   Dune::BiCGSTABSolver (dune-istl 2.3 solvers.hh) as driven by
+//              ISTLBackend_{SEQ,OVLP}_BCGS_ILUn (acme2_cyl_setup.hh:764-765,797-798)     [ext]
+//   overlap    OverlappingOperator / OverlappingWrappedPreconditioner / OVLPScalarProduct,
+//              restated in dune/ax1/common/ax1_solverbackend.hh:306-443
+//   Newton     PDELab NewtonSolver::apply [ext] + Ax1Newton::{defect,prepare_step,line_search}
+//              dune/ax1/common/ax1_newton.hh:194-205, 216-293, 308-503
+// Krylov scalars (rho, alpha, omega, norms, convergence flag) live on the device; the host only
+// polls the flag, so a solve is a stream of kernel launches without per-iteration round trips.
+#include <cmath>
+#include <cstring>
+#include "ctx.h"
+
+namespace ax1 {
+
+#define AX1_LAUNCH_CHECK(c)                                  \
+  do {                                                       \
+    (c)->launches++;                                         \
+    cudaError_t e_ = cudaGetLastError();                     \
+    if (e_ != cudaSuccess) {                                 \
+      set_error(std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+      return AX1GPU_ECUDA;                                   \
+    }                                                        \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// vector kernels: one thread per vertex block (4 doubles), grid-stride
+struct Own { int lo, hi, nvx, masked; };
+
+__device__ __forceinline__ bool owned(const Own& o, int v) {
+  if (!o.masked) return true;
+  const int i = v % o.nvx;
+  return i >= o.lo && i <= o.hi;
+}
+
+template <int NS>
+__device__ __forceinline__ void block_reduce_store(double (&s)[NS], double* partials) {
+  __shared__ double sh[NS][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    if (lane == 0) sh[k][w] = s[k];
+  }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      double t = lane < nw ? sh[k][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) partials[k * gridDim.x + blockIdx.x] = t;
+    }
+  }
+}
+
+__device__ __forceinline__ void ld4v(const double* p, double* o) {
+  const double2 lo = *reinterpret_cast<const double2*>(p);
+  const double2 hi = *reinterpret_cast<const double2*>(p + 2);
+  o[0] = lo.x; o[1] = lo.y; o[2] = hi.x; o[3] = hi.y;
+}
+__device__ __forceinline__ void st4v(double* p, const double* v) {
+  reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
+  reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+}
+
+// sums[0] = <a,b>, sums[1] = <c,d> (if two)
+__global__ void __launch_bounds__(256) dot_kernel(int nv, const double* __restrict__ a, const double* __restrict__ b,
+                                                  const double* __restrict__ c, const double* __restrict__ d, int two,
+                                                  Own own, const Scalars* sc, double* partials) {
+  double s[2] = {0.0, 0.0};
+  if (!(sc && sc->done)) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+      if (!owned(own, v)) continue;
+      double x[4], y[4];
+      ld4v(a + 4 * (size_t)v, x); ld4v(b + 4 * (size_t)v, y);
+      s[0] += x[0] * y[0]; s[0] += x[1] * y[1]; s[0] += x[2] * y[2]; s[0] += x[3] * y[3];
+      if (two) {
+        ld4v(c + 4 * (size_t)v, x); ld4v(d + 4 * (size_t)v, y);
+        s[1] += x[0] * y[0]; s[1] += x[1] * y[1]; s[1] += x[2] * y[2]; s[1] += x[3] * y[3];
+      }
+    }
+  }
+  block_reduce_store<2>(s, partials);
+}
+
+// p = r (first) or p = (p - omega v) beta + r
+__global__ void __launch_bounds__(256) pupdate_kernel(int nv, double* p, const double* __restrict__ v,
+                                                      const double* __restrict__ r, const Scalars* sc, int first) {
+  if (sc->done) return;
+  const double omega = sc->omega, beta = sc->beta;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
+    double pr[4], rr[4];
+    ld4v(r + 4 * (size_t)k, rr);
+    if (first) {
+      st4v(p + 4 * (size_t)k, rr);
+    } else {
+      double vv[4];
+      ld4v(p + 4 * (size_t)k, pr); ld4v(v + 4 * (size_t)k, vv);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { double t = pr[c] + (-omega) * vv[c]; t *= beta; t += rr[c]; pr[c] = t; }
+      st4v(p + 4 * (size_t)k, pr);
+    }
+  }
+}
+
+// x += s y ; r -= s w ; partial <r,r>   (s = alpha or omega)
+__global__ void __launch_bounds__(256) xr_update_kernel(int nv, double* x, const double* __restrict__ y, double* r,
+                                                        const double* __restrict__ w, const Scalars* sc, int use_omega,
+                                                        Own own, double* partials) {
+  double s[2] = {0.0, 0.0};
+  if (!sc->done) {
+    const double a = use_omega ? sc->omega : sc->alpha;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
+      double xv[4], yv[4], rv[4], wv[4];
+      ld4v(x + 4 * (size_t)k, xv); ld4v(y + 4 * (size_t)k, yv); ld4v(r + 4 * (size_t)k, rv); ld4v(w + 4 * (size_t)k, wv);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { xv[c] += a * yv[c]; rv[c] += (-a) * wv[c]; }
+      st4v(x + 4 * (size_t)k, xv); st4v(r + 4 * (size_t)k, rv);
+      if (owned(own, k)) { s[0] += rv[0] * rv[0]; s[0] += rv[1] * rv[1]; s[0] += rv[2] * rv[2]; s[0] += rv[3] * rv[3]; }
+    }
+  }
+  block_reduce_store<2>(s, partials);
+}
+
+// u = uprev - lambda z
+__global__ void __launch_bounds__(256) newton_update_kernel(int nv, double* u, const double* __restrict__ uprev,
+                                                            const double* __restrict__ z, double lambda) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
+    double a[4], b[4];
+    ld4v(uprev + 4 * (size_t)k, a); ld4v(z + 4 * (size_t)k, b);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) a[c] += (-lambda) * b[c];
+    st4v(u + 4 * (size_t)k, a);
+  }
+}
+
+__global__ void __launch_bounds__(1024) reduce_final_kernel(const double* partials, int nblocks, double* sums) {
+  __shared__ double sh[2][32];
+  double s[2] = {0.0, 0.0};
+  for (int k = threadIdx.x; k < nblocks; k += blockDim.x) { s[0] += partials[k]; s[1] += partials[nblocks + k]; }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+    if (lane == 0) sh[q][w] = s[q];
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      double t = sh[q][lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) sums[q] = t;
+    }
+  }
+}
+
+enum { OP_NORM0 = 0, OP_RHO, OP_H, OP_NORM_A, OP_OMEGA, OP_NORM_B, OP_PLAIN_NORM };
+
+__global__ void scalar_kernel(int op, Scalars* sc, const double* sums, double reduction, double* out) {
+  const double EPSILON = 1e-80;
+  if (op == OP_PLAIN_NORM) { out[0] = sqrt(sums[0]); return; }
+  if (sc->done) return;
+  switch (op) {
+    case OP_NORM0:
+      sc->norm = sc->norm0 = sqrt(sums[0]);
+      sc->rho = sc->alpha = sc->omega = 1.0;
+      sc->it_half = 0.5; sc->converged = 0; sc->breakdown = 0;
+      if (sc->norm < reduction * sc->norm0 || sc->norm < 1e-30) { sc->converged = 1; sc->done = 1; sc->it_half = 0.0; }
+      break;
+    case OP_RHO:
+      sc->rho_new = sums[0];
+      if (fabs(sc->rho) <= EPSILON || fabs(sc->omega) <= EPSILON) { sc->breakdown = 1; sc->done = 1; break; }
+      sc->beta = (sc->rho_new / sc->rho) * (sc->alpha / sc->omega);
+      break;
+    case OP_H:
+      sc->h = sums[0];
+      if (fabs(sc->h) < EPSILON) { sc->breakdown = 1; sc->done = 1; break; }
+      sc->alpha = sc->rho_new / sc->h;
+      break;
+    case OP_NORM_A:
+      sc->norm = sqrt(sums[0]);
+      if (sc->norm < reduction * sc->norm0) { sc->converged = 1; sc->done = 1; break; }
+      sc->it_half += 0.5;
+      break;
+    case OP_OMEGA:
+      sc->tr = sums[0]; sc->tt = sums[1];
+      sc->omega = sc->tr / sc->tt;
+      break;
+    case OP_NORM_B:
+      sc->rho = sc->rho_new;
+      sc->norm = sqrt(sums[0]);
+      if (sc->norm < reduction * sc->norm0 || sc->norm < 1e-30) { sc->converged = 1; sc->done = 1; break; }
+      sc->it_half += 0.5;
+      break;
+  }
+}
+
+// halo pack / unpack-add of 3 vertex columns per processor-boundary side
+__global__ void halo_pack_kernel(Dev g, const double* v, double* buf, int c0, int side_off) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = 3 * g.nvy * 4;
+  if (t >= n) return;
+  const int k = t & 3, j = (t >> 2) % g.nvy, c = (t >> 2) / g.nvy;
+  buf[side_off + t] = v[4 * (size_t)(c0 + c + g.nvx * j) + k];
+}
+__global__ void halo_add_kernel(Dev g, double* v, const double* buf, int c0, int side_off) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = 3 * g.nvy * 4;
+  if (t >= n) return;
+  const int k = t & 3, j = (t >> 2) % g.nvy, c = (t >> 2) / g.nvy;
+  v[4 * (size_t)(c0 + c + g.nvx * j) + k] += buf[side_off + t];
+}
+
+// ------------------------------------------------------------------------------------------
+static inline int vec_grid(const ax1gpu_ctx* c) { return c->nred_blocks; }
+static inline Own own_of(const ax1gpu_ctx* c) { return Own{c->own_lo, c->own_hi, c->g.nvx, c->nranks > 1}; }
+
+#define AX1_NCCL(c, call)                                                             \
+  do {                                                                                \
+    ncclResult_t r_ = (call);                                                         \
+    if (r_ != ncclSuccess) {                                                          \
+      set_error(std::string(#call) + ": " + (c)->nccl.GetErrorString(r_));            \
+      return AX1GPU_ENCCL;                                                            \
+    }                                                                                 \
+  } while (0)
+
+// partials -> sums (+ allreduce over ranks)
+static int finish_reduce(ax1gpu_ctx* c, int nsums) {
+  reduce_final_kernel<<<1, 1024, 0, c->stream>>>(c->d_partials, c->nred_blocks, c->d_sums);
+  AX1_LAUNCH_CHECK(c);
+  if (c->nranks > 1)
+    AX1_NCCL(c, c->nccl.AllReduce(c->d_sums, c->d_sums, nsums, ncclDouble, ncclSum, c->comm, c->stream));
+  return 0;
+}
+
+static int scalar_op(ax1gpu_ctx* c, int op, double reduction, double* out = nullptr) {
+  scalar_kernel<<<1, 1, 0, c->stream>>>(op, c->d_sc, c->d_sums, reduction, out);
+  AX1_LAUNCH_CHECK(c);
+  return 0;
+}
+
+static int halo_add(ax1gpu_ctx* c, double* v) {
+  if (c->nranks <= 1) return 0;
+  const Dev& g = c->g;
+  const int n = 3 * g.nvy * 4, bs = 256, nb = (n + bs - 1) / bs;
+  if (c->left_pb) { halo_pack_kernel<<<nb, bs, 0, c->stream>>>(g, v, c->d_halo_send, 0, 0); AX1_LAUNCH_CHECK(c); }
+  if (c->right_pb) { halo_pack_kernel<<<nb, bs, 0, c->stream>>>(g, v, c->d_halo_send, g.nvx - 3, n); AX1_LAUNCH_CHECK(c); }
+  AX1_NCCL(c, c->nccl.GroupStart());
+  if (c->left_pb) {
+    AX1_NCCL(c, c->nccl.Send(c->d_halo_send, n, ncclDouble, c->rank - 1, c->comm, c->stream));
+    AX1_NCCL(c, c->nccl.Recv(c->d_halo_recv, n, ncclDouble, c->rank - 1, c->comm, c->stream));
+  }
+  if (c->right_pb) {
+    AX1_NCCL(c, c->nccl.Send(c->d_halo_send + n, n, ncclDouble, c->rank + 1, c->comm, c->stream));
+    AX1_NCCL(c, c->nccl.Recv(c->d_halo_recv + n, n, ncclDouble, c->rank + 1, c->comm, c->stream));
+  }
+  AX1_NCCL(c, c->nccl.GroupEnd());
+  if (c->left_pb) { halo_add_kernel<<<nb, bs, 0, c->stream>>>(g, v, c->d_halo_recv, 0, 0); AX1_LAUNCH_CHECK(c); }
+  if (c->right_pb) { halo_add_kernel<<<nb, bs, 0, c->stream>>>(g, v, c->d_halo_recv, g.nvx - 3, n); AX1_LAUNCH_CHECK(c); }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+int drv_refresh_dev(ax1gpu_ctx* c) {
+  Dev& g = c->g;
+  const ax1gpu_params& p = c->prm;
+  g.dt = c->dt;
+  const double t_lop = c->time + c->dt;  // OneStepMethod sets the LOP time to t+dt
+  g.stim_on = p.do_stimulation && (t_lop > p.tinj_start && t_lop < p.tinj_end);
+  g.equil = p.do_equilibration && c->time < p.t_equilibrium;
+  return 0;
+}
+
+int drv_set_uold(ax1gpu_ctx* c) {
+  drv_refresh_dev(c);
+  launch_residual(c->g, c->d_uold, nullptr, c->d_r0, 1, c->stream);
+  AX1_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int drv_update_state(ax1gpu_ctx* c, const double* d_u) {  // membranefluxgridfunction_implicit.hh:429-501
+  const ax1gpu_params& p = c->prm;
+  if (!p.membrane_active) return 0;
+  if (!c->channels_initialized && c->channels_partially_initialized) return 0;
+  drv_refresh_dev(c);
+  if (!c->channels_initialized) {
+    if (!p.do_equilibration || (std::fabs(c->time - p.t_equilibrium) < 1e-6 || c->time > p.t_equilibrium)) {
+      launch_channels(c->g, c->ch, d_u, 0, 0.0, p.automatic_channel_init, p.channel_resting_potential, c->d_err,
+                      c->stream);
+      AX1_LAUNCH_CHECK(c);
+      c->channels_partially_initialized = true;
+    }
+  } else {
+    const double real_dt = c->dt * p.time_scale;
+    const double dt_ms = real_dt / 1e-3;  // DynamicChannelSet::TIME_SCALE
+    launch_channels(c->g, c->ch, d_u, 1, dt_ms, 0, 0.0, c->d_err, c->stream);
+    AX1_LAUNCH_CHECK(c);
+  }
+  return 0;
+}
+
+int drv_accept_state(ax1gpu_ctx* c) {  // :524-546
+  if (!c->prm.membrane_active) return 0;
+  if (c->channels_partially_initialized) {
+    c->channels_initialized = true;
+    c->channels_partially_initialized = false;
+  }
+  launch_channel_accept(c->g.nx, c->ch, c->stream);
+  AX1_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int drv_norm(ax1gpu_ctx* c, const double* a, double* out_host) {
+  dot_kernel<<<vec_grid(c), 256, 0, c->stream>>>(c->g.nv, a, a, nullptr, nullptr, 0, own_of(c), nullptr, c->d_partials);
+  AX1_LAUNCH_CHECK(c);
+  int rc = finish_reduce(c, 1);
+  if (rc) return rc;
+  rc = scalar_op(c, OP_PLAIN_NORM, 0.0, c->d_sums + 2);
+  if (rc) return rc;
+  AX1_CUDA(cudaMemcpyAsync(c->h_pin, c->d_sums + 2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  AX1_CUDA(cudaStreamSynchronize(c->stream));
+  *out_host = c->h_pin[0];
+  return 0;
+}
+
+int drv_residual(ax1gpu_ctx* c, const double* d_u, double* d_r, double* norm_host) {
+  drv_refresh_dev(c);
+  launch_residual(c->g, d_u, c->d_r0, d_r, 0, c->stream);
+  AX1_LAUNCH_CHECK(c);
+  if (norm_host) return drv_norm(c, d_r, norm_host);
+  return 0;
+}
+
+int drv_jacobian(ax1gpu_ctx* c, const double* d_u) {
+  drv_refresh_dev(c);
+  launch_jacobian_volume(c->g, d_u, c->d_A, c->stream);
+  AX1_LAUNCH_CHECK(c);
+  if (c->prm.membrane_active) {
+    launch_jacobian_boundary_fd(c->g, d_u, c->d_A, c->stream);
+    AX1_LAUNCH_CHECK(c);
+  }
+  c->factored = false;
+  return 0;
+}
+
+int drv_factor(ax1gpu_ctx* c, int slab_w) {
+  if (slab_w <= 0) slab_w = c->slab_w > 0 ? c->slab_w : 128;
+  if (slab_w > c->g.nvx) slab_w = c->g.nvx;
+  c->slab_w = slab_w;
+  launch_ilu_factor(c->g, c->d_A, c->d_LU, slab_w, c->stream);
+  AX1_LAUNCH_CHECK(c);
+  c->factored = true;
+  return 0;
+}
+
+int drv_prec_apply(ax1gpu_ctx* c, const double* d, double* v) {
+  launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->nranks > 1, c->stream);
+  AX1_LAUNCH_CHECK(c);
+  return halo_add(c, v);
+}
+
+int drv_op_apply(ax1gpu_ctx* c, const double* x, double* y) {
+  launch_spmv(c->g, c->d_A, x, y, c->nranks > 1, c->stream);
+  AX1_LAUNCH_CHECK(c);
+  return 0;
+}
+
+static int poll_scalars(ax1gpu_ctx* c) {
+  AX1_CUDA(cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
+  AX1_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// BiCGStab on A z = rhs from z = 0; rhs is overwritten with the final residual (ISTL aliases r = b)
+int drv_solve(ax1gpu_ctx* c, double* r, double* x, double reduction, int maxit, ax1gpu_lin_result* res) {
+  const int nv = c->g.nv;
+  const size_t bytes = 4 * (size_t)nv * sizeof(double);
+  const Own own = own_of(c);
+  const int G = vec_grid(c);
+  int rc;
+  if (!c->factored) { rc = drv_factor(c, c->slab_w); if (rc) return rc; }
+  AX1_CUDA(cudaMemsetAsync(x, 0, bytes, c->stream));
+  AX1_CUDA(cudaMemsetAsync(c->d_sc, 0, sizeof(Scalars), c->stream));
+  // r = b - A*0 = b ; rt = r
+  AX1_CUDA(cudaMemcpyAsync(c->d_rt, r, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  dot_kernel<<<G, 256, 0, c->stream>>>(nv, r, r, nullptr, nullptr, 0, own, nullptr, c->d_partials);
+  AX1_LAUNCH_CHECK(c);
+  if ((rc = finish_reduce(c, 1))) return rc;
+  if ((rc = scalar_op(c, OP_NORM0, reduction))) return rc;
+  int k = 0;
+  const int poll_every = 4;
+  for (k = 0; 0.5 + k < maxit; ++k) {
+    dot_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_rt, r, nullptr, nullptr, 0, own, c->d_sc, c->d_partials);
+    AX1_LAUNCH_CHECK(c);
+    if ((rc = finish_reduce(c, 1))) return rc;
+    if ((rc = scalar_op(c, OP_RHO, reduction))) return rc;
+    pupdate_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_p, c->d_v, r, c->d_sc, k == 0);
+    AX1_LAUNCH_CHECK(c);
+    if ((rc = drv_prec_apply(c, c->d_p, c->d_y2))) return rc;
+    if ((rc = drv_op_apply(c, c->d_y2, c->d_v))) return rc;
+    dot_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_rt, c->d_v, nullptr, nullptr, 0, own, c->d_sc, c->d_partials);
+    AX1_LAUNCH_CHECK(c);
+    if ((rc = finish_reduce(c, 1))) return rc;
+    if ((rc = scalar_op(c, OP_H, reduction))) return rc;
+    xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, x, c->d_y2, r, c->d_v, c->d_sc, 0, own, c->d_partials);
+    AX1_LAUNCH_CHECK(c);
+    if ((rc = finish_reduce(c, 1))) return rc;
+    if ((rc = scalar_op(c, OP_NORM_A, reduction))) return rc;
+    if ((rc = drv_prec_apply(c, r, c->d_y2))) return rc;
+    if ((rc = drv_op_apply(c, c->d_y2, c->d_t))) return rc;
+    dot_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_t, r, c->d_t, c->d_t, 1, own, c->d_sc, c->d_partials);
+    AX1_LAUNCH_CHECK(c);
+    if ((rc = finish_reduce(c, 2))) return rc;
+    if ((rc = scalar_op(c, OP_OMEGA, reduction))) return rc;
+    xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, x, c->d_y2, r, c->d_t, c->d_sc, 1, own, c->d_partials);
+    AX1_LAUNCH_CHECK(c);
+    if ((rc = finish_reduce(c, 1))) return rc;
+    if ((rc = scalar_op(c, OP_NORM_B, reduction))) return rc;
+    if (reduction > 0.0 && (k % poll_every) == poll_every - 1) {
+      if ((rc = poll_scalars(c))) return rc;
+      if (c->h_sc->done) break;
+    }
+  }
+  if ((rc = poll_scalars(c))) return rc;
+  const Scalars& s = *c->h_sc;
+  if (s.breakdown) { set_error("breakdown in BiCGSTAB"); res->converged = 0; return AX1GPU_ESTATE; }
+  double it = s.it_half;
+  if (it > maxit) it = maxit;
+  res->converged = s.converged;
+  res->it_half = it;
+  res->iterations = (int)std::ceil(it);
+  res->reduction = s.norm0 > 0 ? s.norm / s.norm0 : 0.0;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+
+int drv_newton(ax1gpu_ctx* c, const ax1gpu_newton_opts* o, ax1gpu_newton_result* res) {
+  const int nv = c->g.nv;
+  const size_t bytes = 4 * (size_t)nv * sizeof(double);
+  const int G = vec_grid(c);
+  std::memset(res, 0, sizeof(*res));
+  res->reduction = 1.0; res->conv_rate = 1.0;
+  int rc;
+  double t_asm_ms = 0, t_lin_ms = 0;
+  cudaEvent_t e0 = c->ev[0], e1 = c->ev[1], e2 = c->ev[2], e3 = c->ev[3];
+  AX1_CUDA(cudaEventRecord(e3, c->stream));
+  auto defect = [&](bool& finite) -> int {
+    double nrm = 0.0;
+    int r_ = drv_residual(c, c->d_u, c->d_r, &nrm);
+    if (r_) return r_;
+    res->residual_evals++;
+    res->defect = nrm;
+    finite = std::isfinite(nrm);
+    return 0;
+  };
+  bool finite = true;
+  if ((rc = defect(finite))) return rc;
+  if (!finite) { res->status = AX1GPU_NEWTON_DEFECT_NAN; return 0; }
+  res->first_defect = res->defect;
+  double prev_defect = res->defect;
+  double linear_reduction = o->min_lin_reduction;
+  while (true) {
+    if (!(o->force_iteration && res->iterations == 0)) {
+      res->converged = res->defect < o->abs_limit || res->defect < res->first_defect * o->reduction;
+      if (o->fixed_work) res->converged = res->iterations >= o->maxit;
+      if (res->converged) break;
+      if (res->iterations >= o->maxit) { res->status = AX1GPU_NEWTON_NOT_CONVERGED; break; }
+    }
+    // prepare_step: preAssembly (gating) + Jacobian + linear reduction
+    AX1_CUDA(cudaEventRecord(e0, c->stream));
+    if ((rc = drv_update_state(c, c->d_u))) return rc;
+    if ((rc = drv_jacobian(c, c->d_u))) return rc;
+    if (o->fixed_lin_reduction) linear_reduction = o->min_lin_reduction;
+    else {
+      const double stop_defect = std::max(res->first_defect * o->reduction, o->abs_limit);
+      if (stop_defect / (10 * res->defect) > res->defect * res->defect / (prev_defect * prev_defect))
+        linear_reduction = stop_defect / (10 * res->defect);
+      else
+        linear_reduction = std::min(o->min_lin_reduction, res->defect * res->defect / (prev_defect * prev_defect));
+    }
+    prev_defect = res->defect;
+    if (c->prm.use_rownorm_preconditioner) { launch_rownorm(c->g, c->d_A, c->d_r, c->stream); AX1_LAUNCH_CHECK(c); }
+    AX1_CUDA(cudaEventRecord(e1, c->stream));
+    // linear solve (ILU0 re-factorised every Newton iteration, like SeqILUn in the backend's apply)
+    ax1gpu_lin_result lr{};
+    if ((rc = drv_factor(c, o->slab_w))) return rc;
+    rc = drv_solve(c, c->d_r, c->d_z, o->fixed_work ? 0.0 : linear_reduction, o->lin_maxit, &lr);
+    AX1_CUDA(cudaEventRecord(e2, c->stream));
+    AX1_CUDA(cudaEventSynchronize(e2));
+    t_asm_ms += ev_ms(e0, e1);
+    t_lin_ms += ev_ms(e1, e2);
+    if (rc == AX1GPU_ESTATE) { res->status = AX1GPU_NEWTON_LINSOLVE_FAILED; break; }
+    if (rc) return rc;
+    res->lin_iterations += lr.iterations;
+    if (!lr.converged && !o->fixed_work) { res->status = AX1GPU_NEWTON_LINSOLVE_FAILED; break; }
+    // line search, strategy hackbuschReuskenAcceptBestNoThrow (ax1_newton.hh:372-502)
+    AX1_CUDA(cudaEventRecord(e0, c->stream));
+    AX1_CUDA(cudaMemcpyAsync(c->d_uprev, c->d_u, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    auto step = [&](double lam) -> int {
+      newton_update_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_u, c->d_uprev, c->d_z, lam);
+      AX1_LAUNCH_CHECK(c);
+      int r_ = drv_update_state(c, c->d_u);
+      if (r_) return r_;
+      return defect(finite);
+    };
+    if (o->disable_line_search || o->fixed_work) {
+      if ((rc = step(1.0))) return rc;
+      if (!finite) { res->status = AX1GPU_NEWTON_DEFECT_NAN; break; }
+    } else {
+      double lambda = 1.0, best_lambda = 0.0, best_defect = res->defect;
+      int i = 0;
+      while (true) {
+        if ((rc = step(lambda))) return rc;
+        if (res->defect <= (1.0 - lambda / 4) * prev_defect) break;
+        if (res->defect < best_defect) { best_defect = res->defect; best_lambda = lambda; }
+        if (++i >= o->line_search_maxit) {
+          if (best_lambda == 0.0) {
+            best_lambda = 1.0;
+            if ((rc = step(best_lambda))) return rc;
+          }
+          if (best_lambda != lambda) {
+            if ((rc = step(best_lambda))) return rc;
+          }
+          break;
+        }
+        lambda *= 0.5;
+      }
+      if (!std::isfinite(res->defect)) { res->status = AX1GPU_NEWTON_DEFECT_NAN; break; }
+    }
+    AX1_CUDA(cudaEventRecord(e1, c->stream));
+    AX1_CUDA(cudaEventSynchronize(e1));
+    t_asm_ms += ev_ms(e0, e1);
+    res->reduction = res->defect / res->first_defect;
+    res->iterations++;
+    res->conv_rate = std::pow(res->reduction, 1.0 / res->iterations);
+  }
+  AX1_CUDA(cudaEventRecord(e2, c->stream));
+  AX1_CUDA(cudaEventSynchronize(e2));
+  res->t_assembler = t_asm_ms * 1e-3;
+  res->t_lin_solv = t_lin_ms * 1e-3;
+  res->t_elapsed = ev_ms(e3, e2) * 1e-3;
+  // channel-kernel error flag (leak ratio outside [0,1], channelset.hh:298-299)
+  int herr = 0;
+  AX1_CUDA(cudaMemcpy(&herr, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (herr) { set_error("Calculated leak channel ratio outside [0,1]"); return AX1GPU_ESTATE; }
+  return 0;
+}
+
+// mean device time of one kernel on resident data (roofline evidence for bench.py)
+int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms) {
+  const std::string n(name);
+  const int nv = c->g.nv;
+  const int G = vec_grid(c);
+  drv_refresh_dev(c);
+  auto run = [&]() -> int {
+    if (n == "residual") { launch_residual(c->g, c->d_u, c->d_r0, c->d_r, 0, c->stream); }
+    else if (n == "jacobian") { launch_jacobian_volume(c->g, c->d_u, c->d_A, c->stream); }
+    else if (n == "spmv") { launch_spmv(c->g, c->d_A, c->d_y2, c->d_v, 0, c->stream); }
+    else if (n == "ilu_factor") { launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->stream); }
+    else if (n == "ilu_apply") { launch_ilu_apply(c->g, c->d_LU, c->d_p, c->d_y2, c->slab_w, 0, c->stream); }
+    else if (n == "dot") { dot_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_rt, c->d_v, nullptr, nullptr, 0, own_of(c), nullptr, c->d_partials); }
+    else if (n == "axpy") { xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_tmp, c->d_y2, c->d_t, c->d_v, c->d_sc, 0, own_of(c), c->d_partials); }
+    else { set_error("unknown kernel name"); return AX1GPU_EINVAL; }
+    AX1_LAUNCH_CHECK(c);
+    return 0;
+  };
+  if (c->slab_w <= 0) c->slab_w = std::min(128, c->g.nvx);
+  AX1_CUDA(cudaMemsetAsync(c->d_sc, 0, sizeof(Scalars), c->stream));
+  int rc = run();
+  if (rc) return rc;
+  AX1_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  for (int i = 0; i < reps; ++i) if ((rc = run())) return rc;
+  AX1_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  AX1_CUDA(cudaEventSynchronize(c->ev[1]));
+  *ms = ev_ms(c->ev[0], c->ev[1]) / reps;
+  return 0;
+}
+
+}  // namespace ax1

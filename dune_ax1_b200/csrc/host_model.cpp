@@ -1,0 +1,216 @@
+// host_model.cpp -- host-side model of the reference's "Physics" precomputations, part of the
+// product (libax1gpu.so). It lets the device path be driven without DUNE: radial grid vector,
+// subdomain tags, node volumes, Dirichlet masks and the z-slab partition. When the library is
+// dropped into acme2_cyl_par these arrays come from the reference's own Physics object instead
+//  and this file is not needed.
+//
+//   radial grid vector   dune/ax1/common/ax1_gridvector.hh, ax1_gridgenerator.hh:74-149,232-277,357-450
+//   subdomain tags       dune/ax1/common/ax1_gridgenerator.hh:806-828
+//   node volumes         dune/ax1/acme2_cyl/common/acme2_cyl_physics.hh:2286-2397
+//   boundary types       configurations/default/default_{nernst_planck,poisson}_parameters.hh (bctype)
+//   overlap constraints  dune/ax1/common/ax1_parallelconstraintshelper.hh:36-41
+//   slab partition       dune/ax1/common/ax1_gridgenerator.hh:601-631, ax1_yaspgrid_loadbalancer.hh:17-38
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/ax1gpu.h"
+
+namespace ax1 { void set_error(const std::string& s); }
+
+namespace {
+
+const double kPi = 3.1415926535897932384626433;
+
+// ---- grid vector pieces -------------------------------------------------------------------
+struct Axis {
+  std::vector<double> p;
+  double last() const { return p.back(); }
+  void uniform_steps(int n, double h) { for (int k = 0; k < n; ++k) p.push_back(last() + h); }
+  void uniform_to(int n, double end) {
+    const double h = (end - last()) / n;
+    for (int k = 0; k + 1 < n; ++k) p.push_back(last() + h);
+    p.push_back(end);
+  }
+  // root of  -q^n + m q - m + 1 = 0  by Newton (ratio of a geometric progression of n steps
+  // starting with step h that exactly spans [s,e])
+  static double ratio(int n, double s, double e, double h) {
+    const double m = (e - s) / h;
+    auto iterate = [&](double from, double prev) {
+      double cur = from;
+      while (std::fabs(cur - prev) > 1E-8) {
+        prev = cur;
+        cur = prev - (-std::pow(prev, n) + m * prev - m + 1) / (-n * std::pow(prev, n - 1) + m);
+      }
+      return cur;
+    };
+    double q = iterate(e - s, 0.0);
+    if (std::fabs(q - 1) < 1E-6) q = iterate(0.0, e - s);
+    return q;
+  }
+  void geometric_first(int n, double h0, double end) {  // first step fixed
+    const double q = ratio(n, last(), end, h0);
+    double h = h0;
+    for (int k = 0; k + 1 < n; ++k) { p.push_back(last() + h); h *= q; }
+    p.push_back(end);
+  }
+  void geometric_last(int n, double hend, double end) {  // last step fixed
+    const double q = ratio(n, last(), end, hend);
+    double h = hend * std::pow(q, n - 1);
+    for (int k = 0; k + 1 < n; ++k) { p.push_back(last() + h); h /= q; }
+    p.push_back(end);
+  }
+  void geometric(double h0, double hend, double end, bool fix_last) {
+    const double q = (end - last() - h0) / (end - last() - hend);
+    const int n = (int)(std::log(hend / h0) / std::log(q)) + 1;
+    if (fix_last) geometric_last(n, hend, end); else geometric_first(n, h0, end);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int ax1host_generate_y(double ymin, double ymax, double ymemb, double dmemb, double dy_cell, double dy_cell_min,
+                       int n_dy_cell_min, double dy, double dy_min, int n_dy_min, double* out, int cap) {
+  const double q = 0.7;  // qTransition
+  Axis y;
+  y.p.push_back(ymin);
+  if (ymemb > y.last() + 1e-6) {  // cytosol: equidistant, then geometric refinement towards the membrane
+    const int nt = (int)std::ceil(std::fabs(std::log(dy_cell_min / dy_cell) / std::log(q)));
+    const double range = std::max(dy_cell, dy_cell_min) * (std::pow(q, nt + 1) - 1) / (q - 1);
+    const double dist = n_dy_cell_min * dy_cell_min + range;
+    if (ymemb - dist < y.last()) { ax1::set_error("cytosol too thin for the requested dy_cell_min"); return -1; }
+    const int neq = (int)std::floor((ymemb - dist - y.last()) / dy_cell);
+    if (neq > 0) y.uniform_steps(neq, dy_cell);
+    y.geometric(dy_cell, dy_cell_min, ymemb - n_dy_cell_min * dy_cell_min, false);
+    y.uniform_steps(n_dy_cell_min, dy_cell_min);
+  }
+  if (ymemb + dmemb > y.last() + 1e-6 && dmemb > 0) y.uniform_steps(1, dmemb);  // one membrane cell layer
+  {  // extracellular: fine layer, geometric coarsening, equidistant far field
+    const double y0 = y.last();
+    y.uniform_steps(n_dy_min, dy_min);
+    const int nt = (int)std::ceil(std::fabs(std::log(dy_min / dy) / std::log(q)));
+    const double range = dy * (std::pow(q, nt + 1) - 1) / (q - 1);
+    const int neq = (int)std::floor((ymax - y0 - (n_dy_min * dy_min + range)) / dy);
+    y.geometric(dy_min, dy, ymax - (neq * dy), true);
+    if (neq > 0) y.uniform_to(neq, ymax);
+  }
+  if (std::fabs(y.last() - ymax) > 1e-6) { ax1::set_error("radial grid does not end at ymax"); return -1; }
+  if (out) for (int k = 0; k < (int)y.p.size() && k < cap; ++k) out[k] = y.p[k];
+  return (int)y.p.size();
+}
+
+int ax1host_physics_maps(const ax1gpu_grid* grid, double ymemb, double dmemb, double xmin_global, double xmax_global,
+                         double ymin, double ymax, int do_volume_scaling, double volume_scaling_threshold,
+                         const ax1host_bc* bc, unsigned char* cell_subdomain, double* node_volume,
+                         unsigned char* dirichlet_mask) {
+  if (!grid || !bc) { ax1::set_error("null argument"); return AX1GPU_EINVAL; }
+  const int nx = grid->nx, ny = grid->ny, nvx = nx + 1, nvy = ny + 1;
+  const double* x = grid->x;
+  const double* y = grid->y;
+  // row classification by cell-centre height
+  std::vector<unsigned char> row_sd(ny);
+  for (int j = 0; j < ny; ++j) {
+    const double yc = 0.5 * (y[j] + y[j + 1]);
+    row_sd[j] = (yc > ymemb && yc < ymemb + dmemb) ? 2 : (yc > ymemb + dmemb ? 1 : 0);
+  }
+  if (cell_subdomain)
+    for (int j = 0; j < ny; ++j) std::memset(cell_subdomain + (size_t)j * nx, row_sd[j], nx);
+
+  if (node_volume) {
+    // Order-dependent by construction in the reference (cells visited x-fastest; min over scaled
+    // cells, overwrite with 1 by unscaled ones; reference volume = first scaled cell on this rank).
+    // Rows are visited bottom-up, so a vertex row j sees cell rows j-1 then j; within a row the
+    // left cell comes before the right one.
+    const double threshold = volume_scaling_threshold >= 0 ? volume_scaling_threshold : ymemb + dmemb + ymemb;
+    std::vector<char> scaled(ny);
+    int jfirst = -1;
+    for (int j = 0; j < ny; ++j) {
+      scaled[j] = do_volume_scaling && (0.5 * (y[j] + y[j + 1]) > threshold);
+      if (scaled[j] && jfirst < 0) jfirst = j;
+    }
+    auto cellvol = [&](int i, int j) { return (kPi * (y[j + 1] + y[j])) * ((x[i + 1] - x[i]) * (y[j + 1] - y[j])); };
+    const double ref = jfirst >= 0 ? cellvol(0, jfirst) : 1.0;
+    for (int jv = 0; jv < nvy; ++jv)
+      for (int iv = 0; iv < nvx; ++iv) {
+        double val = 0.0;
+        bool have = false;
+        for (int cj = jv - 1; cj <= jv; ++cj) {
+          if (cj < 0 || cj >= ny) continue;
+          for (int ci = iv - 1; ci <= iv; ++ci) {
+            if (ci < 0 || ci >= nx) continue;
+            if (scaled[cj]) {
+              const double r = cellvol(ci, cj) / ref;
+              val = have ? std::min(val, r) : r;
+            } else {
+              val = 1.0;
+            }
+            have = true;
+          }
+        }
+        node_volume[(size_t)iv + (size_t)nvx * jv] = val;
+      }
+  }
+
+  if (dirichlet_mask) {
+    std::memset(dirichlet_mask, 0, (size_t)nvx * nvy);
+    const double w = bc->debye_layer_width;
+    auto side_flags = [&](bool left, double yc, int which) {
+      if (yc - 1e-6 < ymemb - w) return left ? bc->left_cytosol[which] : bc->right_cytosol[which];
+      if (yc + 1e-6 > ymemb - w && yc - 1e-6 < ymemb + dmemb + w) return left ? bc->left_debye[which] : bc->right_debye[which];
+      return left ? bc->left_extra[which] : bc->right_extra[which];
+    };
+    auto bits = [&](bool memb_cell, int con, int pot) -> unsigned char {
+      return (unsigned char)(((con && !memb_cell) ? 0x7 : 0) | (pot ? 0x8 : 0));
+    };
+    // bottom / top faces (face centre decides: top tested before bottom, both before the sides)
+    for (int i = 0; i < nx; ++i) {
+      const bool top_is_top = y[ny] + 1e-6 > ymax, bot_is_bot = y[0] - 1e-6 < ymin;
+      if (bot_is_bot) {
+        const unsigned char m = bits(row_sd[0] == 2, bc->bottom[0], bc->bottom[1]);
+        dirichlet_mask[i] |= m; dirichlet_mask[i + 1] |= m;
+      }
+      if (top_is_top) {
+        const unsigned char m = bits(row_sd[ny - 1] == 2, bc->top[0], bc->top[1]);
+        dirichlet_mask[(size_t)nvx * ny + i] |= m; dirichlet_mask[(size_t)nvx * ny + i + 1] |= m;
+      }
+    }
+    for (int j = 0; j < ny; ++j) {
+      const double yc = 0.5 * (y[j] + y[j + 1]);
+      const bool memb = row_sd[j] == 2;
+      if (!grid->left_proc_boundary && x[0] - 1e-6 < xmin_global) {
+        const unsigned char m = bits(memb, side_flags(true, yc, 0), side_flags(true, yc, 1));
+        dirichlet_mask[(size_t)nvx * j] |= m; dirichlet_mask[(size_t)nvx * (j + 1)] |= m;
+      }
+      if (!grid->right_proc_boundary && x[nx] + 1e-6 > xmax_global) {
+        const unsigned char m = bits(memb, side_flags(false, yc, 0), side_flags(false, yc, 1));
+        dirichlet_mask[(size_t)nvx * j + nx] |= m; dirichlet_mask[(size_t)nvx * (j + 1) + nx] |= m;
+      }
+    }
+    for (int j = 0; j < nvy; ++j) {  // processor boundaries of the overlap: all four components
+      if (grid->left_proc_boundary) dirichlet_mask[(size_t)nvx * j] = 0xF;
+      if (grid->right_proc_boundary) dirichlet_mask[(size_t)nvx * j + nx] = 0xF;
+    }
+  }
+  return AX1GPU_OK;
+}
+
+int ax1host_slab(int nx_global, int nranks, int rank, int* c0, int* c1, int* l0, int* l1) {
+  if (nranks < 1 || rank < 0 || rank >= nranks || nranks > nx_global) {
+    ax1::set_error("invalid slab partition (px must not exceed Nx)");
+    return AX1GPU_EINVAL;
+  }
+  // YaspGrid-style block partition of the cell columns: the first (nx % p) ranks get one more
+  const int base = nx_global / nranks, rem = nx_global % nranks;
+  const int a = rank * base + std::min(rank, rem);
+  const int b = a + base + (rank < rem ? 1 : 0);
+  if (c0) *c0 = a;
+  if (c1) *c1 = b;
+  if (l0) *l0 = a - (rank > 0 ? 1 : 0);
+  if (l1) *l1 = b + (rank < nranks - 1 ? 1 : 0);
+  return AX1GPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,39 @@
+// kernels.h -- launch wrappers shared between the translation units of libax1gpu.
+#pragma once
+#include "common.cuh"
+
+namespace ax1 {
+
+struct ChannelDev {
+  const double* gbar[3];  // leak, Nav, Kv
+  double* ratio[2];       // Na_leak, K_leak
+  double* gate[3];        // m, h, n accepted
+  double* gate_new[3];
+  double* geff;           // 4*nx
+  double* v_rest;         // device scalar
+};
+
+// assembly.cu
+void launch_residual(const Dev& g, const double* u, const double* r0, double* r, int mode, cudaStream_t st);
+void launch_jacobian_volume(const Dev& g, const double* u, double* A, cudaStream_t st);
+void launch_channels(const Dev& g, const ChannelDev& ch, const double* u, int mode, double dt_ms, int automatic,
+                     double v_fixed, int* err, cudaStream_t st);
+void launch_channel_accept(int nx, const ChannelDev& ch, cudaStream_t st);
+void launch_memb_pot(const Dev& g, const double* u, double* vm, cudaStream_t st);
+// boundary_fd.cu (compiled with --fmad=false)
+void launch_jacobian_boundary_fd(const Dev& g, const double* u, double* A, cudaStream_t st);
+
+// solver.cu
+struct Scalars {  // device-resident Krylov scalars
+  double rho, rho_new, alpha, omega, beta, h, norm, norm0, tr, tt, it_half, reduction;
+  int done, converged, breakdown, pad;
+};
+void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int zero_constrained, cudaStream_t st);
+void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, cudaStream_t st);
+void launch_ilu_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, int zero_constrained,
+                      cudaStream_t st);
+void launch_rownorm(const Dev& g, double* A, double* r, cudaStream_t st);
+void launch_compact_bcrs(const Dev& g, const double* A9, double* blocks, const int* rowptr, cudaStream_t st);
+void launch_expand_bcrs(const Dev& g, const double* blocks, double* A9, const int* rowptr, cudaStream_t st);
+
+}  // namespace ax1

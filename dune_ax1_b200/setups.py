@@ -1,0 +1,85 @@
+"""Problem set-ups of the BASELINE configs as plain arrays (grid, Physics maps, channel densities,
+initial state), shared by bench.py, the tests and the examples.
+
+  paper      src/config/square10mm.config: x 0..1e7 nm, dx 100e3 (Nx=100), 181-point radial vector
+  synthetic  SURVEY 8(d): same radial vector, x equidistant with dx = 100 nm, Nx cell columns,
+             HH channels everywhere, deterministic perturbation of the replicated equilibrium column
+The equilibrium column is the state file the reference ships
+(src/simulation_states/equilibrium/cyl/yasp_square10mm_p0.dat, extracted to tests/golden/).
+"""
+import json
+import os
+
+import numpy as np
+
+from . import api
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(_ROOT, "tests", "golden", "yasp_square10mm.json")
+
+
+def equidistant_x(xmin, xmax, n):
+    """GridVector::equidistant_n_xend (ax1_gridvector.hh:23-31): repeated addition, exact end point."""
+    x = [float(xmin)]
+    h = (xmax - xmin) / n
+    for _ in range(n - 1):
+        x.append(x[-1] + h)
+    x.append(float(xmax))
+    return np.array(x)
+
+
+def load_equilibrium_column(path=GOLDEN):
+    g = json.load(open(path))
+    y = np.array(g["y"])
+    u = np.array(g["unew"]).reshape(len(y), 2, 4)[:, 0, :].copy()  # one vertex column [j][comp]
+    return y, u, np.array(g["channelStates"])
+
+
+def replicate_column(ucol, nvx):
+    """doExtrapolateXData: copy the 1-column equilibrium to every x (vertex-blocked, x fastest)."""
+    nvy = ucol.shape[0]
+    u = np.empty((nvy, nvx, 4))
+    u[:, :, :] = ucol[:, None, :]
+    return u.reshape(-1)
+
+
+def perturb(u, nvx, nvy, amp=1e-3, i_offset=0):
+    """Deterministic synthetic perturbation u (1 + amp sin(2 pi i/97) cos(2 pi j/31)), SURVEY 8(d)."""
+    i = np.arange(nvx) + i_offset
+    j = np.arange(nvy)
+    f = 1.0 + amp * np.sin(2 * np.pi * i / 97.0)[None, :] * np.cos(2 * np.pi * j / 31.0)[:, None]
+    return (u.reshape(nvy, nvx, 4) * f[:, :, None]).reshape(-1)
+
+
+def make_setup(nx, dx=None, xmax=None, stimulation=False, hh=True, equilibration=False, bc=None,
+               rank=0, nranks=1, perturbation=0.0, y=None, ucol=None):
+    """Arrays of one rank's local problem. Returns a dict usable for api.Ax1Gpu and for the oracle."""
+    if y is None or ucol is None:
+        y, ucol, _ = load_equilibrium_column()
+    if xmax is None:
+        xmax = nx * (dx if dx is not None else 100.0e3)
+    xg = equidistant_x(0.0, xmax, nx)
+    c0, c1, l0, l1 = api.slab(nx, nranks, rank) if nranks > 1 else (0, nx, 0, nx)
+    x = xg[l0:l1 + 1].copy()
+    left_pb, right_pb = rank > 0, rank < nranks - 1
+    nxl = len(x) - 1
+    bc = bc or api.BoundaryConfig()
+    cs, nvol, dm = api.physics_maps(x, y, xmin_global=0.0, xmax_global=xmax, bc=bc, left_pb=left_pb,
+                                    right_pb=right_pb)
+    u0 = replicate_column(ucol, nxl + 1)
+    if perturbation:
+        u0 = perturb(u0, nxl + 1, len(y), perturbation, i_offset=l0)
+    params = dict(do_stimulation=int(stimulation), tinj_start=20.0, tinj_end=2.0e3, stim_x=150.0e3, stim_y=0.0,
+                  I_inj=1.0e13, do_equilibration=int(equilibration), t_equilibrium=1.0e9 if equilibration else 0.0,
+                  dummy_value=10.0 if equilibration else 1.0)
+    return dict(x=x, y=y, nx=nxl, ny=len(y) - 1, xmax=xmax, cell_subdomain=cs, node_volume=nvol, dirichlet=dm,
+                eps_memb=np.full(nxl, 2.0), g_leak=np.full(nxl, 0.5), g_nav=np.full(nxl, 120.0 if hh else 0.0),
+                g_kv=np.full(nxl, 36.0 if hh else 0.0), u0=u0, params=params, left_pb=left_pb, right_pb=right_pb,
+                bc=bc, slab=(c0, c1, l0, l1))
+
+
+def make_device(s, device=0, stream=None):
+    p = api.default_params(**s["params"])
+    return api.Ax1Gpu(s["x"], s["y"], s["cell_subdomain"], s["eps_memb"], s["node_volume"], s["dirichlet"], p,
+                      s["g_leak"], s["g_nav"], s["g_kv"], left_pb=s["left_pb"], right_pb=s["right_pb"],
+                      device=device, stream=stream)

@@ -1,0 +1,184 @@
+/* include/ax1gpu.h -- C ABI of libax1gpu.so: the B200-native PNP Newton hot path of dune-ax1.
+ *
+ * The reference (jurgispods/dune-ax1) has no FFI boundary; the seam this library replaces is the
+ * set of C++ template concepts instantiated in Acme2CylSetup::setup
+ * (dune/ax1/acme2_cyl/common/acme2_cyl_setup.hh:226-1018):
+ *   GridOperator  IGO::residual(x,r) / IGO::jacobian(x,A)     acme2_cyl_setup.hh:700-708
+ *   Solver backend LS::apply(A,z,r,reduction) / norm / result  acme2_cyl_setup.hh:727-811
+ *   PDE solver    Ax1Newton::apply(u), result()                acme2_cyl_setup.hh:822-854,
+ *                                                              dune/ax1/common/ax1_newton.hh:541-617
+ *   membrane flux gfMembFlux.updateState / acceptTimeStep      dune/ax1/common/
+ *                                                              membranefluxgridfunction_implicit.hh:402-546
+ * A header-only C++ shim that models those concepts on top of this ABI is in
+ * include/ax1gpu_pdelab_shim.hh; INTEGRATION.md shows the lines a maintainer changes.
+ *
+ * Conventions: every function returns 0 on success, a negative AX1GPU_E* code on failure and
+ * never throws across the boundary; ax1gpu_last_error() gives the message. Vectors are
+ * vertex-blocked [Na,K,Cl,pot], vertices x-fastest (Dune::BlockVector<FieldVector<double,4>>,
+ * istl::raw(v)); the Jacobian is block-CSR with row-major 4x4 blocks, columns ascending
+ * (Dune::BCRSMatrix<FieldMatrix<double,4,4>>). All pointers are HOST pointers unless the
+ * function name ends in _dev. There is no CPU fallback: without a CUDA device every compute
+ * entry point fails with AX1GPU_ENODEVICE.
+ */
+#ifndef AX1GPU_H
+#define AX1GPU_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AX1GPU_OK 0
+#define AX1GPU_EINVAL (-1)
+#define AX1GPU_ENODEVICE (-2)
+#define AX1GPU_ECUDA (-3)
+#define AX1GPU_ENCCL (-4)
+#define AX1GPU_ESTATE (-5)
+
+/* Newton status codes; the shim re-throws the matching Dune::PDELab::NewtonError subclass
+ * (caught by the time loop, acme2_cyl_simulation.hh:593-692). */
+#define AX1GPU_NEWTON_OK 0
+#define AX1GPU_NEWTON_NOT_CONVERGED 1   /* NewtonNotConverged      */
+#define AX1GPU_NEWTON_LINSOLVE_FAILED 2 /* NewtonLinearSolverError */
+#define AX1GPU_NEWTON_DEFECT_NAN 3      /* NewtonDefectError       */
+#define AX1GPU_NEWTON_LINESEARCH_FAILED 4
+
+typedef struct ax1gpu_ctx* ax1gpu_handle;
+
+/* Local tensor grid of this rank: interior + one overlap cell column per interior side
+ * (dune/ax1/common/ax1_gridgenerator.hh:601-631). */
+typedef struct ax1gpu_grid {
+  int nx, ny;          /* local cells */
+  const double* x;     /* nx+1 axial coordinates [nm]  */
+  const double* y;     /* ny+1 radial coordinates [nm] */
+  int left_proc_boundary, right_proc_boundary; /* side is a processor boundary (overlap) */
+} ax1gpu_grid;
+
+/* Physical constants and run-time switches (Physics / Acme2CylParameters getters used on the path). */
+typedef struct ax1gpu_params {
+  double temperature;        /* electrolyte.hh: 279.45 K                                        */
+  double eps_elec;           /* default_config.hh:71  (80)                                      */
+  double length_scale, time_scale; /* default_config.hh:113-116                                 */
+  double diff_water[3];      /* default_config.hh:119-123 [m^2/s]                               */
+  int valence[3];            /* default_config.hh:77,83,89                                      */
+  double pot_residual_scale; /* acme2_cyl_parametertree.hh:300-303                              */
+  int do_volume_scaling;     /* use node_volume (acme2_cyl_operator_fully_coupled.hh:142-156)   */
+  int do_stimulation;        /* default_nernst_planck_parameters.hh:168-216                     */
+  double tinj_start, tinj_end, stim_x, stim_y, I_inj;
+  int do_equilibration;      /* membranefluxgridfunction_implicit.hh:223-265                    */
+  double t_equilibrium, dummy_value;
+  int membrane_active, automatic_channel_init;
+  double channel_resting_potential;
+  int use_rownorm_preconditioner; /* rownorm_preconditioner.hh:65-155                           */
+  double leak_ratio_na, leak_ratio_k; /* [equilibration] Na_leak / K_leak                       */
+} ax1gpu_params;
+
+typedef struct ax1gpu_newton_opts {
+  double reduction, abs_limit, min_lin_reduction; /* acme2_cyl_setup.hh:828-833 */
+  int fixed_lin_reduction, maxit, line_search_maxit, lin_maxit;
+  int force_iteration, disable_line_search;
+  int slab_w;      /* vertex columns per ILU0 sub-slab (<=0: library default)                  */
+  int fixed_work;  /* benchmark mode: exactly maxit Newton x lin_maxit BiCGStab iterations     */
+} ax1gpu_newton_opts;
+
+typedef struct ax1gpu_newton_result { /* PDELab NewtonResult + ax1_newton.hh:600-607 */
+  int converged, iterations, lin_iterations, status, residual_evals;
+  double first_defect, defect, reduction, conv_rate;
+  double t_assembler, t_lin_solv, t_elapsed; /* seconds, device time from CUDA events */
+} ax1gpu_newton_result;
+
+typedef struct ax1gpu_lin_result { /* Dune::InverseOperatorResult */
+  int converged, iterations;
+  double reduction, it_half;
+} ax1gpu_lin_result;
+
+const char* ax1gpu_last_error(void);
+void ax1gpu_params_default(ax1gpu_params* p);
+void ax1gpu_newton_opts_default(ax1gpu_newton_opts* o);
+int ax1gpu_sizeof_params(void);
+int ax1gpu_device_count(void);
+
+/* Create the device-resident problem. Arrays are the Physics maps of the reference
+ * (acme2_cyl_physics.hh): cell_subdomain nx*ny {0 CYTOSOL,1 ES,2 MEMBRANE}; memb_perm nx
+ * (initPermittivities :2424-2606); node_volume (nx+1)*(ny+1) (calcNodeVolumes :2286-2397);
+ * dirichlet_mask (nx+1)*(ny+1), bit c = component c constrained (setup.hh:646-665);
+ * g_leak/g_nav/g_kv nx channel densities per membrane column [mS/cm^2] (channelset.hh:133-182).
+ * stream: a cudaStream_t to run on (NULL: the library creates one). */
+int ax1gpu_create(const ax1gpu_grid* grid, const unsigned char* cell_subdomain, const double* memb_perm,
+                  const double* node_volume, const unsigned char* dirichlet_mask, const ax1gpu_params* params,
+                  const double* g_leak, const double* g_nav, const double* g_kv, int device, void* stream,
+                  ax1gpu_handle* out);
+int ax1gpu_destroy(ax1gpu_handle h);
+
+/* BCRS sparsity pattern (FullVolumePattern on Q1 vertices). Pass NULLs to query *nblocks. */
+int ax1gpu_pattern(ax1gpu_handle h, int* rowptr, int* colidx, int* nblocks);
+
+/* OneStepMethod::apply(time,dt,uold,unew): flux GF time = t, LOP time = t+dt; builds r0=-M(uold). */
+int ax1gpu_set_time(ax1gpu_handle h, double t, double dt);
+int ax1gpu_set_uold(ax1gpu_handle h, const double* uold);
+/* gfMembFlux.updateState() / acceptTimeStep(); channel state layout =
+ * DynamicChannelSet::serializeChannelStates: [ratioNa|ratioK|m|h|n] each nx long. */
+int ax1gpu_update_state(ax1gpu_handle h, const double* u);
+int ax1gpu_accept_state(ax1gpu_handle h);
+int ax1gpu_get_channel_state(ax1gpu_handle h, double* s, int newstate, double* v_rest);
+int ax1gpu_set_channel_state(ax1gpu_handle h, const double* s, double v_rest, int initialized);
+int ax1gpu_membrane_potential(ax1gpu_handle h, const double* u, double* vm_mV);
+
+/* IGO::residual + LS::norm. u == NULL: use the device-resident iterate. r/norm may be NULL. */
+int ax1gpu_residual(ax1gpu_handle h, const double* u, double* r, double* norm);
+/* IGO::jacobian; blocks (BCRS order, 16 doubles per block) may be NULL (stay on device). */
+int ax1gpu_jacobian(ax1gpu_handle h, const double* u, double* blocks);
+/* overwrite the device Jacobian with host BCRS values (used by the shim when A was modified on host) */
+int ax1gpu_set_jacobian(ax1gpu_handle h, const double* blocks);
+int ax1gpu_get_jacobian(ax1gpu_handle h, double* blocks);
+/* LS::apply(A,z,r,reduction): block-ILU0(sub-slab) BiCGStab on the device Jacobian.
+ * r == NULL: use the device residual of the last ax1gpu_residual. r (if given) is overwritten by
+ * the final linear residual as ISTL does. */
+int ax1gpu_solve(ax1gpu_handle h, double* r, double reduction, int maxit, int slab_w, double* z,
+                 ax1gpu_lin_result* res);
+/* Ax1Newton::apply(u): u in/out. */
+int ax1gpu_newton(ax1gpu_handle h, const ax1gpu_newton_opts* opts, double* u, ax1gpu_newton_result* res);
+
+/* ---- device-resident variants (value metric: no host<->device traffic in the call) ---- */
+int ax1gpu_upload_u(ax1gpu_handle h, const double* u);
+int ax1gpu_download_u(ax1gpu_handle h, double* u);
+int ax1gpu_set_uold_dev(ax1gpu_handle h); /* uold := device iterate */
+int ax1gpu_newton_dev(ax1gpu_handle h, const ax1gpu_newton_opts* opts, ax1gpu_newton_result* res);
+
+/* ---- building blocks exposed for parity tests and profiling ---- */
+int ax1gpu_spmv(ax1gpu_handle h, const double* x, double* y);
+int ax1gpu_ilu_factor(ax1gpu_handle h, int slab_w);
+int ax1gpu_ilu_apply(ax1gpu_handle h, const double* d, double* v);
+int ax1gpu_rownorm(ax1gpu_handle h, double* r); /* scales device Jacobian and r */
+/* run `reps` launches of one named kernel on device-resident data and return the mean device time
+ * [ms] from CUDA events ("residual","jacobian","spmv","ilu_factor","ilu_apply","dot","axpy") */
+int ax1gpu_time_kernel(ax1gpu_handle h, const char* name, int reps, double* ms);
+long long ax1gpu_launch_count(ax1gpu_handle h); /* kernels launched so far by this handle */
+void* ax1gpu_stream(ax1gpu_handle h);
+
+/* ---- multi-GPU (z-slabs along the axon, one process per GPU, NCCL) ----
+ * Replaces Dune::CollectiveCommunication / YaspGrid::communicate on the path
+ * (AddDataHandle halo sum + allreduce, ax1_solverbackend.hh:346-381,413-437). */
+int ax1gpu_nccl_unique_id(const char* libnccl_path, char* id128);
+int ax1gpu_comm_init(ax1gpu_handle h, const char* libnccl_path, const char* id128, int rank, int nranks);
+
+/* ---- host model: restatement of the reference's host-side Physics precomputations, so that the
+ * library can be driven without DUNE (bench, tests, examples). No GPU needed. ---- */
+typedef struct ax1host_bc { /* [boundary.concentration] / [boundary.potential]; index 0 con, 1 pot */
+  int top[2], bottom[2], left_cytosol[2], right_cytosol[2], left_debye[2], right_debye[2],
+      left_extra[2], right_extra[2];
+  double debye_layer_width;
+} ax1host_bc;
+int ax1host_generate_y(double ymin, double ymax, double ymemb, double dmemb, double dy_cell,
+                       double dy_cell_min, int n_dy_cell_min, double dy, double dy_min, int n_dy_min,
+                       double* out, int cap);
+int ax1host_physics_maps(const ax1gpu_grid* grid, double ymemb, double dmemb, double xmin_global,
+                         double xmax_global, double ymin, double ymax, int do_volume_scaling,
+                         double volume_scaling_threshold, const ax1host_bc* bc,
+                         unsigned char* cell_subdomain, double* node_volume, unsigned char* dirichlet_mask);
+/* z-slab partition of nx_global cell columns over nranks (Ax1YaspPartition, px = nranks, py = 1):
+ * interior cells [c0,c1) and local cells [l0,l1) incl. one overlap column per interior side. */
+int ax1host_slab(int nx_global, int nranks, int rank, int* c0, int* c1, int* l0, int* l1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

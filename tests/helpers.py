@@ -1,0 +1,31 @@
+"""Shared helpers of the parity tests: build the SAME problem in the oracle and on the device."""
+import numpy as np
+
+from dune_ax1_b200 import setups
+
+
+def oracle_problem(O, s, analytic=1, **cfg_over):
+    p = s["params"]
+    bc = s["bc"].c
+    cfg = O.default_config(
+        xmin_global=0.0, xmax_global=s["xmax"], ymin=float(s["y"][0]), ymax=float(s["y"][-1]),
+        do_stimulation=p["do_stimulation"], tinj_start=p["tinj_start"], tinj_end=p["tinj_end"], stim_x=p["stim_x"],
+        stim_y=p["stim_y"], I_inj=p["I_inj"], do_equilibration=p["do_equilibration"],
+        t_equilibrium=p["t_equilibrium"], dummy_value=p["dummy_value"], analytic_volume_jacobian=analytic,
+        top_dirichlet=list(bc.top), bottom_dirichlet=list(bc.bottom),
+        left_cytosol_dirichlet=list(bc.left_cytosol), right_cytosol_dirichlet=list(bc.right_cytosol),
+        left_debye_dirichlet=list(bc.left_debye), right_debye_dirichlet=list(bc.right_debye),
+        left_extra_dirichlet=list(bc.left_extra), right_extra_dirichlet=list(bc.right_extra),
+        debye_layer_width=bc.debye_layer_width, **cfg_over)
+    return O.Problem(cfg, s["x"], s["y"], left_pb=s["left_pb"], right_pb=s["right_pb"], eps_memb=s["eps_memb"],
+                     g_leak=s["g_leak"], g_nav=s["g_nav"], g_kv=s["g_kv"])
+
+
+def small_setup(nx=6, **kw):
+    kw.setdefault("dx", 100.0e3)
+    kw.setdefault("perturbation", 1e-3)
+    return setups.make_setup(nx, **kw)
+
+
+def rel_err(a, b, scale):
+    return float(np.max(np.abs(a - b) / (scale + 1e-300)))
