@@ -87,6 +87,12 @@ void elec_alpha_volume(const Problem& p, const Cell& c, const double* xl, double
         for (int k = 0; k < 4; ++k) { sx += xl[4 * j + k] * gx[k]; sy += xl[4 * j + k] * gy[k]; }
         gcx[j] = sx; gcy[j] = sy;
       }
+      // magnitudes before cancellation (forward-error scale for the parity tolerance)
+      double agpx = 0, agpy = 0, achg = 0;
+      if (ra) {
+        for (int k = 0; k < 4; ++k) { agpx += std::fabs(xl[12 + k] * gx[k]); agpy += std::fabs(xl[12 + k] * gy[k]); }
+        for (int j = 0; j < NSPEC; ++j) achg += std::fabs(uCon[j]);
+      }
       // A grad u; Poisson tensor = -eps I (default_poisson_parameters.hh:86-105)
       double Apx = (-eps) * gpx, Apy = (-eps) * gpy;
       double chargeDensity = 0.0;
@@ -97,7 +103,7 @@ void elec_alpha_volume(const Problem& p, const Cell& c, const double* xl, double
       for (int k = 0; k < 4; ++k) {
         double val = (Apx * gx[k] + Apy * gy[k]) - uPot * (0.0 * gx[k] + 0.0 * gy[k]) + (0.0 * uPot - fPot) * phi[k];
         r[12 + k] += weight * (val * factor * c.vs[k] * S);
-        if (ra) ra[12 + k] += std::fabs(weight) * ((std::fabs(Apx * gx[k]) + std::fabs(Apy * gy[k]) + std::fabs(fPot * phi[k])) * factor * c.vs[k] * S);
+        if (ra) ra[12 + k] += std::fabs(weight) * ((eps * agpx * std::fabs(gx[k]) + eps * agpy * std::fabs(gy[k]) + p.PC * achg * phi[k]) * factor * c.vs[k] * S);
       }
       for (int j = 0; j < NSPEC; ++j) {
         double D = p.D[j];
@@ -107,8 +113,13 @@ void elec_alpha_volume(const Problem& p, const Cell& c, const double* xl, double
           double val = (Acx * gx[k] + Acy * gy[k]) - uCon[j] * (bx * gx[k] + by * gy[k]) +
                        (0.0 * uCon[j] - fsrc[j]) * phi[k];
           r[4 * j + k] += weight * (val * factor * c.vs[k]);
-          if (ra) ra[4 * j + k] += std::fabs(weight) * ((std::fabs(Acx * gx[k]) + std::fabs(Acy * gy[k]) + std::fabs(uCon[j] * bx * gx[k]) +
-                                                       std::fabs(uCon[j] * by * gy[k]) + std::fabs(fsrc[j] * phi[k])) * factor * c.vs[k]);
+          if (ra) {
+            double agcx = 0, agcy = 0;
+            for (int m = 0; m < 4; ++m) { agcx += std::fabs(xl[4 * j + m] * gx[m]); agcy += std::fabs(xl[4 * j + m] * gy[m]); }
+            ra[4 * j + k] += std::fabs(weight) * ((D * agcx * std::fabs(gx[k]) + D * agcy * std::fabs(gy[k]) +
+                                                   std::fabs(uCon[j]) * D * (agpx * std::fabs(gx[k]) + agpy * std::fabs(gy[k])) +
+                                                   std::fabs(fsrc[j] * phi[k])) * factor * c.vs[k]);
+          }
         }
       }
     }
@@ -132,7 +143,11 @@ void memb_alpha_volume(const Problem& p, const Cell& c, const double* xpot, doub
       for (int k = 0; k < 4; ++k) {
         double val = (Ax * gx[k] + Ay * gy[k]) - u * (0.0) + (0.0 * u - 0.0) * phi[k];
         r[k] += weight * (val * factor * c.vs[k] * S);
-        if (ra) ra[k] += std::fabs(weight) * ((std::fabs(Ax * gx[k]) + std::fabs(Ay * gy[k])) * factor * c.vs[k] * S);
+        if (ra) {
+          double agx = 0, agy = 0;
+          for (int m = 0; m < 4; ++m) { agx += std::fabs(xpot[m] * gx[m]); agy += std::fabs(xpot[m] * gy[m]); }
+          ra[k] += std::fabs(weight) * ((eps * agx * std::fabs(gx[k]) + eps * agy * std::fabs(gy[k])) * factor * c.vs[k] * S);
+        }
       }
     }
 }
@@ -212,7 +227,7 @@ void elec_alpha_boundary(const Problem& p, const Cell& c, const double* xl, cons
         double flux = driftTerm;
         flux -= diffTerm;
         totalFlux += flux;
-        absFlux += std::fabs(driftTerm) + std::fabs(diffTerm);
+        absFlux += std::fabs(C * C1) * (std::fabs(pot2) + std::fabs(uPot)) + std::fabs(diffTerm);
       }
       double yj = totalFlux * n_y;
       yj *= surfaceScaleFactor;
