@@ -203,7 +203,7 @@ int ax1gpu_destroy(ax1gpu_handle c) {
                   (void*)c->d_LU, (void*)c->d_rt, (void*)c->d_p, (void*)c->d_v, (void*)c->d_y2, (void*)c->d_t, (void*)c->d_tmp,
                   (void*)c->d_bcrs, (void*)c->d_gbar, (void*)c->d_chstate, (void*)c->d_geff, (void*)c->d_vrest, (void*)c->d_vm,
                   (void*)c->d_err, (void*)c->d_partials, (void*)c->d_sums, (void*)c->d_sc, (void*)c->d_halo_send,
-                  (void*)c->d_halo_recv})
+                  (void*)c->d_halo_recv, (void*)c->d_lvl})
     if (p) cudaFree(p);
   if (c->h_sc) cudaFreeHost(c->h_sc);
   if (c->h_pin) cudaFreeHost(c->h_pin);

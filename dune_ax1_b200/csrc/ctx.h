@@ -39,6 +39,8 @@ struct ax1gpu_ctx {
   int nred_blocks = 0;
   // ILU
   int slab_w = 0;
+  int lvl_slab_w = 0;          // slab width the level tables were built for
+  int* d_lvl = nullptr;        // level prefix tables (solver.cu)
   bool factored = false;
   // multi-GPU
   ax1::NcclApi nccl;

@@ -351,18 +351,32 @@ int drv_jacobian(ax1gpu_ctx* c, const double* d_u) {
   return 0;
 }
 
+static int ensure_level_tables(ax1gpu_ctx* c) {
+  if (c->d_lvl && c->lvl_slab_w == c->slab_w) return 0;
+  std::vector<int> tab;
+  ilu_level_tables(c->g, c->slab_w, tab);
+  if (!c->d_lvl) AX1_CUDA(cudaMalloc((void**)&c->d_lvl, 2 * (size_t)(128 + 2 * c->g.nvy + 1) * sizeof(int)));
+  AX1_CUDA(cudaMemcpyAsync(c->d_lvl, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  AX1_CUDA(cudaStreamSynchronize(c->stream));  // tab is a local
+  c->lvl_slab_w = c->slab_w;
+  return 0;
+}
+
 int drv_factor(ax1gpu_ctx* c, int slab_w) {
   if (slab_w <= 0) slab_w = c->slab_w > 0 ? c->slab_w : 128;
+  if (slab_w > 128) slab_w = 128;  // one quad per wavefront row with 256-thread CTAs (solver.cu)
   if (slab_w > c->g.nvx) slab_w = c->g.nvx;
   c->slab_w = slab_w;
-  launch_ilu_factor(c->g, c->d_A, c->d_LU, slab_w, c->stream);
+  int rc = ensure_level_tables(c);
+  if (rc) return rc;
+  launch_ilu_factor(c->g, c->d_A, c->d_LU, slab_w, c->d_lvl, c->stream);
   AX1_LAUNCH_CHECK(c);
   c->factored = true;
   return 0;
 }
 
 int drv_prec_apply(ax1gpu_ctx* c, const double* d, double* v) {
-  launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->nranks > 1, c->stream);
+  launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
   AX1_LAUNCH_CHECK(c);
   return halo_add(c, v);
 }
@@ -570,8 +584,8 @@ int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms) {
     if (n == "residual") { launch_residual(c->g, c->d_u, c->d_r0, c->d_r, 0, c->stream); }
     else if (n == "jacobian") { launch_jacobian_volume(c->g, c->d_u, c->d_A, c->stream); }
     else if (n == "spmv") { launch_spmv(c->g, c->d_A, c->d_y2, c->d_v, 0, c->stream); }
-    else if (n == "ilu_factor") { launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->stream); }
-    else if (n == "ilu_apply") { launch_ilu_apply(c->g, c->d_LU, c->d_p, c->d_y2, c->slab_w, 0, c->stream); }
+    else if (n == "ilu_factor") { launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream); }
+    else if (n == "ilu_apply") { launch_ilu_apply(c->g, c->d_LU, c->d_p, c->d_y2, c->slab_w, c->d_lvl, c->stream); }
     else if (n == "dot") { dot_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_rt, c->d_v, nullptr, nullptr, 0, own_of(c), nullptr, c->d_partials); }
     else if (n == "axpy") { xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_tmp, c->d_y2, c->d_t, c->d_v, c->d_sc, 0, own_of(c), c->d_partials); }
     else { set_error("unknown kernel name"); return AX1GPU_EINVAL; }
@@ -579,6 +593,7 @@ int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms) {
     return 0;
   };
   if (c->slab_w <= 0) c->slab_w = std::min(128, c->g.nvx);
+  { int rc0 = ensure_level_tables(c); if (rc0) return rc0; }
   AX1_CUDA(cudaMemsetAsync(c->d_sc, 0, sizeof(Scalars), c->stream));
   int rc = run();
   if (rc) return rc;

@@ -29,8 +29,9 @@ struct Scalars {  // device-resident Krylov scalars
   int done, converged, breakdown, pad;
 };
 void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int zero_constrained, cudaStream_t st);
-void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, cudaStream_t st);
-void launch_ilu_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, int zero_constrained,
+void ilu_level_tables(const Dev& g, int slab_w, std::vector<int>& tab);
+void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st);
+void launch_ilu_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, const int* lvl_tab,
                       cudaStream_t st);
 void launch_rownorm(const Dev& g, double* A, double* r, cudaStream_t st);
 void launch_compact_bcrs(const Dev& g, const double* A9, double* blocks, const int* rowptr, cudaStream_t st);

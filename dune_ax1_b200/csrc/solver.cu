@@ -9,6 +9,9 @@
 // one CTA factors / solves one sub-slab, sweeping the wavefronts level = i + 2 j of the x-fastest
 // 9-point stencil (row (i,j) depends on (i-1,j-1),(i,j-1),(i+1,j-1),(i-1,j)). Couplings across
 // sub-slab borders are dropped from the preconditioner only (the operator keeps them).
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
 #include "kernels.h"
 
 namespace ax1 {
@@ -94,14 +97,45 @@ __device__ __forceinline__ int lev_jlo(int L, int wc) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Wavefront-packed factor layout. The factor is private to the preconditioner, so it is stored in
+// the order the sweeps consume it: sub-slab major, then level L = il + 2 j, then row within the
+// level (q = j - jlo(L)). LF holds the 4 lower blocks of a row (512 B), LB the inverted diagonal
+// block followed by the 4 upper blocks (640 B). A CTA therefore streams two contiguous arrays
+// instead of touching Ny+1 pages that lie (Nx+1)*1152 B apart at every level.
+//   row position  p(il, j) = lvl[L] + j - jlo(L),  lvl = prefix sum of the level sizes
+//   LF[(slab_off + p) * 64 + s * 16 + r * 4 + c],  LB[(slab_off + p) * 80 + t * 16 + r * 4 + c]
+struct SlabGeom {
+  int i0, wc, nlev;
+  size_t row_off;   // packed row offset of this sub-slab
+  const int* lvl;   // level prefix table (shared memory)
+};
+__device__ __forceinline__ int packed_pos(const SlabGeom& sg, int il, int j) {
+  const int L = il + 2 * j;
+  return sg.lvl[L] + j - lev_jlo(L, sg.wc);
+}
+__device__ __forceinline__ SlabGeom slab_geom(const Dev& g, int slab_w, const int* __restrict__ lvl_tab, int* lvl_sh) {
+  SlabGeom sg;
+  sg.i0 = blockIdx.x * slab_w;
+  sg.wc = min(slab_w, g.nvx - sg.i0);
+  sg.nlev = sg.wc + 2 * (g.nvy - 1);
+  sg.row_off = (size_t)blockIdx.x * slab_w * g.nvy;
+  const int stride = slab_w + 2 * (g.nvy - 1) + 1;
+  const int* src = lvl_tab + (sg.wc == slab_w ? 0 : stride);
+  for (int k = threadIdx.x; k <= sg.nlev; k += blockDim.x) lvl_sh[k] = src[k];
+  __syncthreads();
+  sg.lvl = lvl_sh;
+  return sg;
+}
+
 // block ILU0 of one sub-slab per CTA (bilu0_decomposition: L_ij = A_ij * A_jj^-1, diagonal stored inverted)
-__global__ void __launch_bounds__(256) ilu_factor_kernel(Dev g, const double* __restrict__ A, double* LU, int slab_w) {
-  const int i0 = blockIdx.x * slab_w;
-  const int wc = min(slab_w, g.nvx - i0);
+__global__ void __launch_bounds__(256) ilu_factor_kernel(Dev g, const double* __restrict__ A, double* LF, double* LB,
+                                                         int slab_w, const int* __restrict__ lvl_tab) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SlabGeom sg = slab_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(smem_raw));
+  const int i0 = sg.i0, wc = sg.wc;
   const int q = threadIdx.x >> 2, r = threadIdx.x & 3, nq = blockDim.x >> 2;
   const unsigned qmask = 0xFu << (threadIdx.x & 28);
-  const int nlev = wc + 2 * (g.nvy - 1);
-  for (int L = 0; L < nlev; ++L) {
+  for (int L = 0; L < sg.nlev; ++L) {
     const int jlo = lev_jlo(L, wc), jhi = min(g.nvy - 1, L >> 1);
     for (int j = jlo + q; j <= jhi; j += nq) {
       const int il = L - 2 * j;
@@ -119,12 +153,12 @@ __global__ void __launch_bounds__(256) ilu_factor_kernel(Dev g, const double* __
       for (int s = 0; s < 4; ++s) {
         if (!ex[s]) continue;
         const int dis = s % 3 - 1, djs = s / 3 - 1;
-        const size_t k = (size_t)(v + dis + djs * g.nvx);
+        const double* kb = LB + (sg.row_off + packed_pos(sg, il + dis, j + djs)) * 80;  // row k: [Dinv, U5..U8]
         double lrow[4];
         {
           double dinv[16];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) ldcg4(LU + (k * 9 + 4) * 16 + m * 4, dinv + 4 * m);
+          for (int m = 0; m < 4; ++m) ldcg4(kb + m * 4, dinv + 4 * m);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             double sum = 0.0;
@@ -143,7 +177,7 @@ __global__ void __launch_bounds__(256) ilu_factor_kernel(Dev g, const double* __
           if (!ex[s2]) continue;
           double ub[16];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) ldcg4(LU + (k * 9 + tt) * 16 + m * 4, ub + 4 * m);
+          for (int m = 0; m < 4; ++m) ldcg4(kb + (tt - 4) * 16 + m * 4, ub + 4 * m);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             double sum = 0.0;
@@ -168,8 +202,11 @@ __global__ void __launch_bounds__(256) ilu_factor_kernel(Dev g, const double* __
         if (r == 3) val = dinv[3][c];
         row[4][c] = val;
       }
+      const size_t p = sg.row_off + (size_t)(sg.lvl[L] + j - jlo);
 #pragma unroll
-      for (int s = 0; s < 9; ++s) st4(LU + ((size_t)v * 9 + s) * 16 + r * 4, row[s]);
+      for (int s = 0; s < 4; ++s) st4(LF + p * 64 + s * 16 + r * 4, row[s]);
+#pragma unroll
+      for (int s = 4; s < 9; ++s) st4(LB + p * 80 + (s - 4) * 16 + r * 4, row[s]);
     }
     __syncthreads();
   }
@@ -178,63 +215,169 @@ __global__ void __launch_bounds__(256) ilu_factor_kernel(Dev g, const double* __
 // ------------------------------------------------------------------------------------------
 // v = (LU)^-1 d for one sub-slab per CTA (bilu_backsolve): forward sweep with unit lower blocks,
 // backward sweep with the stored inverse diagonal; both sweeps in one launch.
-__global__ void __launch_bounds__(256) ilu_apply_kernel(Dev g, const double* __restrict__ LU, const double* __restrict__ d,
-                                                        double* v_out, int slab_w, int zero_con) {
-  const int i0 = blockIdx.x * slab_w;
-  const int wc = min(slab_w, g.nvx - i0);
-  const int q = threadIdx.x >> 2, r = threadIdx.x & 3, nq = blockDim.x >> 2;
-  const unsigned qmask = 0xFu << (threadIdx.x & 28);
-  const int nlev = wc + 2 * (g.nvy - 1);
-  for (int L = 0; L < nlev; ++L) {
-    const int jlo = lev_jlo(L, wc), jhi = min(g.nvy - 1, L >> 1);
-    for (int j = jlo + q; j <= jhi; j += nq) {
-      const int il = L - 2 * j;
-      const int v = i0 + il + g.nvx * j;
-      double acc = d[4 * (size_t)v + r];
-      if (zero_con && ((g.dmask[v] >> r) & 1)) acc = 0.0;
+//
+// The sweep is strictly sequential over ~W+2Ny wavefront levels, so HBM latency must be hidden by
+// a deep software pipeline: every thread (lane r of the quad that owns a wavefront row) streams
+// "its" scalar row of the 4-5 factor blocks of the next D levels into a private shared-memory slot
+// with cp.async (LDGSTS) and consumes it D levels later -- no barrier is needed for the staged
+// factor data, only cp.async.wait_group. The solution values of the last three levels, which the
+// next level depends on, are exchanged through a small shared-memory ring (one __syncthreads per
+// level) instead of an L2 round trip.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct LevelRow {
+  int v, il, j;  // v < 0: this quad has no row at this level
+};
+__device__ __forceinline__ LevelRow level_row(const Dev& g, int L, int nlev, int i0, int wc, int q) {
+  LevelRow o;
+  o.v = -1; o.il = 0; o.j = 0;
+  if (L < 0 || L >= nlev) return o;
+  const int j = lev_jlo(L, wc) + q;
+  if (j > min(g.nvy - 1, L >> 1)) return o;
+  o.j = j; o.il = L - 2 * j;
+  o.v = i0 + o.il + g.nvx * j;
+  return o;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) ilu_apply_kernel(Dev g, const double* __restrict__ LF,
+                                                        const double* __restrict__ LB, const double* __restrict__ d,
+                                                        double* v_out, int slab_w, const int* __restrict__ lvl_tab) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nt = blockDim.x, tid = threadIdx.x;
+  const int q = tid >> 2, r = tid & 3, nq = nt >> 2;
+  double* stageM = reinterpret_cast<double*>(smem_raw);   // [D][5][nt][4]
+  double* stageR = stageM + (size_t)D * 5 * nt * 4;       // [D][nt]
+  double* ring = stageR + (size_t)D * nt;                 // [4][nq][4]
+  const SlabGeom sg = slab_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(ring + 4 * (size_t)nq * 4));
+  const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
+
+  // ---------------- forward: y = L^-1 d ----------------
+  auto issue_fwd = [&](int L) {
+    const LevelRow w = level_row(g, L, nlev, i0, wc, q);
+    if (w.v >= 0) {
+      const int st = L % D;
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         const int di = s % 3 - 1, dj = s / 3 - 1;
-        if (il + di < 0 || il + di >= wc || j + dj < 0) continue;
-        double l[4], yk[4];
-        ldg4(LU + ((size_t)v * 9 + s) * 16 + r * 4, l);
-        ldcg4(v_out + 4 * (size_t)(v + di + dj * g.nvx), yk);
-        acc -= l[0] * yk[0];
-        acc -= l[1] * yk[1];
-        acc -= l[2] * yk[2];
-        acc -= l[3] * yk[3];
+        if ((w.il + di >= 0) && (w.il + di < wc) && (w.j + dj >= 0)) {
+          const double* src = LF + (sg.row_off + (size_t)(sg.lvl[L] + q)) * 64 + s * 16 + r * 4;
+          double* dst = stageM + ((size_t)(st * 5 + s) * nt + tid) * 4;
+          cp_async16(dst, src);
+          cp_async16(dst + 2, src + 2);
+        }
       }
-      v_out[4 * (size_t)v + r] = acc;
+      cp_async8(stageR + st * nt + tid, d + 4 * (size_t)w.v + r);
+    }
+    cp_async_commit();
+  };
+  for (int L = 0; L < D; ++L) issue_fwd(L);
+  for (int L = 0; L < nlev; ++L) {
+    cp_async_wait<D - 1>();
+    const LevelRow w = level_row(g, L, nlev, i0, wc, q);
+    if (w.v >= 0) {
+      const int st = L % D;
+      double acc = stageR[st * nt + tid];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int di = s % 3 - 1, dj = s / 3 - 1;
+        if ((w.il + di >= 0) && (w.il + di < wc) && (w.j + dj >= 0)) {
+          const double* lp = stageM + ((size_t)(st * 5 + s) * nt + tid) * 4;
+          const double2 l01 = *reinterpret_cast<const double2*>(lp);
+          const double2 l23 = *reinterpret_cast<const double2*>(lp + 2);
+          const int Ln = L + di + 2 * dj;
+          const int qn = (w.j + dj) - lev_jlo(Ln, wc);
+          const double* yp = ring + ((size_t)(Ln & 3) * nq + qn) * 4;
+          const double2 y01 = *reinterpret_cast<const double2*>(yp);
+          const double2 y23 = *reinterpret_cast<const double2*>(yp + 2);
+          double t = l01.x * y01.x;
+          t += l01.y * y01.y;
+          t += l23.x * y23.x;
+          t += l23.y * y23.y;
+          acc -= t;
+        }
+      }
+      ring[((size_t)(L & 3) * nq + q) * 4 + r] = acc;
+      v_out[4 * (size_t)w.v + r] = acc;
     }
     __syncthreads();
+    issue_fwd(L + D);
   }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---------------- backward: x = U^-1 y ----------------
+  auto issue_bwd = [&](int L) {  // L counts down; stage index by distance from the top level
+    const LevelRow w = level_row(g, L, nlev, i0, wc, q);
+    if (w.v >= 0) {
+      const int st = (nlev - 1 - L) % D;
+#pragma unroll
+      for (int s = 4; s < 9; ++s) {
+        const int di = s % 3 - 1, dj = s / 3 - 1;
+        if (s == 4 || ((w.il + di >= 0) && (w.il + di < wc) && (w.j + dj < g.nvy))) {
+          const double* src = LB + (sg.row_off + (size_t)(sg.lvl[L] + q)) * 80 + (s - 4) * 16 + r * 4;
+          double* dst = stageM + ((size_t)(st * 5 + (s - 4)) * nt + tid) * 4;
+          cp_async16(dst, src);
+          cp_async16(dst + 2, src + 2);
+        }
+      }
+      cp_async8(stageR + st * nt + tid, v_out + 4 * (size_t)w.v + r);  // own forward result
+    }
+    cp_async_commit();
+  };
+  for (int k = 0; k < D; ++k) issue_bwd(nlev - 1 - k);
   for (int L = nlev - 1; L >= 0; --L) {
-    const int jlo = lev_jlo(L, wc), jhi = min(g.nvy - 1, L >> 1);
-    for (int j = jlo + q; j <= jhi; j += nq) {
-      const int il = L - 2 * j;
-      const int v = i0 + il + g.nvx * j;
-      double acc = __ldcg(v_out + 4 * (size_t)v + r);
+    cp_async_wait<D - 1>();
+    const LevelRow w = level_row(g, L, nlev, i0, wc, q);
+    if (w.v >= 0) {
+      const int st = (nlev - 1 - L) % D;
+      double acc = stageR[st * nt + tid];
 #pragma unroll
       for (int s = 5; s < 9; ++s) {
         const int di = s % 3 - 1, dj = s / 3 - 1;
-        if (il + di < 0 || il + di >= wc || j + dj >= g.nvy) continue;
-        double ub[4], xk[4];
-        ldg4(LU + ((size_t)v * 9 + s) * 16 + r * 4, ub);
-        ldcg4(v_out + 4 * (size_t)(v + di + dj * g.nvx), xk);
-        acc -= ub[0] * xk[0];
-        acc -= ub[1] * xk[1];
-        acc -= ub[2] * xk[2];
-        acc -= ub[3] * xk[3];
+        if ((w.il + di >= 0) && (w.il + di < wc) && (w.j + dj < g.nvy)) {
+          const double* up = stageM + ((size_t)(st * 5 + (s - 4)) * nt + tid) * 4;
+          const double2 u01 = *reinterpret_cast<const double2*>(up);
+          const double2 u23 = *reinterpret_cast<const double2*>(up + 2);
+          const int Ln = L + di + 2 * dj;
+          const int qn = (w.j + dj) - lev_jlo(Ln, wc);
+          const double* xp = ring + ((size_t)(Ln & 3) * nq + qn) * 4;
+          const double2 x01 = *reinterpret_cast<const double2*>(xp);
+          const double2 x23 = *reinterpret_cast<const double2*>(xp + 2);
+          double t = u01.x * x01.x;
+          t += u01.y * x01.y;
+          t += u23.x * x23.x;
+          t += u23.y * x23.y;
+          acc -= t;
+        }
       }
-      double dv[4];
-      ldg4(LU + ((size_t)v * 9 + 4) * 16 + r * 4, dv);
-      double xr = 0.0;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) xr += dv[c] * __shfl_sync(qmask, acc, (threadIdx.x & 28) + c);
-      v_out[4 * (size_t)v + r] = xr;
+      // x_r = sum_c Dinv[r][c] * acc_c : exchange acc within the quad through the ring slot
+      const double* dp = stageM + ((size_t)(st * 5 + 0) * nt + tid) * 4;
+      const double2 d01 = *reinterpret_cast<const double2*>(dp);
+      const double2 d23 = *reinterpret_cast<const double2*>(dp + 2);
+      const unsigned qmask = 0xFu << (tid & 28);
+      const int qb = tid & 28;
+      double xo = d01.x * __shfl_sync(qmask, acc, qb + 0);
+      xo += d01.y * __shfl_sync(qmask, acc, qb + 1);
+      xo += d23.x * __shfl_sync(qmask, acc, qb + 2);
+      xo += d23.y * __shfl_sync(qmask, acc, qb + 3);
+      ring[((size_t)(L & 3) * nq + q) * 4 + r] = xo;
+      v_out[4 * (size_t)w.v + r] = xo;
     }
     __syncthreads();
+    issue_bwd(L - D);
   }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -288,6 +431,7 @@ void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int 
   const long long nt = 4LL * g.nv;
   spmv_kernel<<<(unsigned)((nt + bs - 1) / bs), bs, 0, st>>>(g, A, x, y, zero_con);
 }
+// one quad per wavefront row: a level of a slab of width w has at most ceil(w/2) rows
 static int slab_threads(int slab_w) {
   int rows = (slab_w + 1) / 2;
   int t = 4 * rows;
@@ -296,14 +440,58 @@ static int slab_threads(int slab_w) {
   if (t < 32) t = 32;
   return t;
 }
-void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, cudaStream_t st) {
-  const int nslab = (g.nvx + slab_w - 1) / slab_w;
-  ilu_factor_kernel<<<nslab, slab_threads(slab_w), 0, st>>>(g, A, LU, slab_w);
+// level prefix tables for full-width sub-slabs and for the (narrower) last one: 2 x (slab_w + 2 Ny + 1) ints
+void ilu_level_tables(const Dev& g, int slab_w, std::vector<int>& tab) {
+  const int stride = slab_w + 2 * (g.nvy - 1) + 1;
+  tab.assign(2 * (size_t)stride, 0);
+  const int last_wc = g.nvx - ((g.nvx - 1) / slab_w) * slab_w;
+  const int wcs[2] = {slab_w, last_wc};
+  for (int t = 0; t < 2; ++t) {
+    const int wc = wcs[t], nlev = wc + 2 * (g.nvy - 1);
+    int acc = 0;
+    for (int L = 0; L < nlev; ++L) {
+      tab[(size_t)t * stride + L] = acc;
+      const int a = L - wc + 1;
+      const int jlo = a <= 0 ? 0 : (a + 1) / 2;
+      const int jhi = std::min(g.nvy - 1, L >> 1);
+      if (jhi >= jlo) acc += jhi - jlo + 1;
+    }
+    tab[(size_t)t * stride + nlev] = acc;
+  }
 }
-void launch_ilu_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, int zero_con,
-                      cudaStream_t st) {
+void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st) {
   const int nslab = (g.nvx + slab_w - 1) / slab_w;
-  ilu_apply_kernel<<<nslab, slab_threads(slab_w), 0, st>>>(g, LU, d, v, slab_w, zero_con);
+  const size_t smem = (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
+  ilu_factor_kernel<<<nslab, slab_threads(slab_w), smem, st>>>(g, A, LU, LU + (size_t)g.nv * 64, slab_w, lvl_tab);
+}
+static int ilu_stages() {
+  static const int d = getenv("AX1_ILU_STAGES") ? atoi(getenv("AX1_ILU_STAGES")) : 2;
+  return d;
+}
+template <int D>
+static void launch_ilu_apply_t(const Dev& g, const double* LU, const double* d, double* v, int slab_w,
+                               const int* lvl_tab, cudaStream_t st) {
+  const int nslab = (g.nvx + slab_w - 1) / slab_w;
+  const int nt = slab_threads(slab_w);
+  const size_t smem = (size_t)D * nt * (5 * 32 + 8) + 4 * (size_t)(nt / 4) * 32 + (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ilu_apply_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  ilu_apply_kernel<D><<<nslab, nt, smem, st>>>(g, LU, LU + (size_t)g.nv * 64, d, v, slab_w, lvl_tab);
+}
+void launch_ilu_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, const int* lvl_tab,
+                      cudaStream_t st) {
+  // the inputs of the preconditioner are already zero on constrained DOFs (see driver.cu)
+  switch (ilu_stages()) {
+    case 3: launch_ilu_apply_t<3>(g, LU, d, v, slab_w, lvl_tab, st); break;
+    case 5: launch_ilu_apply_t<5>(g, LU, d, v, slab_w, lvl_tab, st); break;
+    case 6: launch_ilu_apply_t<6>(g, LU, d, v, slab_w, lvl_tab, st); break;
+    case 8: launch_ilu_apply_t<8>(g, LU, d, v, slab_w, lvl_tab, st); break;
+    case 4: launch_ilu_apply_t<4>(g, LU, d, v, slab_w, lvl_tab, st); break;
+    default: launch_ilu_apply_t<2>(g, LU, d, v, slab_w, lvl_tab, st); break;
+  }
 }
 void launch_rownorm(const Dev& g, double* A, double* r, cudaStream_t st) {
   const int bs = 256;

@@ -9,7 +9,8 @@ dev.set_time(0.0, 1.0); dev.upload_u(s["u0"]); dev.set_uold_dev(); dev.update_st
 dev.set_time(1.0, 1.0); dev.update_state(); dev.set_uold_dev()
 dev.residual(None, want_r=False)
 dev.jacobian(None, download=False)
-dev.ilu_factor(128)
-for name in ("ilu_apply", "spmv", "residual", "jacobian", "ilu_factor", "dot", "axpy"):
+sw = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+dev.ilu_factor(sw)
+for name in (sys.argv[3].split(",") if len(sys.argv) > 3 else ("ilu_apply", "spmv", "residual", "jacobian", "ilu_factor", "dot", "axpy")):
     print(name, dev.time_kernel(name, reps=2))
 dev.close()
