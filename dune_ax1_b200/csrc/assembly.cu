@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(128) residual_kernel(Dev g, const double* __re
 // ------------------------------------------------------------------------------------------
 // Jacobian: 4 lanes per vertex row, lane ri owns scalar row ri of the 9 blocks of the block row.
 // Analytic volume blocks (the reference's use*OperatorJacobianVolume = yes mode) + mass blocks.
-// Constrained rows -> unit row, constrained columns dropped (PDELab Dirichlet constraints).
+// Constrained rows -> unit row; constrained columns are kept (PDELab's default non-symmetric etadd).
 __global__ void __launch_bounds__(128) jacobian_kernel(Dev g, const double* __restrict__ u, double* __restrict__ A) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int v = t >> 2, ri = t & 3;
@@ -135,14 +135,8 @@ __global__ void __launch_bounds__(128) jacobian_kernel(Dev g, const double* __re
   const bool row_con = (g.dmask[v] >> ri) & 1;
 #pragma unroll
   for (int s = 0; s < 9; ++s) {
-    const int ii = i + slot_di(s), jj = j + slot_dj(s);
-    const bool inb = ii >= 0 && ii < g.nvx && jj >= 0 && jj < g.nvy;
-    uint8_t cm = inb ? g.dmask[ii + g.nvx * jj] : 0xF;
     double o0 = acc[s][0], o1 = acc[s][1], o2 = acc[s][2], o3 = acc[s][3];
-    if (row_con || (cm & 1)) o0 = 0.0;
-    if (row_con || (cm & 2)) o1 = 0.0;
-    if (row_con || (cm & 4)) o2 = 0.0;
-    if (row_con || (cm & 8)) o3 = 0.0;
+    if (row_con) { o0 = 0.0; o1 = 0.0; o2 = 0.0; o3 = 0.0; }
     if (row_con && s == 4) {
       if (ri == 0) o0 = 1.0;
       if (ri == 1) o1 = 1.0;

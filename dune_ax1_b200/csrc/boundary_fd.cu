@@ -39,14 +39,12 @@ __global__ void jacobian_boundary_fd_kernel(Dev g, const double* __restrict__ u,
       for (int fv = 0; fv < 2; ++fv) {
         const int lc = comp * 4 + vbase + fv;
         const int colv_i = ci + fv;
-        const uint8_t cmask = g.dmask[colv_i + g.nvx * jr];
         const double orig = c.xl[lc];
         const double delta = fd_eps * (1.0 + fabs(orig));
         c.xl[lc] += delta;
         double up[3] = {0.0, 0.0, 0.0};
         elec_boundary_row(g, f, ci, c.xl, k, vs, up);
         c.xl[lc] = orig;
-        if ((cmask >> comp) & 1) continue;  // constrained column dropped
         const int s = 3 + (colv_i - i + 1);
         double* blk = A + ((size_t)v * 9 + s) * 16;
         for (int j = 0; j < 3; ++j) {

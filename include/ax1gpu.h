@@ -99,7 +99,8 @@ int ax1gpu_device_count(void);
 /* Create the device-resident problem. Arrays are the Physics maps of the reference
  * (acme2_cyl_physics.hh): cell_subdomain nx*ny {0 CYTOSOL,1 ES,2 MEMBRANE}; memb_perm nx
  * (initPermittivities :2424-2606); node_volume (nx+1)*(ny+1) (calcNodeVolumes :2286-2397);
- * dirichlet_mask (nx+1)*(ny+1), bit c = component c constrained (setup.hh:646-665);
+ * dirichlet_mask (nx+1)*(ny+1), bit c = component c constrained (setup.hh:646-665; rows become
+ * unit rows, columns are kept as in PDELab's default non-symmetric constraints handling);
  * g_leak/g_nav/g_kv nx channel densities per membrane column [mS/cm^2] (channelset.hh:133-182).
  * stream: a cudaStream_t to run on (NULL: the library creates one). */
 int ax1gpu_create(const ax1gpu_grid* grid, const unsigned char* cell_subdomain, const double* memb_perm,

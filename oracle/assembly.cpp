@@ -8,7 +8,8 @@
 //   mass operator     dune/ax1/acme2_cyl/operator/acme2_cyl_toperator.hh:56-154,168-256
 //   FD Jacobian       PDELab NumericalJacobian{Volume,Boundary}; formula stuff/idefault_patch.dat:14-23
 //   one-step method   implicit Euler r = M(u) - M(uold) + dt*A(u)  (acme2_cyl_setup.hh:704-708,861-868)
-//   constraints       rows AND columns of constrained DOFs eliminated, unit diagonal [ext, PDELab 2.0]
+//   constraints       rows of constrained DOFs -> unit rows; their COLUMNS are kept (PDELab's default,
+//                     non-symmetric etadd) -- the overlapping operator needs the front-vertex columns [ext]
 #include "oracle.hpp"
 #include <algorithm>
 #include <cstring>
@@ -391,7 +392,6 @@ void jacobian(const Problem& p, const double* u, BCRS& A) {
             int row = c.v[vi], col = c.v[vj];
             int ri = comps[ci], cjj = comps[cj];
             if ((p.dirichlet[row] >> ri) & 1) continue;   // constrained row dropped
-            if ((p.dirichlet[col] >> cjj) & 1) continue;  // constrained column dropped
             int k = A.find(row, col);
             A.block(k)[ri * 4 + cjj] += val;
           }

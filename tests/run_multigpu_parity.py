@@ -1,0 +1,72 @@
+"""Multi-GPU parity (run under torchrun, one rank per GPU): z-slab ranks with NCCL halo-add and
+allreduce vs the oracle's overlapping multi-rank solve on the same partition.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/run_multigpu_parity.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from dune_ax1_b200 import api, setups  # noqa: E402
+from helpers import oracle_problem  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    nx, slab_w = 6 * world, 4
+    s = setups.make_setup(nx, dx=100.0e3, rank=rank, nranks=world, perturbation=1e-3)
+    dev = setups.make_device(s, device=local_rank)
+    ids = [api.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    dev.comm_init(ids[0], rank, world)
+    dev.set_time(0.0, 1.0); dev.set_uold(s["u0"]); dev.update_state(s["u0"])
+    kw = dict(reduction=1e-9, abs_limit=1e-14, min_lin_reduction=1e-10)
+    ug, rg = dev.newton(s["u0"], api.default_newton_opts(slab_w=slab_w, **kw))
+    # linear-solve building blocks on the first Jacobian
+    r0, nrm = dev.residual(s["u0"])
+    dev.jacobian(s["u0"], download=False)
+    zg, _, lres = dev.solve(r0, 1e-8, maxit=500, slab_w=slab_w)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, dict(u=ug, z=zg, nrm=nrm, its=rg.iterations, lin=rg.lin_iterations,
+                                          status=rg.status, lit=lres.iterations))
+    ok = True
+    if rank == 0:
+        from oracle import pyoracle as O
+        probs, us = [], []
+        for r in range(world):
+            sr = setups.make_setup(nx, dx=100.0e3, rank=r, nranks=world, perturbation=1e-3)
+            P = oracle_problem(O, sr)
+            P.set_time(0.0, 1.0); P.set_uold(sr["u0"]); P.update_state(sr["u0"])
+            probs.append(P); us.append(sr["u0"])
+        out, res, st = O.newton_mt(probs, us, O.default_newton_opts(ilu_fill=0, slab_w=slab_w, **kw))
+        assert st == 0
+        for r in range(world):
+            g = gathered[r]
+            scale = np.max(np.abs(out[r].reshape(-1, 4)), axis=0)
+            err = np.max(np.abs(g["u"] - out[r]).reshape(-1, 4) / scale, axis=0)
+            print("rank %d: status %d its gpu/cpu %d/%d lin %d/%d field err %s defect-norm %.6e"
+                  % (r, g["status"], g["its"], res[r].iterations, g["lin"], res[r].lin_iterations, err, g["nrm"]))
+            ok &= g["status"] == 0 and g["its"] == res[r].iterations
+            ok &= bool(np.all(err[:3] < 1e-8) and err[3] < 5e-7)
+        # the masked defect norm is global: identical on every rank
+        ok &= len({g["nrm"] for g in gathered}) == 1
+        print("MULTIGPU PARITY", "OK" if ok else "FAILED")
+    flag = [ok]
+    dist.broadcast_object_list(flag, src=0)
+    dev.close()
+    dist.destroy_process_group()
+    sys.exit(0 if flag[0] else 1)
+
+
+if __name__ == "__main__":
+    main()

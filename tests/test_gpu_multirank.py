@@ -1,0 +1,21 @@
+"""Launch the multi-GPU parity script when the box has >= 2 GPUs (gpurun --gpus 2)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_gpu_parity():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "run_multigpu_parity.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(out.stdout[-3000:])
+    sys.stderr.write(out.stderr[-3000:])
+    assert out.returncode == 0 and "MULTIGPU PARITY OK" in out.stdout
