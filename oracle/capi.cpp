@@ -169,7 +169,7 @@ int ax1o_ilu_apply(const ax1o_problem* h, const double* vals, int ilu_fill, int 
 int ax1o_ilu_num_blocks(const ax1o_problem* h, int ilu_fill, int slab_w) {
   AX1O_TRY
   BCRS A; build_pattern(h->p, A);
-  for (size_t k = 0; k < A.col.size(); ++k) { double* b = A.block((int)k); for (int q = 0; q < 4; ++q) b[5 * q] = 1.0; }
+  for (int i = 0; i < A.n; ++i) { double* b = A.block(A.find(i, i)); for (int q = 0; q < 4; ++q) b[5 * q] = 1.0; }
   ILU M; ilu_factor(h->p, A, ilu_fill, slab_w, M);
   return (int)M.LU.col.size();
   AX1O_CATCH(-1)
