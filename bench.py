@@ -287,8 +287,14 @@ def main():
                       "GBps": BYTES[name] * nv / (t_ms * 1e-3) / 1e9,
                       "share_of_step": counts[name] * t_ms / (ms / args.steps)}
     dom = max(kern, key=lambda k: kern[k]["share_of_step"])
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (named workload only)
+    traffic = None
+    if args.nx == NX_PER_GPU and args.slab_w == SLAB_W:
+        traffic = {"ilu_apply": 20.352319e9 + 1.073509e9, "ilu_factor": 19.261465e9 + 19.390245e9,
+                   "jacobian": 1.421249e9 + 19.379517e9}.get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["GBps"] / peak, "traffic": None, "peak_kind": peak_kind,
+                "frac": kern[dom]["GBps"] / peak, "traffic": traffic,
+                "traffic_source": "profiles/r01_top_kernels_ncu.json", "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": BYTES[dom] * nv, "kernels": kern}
     # whole-step algorithmic traffic (SURVEY 8(d) formula, l = 1 line-search residual, k Krylov its)
     step_bytes = NEWTON_ITS * (1184 + 2384 + 2 * 104 + KRYLOV_ITS * (2 * 1256 + 2 * 1384 + 416)) * nv
