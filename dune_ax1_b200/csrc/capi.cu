@@ -139,6 +139,7 @@ int ax1gpu_create(const ax1gpu_grid* grid, const unsigned char* cell_subdomain, 
   }
   c->nred_blocks = 148 * 8;
   TRY(dev_alloc(&c->d_partials, 2 * (size_t)c->nred_blocks));
+  TRY(dev_alloc(&c->d_spartials, 2 * (size_t)((4 * nv + 255) / 256)));
   TRY(dev_alloc(&c->d_sums, 8));
   TRY(dev_alloc(&c->d_sc, 1));
   if (cudaMallocHost((void**)&c->h_sc, sizeof(Scalars)) != cudaSuccess ||
@@ -203,7 +204,7 @@ int ax1gpu_destroy(ax1gpu_handle c) {
                   (void*)c->d_LU, (void*)c->d_rt, (void*)c->d_p, (void*)c->d_v, (void*)c->d_y2, (void*)c->d_t, (void*)c->d_tmp,
                   (void*)c->d_bcrs, (void*)c->d_gbar, (void*)c->d_chstate, (void*)c->d_geff, (void*)c->d_vrest, (void*)c->d_vm,
                   (void*)c->d_err, (void*)c->d_partials, (void*)c->d_sums, (void*)c->d_sc, (void*)c->d_halo_send,
-                  (void*)c->d_halo_recv, (void*)c->d_lvl})
+                  (void*)c->d_halo_recv, (void*)c->d_lvl, (void*)c->d_spartials})
     if (p) cudaFree(p);
   if (c->h_sc) cudaFreeHost(c->h_sc);
   if (c->h_pin) cudaFreeHost(c->h_pin);

@@ -32,6 +32,7 @@ struct ax1gpu_ctx {
   bool channels_initialized = false, channels_partially_initialized = false;
   // reductions / Krylov scalars
   double* d_partials = nullptr;   // 2 * nred_blocks
+  double* d_spartials = nullptr;  // 2 * spmv blocks (dot products fused into the SpMV)
   double* d_sums = nullptr;       // [4]
   ax1::Scalars* d_sc = nullptr;
   ax1::Scalars* h_sc = nullptr;   // pinned

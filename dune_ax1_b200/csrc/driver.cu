@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #include "ctx.h"
+#include "reduce.cuh"
 
 namespace ax1 {
 
@@ -27,37 +28,6 @@ namespace ax1 {
 
 // ------------------------------------------------------------------------------------------
 // vector kernels: one thread per vertex block (4 doubles), grid-stride
-struct Own { int lo, hi, nvx, masked; };
-
-__device__ __forceinline__ bool owned(const Own& o, int v) {
-  if (!o.masked) return true;
-  const int i = v % o.nvx;
-  return i >= o.lo && i <= o.hi;
-}
-
-template <int NS>
-__device__ __forceinline__ void block_reduce_store(double (&s)[NS], double* partials) {
-  __shared__ double sh[NS][32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < NS; ++k) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
-    if (lane == 0) sh[k][w] = s[k];
-  }
-  __syncthreads();
-  if (w == 0) {
-    const int nw = blockDim.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NS; ++k) {
-      double t = lane < nw ? sh[k][lane] : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) partials[k * gridDim.x + blockIdx.x] = t;
-    }
-  }
-}
-
 __device__ __forceinline__ void ld4v(const double* p, double* o) {
   const double2 lo = *reinterpret_cast<const double2*>(p);
   const double2 hi = *reinterpret_cast<const double2*>(p + 2);
@@ -108,10 +78,10 @@ __global__ void __launch_bounds__(256) pupdate_kernel(int nv, double* p, const d
   }
 }
 
-// x += s y ; r -= s w ; partial <r,r>   (s = alpha or omega)
+// x += s y ; r -= s w ; partial <r,r> and (rt given) <rt,r> for the next rho   (s = alpha or omega)
 __global__ void __launch_bounds__(256) xr_update_kernel(int nv, double* x, const double* __restrict__ y, double* r,
-                                                        const double* __restrict__ w, const Scalars* sc, int use_omega,
-                                                        Own own, double* partials) {
+                                                        const double* __restrict__ w, const double* __restrict__ rt,
+                                                        const Scalars* sc, int use_omega, Own own, double* partials) {
   double s[2] = {0.0, 0.0};
   if (!sc->done) {
     const double a = use_omega ? sc->omega : sc->alpha;
@@ -121,7 +91,14 @@ __global__ void __launch_bounds__(256) xr_update_kernel(int nv, double* x, const
 #pragma unroll
       for (int c = 0; c < 4; ++c) { xv[c] += a * yv[c]; rv[c] += (-a) * wv[c]; }
       st4v(x + 4 * (size_t)k, xv); st4v(r + 4 * (size_t)k, rv);
-      if (owned(own, k)) { s[0] += rv[0] * rv[0]; s[0] += rv[1] * rv[1]; s[0] += rv[2] * rv[2]; s[0] += rv[3] * rv[3]; }
+      if (owned(own, k)) {
+        s[0] += rv[0] * rv[0]; s[0] += rv[1] * rv[1]; s[0] += rv[2] * rv[2]; s[0] += rv[3] * rv[3];
+        if (rt) {
+          double tv[4];
+          ld4v(rt + 4 * (size_t)k, tv);
+          s[1] += tv[0] * rv[0]; s[1] += tv[1] * rv[1]; s[1] += tv[2] * rv[2]; s[1] += tv[3] * rv[3];
+        }
+      }
     }
   }
   block_reduce_store<2>(s, partials);
@@ -139,32 +116,10 @@ __global__ void __launch_bounds__(256) newton_update_kernel(int nv, double* u, c
   }
 }
 
-__global__ void __launch_bounds__(1024) reduce_final_kernel(const double* partials, int nblocks, double* sums) {
-  __shared__ double sh[2][32];
-  double s[2] = {0.0, 0.0};
-  for (int k = threadIdx.x; k < nblocks; k += blockDim.x) { s[0] += partials[k]; s[1] += partials[nblocks + k]; }
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
-    if (lane == 0) sh[q][w] = s[q];
-  }
-  __syncthreads();
-  if (w == 0) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      double t = sh[q][lane];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) sums[q] = t;
-    }
-  }
-}
+enum { OP_NONE = -1, OP_NORM0 = 0, OP_H, OP_NORM_A, OP_OMEGA, OP_NORM_B, OP_PLAIN_NORM };
 
-enum { OP_NORM0 = 0, OP_RHO, OP_H, OP_NORM_A, OP_OMEGA, OP_NORM_B, OP_PLAIN_NORM };
-
-__global__ void scalar_kernel(int op, Scalars* sc, const double* sums, double reduction, double* out) {
+// the Krylov scalar recurrences of Dune::BiCGSTABSolver, executed by one thread on the device
+__device__ void scalar_step(int op, Scalars* sc, const double* sums, double reduction, double* out) {
   const double EPSILON = 1e-80;
   if (op == OP_PLAIN_NORM) { out[0] = sqrt(sums[0]); return; }
   if (sc->done) return;
@@ -172,13 +127,9 @@ __global__ void scalar_kernel(int op, Scalars* sc, const double* sums, double re
     case OP_NORM0:
       sc->norm = sc->norm0 = sqrt(sums[0]);
       sc->rho = sc->alpha = sc->omega = 1.0;
+      sc->rho_new = sums[0];  // rt = r  ->  <rt, r> = <r, r>
       sc->it_half = 0.5; sc->converged = 0; sc->breakdown = 0;
       if (sc->norm < reduction * sc->norm0 || sc->norm < 1e-30) { sc->converged = 1; sc->done = 1; sc->it_half = 0.0; }
-      break;
-    case OP_RHO:
-      sc->rho_new = sums[0];
-      if (fabs(sc->rho) <= EPSILON || fabs(sc->omega) <= EPSILON) { sc->breakdown = 1; sc->done = 1; break; }
-      sc->beta = (sc->rho_new / sc->rho) * (sc->alpha / sc->omega);
       break;
     case OP_H:
       sc->h = sums[0];
@@ -199,8 +150,41 @@ __global__ void scalar_kernel(int op, Scalars* sc, const double* sums, double re
       sc->norm = sqrt(sums[0]);
       if (sc->norm < reduction * sc->norm0 || sc->norm < 1e-30) { sc->converged = 1; sc->done = 1; break; }
       sc->it_half += 0.5;
+      // top of the next iteration: rho_new = <rt, r> (fused into the x,r update), breakdown tests, beta
+      sc->rho_new = sums[1];
+      if (fabs(sc->rho) <= EPSILON || fabs(sc->omega) <= EPSILON) { sc->breakdown = 1; sc->done = 1; break; }
+      sc->beta = (sc->rho_new / sc->rho) * (sc->alpha / sc->omega);
       break;
   }
+}
+
+// partials -> sums (fixed order) and, on one GPU, the scalar recurrence in the same launch
+__global__ void __launch_bounds__(1024) reduce_final_kernel(const double* partials, int nblocks, double* sums, int op,
+                                                            Scalars* sc, double reduction, double* out) {
+  __shared__ double sh[2][32];
+  double s[2] = {0.0, 0.0};
+  for (int k = threadIdx.x; k < nblocks; k += blockDim.x) { s[0] += partials[k]; s[1] += partials[nblocks + k]; }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+    if (lane == 0) sh[q][w] = s[q];
+  }
+  __syncthreads();
+  if (w == 0) {
+    double t0 = sh[0][lane], t1 = sh[1][lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
+    if (lane == 0) {
+      sums[0] = t0; sums[1] = t1;
+      if (op != OP_NONE) scalar_step(op, sc, sums, reduction, out);
+    }
+  }
+}
+
+__global__ void scalar_kernel(int op, Scalars* sc, const double* sums, double reduction, double* out) {
+  scalar_step(op, sc, sums, reduction, out);
 }
 
 // halo pack / unpack-add of 3 vertex columns per processor-boundary side
@@ -232,19 +216,23 @@ static inline Own own_of(const ax1gpu_ctx* c) { return Own{c->own_lo, c->own_hi,
     }                                                                                 \
   } while (0)
 
-// partials -> sums (+ allreduce over ranks)
-static int finish_reduce(ax1gpu_ctx* c, int nsums) {
-  reduce_final_kernel<<<1, 1024, 0, c->stream>>>(c->d_partials, c->nred_blocks, c->d_sums);
-  AX1_LAUNCH_CHECK(c);
-  if (c->nranks > 1)
+// partials -> sums (+ allreduce over ranks) -> scalar recurrence `op`
+static int reduce_op_from(ax1gpu_ctx* c, const double* partials, int nblocks, int nsums, int op, double reduction,
+                          double* out = nullptr) {
+  if (c->nranks > 1) {
+    reduce_final_kernel<<<1, 1024, 0, c->stream>>>(partials, nblocks, c->d_sums, OP_NONE, c->d_sc, reduction, out);
+    AX1_LAUNCH_CHECK(c);
     AX1_NCCL(c, c->nccl.AllReduce(c->d_sums, c->d_sums, nsums, ncclDouble, ncclSum, c->comm, c->stream));
+    scalar_kernel<<<1, 1, 0, c->stream>>>(op, c->d_sc, c->d_sums, reduction, out);
+    AX1_LAUNCH_CHECK(c);
+  } else {
+    reduce_final_kernel<<<1, 1024, 0, c->stream>>>(partials, nblocks, c->d_sums, op, c->d_sc, reduction, out);
+    AX1_LAUNCH_CHECK(c);
+  }
   return 0;
 }
-
-static int scalar_op(ax1gpu_ctx* c, int op, double reduction, double* out = nullptr) {
-  scalar_kernel<<<1, 1, 0, c->stream>>>(op, c->d_sc, c->d_sums, reduction, out);
-  AX1_LAUNCH_CHECK(c);
-  return 0;
+static int reduce_op(ax1gpu_ctx* c, int nblocks, int nsums, int op, double reduction, double* out = nullptr) {
+  return reduce_op_from(c, c->d_partials, nblocks, nsums, op, reduction, out);
 }
 
 static int halo_add(ax1gpu_ctx* c, double* v) {
@@ -321,9 +309,7 @@ int drv_accept_state(ax1gpu_ctx* c) {  // :524-546
 int drv_norm(ax1gpu_ctx* c, const double* a, double* out_host) {
   dot_kernel<<<vec_grid(c), 256, 0, c->stream>>>(c->g.nv, a, a, nullptr, nullptr, 0, own_of(c), nullptr, c->d_partials);
   AX1_LAUNCH_CHECK(c);
-  int rc = finish_reduce(c, 1);
-  if (rc) return rc;
-  rc = scalar_op(c, OP_PLAIN_NORM, 0.0, c->d_sums + 2);
+  int rc = reduce_op(c, c->nred_blocks, 1, OP_PLAIN_NORM, 0.0, c->d_sums + 2);
   if (rc) return rc;
   AX1_CUDA(cudaMemcpyAsync(c->h_pin, c->d_sums + 2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   AX1_CUDA(cudaStreamSynchronize(c->stream));
@@ -407,37 +393,31 @@ int drv_solve(ax1gpu_ctx* c, double* r, double* x, double reduction, int maxit, 
   AX1_CUDA(cudaMemcpyAsync(c->d_rt, r, bytes, cudaMemcpyDeviceToDevice, c->stream));
   dot_kernel<<<G, 256, 0, c->stream>>>(nv, r, r, nullptr, nullptr, 0, own, nullptr, c->d_partials);
   AX1_LAUNCH_CHECK(c);
-  if ((rc = finish_reduce(c, 1))) return rc;
-  if ((rc = scalar_op(c, OP_NORM0, reduction))) return rc;
+  if ((rc = reduce_op(c, G, 1, OP_NORM0, reduction))) return rc;
   int k = 0;
   const int poll_every = 4;
+  const int SB = spmv_blocks(c->g);
+  const int zc = c->nranks > 1;
   for (k = 0; 0.5 + k < maxit; ++k) {
-    dot_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_rt, r, nullptr, nullptr, 0, own, c->d_sc, c->d_partials);
-    AX1_LAUNCH_CHECK(c);
-    if ((rc = finish_reduce(c, 1))) return rc;
-    if ((rc = scalar_op(c, OP_RHO, reduction))) return rc;
+    // rho_new, the breakdown tests and beta were produced by OP_NORM0 / OP_NORM_B of the step before
     pupdate_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_p, c->d_v, r, c->d_sc, k == 0);
     AX1_LAUNCH_CHECK(c);
     if ((rc = drv_prec_apply(c, c->d_p, c->d_y2))) return rc;
-    if ((rc = drv_op_apply(c, c->d_y2, c->d_v))) return rc;
-    dot_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_rt, c->d_v, nullptr, nullptr, 0, own, c->d_sc, c->d_partials);
+    launch_spmv_dot(c->g, c->d_A, c->d_y2, c->d_v, zc, 1, c->d_rt, own.lo, own.hi, own.masked, c->d_sc, c->d_spartials,
+                    c->stream);                                   // v = A y, h = <rt, v>
     AX1_LAUNCH_CHECK(c);
-    if ((rc = finish_reduce(c, 1))) return rc;
-    if ((rc = scalar_op(c, OP_H, reduction))) return rc;
-    xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, x, c->d_y2, r, c->d_v, c->d_sc, 0, own, c->d_partials);
+    if ((rc = reduce_op_from(c, c->d_spartials, SB, 1, OP_H, reduction))) return rc;
+    xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, x, c->d_y2, r, c->d_v, nullptr, c->d_sc, 0, own, c->d_partials);
     AX1_LAUNCH_CHECK(c);
-    if ((rc = finish_reduce(c, 1))) return rc;
-    if ((rc = scalar_op(c, OP_NORM_A, reduction))) return rc;
+    if ((rc = reduce_op(c, G, 1, OP_NORM_A, reduction))) return rc;
     if ((rc = drv_prec_apply(c, r, c->d_y2))) return rc;
-    if ((rc = drv_op_apply(c, c->d_y2, c->d_t))) return rc;
-    dot_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_t, r, c->d_t, c->d_t, 1, own, c->d_sc, c->d_partials);
+    launch_spmv_dot(c->g, c->d_A, c->d_y2, c->d_t, zc, 2, r, own.lo, own.hi, own.masked, c->d_sc, c->d_spartials,
+                    c->stream);                                   // t = A y, <t, r>, <t, t>
     AX1_LAUNCH_CHECK(c);
-    if ((rc = finish_reduce(c, 2))) return rc;
-    if ((rc = scalar_op(c, OP_OMEGA, reduction))) return rc;
-    xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, x, c->d_y2, r, c->d_t, c->d_sc, 1, own, c->d_partials);
+    if ((rc = reduce_op_from(c, c->d_spartials, SB, 2, OP_OMEGA, reduction))) return rc;
+    xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, x, c->d_y2, r, c->d_t, c->d_rt, c->d_sc, 1, own, c->d_partials);
     AX1_LAUNCH_CHECK(c);
-    if ((rc = finish_reduce(c, 1))) return rc;
-    if ((rc = scalar_op(c, OP_NORM_B, reduction))) return rc;
+    if ((rc = reduce_op(c, G, 2, OP_NORM_B, reduction))) return rc;
     if (reduction > 0.0 && (k % poll_every) == poll_every - 1) {
       if ((rc = poll_scalars(c))) return rc;
       if (c->h_sc->done) break;
@@ -445,7 +425,9 @@ int drv_solve(ax1gpu_ctx* c, double* r, double* x, double reduction, int maxit, 
   }
   if ((rc = poll_scalars(c))) return rc;
   const Scalars& s = *c->h_sc;
-  if (s.breakdown) { set_error("breakdown in BiCGSTAB"); res->converged = 0; return AX1GPU_ESTATE; }
+  // ISTL tests for a break-down at the top of the NEXT iteration; one flagged by the last permitted
+  // iteration is therefore not an error, the solve just ends unconverged
+  if (s.breakdown && s.it_half < maxit) { set_error("breakdown in BiCGSTAB"); res->converged = 0; return AX1GPU_ESTATE; }
   double it = s.it_half;
   if (it > maxit) it = maxit;
   res->converged = s.converged;
@@ -587,7 +569,7 @@ int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms) {
     else if (n == "ilu_factor") { launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream); }
     else if (n == "ilu_apply") { launch_ilu_apply(c->g, c->d_LU, c->d_p, c->d_y2, c->slab_w, c->d_lvl, c->stream); }
     else if (n == "dot") { dot_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_rt, c->d_v, nullptr, nullptr, 0, own_of(c), nullptr, c->d_partials); }
-    else if (n == "axpy") { xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_tmp, c->d_y2, c->d_t, c->d_v, c->d_sc, 0, own_of(c), c->d_partials); }
+    else if (n == "axpy") { xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_tmp, c->d_y2, c->d_t, c->d_v, c->d_rt, c->d_sc, 1, own_of(c), c->d_partials); }
     else { set_error("unknown kernel name"); return AX1GPU_EINVAL; }
     AX1_LAUNCH_CHECK(c);
     return 0;

@@ -12,7 +12,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
-#include "kernels.h"
+#include "reduce.cuh"
 
 namespace ax1 {
 
@@ -33,30 +33,45 @@ __device__ __forceinline__ void st4(double* p, const double* v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// y = A x ; 4 lanes per block row, lane r = scalar row r
+// y = A x ; 4 lanes per block row, lane r = scalar row r.
+// DOT = 1: also partial <w, y> (BiCGStab h = <rt, v>);  DOT = 2: partial <y, w> and <y, y>
+// (omega = <t, r> / <t, t>): the SpMV result is reduced while it is still in registers.
+template <int DOT>
 __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restrict__ A, const double* __restrict__ x,
-                                                   double* __restrict__ y, int zero_con) {
+                                                   double* __restrict__ y, int zero_con, const double* __restrict__ w,
+                                                   Own own, const Scalars* sc, double* partials) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int v = (int)(t >> 2), r = (int)(t & 3);
-  if (v >= g.nv) return;
-  const int i = v % g.nvx, j = v / g.nvx;
-  const double* Arow = A + (size_t)v * 144 + r * 4;
-  double acc = 0.0;
+  double s[2] = {0.0, 0.0};
+  const bool active = (v < g.nv) && !(DOT && sc && sc->done);
+  if (active) {
+    const int i = v % g.nvx, j = v / g.nvx;
+    const double* Arow = A + (size_t)v * 144 + r * 4;
+    double acc = 0.0;
 #pragma unroll
-  for (int s = 0; s < 9; ++s) {
-    const int di = s % 3 - 1, dj = s / 3 - 1;
-    const int ii = i + di, jj = j + dj;
-    if (ii < 0 || ii >= g.nvx || jj < 0 || jj >= g.nvy) continue;
-    double a[4], xv[4];
-    ldg4(Arow + s * 16, a);
-    ldg4(x + 4 * (size_t)(v + di + dj * g.nvx), xv);
-    acc += a[0] * xv[0];
-    acc += a[1] * xv[1];
-    acc += a[2] * xv[2];
-    acc += a[3] * xv[3];
+    for (int sl = 0; sl < 9; ++sl) {
+      const int di = sl % 3 - 1, dj = sl / 3 - 1;
+      const int ii = i + di, jj = j + dj;
+      if (ii < 0 || ii >= g.nvx || jj < 0 || jj >= g.nvy) continue;
+      double a[4], xv[4];
+      ldg4(Arow + sl * 16, a);
+      ldg4(x + 4 * (size_t)(v + di + dj * g.nvx), xv);
+      acc += a[0] * xv[0];
+      acc += a[1] * xv[1];
+      acc += a[2] * xv[2];
+      acc += a[3] * xv[3];
+    }
+    if (zero_con && ((g.dmask[v] >> r) & 1)) acc = 0.0;
+    y[4 * (size_t)v + r] = acc;
+    if (DOT) {
+      if (!own.masked || (i >= own.lo && i <= own.hi)) {
+        const double wv = __ldg(w + 4 * (size_t)v + r);
+        s[0] = acc * wv;
+        if (DOT == 2) s[1] = acc * acc;
+      }
+    }
   }
-  if (zero_con && ((g.dmask[v] >> r) & 1)) acc = 0.0;
-  y[4 * (size_t)v + r] = acc;
+  if (DOT) block_reduce_store<2>(s, partials);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -426,10 +441,16 @@ __global__ void bcrs_copy_kernel(Dev g, double* A9, double* blocks, const int* _
 }
 
 // ------------------------------------------------------------------------------------------
+int spmv_blocks(const Dev& g) { return (int)((4LL * g.nv + 255) / 256); }
 void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int zero_con, cudaStream_t st) {
-  const int bs = 256;
-  const long long nt = 4LL * g.nv;
-  spmv_kernel<<<(unsigned)((nt + bs - 1) / bs), bs, 0, st>>>(g, A, x, y, zero_con);
+  spmv_kernel<0><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, nullptr, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
+}
+void launch_spmv_dot(const Dev& g, const double* A, const double* x, double* y, int zero_con, int dot_mode,
+                     const double* w, int own_lo, int own_hi, int masked, const Scalars* sc, double* partials,
+                     cudaStream_t st) {
+  const Own own{own_lo, own_hi, g.nvx, masked};
+  if (dot_mode == 1) spmv_kernel<1><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
+  else spmv_kernel<2><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
 }
 // one quad per wavefront row: a level of a slab of width w has at most ceil(w/2) rows
 static int slab_threads(int slab_w) {
