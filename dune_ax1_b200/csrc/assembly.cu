@@ -61,17 +61,29 @@ __global__ void __launch_bounds__(128) residual_kernel(Dev g, const double* __re
 // Jacobian: 4 lanes per vertex row, lane ri owns scalar row ri of the 9 blocks of the block row.
 // Analytic volume blocks (the reference's use*OperatorJacobianVolume = yes mode) + mass blocks.
 // Constrained rows -> unit row; constrained columns are kept (PDELab's default non-symmetric etadd).
-__global__ void __launch_bounds__(128) jacobian_kernel(Dev g, const double* __restrict__ u, double* __restrict__ A) {
+//
+// Per cell and Gauss point the entries factor as (test k, trial j, G_jk = grad psi_j . grad psi_k):
+//   con_i <- con_i : dt W [ D G_jk - psi_j (b . grad psi_k) ] + W psi_j psi_k,  b = -D z grad(phi)
+//   con_i <- pot   : dt W c_i D z G_jk
+//   pot   <- con_i : dt W S PC z_i psi_j psi_k
+//   pot   <- pot   : dt W S (-eps) G_jk
+// (acme2_cyl_operator_fully_coupled.hh:516-561, acme2_cyl_toperator.hh:251, convectiondiffusionfem.hh:317-318)
+// so each lane needs only the potential coefficients and those of its own species.
+__global__ void __launch_bounds__(128, 4) jacobian_kernel(Dev g, const double* __restrict__ u, double* __restrict__ A) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int v = t >> 2, ri = t & 3;
   if (v >= g.nv) return;
   const int i = v % g.nvx, j = v / g.nvx;
-  double acc[9][4];
+  // every lane accumulates two scalar columns per slot:  a0 += alpha G + beta psi_j,  a1 += gamma G
+  //   con row i: a0 -> column i,  a1 -> column pot;   alpha = dt W D, beta = W psi_k - dt W (b.grad psi_k), gamma = dt W c_i D z
+  //   pot row  : a0 -> columns con (times z_kk), a1 -> column pot; alpha = 0, beta = dt W S PC psi_k, gamma = dt W S (-eps)
+  double a0[9], a1[9];
 #pragma unroll
-  for (int s = 0; s < 9; ++s)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[s][c] = 0.0;
+  for (int s = 0; s < 9; ++s) { a0[s] = 0.0; a1[s] = 0.0; }
   const double vs = g.do_volume_scaling ? 1. / g.node_vol[v] : 1.0;
+  const bool potrow = (ri == 3);
+  const double Di = potrow ? 0.0 : g.D[ri];
+  const double Dz = potrow ? 0.0 : Di * g.valence[ri];
 #pragma unroll
   for (int b = 0; b < 2; ++b)
 #pragma unroll
@@ -80,68 +92,65 @@ __global__ void __launch_bounds__(128) jacobian_kernel(Dev g, const double* __re
       if (ci < 0 || ci >= g.nx || cj < 0 || cj >= g.ny) continue;
       const int k = (1 - a) + 2 * (1 - b);
       const int ka = 1 - a, kb = 1 - b;
-      CellCtx c;
-      load_cell(g, u, ci, cj, c);
       const bool memb = (cj == g.jm);
+      if (memb && !potrow) continue;  // membrane cells carry the potential only
+      const double x0 = g.x[ci], x1 = g.x[ci + 1], y0 = g.y[cj], y1 = g.y[cj + 1];
+      const double hx = x1 - x0, hy = y1 - y0, ihx = 1.0 / hx, ihy = 1.0 / hy;
+      const int v0 = ci + g.nvx * cj;
+      const int vv[4] = {v0, v0 + 1, v0 + g.nvx, v0 + g.nvx + 1};
+      double pot[4], own[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        pot[m] = potrow ? 0.0 : u[4 * (size_t)vv[m] + 3];
+        own[m] = potrow ? 0.0 : u[4 * (size_t)vv[m] + ri];
+      }
       const double eps = memb ? g.eps_memb[ci] : g.eps_elec;
+      const double cS = g.dt * g.S_pot;
 #pragma unroll
       for (int qa = 0; qa < 2; ++qa)
 #pragma unroll
         for (int qb = 0; qb < 2; ++qb) {
-          QP q;
-          make_qp(c, qa ? AX1_GP1 : AX1_GP0, qb ? AX1_GP1 : AX1_GP0, q);
-          double gpx = 0, gpy = 0;
+          const double xi = qa ? AX1_GP1 : AX1_GP0, eta = qb ? AX1_GP1 : AX1_GP0;
+          double phi[4], dxi[4], deta[4], gx[4], gy[4];
+          q1(xi, eta, phi, dxi, deta);
 #pragma unroll
-          for (int m = 0; m < 4; ++m) { gpx += c.xl[12 + m] * q.gx[m]; gpy += c.xl[12 + m] * q.gy[m]; }
-          double uk = 0.0, D = 0.0, bx = 0.0, by = 0.0;
-          int z = 0;
-          if (ri < 3 && !memb) {
+          for (int m = 0; m < 4; ++m) { gx[m] = ihx * dxi[m]; gy[m] = ihy * deta[m]; }
+          const double yq = y0 + eta * hy;
+          const double W = (0.25 * ((2 * con_pi * yq) * (hx * hy))) * vs;
+          double alpha, beta, gamma;
+          if (potrow) {
+            alpha = 0.0;
+            beta = memb ? 0.0 : cS * W * g.PC * phi[k];
+            gamma = cS * W * (-eps);
+          } else {
+            double gpx = 0, gpy = 0, uk = 0;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) uk += c.xl[4 * ri + m] * q.phi[m];
-            D = g.D[ri]; z = g.valence[ri];
-            bx = -D * z * gpx; by = -D * z * gpy;
+            for (int m = 0; m < 4; ++m) { gpx += pot[m] * gx[m]; gpy += pot[m] * gy[m]; uk += own[m] * phi[m]; }
+            const double Wdt = g.dt * W;
+            const double bk = -Dz * (gpx * gx[k] + gpy * gy[k]);  // b . grad psi_k
+            alpha = Wdt * Di;
+            beta = W * phi[k] - Wdt * bk;
+            gamma = Wdt * uk * Dz;
           }
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
-            const int ja = jj & 1, jb = jj >> 1;
-            const int s = (jb - kb + 1) * 3 + (ja - ka + 1);  // compile-time after unrolling
-            if (ri == 3) {
-              if (!memb) {
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk) {
-                  const double dfPot_du = -g.valence[kk] * q.phi[jj] * g.PC;
-                  acc[s][kk] += g.dt * ((-dfPot_du * q.phi[k]) * q.factor * vs * g.S_pot);
-                }
-              }
-              const double val = (((-eps) * q.gx[jj]) * q.gx[k] + ((-eps) * q.gy[jj]) * q.gy[k]);
-              acc[s][3] += g.dt * (val * q.factor * vs * g.S_pot);
-            } else if (!memb) {
-              const double cc = ((D * q.gx[jj]) * q.gx[k] + (D * q.gy[jj]) * q.gy[k]) -
-                                q.phi[jj] * (bx * q.gx[k] + by * q.gy[k]);
-              double e = g.dt * (cc * q.factor * vs);
-              e += 1.0 * (q.phi[jj] * q.phi[k] * q.factor * vs);  // mass block (toperator.hh:251)
-              const double dbx = q.gx[jj] * (-D * z), dby = q.gy[jj] * (-D * z);
-              const double cp = g.dt * ((-uk * (dbx * q.gx[k] + dby * q.gy[k])) * q.factor * vs);
-              // scalar column ri of the block = own species, column 3 = potential
-              if (ri == 0) acc[s][0] += e;
-              if (ri == 1) acc[s][1] += e;
-              if (ri == 2) acc[s][2] += e;
-              acc[s][3] += cp;
-            }
+            const int s = ((jj >> 1) - kb + 1) * 3 + ((jj & 1) - ka + 1);  // compile-time after unrolling
+            const double G = gx[jj] * gx[k] + gy[jj] * gy[k];
+            a0[s] += alpha * G + beta * phi[jj];
+            a1[s] += gamma * G;
           }
         }
     }
-  // constraints
   const bool row_con = (g.dmask[v] >> ri) & 1;
+  const double z0 = g.valence[0], z1 = g.valence[1], z2 = g.valence[2];
 #pragma unroll
   for (int s = 0; s < 9; ++s) {
-    double o0 = acc[s][0], o1 = acc[s][1], o2 = acc[s][2], o3 = acc[s][3];
-    if (row_con) { o0 = 0.0; o1 = 0.0; o2 = 0.0; o3 = 0.0; }
-    if (row_con && s == 4) {
-      if (ri == 0) o0 = 1.0;
-      if (ri == 1) o1 = 1.0;
-      if (ri == 2) o2 = 1.0;
-      if (ri == 3) o3 = 1.0;
+    double o0, o1, o2;
+    const double o3 = row_con ? ((s == 4 && ri == 3) ? 1.0 : 0.0) : a1[s];
+    if (potrow) { o0 = z0 * a0[s]; o1 = z1 * a0[s]; o2 = z2 * a0[s]; }
+    else { o0 = ri == 0 ? a0[s] : 0.0; o1 = ri == 1 ? a0[s] : 0.0; o2 = ri == 2 ? a0[s] : 0.0; }
+    if (row_con) {
+      o0 = (s == 4 && ri == 0) ? 1.0 : 0.0; o1 = (s == 4 && ri == 1) ? 1.0 : 0.0; o2 = (s == 4 && ri == 2) ? 1.0 : 0.0;
     }
     double2* dst = reinterpret_cast<double2*>(A + ((size_t)v * 9 + s) * 16 + ri * 4);
     dst[0] = make_double2(o0, o1);

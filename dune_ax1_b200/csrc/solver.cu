@@ -143,7 +143,7 @@ __device__ __forceinline__ SlabGeom slab_geom(const Dev& g, int slab_w, const in
 }
 
 // block ILU0 of one sub-slab per CTA (bilu0_decomposition: L_ij = A_ij * A_jj^-1, diagonal stored inverted)
-__global__ void __launch_bounds__(256) ilu_factor_kernel(Dev g, const double* __restrict__ A, double* LF, double* LB,
+__global__ void __launch_bounds__(256, 2) ilu_factor_kernel(Dev g, const double* __restrict__ A, double* LF, double* LB,
                                                          int slab_w, const int* __restrict__ lvl_tab) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SlabGeom sg = slab_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(smem_raw));
