@@ -143,18 +143,21 @@ __global__ void __launch_bounds__(128, 4) jacobian_kernel(Dev g, const double* _
     }
   const bool row_con = (g.dmask[v] >> ri) & 1;
   const double z0 = g.valence[0], z1 = g.valence[1], z2 = g.valence[2];
+  double* Arow = A + (size_t)v * AX1_ROW;
 #pragma unroll
   for (int s = 0; s < 9; ++s) {
-    double o0, o1, o2;
-    const double o3 = row_con ? ((s == 4 && ri == 3) ? 1.0 : 0.0) : a1[s];
-    if (potrow) { o0 = z0 * a0[s]; o1 = z1 * a0[s]; o2 = z2 * a0[s]; }
-    else { o0 = ri == 0 ? a0[s] : 0.0; o1 = ri == 1 ? a0[s] : 0.0; o2 = ri == 2 ? a0[s] : 0.0; }
-    if (row_con) {
-      o0 = (s == 4 && ri == 0) ? 1.0 : 0.0; o1 = (s == 4 && ri == 1) ? 1.0 : 0.0; o2 = (s == 4 && ri == 2) ? 1.0 : 0.0;
+    const double unit = (row_con && s == 4) ? 1.0 : 0.0;
+    if (potrow) {
+      double o0 = z0 * a0[s], o1 = z1 * a0[s], o2 = z2 * a0[s], o3 = a1[s];
+      if (row_con) { o0 = 0.0; o1 = 0.0; o2 = 0.0; o3 = unit; }
+      double2* dst = reinterpret_cast<double2*>(Arow + s * AX1_BLK + 6);
+      dst[0] = make_double2(o0, o1);
+      dst[1] = make_double2(o2, o3);
+    } else {
+      double d = a0[s], c = a1[s];
+      if (row_con) { d = unit; c = 0.0; }
+      *reinterpret_cast<double2*>(Arow + s * AX1_BLK + 2 * ri) = make_double2(d, c);
     }
-    double2* dst = reinterpret_cast<double2*>(A + ((size_t)v * 9 + s) * 16 + ri * 4);
-    dst[0] = make_double2(o0, o1);
-    dst[1] = make_double2(o2, o3);
   }
 }
 

@@ -46,10 +46,13 @@ __global__ void jacobian_boundary_fd_kernel(Dev g, const double* __restrict__ u,
         elec_boundary_row(g, f, ci, c.xl, k, vs, up);
         c.xl[lc] = orig;
         const int s = 3 + (colv_i - i + 1);
-        double* blk = A + ((size_t)v * 9 + s) * 16;
+        double* blk = A + ((size_t)v * 9 + s) * AX1_BLK;
+        // the flux of species j depends on c_j and phi only: columns other than j and pot get
+        // (up - down) == 0 exactly, which keeps the arrow shape of the block
         for (int j = 0; j < 3; ++j) {
           if ((rmask >> j) & 1) continue;   // constrained row
-          blk[j * 4 + comp] += (up[j] - down[j]) / delta;
+          if (comp == j) blk[2 * j] += (up[j] - down[j]) / delta;
+          else if (comp == 3) blk[2 * j + 1] += (up[j] - down[j]) / delta;
         }
       }
   }

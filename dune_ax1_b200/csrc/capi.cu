@@ -117,7 +117,7 @@ int ax1gpu_create(const ax1gpu_grid* grid, const unsigned char* cell_subdomain, 
     TRY(dev_alloc(p, n4));
     if (cudaMemsetAsync(*p, 0, n4 * sizeof(double), st) != cudaSuccess) { ax1gpu_destroy(c); return AX1GPU_ECUDA; }
   }
-  TRY(dev_alloc(&c->d_A, nv * 144));
+  TRY(dev_alloc(&c->d_A, nv * AX1_ROW));
   TRY(dev_alloc(&c->d_LU, nv * 144));
   // channels: gbar[3], state = ratio[2] + gate[3] + gate_new[3], geff[4]
   {
@@ -130,8 +130,8 @@ int ax1gpu_create(const ax1gpu_grid* grid, const unsigned char* cell_subdomain, 
     TRY(dev_alloc(&c->d_geff, 4 * (size_t)nx));
     TRY(dev_alloc(&c->d_vrest, 1));
     TRY(dev_alloc(&c->d_vm, nx));
-    TRY(dev_alloc(&c->d_err, 1));
-    if (cudaMemsetAsync(c->d_err, 0, sizeof(int), st) != cudaSuccess) { ax1gpu_destroy(c); return AX1GPU_ECUDA; }
+    TRY(dev_alloc(&c->d_err, 2));
+    if (cudaMemsetAsync(c->d_err, 0, 2 * sizeof(int), st) != cudaSuccess) { ax1gpu_destroy(c); return AX1GPU_ECUDA; }
     for (int k = 0; k < 3; ++k) c->ch.gbar[k] = c->d_gbar + (size_t)k * nx;
     for (int k = 0; k < 2; ++k) c->ch.ratio[k] = c->d_chstate + (size_t)k * nx;
     for (int k = 0; k < 3; ++k) { c->ch.gate[k] = c->d_chstate + (size_t)(2 + k) * nx; c->ch.gate_new[k] = c->d_chstate + (size_t)(5 + k) * nx; }
@@ -336,11 +336,18 @@ int ax1gpu_set_jacobian(ax1gpu_handle c, const double* blocks) {
   int rc = ensure_bcrs(c);
   if (rc) return rc;
   AX1_CUDA(cudaMemcpyAsync(c->d_bcrs, blocks, (size_t)c->nblocks * 16 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  launch_expand_bcrs(c->g, c->d_bcrs, c->d_A, c->d_rowptr, c->stream);
+  AX1_CUDA(cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), c->stream));
+  launch_expand_bcrs(c->g, c->d_bcrs, c->d_A, c->d_rowptr, c->d_err + 1, c->stream);
   c->launches++;
   AX1_CUDA(cudaGetLastError());
+  int viol = 0;
+  AX1_CUDA(cudaMemcpyAsync(&viol, c->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   AX1_CUDA(cudaStreamSynchronize(c->stream));
   c->factored = false;
+  if (viol) {
+    set_error("ax1gpu_set_jacobian: non-zero entry outside the PNP block shape (con_i couples to con_i and pot only)");
+    return AX1GPU_EINVAL;
+  }
   return AX1GPU_OK;
 }
 

@@ -45,8 +45,16 @@ struct Dev {
   double dt;
 };
 
-// Matrix layout: 9 stencil slots per vertex row, slot s = (dj+1)*3 + (di+1), each a row-major 4x4
-// block: A[(v*9 + s)*16 + r*4 + c]. Missing neighbours (domain boundary) hold zero blocks.
+// Matrix layout: 9 stencil slots per vertex row, slot s = (dj+1)*3 + (di+1). Within a 4x4 block the
+// PNP Jacobian is an "arrow": concentration row i couples only to its own species and to the
+// potential, the potential row couples to everything (acme2_cyl_operator_fully_coupled.hh:516-561;
+// the FD boundary blocks and the row-norm scaling keep that shape). A block is therefore stored as
+// 10 doubles (80 B instead of 128 B):
+//     [ d0 c0 | d1 c1 | d2 c2 | p0 p1 p2 p3 ]     d_i = (con_i,con_i), c_i = (con_i,pot), p_k = (pot,k)
+// A[(v*9 + s)*10 + ...]; lane i<3 of a quad reads its 16 B pair, lane 3 its 32 B row.
+// Missing neighbours (domain boundary) hold zero blocks. The ILU factor blocks are dense (solver.cu).
+#define AX1_BLK 10
+#define AX1_ROW 90
 __host__ __device__ inline int slot_di(int s) { return s % 3 - 1; }
 __host__ __device__ inline int slot_dj(int s) { return s / 3 - 1; }
 

@@ -40,6 +40,6 @@ void launch_ilu_apply(const Dev& g, const double* LU, const double* d, double* v
                       cudaStream_t st);
 void launch_rownorm(const Dev& g, double* A, double* r, cudaStream_t st);
 void launch_compact_bcrs(const Dev& g, const double* A9, double* blocks, const int* rowptr, cudaStream_t st);
-void launch_expand_bcrs(const Dev& g, const double* blocks, double* A9, const int* rowptr, cudaStream_t st);
+void launch_expand_bcrs(const Dev& g, const double* blocks, double* A9, const int* rowptr, int* viol, cudaStream_t st);
 
 }  // namespace ax1

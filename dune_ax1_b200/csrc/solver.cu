@@ -46,20 +46,26 @@ __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restri
   const bool active = (v < g.nv) && !(DOT && sc && sc->done);
   if (active) {
     const int i = v % g.nvx, j = v / g.nvx;
-    const double* Arow = A + (size_t)v * 144 + r * 4;
+    const double* Arow = A + (size_t)v * AX1_ROW;
     double acc = 0.0;
 #pragma unroll
     for (int sl = 0; sl < 9; ++sl) {
       const int di = sl % 3 - 1, dj = sl / 3 - 1;
       const int ii = i + di, jj = j + dj;
       if (ii < 0 || ii >= g.nvx || jj < 0 || jj >= g.nvy) continue;
-      double a[4], xv[4];
-      ldg4(Arow + sl * 16, a);
+      double xv[4];
       ldg4(x + 4 * (size_t)(v + di + dj * g.nvx), xv);
-      acc += a[0] * xv[0];
-      acc += a[1] * xv[1];
-      acc += a[2] * xv[2];
-      acc += a[3] * xv[3];
+      // branch-free arrow-row load: every lane issues two 16 B loads (lanes 0-2 read their (d,c) pair
+      // twice) so that all 36 loads of the row can be in flight at once
+      const double* blk = Arow + sl * AX1_BLK;
+      const double2 a = __ldg(reinterpret_cast<const double2*>(blk + (r == 3 ? 6 : 2 * r)));
+      const double2 b2 = __ldg(reinterpret_cast<const double2*>(blk + (r == 3 ? 8 : 2 * r)));
+      const double xa = r == 3 ? xv[0] : (r == 0 ? xv[0] : (r == 1 ? xv[1] : xv[2]));
+      const double xb = r == 3 ? xv[1] : xv[3];
+      acc += a.x * xa;
+      acc += a.y * xb;
+      acc += (r == 3 ? b2.x : 0.0) * xv[2];
+      acc += (r == 3 ? b2.y : 0.0) * xv[3];
     }
     if (zero_con && ((g.dmask[v] >> r) & 1)) acc = 0.0;
     y[4 * (size_t)v + r] = acc;
@@ -142,102 +148,6 @@ __device__ __forceinline__ SlabGeom slab_geom(const Dev& g, int slab_w, const in
   return sg;
 }
 
-// block ILU0 of one sub-slab per CTA (bilu0_decomposition: L_ij = A_ij * A_jj^-1, diagonal stored inverted)
-__global__ void __launch_bounds__(256, 2) ilu_factor_kernel(Dev g, const double* __restrict__ A, double* LF, double* LB,
-                                                         int slab_w, const int* __restrict__ lvl_tab) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SlabGeom sg = slab_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(smem_raw));
-  const int i0 = sg.i0, wc = sg.wc;
-  const int q = threadIdx.x >> 2, r = threadIdx.x & 3, nq = blockDim.x >> 2;
-  const unsigned qmask = 0xFu << (threadIdx.x & 28);
-  for (int L = 0; L < sg.nlev; ++L) {
-    const int jlo = lev_jlo(L, wc), jhi = min(g.nvy - 1, L >> 1);
-    for (int j = jlo + q; j <= jhi; j += nq) {
-      const int il = L - 2 * j;
-      const int v = i0 + il + g.nvx * j;
-      bool ex[9];
-      double row[9][4];
-#pragma unroll
-      for (int s = 0; s < 9; ++s) {
-        const int di = s % 3 - 1, dj = s / 3 - 1;
-        ex[s] = (il + di >= 0) && (il + di < wc) && (j + dj >= 0) && (j + dj < g.nvy);
-        if (ex[s]) ldg4(A + ((size_t)v * 9 + s) * 16 + r * 4, row[s]);
-        else row[s][0] = row[s][1] = row[s][2] = row[s][3] = 0.0;
-      }
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        if (!ex[s]) continue;
-        const int dis = s % 3 - 1, djs = s / 3 - 1;
-        const double* kb = LB + (sg.row_off + packed_pos(sg, il + dis, j + djs)) * 80;  // row k: [Dinv, U5..U8]
-        double lrow[4];
-        {
-          double dinv[16];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) ldcg4(kb + m * 4, dinv + 4 * m);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            double sum = 0.0;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) sum += row[s][m] * dinv[4 * m + c];
-            lrow[c] = sum;
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) row[s][c] = lrow[c];
-#pragma unroll
-        for (int tt = 5; tt < 9; ++tt) {
-          const int di = dis + (tt % 3 - 1), dj = djs + (tt / 3 - 1);
-          if (di < -1 || di > 1 || dj < -1 || dj > 1) continue;
-          const int s2 = (dj + 1) * 3 + (di + 1);
-          if (!ex[s2]) continue;
-          double ub[16];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) ldcg4(kb + (tt - 4) * 16 + m * 4, ub + 4 * m);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            double sum = 0.0;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) sum += lrow[m] * ub[4 * m + c];
-            row[s2][c] -= sum;
-          }
-        }
-      }
-      // invert the pivot block (every lane of the quad holds one row of it)
-      double d[4][4], dinv[4][4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) d[m][c] = __shfl_sync(qmask, row[4][c], (threadIdx.x & 28) + m);
-      invert4(d, dinv);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        double val = dinv[0][c];
-        if (r == 1) val = dinv[1][c];
-        if (r == 2) val = dinv[2][c];
-        if (r == 3) val = dinv[3][c];
-        row[4][c] = val;
-      }
-      const size_t p = sg.row_off + (size_t)(sg.lvl[L] + j - jlo);
-#pragma unroll
-      for (int s = 0; s < 4; ++s) st4(LF + p * 64 + s * 16 + r * 4, row[s]);
-#pragma unroll
-      for (int s = 4; s < 9; ++s) st4(LB + p * 80 + (s - 4) * 16 + r * 4, row[s]);
-    }
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// v = (LU)^-1 d for one sub-slab per CTA (bilu_backsolve): forward sweep with unit lower blocks,
-// backward sweep with the stored inverse diagonal; both sweeps in one launch.
-//
-// The sweep is strictly sequential over ~W+2Ny wavefront levels, so HBM latency must be hidden by
-// a deep software pipeline: every thread (lane r of the quad that owns a wavefront row) streams
-// "its" scalar row of the 4-5 factor blocks of the next D levels into a private shared-memory slot
-// with cp.async (LDGSTS) and consumes it D levels later -- no barrier is needed for the staged
-// factor data, only cp.async.wait_group. The solution values of the last three levels, which the
-// next level depends on, are exchanged through a small shared-memory ring (one __syncthreads per
-// level) instead of an L2 round trip.
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
@@ -264,6 +174,131 @@ __device__ __forceinline__ LevelRow level_row(const Dev& g, int L, int nlev, int
   return o;
 }
 
+// block ILU0 of one sub-slab per CTA (bilu0_decomposition: L_ij = A_ij * A_jj^-1, diagonal stored
+// inverted). One quad per wavefront row. The 720 B Jacobian row of level L+2 is streamed into shared
+// memory with cp.async while level L is eliminated; the finished [Dinv | U] rows of the last three
+// levels -- all a row ever needs from its lower neighbours -- are kept in a shared-memory ring, so
+// the critical path of a level contains no global load.
+#define AX1_RING_ROW 82  // 80 doubles + 2 padding: 8 quads of a warp hit 8 different bank groups
+__global__ void __launch_bounds__(256, 1) ilu_factor_kernel(Dev g, const double* __restrict__ A, double* LF, double* LB,
+                                                            int slab_w, const int* __restrict__ lvl_tab) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, q = tid >> 2, r = tid & 3, nq = blockDim.x >> 2;
+  double* stage = reinterpret_cast<double*>(smem_raw);            // [2][nq][AX1_ROW]
+  double* ring = stage + 2 * (size_t)nq * AX1_ROW;                 // [3][nq][AX1_RING_ROW]
+  const SlabGeom sg = slab_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(ring + 3 * (size_t)nq * AX1_RING_ROW));
+  const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
+  const unsigned qmask = 0xFu << (tid & 28);
+
+  auto issue = [&](int L) {
+    const LevelRow w = level_row(g, L, nlev, i0, wc, q);
+    if (w.v >= 0) {
+      const double* src = A + (size_t)w.v * AX1_ROW;
+      double* dst = stage + ((size_t)(L & 1) * nq + q) * AX1_ROW;
+      for (int c = r; c < AX1_ROW / 2; c += 4) cp_async16(dst + 2 * c, src + 2 * c);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  issue(1);
+  for (int L = 0; L < nlev; ++L) {
+    cp_async_wait<1>();
+    __syncthreads();  // staged row of this level and the ring rows of level L-1 are visible
+    const LevelRow w = level_row(g, L, nlev, i0, wc, q);
+    double row[9][4];
+    if (w.v >= 0) {
+      const int il = w.il, j = w.j;
+      bool ex[9];
+      const double* arow = stage + ((size_t)(L & 1) * nq + q) * AX1_ROW;
+#pragma unroll
+      for (int s = 0; s < 9; ++s) {
+        const int di = s % 3 - 1, dj = s / 3 - 1;
+        ex[s] = (il + di >= 0) && (il + di < wc) && (j + dj >= 0) && (j + dj < g.nvy);
+        // expand the arrow block row (common.cuh), branch-free in the lane index
+        const double* blk = arow + s * AX1_BLK;
+        const double2 a = *reinterpret_cast<const double2*>(blk + (r == 3 ? 6 : 2 * r));
+        const double2 b2 = *reinterpret_cast<const double2*>(blk + (r == 3 ? 8 : 2 * r));
+        row[s][0] = (ex[s] && (r == 3 || r == 0)) ? a.x : 0.0;
+        row[s][1] = ex[s] ? (r == 3 ? a.y : (r == 1 ? a.x : 0.0)) : 0.0;
+        row[s][2] = ex[s] ? (r == 3 ? b2.x : (r == 2 ? a.x : 0.0)) : 0.0;
+        row[s][3] = ex[s] ? (r == 3 ? b2.y : a.y) : 0.0;
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (!ex[s]) continue;
+        const int dis = s % 3 - 1, djs = s / 3 - 1;
+        const int Ln = L + dis + 2 * djs;
+        const int qn = (j + djs) - lev_jlo(Ln, wc);
+        const double* kb = ring + ((size_t)(Ln % 3) * nq + qn) * AX1_RING_ROW;  // row k: [Dinv, U5..U8]
+        double lrow[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double sum = 0.0;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) sum += row[s][m] * kb[4 * m + c];
+          lrow[c] = sum;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) row[s][c] = lrow[c];
+#pragma unroll
+        for (int tt = 5; tt < 9; ++tt) {
+          const int di = dis + (tt % 3 - 1), dj = djs + (tt / 3 - 1);
+          if (di < -1 || di > 1 || dj < -1 || dj > 1) continue;
+          const int s2 = (dj + 1) * 3 + (di + 1);
+          if (!ex[s2]) continue;
+          const double* ub = kb + (tt - 4) * 16;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            double sum = 0.0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) sum += lrow[m] * ub[4 * m + c];
+            row[s2][c] -= sum;
+          }
+        }
+      }
+      // invert the pivot block (every lane of the quad holds one row of it)
+      double d[4][4], dinv[4][4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d[m][c] = __shfl_sync(qmask, row[4][c], (tid & 28) + m);
+      invert4(d, dinv);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        double val = dinv[0][c];
+        if (r == 1) val = dinv[1][c];
+        if (r == 2) val = dinv[2][c];
+        if (r == 3) val = dinv[3][c];
+        row[4][c] = val;
+      }
+      const size_t p = sg.row_off + (size_t)(sg.lvl[L] + q);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) st4(LF + p * 64 + s * 16 + r * 4, row[s]);
+#pragma unroll
+      for (int s = 4; s < 9; ++s) st4(LB + p * 80 + (s - 4) * 16 + r * 4, row[s]);
+    }
+    __syncthreads();  // every read of ring slot L%3 (it held level L-3) is done
+    if (w.v >= 0) {
+      double* kr = ring + ((size_t)(L % 3) * nq + q) * AX1_RING_ROW;
+#pragma unroll
+      for (int s = 4; s < 9; ++s) st4(kr + (s - 4) * 16 + r * 4, row[s]);
+    }
+    issue(L + 2);
+  }
+  cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------
+// v = (LU)^-1 d for one sub-slab per CTA (bilu_backsolve): forward sweep with unit lower blocks,
+// backward sweep with the stored inverse diagonal; both sweeps in one launch.
+//
+// The sweep is strictly sequential over ~W+2Ny wavefront levels, so HBM latency must be hidden by
+// a deep software pipeline: every thread (lane r of the quad that owns a wavefront row) streams
+// "its" scalar row of the 4-5 factor blocks of the next D levels into a private shared-memory slot
+// with cp.async (LDGSTS) and consumes it D levels later -- no barrier is needed for the staged
+// factor data, only cp.async.wait_group. The solution values of the last three levels, which the
+// next level depends on, are exchanged through a small shared-memory ring (one __syncthreads per
+// level) instead of an L2 round trip.
 template <int D>
 __global__ void __launch_bounds__(256) ilu_apply_kernel(Dev g, const double* __restrict__ LF,
                                                         const double* __restrict__ LB, const double* __restrict__ d,
@@ -400,23 +435,30 @@ __global__ void rownorm_kernel(Dev g, double* A, double* rv) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int v = (int)(t >> 2), r = (int)(t & 3);
   if (v >= g.nv) return;
-  double* Arow = A + (size_t)v * 144 + r * 4;
+  double* Arow = A + (size_t)v * AX1_ROW;
+  const int off = r == 3 ? 6 : 2 * r, cnt = r == 3 ? 4 : 2;
   double n = 0.0;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) n = fmax(n, fabs(Arow[4 * 16 + c]));
+  for (int c = 0; c < cnt; ++c) n = fmax(n, fabs(Arow[4 * AX1_BLK + off + c]));
   if (n) {
-#pragma unroll
     for (int s = 0; s < 9; ++s)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) Arow[s * 16 + c] /= n;
+      for (int c = 0; c < cnt; ++c) Arow[s * AX1_BLK + off + c] /= n;
     rv[4 * (size_t)v + r] /= n;
   } else {
-    Arow[4 * 16 + r] = 1.0;
+    Arow[4 * AX1_BLK + (r == 3 ? 9 : 2 * r)] = 1.0;
   }
 }
 
 // 9-slot layout <-> compact BCRS (download / upload of the Jacobian in the reference's layout)
-__global__ void bcrs_copy_kernel(Dev g, double* A9, double* blocks, const int* __restrict__ rowptr, int to_bcrs) {
+// arrow-block position of dense entry (rr, cc), -1 if structurally zero
+__device__ __forceinline__ int arrow_pos(int rr, int cc) {
+  if (rr == 3) return 6 + cc;
+  if (cc == rr) return 2 * rr;
+  if (cc == 3) return 2 * rr + 1;
+  return -1;
+}
+// device layout <-> compact BCRS with dense 4x4 blocks (the reference's BCRSMatrix layout). On upload
+// (to_bcrs = 0) a non-zero outside the arrow shape sets *viol (such a matrix is not a PNP Jacobian).
+__global__ void bcrs_copy_kernel(Dev g, double* A9, double* blocks, const int* __restrict__ rowptr, int to_bcrs, int* viol) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long vs = t >> 4;
   const int e = (int)(t & 15);
@@ -431,13 +473,15 @@ __global__ void bcrs_copy_kernel(Dev g, double* A9, double* blocks, const int* _
     if (k == s) { mine = inb; break; }
     pos += inb;
   }
+  const int ap = arrow_pos(e >> 2, e & 3);
   if (!mine) {
-    if (!to_bcrs) A9[vs * 16 + e] = 0.0;
+    if (!to_bcrs && ap >= 0) A9[vs * AX1_BLK + ap] = 0.0;
     return;
   }
   const size_t b = ((size_t)rowptr[v] + pos) * 16 + e;
-  if (to_bcrs) blocks[b] = A9[vs * 16 + e];
-  else A9[vs * 16 + e] = blocks[b];
+  if (to_bcrs) blocks[b] = ap >= 0 ? A9[vs * AX1_BLK + ap] : 0.0;
+  else if (ap >= 0) A9[vs * AX1_BLK + ap] = blocks[b];
+  else if (blocks[b] != 0.0) atomicExch(viol, 1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -482,8 +526,14 @@ void ilu_level_tables(const Dev& g, int slab_w, std::vector<int>& tab) {
 }
 void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st) {
   const int nslab = (g.nvx + slab_w - 1) / slab_w;
-  const size_t smem = (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
-  ilu_factor_kernel<<<nslab, slab_threads(slab_w), smem, st>>>(g, A, LU, LU + (size_t)g.nv * 64, slab_w, lvl_tab);
+  const int nt = slab_threads(slab_w), nq = nt / 4;
+  const size_t smem = (size_t)nq * (2 * AX1_ROW + 3 * AX1_RING_ROW) * sizeof(double) + (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ilu_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  ilu_factor_kernel<<<nslab, nt, smem, st>>>(g, A, LU, LU + (size_t)g.nv * 64, slab_w, lvl_tab);
 }
 static int ilu_stages() {
   static const int d = getenv("AX1_ILU_STAGES") ? atoi(getenv("AX1_ILU_STAGES")) : 2;
@@ -522,12 +572,12 @@ void launch_rownorm(const Dev& g, double* A, double* r, cudaStream_t st) {
 void launch_compact_bcrs(const Dev& g, const double* A9, double* blocks, const int* rowptr, cudaStream_t st) {
   const int bs = 256;
   const long long nt = 9LL * 16 * g.nv;
-  bcrs_copy_kernel<<<(unsigned)((nt + bs - 1) / bs), bs, 0, st>>>(g, const_cast<double*>(A9), blocks, rowptr, 1);
+  bcrs_copy_kernel<<<(unsigned)((nt + bs - 1) / bs), bs, 0, st>>>(g, const_cast<double*>(A9), blocks, rowptr, 1, nullptr);
 }
-void launch_expand_bcrs(const Dev& g, const double* blocks, double* A9, const int* rowptr, cudaStream_t st) {
+void launch_expand_bcrs(const Dev& g, const double* blocks, double* A9, const int* rowptr, int* viol, cudaStream_t st) {
   const int bs = 256;
   const long long nt = 9LL * 16 * g.nv;
-  bcrs_copy_kernel<<<(unsigned)((nt + bs - 1) / bs), bs, 0, st>>>(g, A9, const_cast<double*>(blocks), rowptr, 0);
+  bcrs_copy_kernel<<<(unsigned)((nt + bs - 1) / bs), bs, 0, st>>>(g, A9, const_cast<double*>(blocks), rowptr, 0, viol);
 }
 
 }  // namespace ax1
