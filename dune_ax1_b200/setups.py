@@ -52,13 +52,17 @@ def perturb(u, nvx, nvy, amp=1e-3, i_offset=0):
 
 
 def make_setup(nx, dx=None, xmax=None, stimulation=False, hh=True, equilibration=False, bc=None,
-               rank=0, nranks=1, perturbation=0.0, y=None, ucol=None):
+               rank=0, nranks=1, perturbation=0.0, y=None, ucol=None, xg=None, groups=None, **param_over):
     """Arrays of one rank's local problem. Returns a dict usable for api.Ax1Gpu and for the oracle."""
     if y is None or ucol is None:
         y, ucol, _ = load_equilibrium_column()
-    if xmax is None:
-        xmax = nx * (dx if dx is not None else 100.0e3)
-    xg = equidistant_x(0.0, xmax, nx)
+    if xg is not None:                      # explicit (possibly non-uniform) global x vector
+        xg = np.asarray(xg, dtype=np.float64)
+        nx, xmax = len(xg) - 1, float(xg[-1])
+    else:
+        if xmax is None:
+            xmax = nx * (dx if dx is not None else 100.0e3)
+        xg = equidistant_x(0.0, xmax, nx)
     c0, c1, l0, l1 = api.slab(nx, nranks, rank) if nranks > 1 else (0, nx, 0, nx)
     x = xg[l0:l1 + 1].copy()
     left_pb, right_pb = rank > 0, rank < nranks - 1
@@ -72,10 +76,21 @@ def make_setup(nx, dx=None, xmax=None, stimulation=False, hh=True, equilibration
     params = dict(do_stimulation=int(stimulation), tinj_start=20.0, tinj_end=2.0e3, stim_x=150.0e3, stim_y=0.0,
                   I_inj=1.0e13, do_equilibration=int(equilibration), t_equilibrium=1.0e9 if equilibration else 0.0,
                   dummy_value=10.0 if equilibration else 1.0)
+    params.update(param_over)
+    eps_memb = np.full(nxl, 2.0)
+    g_leak, g_nav, g_kv = np.full(nxl, 0.5), np.full(nxl, 120.0 if hh else 0.0), np.full(nxl, 36.0 if hh else 0.0)
+    if groups:
+        # membrane groups [membrane.<name>] of the INI file: (x_start, x_end, permittivity, d_memb, leak, Nav, Kv);
+        # a membrane cell belongs to the group that contains its centre; effective permittivity =
+        # permittivity * d_memb_default / d_memb (acme2_cyl_physics.hh:2592-2600)
+        xc = 0.5 * (x[:-1] + x[1:])
+        for (xs, xe, perm, dm_g, gl, gn, gk) in groups:
+            m = (xc >= xs) & (xc < xe)
+            eps_memb[m] = perm * (5.0 / dm_g)
+            g_leak[m], g_nav[m], g_kv[m] = gl, gn, gk
     return dict(x=x, y=y, nx=nxl, ny=len(y) - 1, xmax=xmax, cell_subdomain=cs, node_volume=nvol, dirichlet=dm,
-                eps_memb=np.full(nxl, 2.0), g_leak=np.full(nxl, 0.5), g_nav=np.full(nxl, 120.0 if hh else 0.0),
-                g_kv=np.full(nxl, 36.0 if hh else 0.0), u0=u0, params=params, left_pb=left_pb, right_pb=right_pb,
-                bc=bc, slab=(c0, c1, l0, l1))
+                eps_memb=eps_memb, g_leak=g_leak, g_nav=g_nav, g_kv=g_kv, u0=u0, params=params, left_pb=left_pb,
+                right_pb=right_pb, bc=bc, slab=(c0, c1, l0, l1))
 
 
 def make_device(s, device=0, stream=None):

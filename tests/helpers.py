@@ -16,7 +16,10 @@ def oracle_problem(O, s, analytic=1, **cfg_over):
         left_cytosol_dirichlet=list(bc.left_cytosol), right_cytosol_dirichlet=list(bc.right_cytosol),
         left_debye_dirichlet=list(bc.left_debye), right_debye_dirichlet=list(bc.right_debye),
         left_extra_dirichlet=list(bc.left_extra), right_extra_dirichlet=list(bc.right_extra),
-        debye_layer_width=bc.debye_layer_width, **cfg_over)
+        debye_layer_width=bc.debye_layer_width,
+        use_rownorm_preconditioner=p.get("use_rownorm_preconditioner", 0), membrane_active=p.get("membrane_active", 1),
+        automatic_channel_init=p.get("automatic_channel_init", 1),
+        channel_resting_potential=p.get("channel_resting_potential", -65.0), **cfg_over)
     return O.Problem(cfg, s["x"], s["y"], left_pb=s["left_pb"], right_pb=s["right_pb"], eps_memb=s["eps_memb"],
                      g_leak=s["g_leak"], g_nav=s["g_nav"], g_kv=s["g_kv"])
 

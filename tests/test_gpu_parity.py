@@ -292,3 +292,77 @@ def test_determinism_and_translation_invariance(oracle, axlib):
     z, rr, res = dev.solve(r1, 1e-6, maxit=200, slab_w=128)
     assert res.converged == 1
     dev.close()
+
+
+def _myelin_like():
+    """Non-uniform x (fine nodes of Ranvier, coarse internodes) with three membrane groups: node (high
+    channel density), myelin (thick low-permittivity membrane, no channels, no leak) and a passive soma."""
+    from dune_ax1_b200 import setups
+    xg = np.concatenate([[0.0], np.cumsum([2.0e3] * 3 + [10.0e3, 50.0e3, 50.0e3, 10.0e3] + [1.0e3] * 2 + [40.0e3] * 3)])
+    groups = [(0.0, 6.0e3, 2.0, 5.0, 0.5, 1200.0, 360.0),          # node: 10x channel density
+              (6.0e3, 126.0e3, 6.0, 85.0, 0.0, 0.0, 0.0),          # myelin: d_memb 85 nm, no channels, no leak
+              (126.0e3, 128.0e3, 2.0, 5.0, 0.5, 1200.0, 360.0),    # node
+              (128.0e3, 1.0e9, 2.0, 5.0, 0.5, 0.0, 0.0)]           # passive, leak only
+    return setups.make_setup(0, xg=xg, groups=groups, perturbation=1e-3)
+
+
+def test_membrane_groups_nonuniform_grid(oracle, axlib):
+    s = _myelin_like()
+    dev, P, u0 = _both(oracle, axlib, s)
+    sg, _ = dev.channel_state()
+    assert np.max(np.abs(sg - P.channel_state())) < 1e-13
+    r_g, _ = dev.residual(u0)
+    r_o, a_o = P.residual(u0, with_abs=True)
+    assert np.max(np.abs(r_g - r_o) / (a_o + 1e-300)) < 1e-12
+    Jg, Jo = dev.jacobian(u0).reshape(-1, 4, 4), P.jacobian(u0).reshape(-1, 4, 4)
+    rowptr, _ = P.pattern()
+    rows = np.repeat(np.arange(P.nv), np.diff(rowptr))
+    scale = np.zeros((P.nv, 4))
+    np.maximum.at(scale, rows, np.max(np.abs(Jo), axis=2))
+    assert (np.abs(Jg - Jo) / (scale[rows][:, :, None] + 1e-300)).max() < 1e-6
+    kw = dict(reduction=1e-8, abs_limit=1e-14, min_lin_reduction=1e-9)
+    ug, rg = dev.newton(u0, axlib.default_newton_opts(slab_w=5, **kw))
+    uc, rc = P.newton(u0, oracle.default_newton_opts(ilu_fill=0, slab_w=5, **kw))
+    assert rg.status == 0 and rc.status == 0 and rg.iterations == rc.iterations
+    scale = np.max(np.abs(uc.reshape(-1, 4)), axis=0)
+    err = np.max(np.abs(ug - uc).reshape(-1, 4) / scale, axis=0)
+    assert np.all(err[:3] < 1e-8) and err[3] < 5e-7, err   # potential: attainable accuracy (see DESIGN.md 5)
+    dev.close()
+
+
+@pytest.mark.parametrize("variant", ["rownorm", "passive_membrane", "fixed_vrest"])
+def test_switches(oracle, axlib, variant):
+    """Run-time switches of the path: row-norm equilibration (ax1_newton.hh:255-259), inactive membrane,
+    automaticChannelInitialization = no."""
+    over = {"rownorm": dict(use_rownorm_preconditioner=1), "passive_membrane": dict(membrane_active=0),
+            "fixed_vrest": dict(automatic_channel_init=0, channel_resting_potential=-70.0)}[variant]
+    from dune_ax1_b200 import setups
+    s = setups.make_setup(6, dx=100.0e3, perturbation=1e-3, **over)
+    dev, P, u0 = _both(oracle, axlib, s)
+    r_g, _ = dev.residual(u0)
+    r_o, a_o = P.residual(u0, with_abs=True)
+    assert np.max(np.abs(r_g - r_o) / (a_o + 1e-300)) < 1e-12
+    if variant == "fixed_vrest":
+        sg, vrest = dev.channel_state()
+        assert vrest == -70.0 and abs(P.v_rest() + 70.0) < 1e-15
+        assert np.max(np.abs(sg - P.channel_state())) < 1e-13
+    kw = dict(reduction=1e-8, abs_limit=1e-14, min_lin_reduction=1e-9)
+    ug, rg = dev.newton(u0, axlib.default_newton_opts(slab_w=4, **kw))
+    uc, rc = P.newton(u0, oracle.default_newton_opts(ilu_fill=0, slab_w=4, **kw))
+    assert rg.status == 0 and rc.status == 0
+    scale = np.max(np.abs(uc.reshape(-1, 4)), axis=0)
+    err = np.max(np.abs(ug - uc).reshape(-1, 4) / scale, axis=0)
+    assert np.all(err[:3] < 1e-8) and err[3] < 2e-7, err
+    dev.close()
+
+
+def test_set_jacobian_rejects_non_pnp_blocks(oracle, axlib):
+    s = small_setup(nx=3)
+    dev, P, u0 = _both(oracle, axlib, s)
+    J = P.jacobian(u0)
+    dev.set_jacobian(J)                      # a PNP Jacobian is accepted
+    bad = J.copy().reshape(-1, 4, 4)
+    bad[5, 0, 1] = 1.0                       # Na row coupling to K: not a PNP block shape
+    with pytest.raises(axlib.Ax1GpuError):
+        dev.set_jacobian(bad.reshape(-1))
+    dev.close()
