@@ -143,6 +143,14 @@ def lib():
                                        C.c_double, C.c_int, C.c_double, C.POINTER(HostBC), c_ubyte_p, c_double_p,
                                        c_ubyte_p]
     L.ax1host_slab.argtypes = [C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p]
+    L.ax1host_state_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.ax1host_state_free.argtypes = [C.c_void_p]
+    L.ax1host_state_info.argtypes = [C.c_void_p, c_int_p, c_double_p, c_double_p, c_int_p, c_int_p, c_int_p, c_int_p]
+    L.ax1host_state_vector.argtypes = [C.c_void_p, C.c_char_p, c_double_p, C.c_int]
+    L.ax1host_state_save.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.c_char_p), C.POINTER(c_double_p), c_int_p]
+    L.ax1host_state_extrapolate.argtypes = [C.c_int, c_double_p, C.c_int, c_double_p, c_double_p, C.c_int, c_double_p,
+                                            C.c_int, c_double_p, c_double_p]
     assert L.ax1gpu_sizeof_params() == C.sizeof(Params), "ax1gpu_params layout mismatch"
     _lib = L
     return L
@@ -233,6 +241,50 @@ def physics_maps(x, y, ymemb=500.0, dmemb=5.0, xmin_global=None, xmax_global=Non
         y[-1] if ymax is None else ymax, int(do_volume_scaling), volume_scaling_threshold, C.byref(bc.c),
         cs.ctypes.data_as(c_ubyte_p), _dp(nvol), dm.ctypes.data_as(c_ubyte_p)))
     return cs, nvol, dm
+
+
+# ------------------------------------------------------------------------------------------------
+# simulation-state files (Ax1SimulationState format) and x-extrapolation of a loaded state
+def load_state(path, names=("x", "y", "channelStates", "uold", "unew")):
+    L = lib()
+    h = C.c_void_p()
+    _chk(L.ax1host_state_load(path.encode(), C.byref(h)))
+    try:
+        ne, ts, rk, sz, nvec = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        t, dt = C.c_double(), C.c_double()
+        _chk(L.ax1host_state_info(h, C.byref(ne), C.byref(t), C.byref(dt), C.byref(ts), C.byref(rk), C.byref(sz),
+                                  C.byref(nvec)))
+        out = dict(elements=ne.value, time=t.value, dt=dt.value, timestep=ts.value, mpi_rank=rk.value,
+                   mpi_size=sz.value, nvectors=nvec.value)
+        for n in names:
+            ln = L.ax1host_state_vector(h, n.encode(), None, 0)
+            if ln >= 0:
+                a = np.zeros(ln)
+                L.ax1host_state_vector(h, n.encode(), _dp(a), ln)
+                out[n] = a
+        return out
+    finally:
+        L.ax1host_state_free(h)
+
+
+def save_state(path, nelements, time, dt, vectors, timestep=0, mpi_rank=0, mpi_size=1):
+    """vectors: ordered dict name -> array (the reference writes x, y, channelStates, uold, unew)."""
+    names = list(vectors)
+    arrs = [f64(vectors[n]) for n in names]
+    cn = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    cd = (c_double_p * len(names))(*[_dp(a) for a in arrs])
+    cs = (C.c_int * len(names))(*[len(a) for a in arrs])
+    _chk(lib().ax1host_state_save(path.encode(), int(nelements), int(timestep), float(time), float(dt), int(mpi_rank),
+                                  int(mpi_size), len(names), cn, cd, cs))
+
+
+def extrapolate_state(xs, ys, us, x, y):
+    """doExtrapolateXData: evaluate the loaded state as a Q1 grid function at the vertices of (x, y)."""
+    xs, ys, us, x, y = f64(xs), f64(ys), f64(us), f64(x), f64(y)
+    u = np.zeros(4 * len(x) * len(y))
+    _chk(lib().ax1host_state_extrapolate(len(xs), _dp(xs), len(ys), _dp(ys), _dp(us), len(x), _dp(x), len(y), _dp(y),
+                                         _dp(u)))
+    return u
 
 
 def default_params(**kw):

@@ -214,3 +214,130 @@ int ax1host_slab(int nx_global, int nranks, int rank, int* c0, int* c1, int* l0,
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Simulation-state files: the ASCII checkpoint format of Ax1SimulationState
+// (dune/ax1/common/ax1_simulationstate.hh:30-57; written by Acme2CylOutput::saveState,
+// acme2_cyl_output.hh:937-979, one file per rank "*_p<rank>.dat") and the x-extrapolation of a loaded
+// state onto the simulation grid (doExtrapolateXData, acme2_cyl_simloader.hh:364-...: the loaded state
+// is evaluated as a Q1 grid function at the vertices of the new grid).
+#include <fstream>
+#include <iomanip>
+#include <map>
+#include <sstream>
+
+struct ax1host_state {
+  int nelements = 0, timestep = 0, mpi_rank = 0, mpi_size = 1;
+  double time = 0.0, dt = 0.0;
+  std::vector<std::string> names;
+  std::map<std::string, std::vector<double>> vec;
+};
+
+extern "C" {
+
+int ax1host_state_load(const char* path, ax1host_state** out) {
+  std::ifstream in(path);
+  if (!in.good()) { ax1::set_error(std::string("cannot read state file ") + path); return AX1GPU_EINVAL; }
+  ax1host_state* s = new ax1host_state;
+  std::string key;
+  int nvec = -1;
+  while (nvec < 0 && (in >> key)) {  // header: older files have no timestep / mpi_* lines
+    if (key == "#elements") in >> s->nelements;
+    else if (key == "timestep") in >> s->timestep;
+    else if (key == "time") in >> s->time;
+    else if (key == "dt") in >> s->dt;
+    else if (key == "mpi_rank") in >> s->mpi_rank;
+    else if (key == "mpi_size") in >> s->mpi_size;
+    else if (key == "#vectors") in >> nvec;
+    else { delete s; ax1::set_error("unknown key '" + key + "' in state file header"); return AX1GPU_EINVAL; }
+  }
+  for (int k = 0; k < nvec; ++k) {
+    std::string name;
+    size_t n = 0;
+    if (!(in >> name >> n)) { delete s; ax1::set_error("truncated state file"); return AX1GPU_EINVAL; }
+    std::vector<double>& v = s->vec[name];
+    v.resize(n);
+    for (size_t i = 0; i < n; ++i)
+      if (!(in >> v[i])) { delete s; ax1::set_error("truncated vector '" + name + "'"); return AX1GPU_EINVAL; }
+    s->names.push_back(name);
+  }
+  *out = s;
+  return AX1GPU_OK;
+}
+
+void ax1host_state_free(ax1host_state* s) { delete s; }
+
+int ax1host_state_info(const ax1host_state* s, int* nelements, double* time, double* dt, int* timestep, int* mpi_rank,
+                       int* mpi_size, int* nvectors) {
+  if (!s) return AX1GPU_EINVAL;
+  if (nelements) *nelements = s->nelements;
+  if (time) *time = s->time;
+  if (dt) *dt = s->dt;
+  if (timestep) *timestep = s->timestep;
+  if (mpi_rank) *mpi_rank = s->mpi_rank;
+  if (mpi_size) *mpi_size = s->mpi_size;
+  if (nvectors) *nvectors = (int)s->names.size();
+  return AX1GPU_OK;
+}
+
+// returns the length of vector `name` (-1 if absent); copies min(len, cap) values if out != NULL
+int ax1host_state_vector(const ax1host_state* s, const char* name, double* out, int cap) {
+  auto it = s->vec.find(name);
+  if (it == s->vec.end()) return -1;
+  if (out) std::memcpy(out, it->second.data(), sizeof(double) * std::min<size_t>(it->second.size(), (size_t)cap));
+  return (int)it->second.size();
+}
+
+int ax1host_state_save(const char* path, int nelements, int timestep, double time, double dt, int mpi_rank,
+                       int mpi_size, int nvec, const char* const* names, const double* const* data, const int* sizes) {
+  std::ofstream out(path);
+  if (!out.good()) { ax1::set_error(std::string("cannot create state file ") + path); return AX1GPU_EINVAL; }
+  out << std::scientific << std::setprecision(16);
+  out << "#elements " << nelements << std::endl;
+  out << "timestep " << timestep << std::endl;
+  out << "time " << time << std::endl;
+  out << "dt " << dt << std::endl;
+  out << "mpi_rank " << mpi_rank << std::endl;
+  out << "mpi_size " << mpi_size << std::endl;
+  out << "#vectors " << nvec << std::endl;
+  for (int i = 0; i < nvec; i++) {
+    out << names[i] << " " << sizes[i] << std::endl;
+    for (int j = 0; j < sizes[i]; j++) out << data[i][j] << " ";
+    out << std::endl;
+  }
+  return out.good() ? AX1GPU_OK : AX1GPU_EINVAL;
+}
+
+// Q1 evaluation of a vertex-blocked state given on the tensor grid (xs, ys) at the vertices of (x, y).
+int ax1host_state_extrapolate(int nxs, const double* xs, int nys, const double* ys, const double* us, int nx,
+                              const double* x, int ny, const double* y, double* u) {
+  if (nxs < 2 || nys < 2) { ax1::set_error("state grid needs at least 2x2 vertices"); return AX1GPU_EINVAL; }
+  auto locate = [](const double* g, int n, double p, int& cell, double& loc) {
+    int c = (int)(std::upper_bound(g, g + n, p) - g) - 1;
+    c = std::max(0, std::min(c, n - 2));
+    cell = c;
+    loc = (p - g[c]) / (g[c + 1] - g[c]);
+    loc = std::max(0.0, std::min(1.0, loc));
+  };
+  for (int j = 0; j < ny; ++j) {
+    int cj; double eta;
+    locate(ys, nys, y[j], cj, eta);
+    for (int i = 0; i < nx; ++i) {
+      int ci; double xi;
+      locate(xs, nxs, x[i], ci, xi);
+      const double* a = us + 4 * ((size_t)ci + (size_t)nxs * cj);
+      const double* b = a + 4;
+      const double* c = a + 4 * (size_t)nxs;
+      const double* d = c + 4;
+      double* o = u + 4 * ((size_t)i + (size_t)nx * j);
+      for (int k = 0; k < 4; ++k) {
+        const double lo = a[k] + xi * (b[k] - a[k]);   // exact when the two columns coincide
+        const double hi = c[k] + xi * (d[k] - c[k]);
+        o[k] = lo + eta * (hi - lo);
+      }
+    }
+  }
+  return AX1GPU_OK;
+}
+
+}  // extern "C"

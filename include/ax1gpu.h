@@ -179,6 +179,21 @@ int ax1host_physics_maps(const ax1gpu_grid* grid, double ymemb, double dmemb, do
  * interior cells [c0,c1) and local cells [l0,l1) incl. one overlap column per interior side. */
 int ax1host_slab(int nx_global, int nranks, int rank, int* c0, int* c1, int* l0, int* l1);
 
+
+/* ---- simulation-state files ("next" row 8(f)1): Ax1SimulationState ASCII format
+ * (dune/ax1/common/ax1_simulationstate.hh:30-57, acme2_cyl_output.hh:937-979) and the x-extrapolation
+ * of a loaded state onto the simulation grid (doExtrapolateXData, acme2_cyl_simloader.hh:364). ---- */
+typedef struct ax1host_state ax1host_state;
+int ax1host_state_load(const char* path, ax1host_state** out);
+void ax1host_state_free(ax1host_state* s);
+int ax1host_state_info(const ax1host_state* s, int* nelements, double* time, double* dt, int* timestep,
+                       int* mpi_rank, int* mpi_size, int* nvectors);
+int ax1host_state_vector(const ax1host_state* s, const char* name, double* out, int cap); /* returns length */
+int ax1host_state_save(const char* path, int nelements, int timestep, double time, double dt, int mpi_rank,
+                       int mpi_size, int nvec, const char* const* names, const double* const* data, const int* sizes);
+int ax1host_state_extrapolate(int nxs, const double* xs, int nys, const double* ys, const double* us, int nx,
+                              const double* x, int ny, const double* y, double* u);
+
 #ifdef __cplusplus
 }
 #endif
