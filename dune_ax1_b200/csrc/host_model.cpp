@@ -330,11 +330,9 @@ int ax1host_state_extrapolate(int nxs, const double* xs, int nys, const double* 
       const double* c = a + 4 * (size_t)nxs;
       const double* d = c + 4;
       double* o = u + 4 * ((size_t)i + (size_t)nx * j);
-      for (int k = 0; k < 4; ++k) {
-        const double lo = a[k] + xi * (b[k] - a[k]);   // exact when the two columns coincide
-        const double hi = c[k] + xi * (d[k] - c[k]);
-        o[k] = lo + eta * (hi - lo);
-      }
+      // exact at the nodes of the loaded grid and when neighbouring values coincide
+      auto lerp = [](double p, double q_, double t) { return t <= 0.0 ? p : (t >= 1.0 ? q_ : p + t * (q_ - p)); };
+      for (int k = 0; k < 4; ++k) o[k] = lerp(lerp(a[k], b[k], xi), lerp(c[k], d[k], xi), eta);
     }
   }
   return AX1GPU_OK;
