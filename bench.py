@@ -28,8 +28,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
+# stdout must carry exactly ONE JSON line: libraries (e.g. NCCL's version banner) write to fd 1, so fd 1 is
+# pointed at stderr for the whole run and the result line goes to the saved original stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
 
 METRIC = "PNP assembly+solve throughput (DOF x Newton steps per second)"
 UNIT = "GDOF/s"
@@ -175,7 +183,7 @@ def main():
                "newton_steps_per_s_at_workload_size": NEWTON_ITS / r["sec_per_step"] * (r["nv"] / full_nv),
                "cpu_baseline": {"value": gdof, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
                "e2e": {"value": gdof, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(out))
+        emit(out)
         return
 
     import torch
@@ -354,7 +362,7 @@ def main():
                                                                         r["sec_per_step"], NEWTON_ITS, KRYLOV_ITS),
             "newton_steps_per_s_at_workload_size": NEWTON_ITS / r["sec_per_step"] * (r["nv"] / nv_total)}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     dev.close()
     if world > 1:
         dist.destroy_process_group()
