@@ -366,3 +366,41 @@ def test_set_jacobian_rejects_non_pnp_blocks(oracle, axlib):
     with pytest.raises(axlib.Ax1GpuError):
         dev.set_jacobian(bad.reshape(-1))
     dev.close()
+
+
+def test_interface_mirror_classes(oracle, axlib):
+    """The Python mirror of the reference interface: GridOperator / ISTLBackend / Ax1Newton / MembraneFlux
+    used the way Acme2CylSetup wires IGO, LS and PDESOLVER, incl. the NewtonError the time loop catches."""
+    s = small_setup(nx=5)
+    from dune_ax1_b200 import setups
+    dev = setups.make_device(s)
+    P = oracle_problem(oracle, s)
+    u0 = s["u0"]
+    flux, igo = axlib.MembraneFlux(dev), axlib.GridOperator(dev)
+    ls, newton = axlib.ISTLBackend_BCGS_ILU0(dev, maxiter=500, slab_w=3), axlib.Ax1Newton(dev)
+    flux.updateState(0.0, 1.0, u0)
+    igo.preStep(0.0, 1.0, u0)
+    P.set_time(0.0, 1.0); P.update_state(u0); P.set_uold(u0)
+    r = igo.residual(u0)
+    A = igo.jacobian(u0)
+    r_o, a_o = P.residual(u0, with_abs=True)
+    assert np.max(np.abs(r - r_o) / (a_o + 1e-300)) < 1e-12
+    z = np.zeros_like(r)
+    d0 = ls.norm(r)
+    rr = r.copy()
+    ls.apply(A, z, rr, 1e-8)
+    assert ls.result().converged == 1 and ls.norm(rr) <= 1e-8 * d0
+    assert np.linalg.norm(r - P.spmv(P.jacobian(u0), z)) <= 1e-7 * d0
+    # Newton with maxit = 1 cannot reach 1e-12: NewtonNotConverged must surface as an exception
+    newton.setReduction(1e-12); newton.setAbsoluteLimit(1e-30); newton.setMaxIterations(1); newton.setSlabWidth(3)
+    u = u0.copy()
+    with pytest.raises(axlib.NewtonError) as e:
+        newton.apply(u)
+    assert e.value.status == 1 and "NewtonNotConverged" in str(e.value)
+    # and a normal solve succeeds, followed by acceptTimeStep
+    newton.setReduction(1e-8); newton.setAbsoluteLimit(1e-14); newton.setMaxIterations(50)
+    u = u0.copy()
+    newton.apply(u)
+    assert newton.result().converged == 1
+    flux.acceptTimeStep()
+    dev.close()
