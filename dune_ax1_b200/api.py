@@ -47,7 +47,7 @@ class NewtonOpts(C.Structure):
         ("reduction", C.c_double), ("abs_limit", C.c_double), ("min_lin_reduction", C.c_double),
         ("fixed_lin_reduction", C.c_int), ("maxit", C.c_int), ("line_search_maxit", C.c_int),
         ("lin_maxit", C.c_int), ("force_iteration", C.c_int), ("disable_line_search", C.c_int),
-        ("slab_w", C.c_int), ("fixed_work", C.c_int),
+        ("slab_w", C.c_int), ("fixed_work", C.c_int), ("ilu_fill", C.c_int),
     ]
 
 
@@ -129,6 +129,7 @@ def lib():
     L.ax1gpu_newton_dev.argtypes = [H, C.POINTER(NewtonOpts), C.POINTER(NewtonResult)]
     L.ax1gpu_spmv.argtypes = [H, c_double_p, c_double_p]
     L.ax1gpu_ilu_factor.argtypes = [H, C.c_int]
+    L.ax1gpu_ilu_factor_n.argtypes = [H, C.c_int, C.c_int]
     L.ax1gpu_ilu_apply.argtypes = [H, c_double_p, c_double_p]
     L.ax1gpu_rownorm.argtypes = [H, c_double_p]
     L.ax1gpu_time_kernel.argtypes = [H, C.c_char_p, C.c_int, c_double_p]
@@ -412,18 +413,22 @@ class Ax1Gpu:
         _chk(lib().ax1gpu_spmv(self.h, _dp(f64(x)), _dp(y)))
         return y
 
-    def ilu_factor(self, slab_w=0):
-        _chk(lib().ax1gpu_ilu_factor(self.h, int(slab_w)))
+    def ilu_factor(self, slab_w=0, fill=-1):
+        """SeqILUn(A, n=fill, 1.0) on the device Jacobian; fill < 0 keeps the handle's current level."""
+        _chk(lib().ax1gpu_ilu_factor_n(self.h, int(slab_w), int(fill)))
 
     def ilu_apply(self, d):
         v = np.zeros(self.n)
         _chk(lib().ax1gpu_ilu_apply(self.h, _dp(f64(d)), _dp(v)))
         return v
 
-    def solve(self, r, reduction, maxit=5000, slab_w=0):
+    def solve(self, r, reduction, maxit=5000, slab_w=0, fill=-1):
         r = f64(r).copy()
         z = np.zeros(self.n)
         res = LinResult()
+        if fill >= 0:  # SeqILUn is built inside the backend's apply: factor with the requested n first
+            self.ilu_factor(slab_w, fill)
+            slab_w = 0
         _chk(lib().ax1gpu_solve(self.h, _dp(r), float(reduction), int(maxit), int(slab_w), _dp(z), C.byref(res)))
         return z, r, res
 
@@ -522,6 +527,24 @@ class ISTLBackend_BCGS_ILU0:
         return self.res
 
 
+class ISTLBackend_SEQ_BCGS_ILUn(ISTLBackend_BCGS_ILU0):
+    """LS of the reference's default build: ISTLBackend_SEQ_BCGS_ILUn(n, w, maxiter, verbose)
+    (acme2_cyl_setup.hh:797-798: n = 1, w = 1.0). n = 0 or 1 on the device; w must be 1."""
+
+    def __init__(self, dev, n=1, w=1.0, maxiter=5000, verbose=0, slab_w=0):
+        if w != 1.0:
+            raise ValueError("relaxation factor w != 1 is not supported")
+        super().__init__(dev, maxiter, slab_w, verbose)
+        self.n = int(n)
+
+    def apply(self, A, z, r, reduction):
+        if A is not None:
+            self.dev.set_jacobian(A)
+        zz, rr, self.res = self.dev.solve(r, reduction, self.maxiter, self.slab_w, fill=self.n)
+        z[:] = zz
+        r[:] = rr
+
+
 class MembraneFlux:
     """gfMembFlux: implicit membrane flux grid function state (channels)."""
 
@@ -554,6 +577,7 @@ class Ax1Newton:
     def setLineSearchMaxIterations(self, v): self.opts.line_search_maxit = int(v)
     def setLinearSolverMaxIterations(self, v): self.opts.lin_maxit = int(v)
     def setSlabWidth(self, v): self.opts.slab_w = int(v)
+    def setIluFill(self, n): self.opts.ilu_fill = int(n)
 
     def apply(self, u):
         unew, self.res = self.dev.newton(u, self.opts)

@@ -15,6 +15,7 @@ UNITS = [
     ("assembly.cu", []),
     ("boundary_fd.cu", ["--fmad=false"]),
     ("solver.cu", []),
+    ("ilu1.cu", []),
     ("driver.cu", []),
     ("capi.cu", []),
     ("host_model.cpp", []),

@@ -56,7 +56,7 @@ void ax1gpu_params_default(ax1gpu_params* p) {
 void ax1gpu_newton_opts_default(ax1gpu_newton_opts* o) {
   o->reduction = 1e-5; o->abs_limit = 1e-5; o->min_lin_reduction = 1e-5;
   o->fixed_lin_reduction = 0; o->maxit = 50; o->line_search_maxit = 10; o->lin_maxit = 5000;
-  o->force_iteration = 0; o->disable_line_search = 0; o->slab_w = 0; o->fixed_work = 0;
+  o->force_iteration = 0; o->disable_line_search = 0; o->slab_w = 0; o->fixed_work = 0; o->ilu_fill = 0;
 }
 
 int ax1gpu_sizeof_params(void) { return (int)sizeof(ax1gpu_params); }
@@ -119,6 +119,7 @@ int ax1gpu_create(const ax1gpu_grid* grid, const unsigned char* cell_subdomain, 
   }
   TRY(dev_alloc(&c->d_A, nv * AX1_ROW));
   TRY(dev_alloc(&c->d_LU, nv * 144));
+  c->lu_cap = nv * 144;
   // channels: gbar[3], state = ratio[2] + gate[3] + gate_new[3], geff[4]
   {
     std::vector<double> gb(3 * (size_t)nx);
@@ -383,10 +384,12 @@ int ax1gpu_spmv(ax1gpu_handle c, const double* x, double* y) {
   return down(c, y, c->d_v);
 }
 
-int ax1gpu_ilu_factor(ax1gpu_handle c, int slab_w) {
+int ax1gpu_ilu_factor(ax1gpu_handle c, int slab_w) { return ax1gpu_ilu_factor_n(c, slab_w, -1); }
+
+int ax1gpu_ilu_factor_n(ax1gpu_handle c, int slab_w, int fill) {
   AX1_CHECK_H(c);
   cudaSetDevice(c->device);
-  int rc = drv_factor(c, slab_w);
+  int rc = drv_factor(c, slab_w, fill);
   if (rc) return rc;
   AX1_CUDA(cudaStreamSynchronize(c->stream));
   return AX1GPU_OK;

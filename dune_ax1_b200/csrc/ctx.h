@@ -40,8 +40,12 @@ struct ax1gpu_ctx {
   int nred_blocks = 0;
   // ILU
   int slab_w = 0;
-  int lvl_slab_w = 0;          // slab width the level tables were built for
-  int* d_lvl = nullptr;        // level prefix tables (solver.cu)
+  int ilu_fill = 0;            // 0: block ILU0 (solver.cu), 1: block ILU(1), the reference default (ilu1.cu)
+  int lvl_slab_w = 0;          // slab width / fill level the level tables were built for
+  int lvl_fill = -1;
+  int* d_lvl = nullptr;        // level prefix tables (solver.cu / ilu1.cu)
+  size_t lvl_cap = 0;          // ints allocated for d_lvl
+  size_t lu_cap = 0;           // doubles allocated for d_LU (144 per vertex for ILU0, 208 for ILU(1))
   bool factored = false;
   // multi-GPU
   ax1::NcclApi nccl;
@@ -61,7 +65,7 @@ int drv_update_state(ax1gpu_ctx* c, const double* d_u);
 int drv_accept_state(ax1gpu_ctx* c);
 int drv_residual(ax1gpu_ctx* c, const double* d_u, double* d_r, double* norm_host);
 int drv_jacobian(ax1gpu_ctx* c, const double* d_u);
-int drv_factor(ax1gpu_ctx* c, int slab_w);
+int drv_factor(ax1gpu_ctx* c, int slab_w, int fill = -1);  // fill < 0: keep c->ilu_fill
 int drv_prec_apply(ax1gpu_ctx* c, const double* d, double* v);
 int drv_op_apply(ax1gpu_ctx* c, const double* x, double* y);
 int drv_solve(ax1gpu_ctx* c, double* d_rhs, double* d_zout, double reduction, int maxit, ax1gpu_lin_result* res);

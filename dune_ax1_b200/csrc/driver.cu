@@ -9,6 +9,7 @@
 //              dune/ax1/common/ax1_newton.hh:194-205, 216-293, 308-503
 // Krylov scalars (rho, alpha, omega, norms, convergence flag) live on the device; the host only
 // polls the flag, so a solve is a stream of kernel launches without per-iteration round trips.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include "ctx.h"
@@ -338,31 +339,59 @@ int drv_jacobian(ax1gpu_ctx* c, const double* d_u) {
 }
 
 static int ensure_level_tables(ax1gpu_ctx* c) {
-  if (c->d_lvl && c->lvl_slab_w == c->slab_w) return 0;
+  if (c->d_lvl && c->lvl_slab_w == c->slab_w && c->lvl_fill == c->ilu_fill) return 0;
   std::vector<int> tab;
-  ilu_level_tables(c->g, c->slab_w, tab);
-  if (!c->d_lvl) AX1_CUDA(cudaMalloc((void**)&c->d_lvl, 2 * (size_t)(128 + 2 * c->g.nvy + 1) * sizeof(int)));
+  if (c->ilu_fill == 1) ilu1_level_tables(c->g, c->slab_w, tab);
+  else ilu_level_tables(c->g, c->slab_w, tab);
+  if (tab.size() > c->lvl_cap) {
+    AX1_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->d_lvl) { AX1_CUDA(cudaFree(c->d_lvl)); c->d_lvl = nullptr; }
+    c->lvl_cap = std::max<size_t>(tab.size(), 2 * (size_t)(192 + 3 * c->g.nvy + 1));
+    AX1_CUDA(cudaMalloc((void**)&c->d_lvl, c->lvl_cap * sizeof(int)));
+  }
   AX1_CUDA(cudaMemcpyAsync(c->d_lvl, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   AX1_CUDA(cudaStreamSynchronize(c->stream));  // tab is a local
   c->lvl_slab_w = c->slab_w;
+  c->lvl_fill = c->ilu_fill;
   return 0;
 }
 
-int drv_factor(ax1gpu_ctx* c, int slab_w) {
+// (re)select the preconditioner: fill 0 = block ILU0, fill 1 = block ILU(1) (SeqILUn with n = 1, the
+// reference default, acme2_cyl_setup.hh:764-765); the ILU(1) factor needs 13 instead of 9 blocks per row
+static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill) {
+  if (fill < 0) fill = c->ilu_fill;
+  if (fill > 1) { set_error("block ILU(n) is implemented on the device for n = 0 and n = 1"); return AX1GPU_EINVAL; }
   if (slab_w <= 0) slab_w = c->slab_w > 0 ? c->slab_w : 128;
-  if (slab_w > 128) slab_w = 128;  // one quad per wavefront row with 256-thread CTAs (solver.cu)
+  // one quad per wavefront row with <= 256-thread CTAs: levels are ceil(w/2) (ILU0) / ceil(w/3) (ILU(1)) rows wide
+  const int wmax = fill == 1 ? ilu1_max_slab_w(c->g) : 128;
+  if (slab_w > wmax) slab_w = wmax;
   if (slab_w > c->g.nvx) slab_w = c->g.nvx;
+  const size_t need = (size_t)c->g.nv * (fill == 1 ? 208 : 144);
+  if (need > c->lu_cap) {
+    AX1_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->d_LU) { AX1_CUDA(cudaFree(c->d_LU)); c->d_LU = nullptr; c->lu_cap = 0; }
+    AX1_CUDA(cudaMalloc((void**)&c->d_LU, need * sizeof(double)));
+    c->lu_cap = need;
+  }
+  if (slab_w != c->slab_w || fill != c->ilu_fill) c->factored = false;
   c->slab_w = slab_w;
-  int rc = ensure_level_tables(c);
+  c->ilu_fill = fill;
+  return ensure_level_tables(c);
+}
+
+int drv_factor(ax1gpu_ctx* c, int slab_w, int fill) {
+  int rc = select_preconditioner(c, slab_w, fill);
   if (rc) return rc;
-  launch_ilu_factor(c->g, c->d_A, c->d_LU, slab_w, c->d_lvl, c->stream);
+  if (c->ilu_fill == 1) launch_ilu1_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);
+  else launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);
   AX1_LAUNCH_CHECK(c);
   c->factored = true;
   return 0;
 }
 
 int drv_prec_apply(ax1gpu_ctx* c, const double* d, double* v) {
-  launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
+  if (c->ilu_fill == 1) launch_ilu1_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
+  else launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
   AX1_LAUNCH_CHECK(c);
   return halo_add(c, v);
 }
@@ -493,7 +522,7 @@ int drv_newton(ax1gpu_ctx* c, const ax1gpu_newton_opts* o, ax1gpu_newton_result*
     AX1_CUDA(cudaEventRecord(e1, c->stream));
     // linear solve (ILU0 re-factorised every Newton iteration, like SeqILUn in the backend's apply)
     ax1gpu_lin_result lr{};
-    if ((rc = drv_factor(c, o->slab_w))) return rc;
+    if ((rc = drv_factor(c, o->slab_w, o->ilu_fill))) return rc;
     rc = drv_solve(c, c->d_r, c->d_z, o->fixed_work ? 0.0 : linear_reduction, o->lin_maxit, &lr);
     AX1_CUDA(cudaEventRecord(e2, c->stream));
     AX1_CUDA(cudaEventSynchronize(e2));
@@ -566,16 +595,21 @@ int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms) {
     if (n == "residual") { launch_residual(c->g, c->d_u, c->d_r0, c->d_r, 0, c->stream); }
     else if (n == "jacobian") { launch_jacobian_volume(c->g, c->d_u, c->d_A, c->stream); }
     else if (n == "spmv") { launch_spmv(c->g, c->d_A, c->d_y2, c->d_v, 0, c->stream); }
-    else if (n == "ilu_factor") { launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream); }
-    else if (n == "ilu_apply") { launch_ilu_apply(c->g, c->d_LU, c->d_p, c->d_y2, c->slab_w, c->d_lvl, c->stream); }
+    else if (n == "ilu_factor") {
+      if (c->ilu_fill == 1) launch_ilu1_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);
+      else launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);
+    }
+    else if (n == "ilu_apply") {
+      if (c->ilu_fill == 1) launch_ilu1_apply(c->g, c->d_LU, c->d_p, c->d_y2, c->slab_w, c->d_lvl, c->stream);
+      else launch_ilu_apply(c->g, c->d_LU, c->d_p, c->d_y2, c->slab_w, c->d_lvl, c->stream);
+    }
     else if (n == "dot") { dot_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_rt, c->d_v, nullptr, nullptr, 0, own_of(c), nullptr, c->d_partials); }
     else if (n == "axpy") { xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_tmp, c->d_y2, c->d_t, c->d_v, c->d_rt, c->d_sc, 1, own_of(c), c->d_partials); }
     else { set_error("unknown kernel name"); return AX1GPU_EINVAL; }
     AX1_LAUNCH_CHECK(c);
     return 0;
   };
-  if (c->slab_w <= 0) c->slab_w = std::min(128, c->g.nvx);
-  { int rc0 = ensure_level_tables(c); if (rc0) return rc0; }
+  { int rc0 = select_preconditioner(c, c->slab_w, c->ilu_fill); if (rc0) return rc0; }
   AX1_CUDA(cudaMemsetAsync(c->d_sc, 0, sizeof(Scalars), c->stream));
   int rc = run();
   if (rc) return rc;

@@ -1,0 +1,385 @@
+// ilu1.cu -- block ILU(1) factor / apply: the reference's default preconditioner
+//   ISTLBackend_OVLP_BCGS_ILUn(multigfs, cc, n = 1, ...) / ISTLBackend_SEQ_BCGS_ILUn(1, 1.0, ...)
+//   (dune/ax1/acme2_cyl/common/acme2_cyl_setup.hh:764-765, 797-798) = Dune::SeqILUn ->
+//   bilu_decomposition(A, 1, ILU) + bilu_backsolve (dune-istl 2.3 ilu.hh)                          [ext]
+//
+// Symbolic phase, done by hand for the x-fastest 9-point vertex stencil: a level-1 fill entry (r,c)
+// appears where a level-0 lower entry (r,k) meets a level-0 upper entry (k,c). With r = (i,j):
+//   k = (i-1,j-1) -> (i-2,j);  k = (i+1,j-1) -> (i+2,j-1), (i+2,j);  k = (i-1,j) -> (i-2,j+1)
+// so a row has 13 blocks (6 lower, diagonal, 6 upper), in ascending column order
+//   lower (i-1,j-1) (i,j-1) (i+1,j-1) (i+2,j-1) (i-2,j) (i-1,j) | (i,j) | upper (i+1,j) (i+2,j) (i-2,j+1) (i-1,j+1) (i,j+1) (i+1,j+1)
+// ("13 blocks/row"). Rows whose generating neighbour does not exist (j = 0) keep
+// an exactly-zero block in the fill slot, which is numerically the same as not having the entry.
+// The numeric phase is bilu0_decomposition on that pattern.
+//
+// Parallelisation as for ILU0 (solver.cu): one CTA per x-sub-slab; row (i,j) depends on
+// (i+2,j-1) and (i-1,j), so the wavefronts are level = il + 3 j (<= ceil(w/3) rows each); the factor
+// is stored wavefront-packed: LF 6 lower blocks (768 B), LB inverted diagonal + 6 upper blocks (896 B).
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+#include "ilu_common.cuh"
+
+namespace ax1 {
+
+#define P1_DI(p) ((p) < 4 ? (p)-1 : ((p) < 9 ? (p)-6 : (p)-11))
+#define P1_DJ(p) ((p) < 4 ? -1 : ((p) < 9 ? 0 : 1))
+__host__ __device__ constexpr int p1_idx(int di, int dj) {
+  return dj == -1 ? ((di >= -1 && di <= 2) ? di + 1 : -1)
+                  : dj == 0 ? ((di >= -2 && di <= 2) ? di + 6 : -1)
+                            : dj == 1 ? ((di >= -2 && di <= 1) ? di + 11 : -1) : -1;
+}
+
+__device__ __forceinline__ int lev1_jlo(int L, int wc) {
+  const int a = L - wc + 1;
+  return a <= 0 ? 0 : (a + 2) / 3;
+}
+
+struct Slab1 {
+  int i0, wc, nlev;
+  size_t row_off;
+  const int* lvl;
+};
+__device__ __forceinline__ Slab1 slab1_geom(const Dev& g, int slab_w, const int* __restrict__ lvl_tab, int* lvl_sh) {
+  Slab1 sg;
+  sg.i0 = blockIdx.x * slab_w;
+  sg.wc = min(slab_w, g.nvx - sg.i0);
+  sg.nlev = sg.wc + 3 * (g.nvy - 1);
+  sg.row_off = (size_t)blockIdx.x * slab_w * g.nvy;
+  const int stride = slab_w + 3 * (g.nvy - 1) + 1;
+  const int* src = lvl_tab + (sg.wc == slab_w ? 0 : stride);
+  for (int k = threadIdx.x; k <= sg.nlev; k += blockDim.x) lvl_sh[k] = src[k];
+  __syncthreads();
+  sg.lvl = lvl_sh;
+  return sg;
+}
+
+struct Row1 { int v, il, j; };
+__device__ __forceinline__ Row1 level_row1(const Dev& g, int L, int nlev, int i0, int wc, int q) {
+  Row1 o;
+  o.v = -1; o.il = 0; o.j = 0;
+  if (L < 0 || L >= nlev) return o;
+  const int j = lev1_jlo(L, wc) + q;
+  if (j > min(g.nvy - 1, L / 3)) return o;
+  o.j = j; o.il = L - 3 * j;
+  o.v = i0 + o.il + g.nvx * j;
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// factorisation of one sub-slab per CTA, one quad per wavefront row (lane = scalar row of the blocks).
+// The Jacobian row of level L+2 is staged with cp.async; the finished [Dinv | U x 6] rows of the last
+// four levels (all a row needs from its lower neighbours) sit in a shared-memory ring.
+#define AX1_RING1_ROW 114  // 7 blocks = 112 doubles + 2 padding
+__global__ void __launch_bounds__(256, 1) ilu1_factor_kernel(Dev g, const double* __restrict__ A, double* LF, double* LB,
+                                                             int slab_w, int nq, const int* __restrict__ lvl_tab) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, q = tid >> 2, r = tid & 3;  // nq = rows a level can hold = ceil(slab_w / 3)
+  double* stage = reinterpret_cast<double*>(smem_raw);   // [2][nq][AX1_ROW]
+  double* ring = stage + 2 * (size_t)nq * AX1_ROW;        // [4][nq][AX1_RING1_ROW]
+  const Slab1 sg = slab1_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(ring + 4 * (size_t)nq * AX1_RING1_ROW));
+  const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
+  const unsigned qmask = 0xFu << (tid & 28);
+
+  auto issue = [&](int L) {
+    const Row1 w = level_row1(g, L, nlev, i0, wc, q);
+    if (w.v >= 0) {
+      const double* src = A + (size_t)w.v * AX1_ROW;
+      double* dst = stage + ((size_t)(L & 1) * nq + q) * AX1_ROW;
+      for (int c = r; c < AX1_ROW / 2; c += 4) cp_async16(dst + 2 * c, src + 2 * c);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  issue(1);
+  for (int L = 0; L < nlev; ++L) {
+    cp_async_wait<1>();
+    __syncthreads();  // staged row of this level and the ring rows of level L-1 are visible
+    const Row1 w = level_row1(g, L, nlev, i0, wc, q);
+    double row[13][4];
+    if (w.v >= 0) {
+      const int il = w.il, j = w.j;
+      bool ex[13];
+      const double* arow = stage + ((size_t)(L & 1) * nq + q) * AX1_ROW;
+#pragma unroll
+      for (int p = 0; p < 13; ++p) {
+        const int di = P1_DI(p), dj = P1_DJ(p);
+        ex[p] = (il + di >= 0) && (il + di < wc) && (j + dj >= 0) && (j + dj < g.nvy);
+        if (di >= -1 && di <= 1) {
+          // level-0 entry: expand the arrow block row of the Jacobian (common.cuh), branch-free in the lane index
+          const double* blk = arow + ((dj + 1) * 3 + di + 1) * AX1_BLK;
+          const double2 a = *reinterpret_cast<const double2*>(blk + (r == 3 ? 6 : 2 * r));
+          const double2 b2 = *reinterpret_cast<const double2*>(blk + (r == 3 ? 8 : 2 * r));
+          row[p][0] = (ex[p] && (r == 3 || r == 0)) ? a.x : 0.0;
+          row[p][1] = ex[p] ? (r == 3 ? a.y : (r == 1 ? a.x : 0.0)) : 0.0;
+          row[p][2] = ex[p] ? (r == 3 ? b2.x : (r == 2 ? a.x : 0.0)) : 0.0;
+          row[p][3] = ex[p] ? (r == 3 ? b2.y : a.y) : 0.0;
+        } else {
+          row[p][0] = row[p][1] = row[p][2] = row[p][3] = 0.0;  // level-1 fill entry
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        if (!ex[k]) continue;
+        const int dik = P1_DI(k), djk = P1_DJ(k);
+        const int Ln = L + dik + 3 * djk;
+        const int qn = (j + djk) - lev1_jlo(Ln, wc);
+        const double* kb = ring + ((size_t)(Ln & 3) * nq + qn) * AX1_RING1_ROW;  // row k: [Dinv, U7..U12]
+        double lrow[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double sum = 0.0;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) sum += row[k][m] * kb[4 * m + c];
+          lrow[c] = sum;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) row[k][c] = lrow[c];
+#pragma unroll
+        for (int t = 7; t < 13; ++t) {
+          const int p2 = p1_idx(dik + P1_DI(t), djk + P1_DJ(t));
+          if (p2 < 0) continue;
+          if (!ex[p2]) continue;
+          const double* ub = kb + (t - 6) * 16;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            double sum = 0.0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) sum += lrow[m] * ub[4 * m + c];
+            row[p2][c] -= sum;
+          }
+        }
+      }
+      // invert the pivot block (every lane of the quad holds one row of it)
+      double d[4][4], dinv[4][4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d[m][c] = __shfl_sync(qmask, row[6][c], (tid & 28) + m);
+      invert4(d, dinv);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        double val = dinv[0][c];
+        if (r == 1) val = dinv[1][c];
+        if (r == 2) val = dinv[2][c];
+        if (r == 3) val = dinv[3][c];
+        row[6][c] = val;
+      }
+      const size_t p = sg.row_off + (size_t)(sg.lvl[L] + q);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) st4(LF + p * 96 + k * 16 + r * 4, row[k]);
+#pragma unroll
+      for (int k = 6; k < 13; ++k) st4(LB + p * 112 + (k - 6) * 16 + r * 4, row[k]);
+    }
+    __syncthreads();  // every read of ring slot L&3 (it held level L-4) is done
+    if (w.v >= 0) {
+      double* kr = ring + ((size_t)(L & 3) * nq + q) * AX1_RING1_ROW;
+#pragma unroll
+      for (int k = 6; k < 13; ++k) st4(kr + (k - 6) * 16 + r * 4, row[k]);
+    }
+    issue(L + 2);
+  }
+  cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------
+// v = (LU)^-1 d, forward and backward sweep in one launch; same software pipeline as ilu_apply_kernel
+// (solver.cu): every lane streams its scalar row of the next D levels' blocks into a private
+// shared-memory slot with cp.async, solution values of the last levels go through a small ring.
+template <int D>
+__global__ void __launch_bounds__(256) ilu1_apply_kernel(Dev g, const double* __restrict__ LF,
+                                                         const double* __restrict__ LB, const double* __restrict__ d,
+                                                         double* v_out, int slab_w, int nq,
+                                                         const int* __restrict__ lvl_tab) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nt = 4 * nq, tid = threadIdx.x;  // nq = rows a level can hold; threads beyond 4 nq never own a row
+  const int q = tid >> 2, r = tid & 3;
+  double* stageM = reinterpret_cast<double*>(smem_raw);   // [D][7][nt][4]
+  double* stageR = stageM + (size_t)D * 7 * nt * 4;       // [D][nt]
+  double* ring = stageR + (size_t)D * nt;                 // [8][nq][4]
+  const Slab1 sg = slab1_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(ring + 8 * (size_t)nq * 4));
+  const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
+
+  // ---------------- forward: y = L^-1 d ----------------
+  auto issue_fwd = [&](int L) {
+    const Row1 w = level_row1(g, L, nlev, i0, wc, q);
+    if (w.v >= 0) {
+      const int st = L % D;
+      const double* base = LF + (sg.row_off + (size_t)(sg.lvl[L] + q)) * 96 + r * 4;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int di = P1_DI(k), dj = P1_DJ(k);
+        if ((w.il + di >= 0) && (w.il + di < wc) && (w.j + dj >= 0)) {
+          double* dst = stageM + ((size_t)(st * 7 + k) * nt + tid) * 4;
+          cp_async16(dst, base + k * 16);
+          cp_async16(dst + 2, base + k * 16 + 2);
+        }
+      }
+      cp_async8(stageR + st * nt + tid, d + 4 * (size_t)w.v + r);
+    }
+    cp_async_commit();
+  };
+  for (int L = 0; L < D; ++L) issue_fwd(L);
+  for (int L = 0; L < nlev; ++L) {
+    cp_async_wait<D - 1>();
+    const Row1 w = level_row1(g, L, nlev, i0, wc, q);
+    if (w.v >= 0) {
+      const int st = L % D;
+      double acc = stageR[st * nt + tid];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int di = P1_DI(k), dj = P1_DJ(k);
+        if ((w.il + di >= 0) && (w.il + di < wc) && (w.j + dj >= 0)) {
+          const double* lp = stageM + ((size_t)(st * 7 + k) * nt + tid) * 4;
+          const double2 l01 = *reinterpret_cast<const double2*>(lp);
+          const double2 l23 = *reinterpret_cast<const double2*>(lp + 2);
+          const int Ln = L + di + 3 * dj;
+          const int qn = (w.j + dj) - lev1_jlo(Ln, wc);
+          const double* yp = ring + ((size_t)(Ln & 7) * nq + qn) * 4;
+          const double2 y01 = *reinterpret_cast<const double2*>(yp);
+          const double2 y23 = *reinterpret_cast<const double2*>(yp + 2);
+          double t = l01.x * y01.x;
+          t += l01.y * y01.y;
+          t += l23.x * y23.x;
+          t += l23.y * y23.y;
+          acc -= t;
+        }
+      }
+      ring[((size_t)(L & 7) * nq + q) * 4 + r] = acc;
+      v_out[4 * (size_t)w.v + r] = acc;
+    }
+    __syncthreads();
+    issue_fwd(L + D);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---------------- backward: x = U^-1 y ----------------
+  auto issue_bwd = [&](int L) {  // L counts down; stage index by distance from the top level
+    const Row1 w = level_row1(g, L, nlev, i0, wc, q);
+    if (w.v >= 0) {
+      const int st = (nlev - 1 - L) % D;
+      const double* base = LB + (sg.row_off + (size_t)(sg.lvl[L] + q)) * 112 + r * 4;
+#pragma unroll
+      for (int k = 6; k < 13; ++k) {
+        const int di = P1_DI(k), dj = P1_DJ(k);
+        if (k == 6 || ((w.il + di >= 0) && (w.il + di < wc) && (w.j + dj < g.nvy))) {
+          double* dst = stageM + ((size_t)(st * 7 + (k - 6)) * nt + tid) * 4;
+          cp_async16(dst, base + (k - 6) * 16);
+          cp_async16(dst + 2, base + (k - 6) * 16 + 2);
+        }
+      }
+      cp_async8(stageR + st * nt + tid, v_out + 4 * (size_t)w.v + r);  // own forward result
+    }
+    cp_async_commit();
+  };
+  for (int k = 0; k < D; ++k) issue_bwd(nlev - 1 - k);
+  for (int L = nlev - 1; L >= 0; --L) {
+    cp_async_wait<D - 1>();
+    const Row1 w = level_row1(g, L, nlev, i0, wc, q);
+    if (w.v >= 0) {
+      const int st = (nlev - 1 - L) % D;
+      double acc = stageR[st * nt + tid];
+#pragma unroll
+      for (int k = 7; k < 13; ++k) {
+        const int di = P1_DI(k), dj = P1_DJ(k);
+        if ((w.il + di >= 0) && (w.il + di < wc) && (w.j + dj < g.nvy)) {
+          const double* up = stageM + ((size_t)(st * 7 + (k - 6)) * nt + tid) * 4;
+          const double2 u01 = *reinterpret_cast<const double2*>(up);
+          const double2 u23 = *reinterpret_cast<const double2*>(up + 2);
+          const int Ln = L + di + 3 * dj;
+          const int qn = (w.j + dj) - lev1_jlo(Ln, wc);
+          const double* xp = ring + ((size_t)(Ln & 7) * nq + qn) * 4;
+          const double2 x01 = *reinterpret_cast<const double2*>(xp);
+          const double2 x23 = *reinterpret_cast<const double2*>(xp + 2);
+          double t = u01.x * x01.x;
+          t += u01.y * x01.y;
+          t += u23.x * x23.x;
+          t += u23.y * x23.y;
+          acc -= t;
+        }
+      }
+      const double* dp = stageM + ((size_t)(st * 7 + 0) * nt + tid) * 4;
+      const double2 d01 = *reinterpret_cast<const double2*>(dp);
+      const double2 d23 = *reinterpret_cast<const double2*>(dp + 2);
+      const unsigned qmask = 0xFu << (tid & 28);
+      const int qb = tid & 28;
+      double xo = d01.x * __shfl_sync(qmask, acc, qb + 0);
+      xo += d01.y * __shfl_sync(qmask, acc, qb + 1);
+      xo += d23.x * __shfl_sync(qmask, acc, qb + 2);
+      xo += d23.y * __shfl_sync(qmask, acc, qb + 3);
+      ring[((size_t)(L & 7) * nq + q) * 4 + r] = xo;
+      v_out[4 * (size_t)w.v + r] = xo;
+    }
+    __syncthreads();
+    issue_bwd(L - D);
+  }
+  cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------
+// one quad per wavefront row: a level of a slab of width w has at most ceil(w/3) rows
+static int slab1_threads(int slab_w) {
+  int rows = (slab_w + 2) / 3;
+  int t = 4 * rows;
+  t = ((t + 31) / 32) * 32;
+  if (t > 256) t = 256;
+  if (t < 32) t = 32;
+  return t;
+}
+static int slab1_rows(int slab_w) { return (slab_w + 2) / 3; }
+static size_t factor1_smem(const Dev& g, int slab_w) {
+  const int nq = slab1_rows(slab_w);
+  return (size_t)nq * (2 * AX1_ROW + 4 * AX1_RING1_ROW) * sizeof(double) + (size_t)(slab_w + 3 * g.nvy) * sizeof(int);
+}
+// widest sub-slab the factor kernel can hold in shared memory for this grid (<= 192: 64 quads per CTA)
+int ilu1_max_slab_w(const Dev& g) {
+  int w = 192;
+  while (w > 3 && factor1_smem(g, w) > 227 * 1024) w -= 3;
+  return w;
+}
+// level prefix tables for full-width sub-slabs and for the (narrower) last one: 2 x (slab_w + 3 Ny + 1) ints
+void ilu1_level_tables(const Dev& g, int slab_w, std::vector<int>& tab) {
+  const int stride = slab_w + 3 * (g.nvy - 1) + 1;
+  tab.assign(2 * (size_t)stride, 0);
+  const int last_wc = g.nvx - ((g.nvx - 1) / slab_w) * slab_w;
+  const int wcs[2] = {slab_w, last_wc};
+  for (int t = 0; t < 2; ++t) {
+    const int wc = wcs[t], nlev = wc + 3 * (g.nvy - 1);
+    int acc = 0;
+    for (int L = 0; L < nlev; ++L) {
+      tab[(size_t)t * stride + L] = acc;
+      const int a = L - wc + 1;
+      const int jlo = a <= 0 ? 0 : (a + 2) / 3;
+      const int jhi = std::min(g.nvy - 1, L / 3);
+      if (jhi >= jlo) acc += jhi - jlo + 1;
+    }
+    tab[(size_t)t * stride + nlev] = acc;
+  }
+}
+void launch_ilu1_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st) {
+  const int nslab = (g.nvx + slab_w - 1) / slab_w;
+  const int nt = slab1_threads(slab_w);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ilu1_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  ilu1_factor_kernel<<<nslab, nt, factor1_smem(g, slab_w), st>>>(g, A, LU, LU + (size_t)g.nv * 96, slab_w,
+                                                                 slab1_rows(slab_w), lvl_tab);
+}
+void launch_ilu1_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, const int* lvl_tab,
+                       cudaStream_t st) {
+  constexpr int D = 2;
+  const int nslab = (g.nvx + slab_w - 1) / slab_w;
+  const int nt = slab1_threads(slab_w), nq = slab1_rows(slab_w);
+  const size_t smem = (size_t)D * 4 * nq * (7 * 32 + 8) + 8 * (size_t)nq * 32 + (size_t)(slab_w + 3 * g.nvy) * sizeof(int);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ilu1_apply_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  ilu1_apply_kernel<D><<<nslab, nt, smem, st>>>(g, LU, LU + (size_t)g.nv * 96, d, v, slab_w, nq, lvl_tab);
+}
+
+}  // namespace ax1

@@ -12,25 +12,10 @@
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
+#include "ilu_common.cuh"
 #include "reduce.cuh"
 
 namespace ax1 {
-
-__device__ __forceinline__ void ldg4(const double* p, double* o) {
-  const double2 lo = __ldg(reinterpret_cast<const double2*>(p));
-  const double2 hi = __ldg(reinterpret_cast<const double2*>(p + 2));
-  o[0] = lo.x; o[1] = lo.y; o[2] = hi.x; o[3] = hi.y;
-}
-// L2-coherent loads for data written earlier in the same kernel by other threads of the CTA
-__device__ __forceinline__ void ldcg4(const double* p, double* o) {
-  const double2 lo = __ldcg(reinterpret_cast<const double2*>(p));
-  const double2 hi = __ldcg(reinterpret_cast<const double2*>(p + 2));
-  o[0] = lo.x; o[1] = lo.y; o[2] = hi.x; o[3] = hi.y;
-}
-__device__ __forceinline__ void st4(double* p, const double* v) {
-  reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
-  reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
-}
 
 // ------------------------------------------------------------------------------------------
 // y = A x ; 4 lanes per block row, lane r = scalar row r.
@@ -81,37 +66,6 @@ __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-// 4x4 inverse, Gauss-Jordan with partial pivoting, fully unrolled (static register indexing)
-__device__ __forceinline__ void invert4(double a[4][4], double inv[4][4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) inv[i][j] = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-#pragma unroll
-    for (int r = c + 1; r < 4; ++r) {
-      if (fabs(a[r][c]) > fabs(a[c][c])) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          double t = a[c][k]; a[c][k] = a[r][k]; a[r][k] = t;
-          t = inv[c][k]; inv[c][k] = inv[r][k]; inv[r][k] = t;
-        }
-      }
-    }
-    const double p = 1.0 / a[c][c];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { a[c][k] *= p; inv[c][k] *= p; }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (r == c) continue;
-      const double f = a[r][c];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { a[r][k] -= f * a[c][k]; inv[r][k] -= f * inv[c][k]; }
-    }
-  }
-}
-
 __device__ __forceinline__ int lev_jlo(int L, int wc) {
   const int a = L - wc + 1;
   return a <= 0 ? 0 : (a + 1) / 2;
@@ -147,18 +101,6 @@ __device__ __forceinline__ SlabGeom slab_geom(const Dev& g, int slab_w, const in
   sg.lvl = lvl_sh;
   return sg;
 }
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct LevelRow {
   int v, il, j;  // v < 0: this quad has no row at this level

@@ -77,6 +77,8 @@ typedef struct ax1gpu_newton_opts {
   int force_iteration, disable_line_search;
   int slab_w;      /* vertex columns per ILU0 sub-slab (<=0: library default)                  */
   int fixed_work;  /* benchmark mode: exactly maxit Newton x lin_maxit BiCGStab iterations     */
+  int ilu_fill;    /* n of SeqILUn: 0 = block ILU0, 1 = block ILU(1) (reference default,
+                      acme2_cyl_setup.hh:764-765: ISTLBackend_OVLP_BCGS_ILUn(multigfs,cc,1,...))  */
 } ax1gpu_newton_opts;
 
 typedef struct ax1gpu_newton_result { /* PDELab NewtonResult + ax1_newton.hh:600-607 */
@@ -146,7 +148,9 @@ int ax1gpu_newton_dev(ax1gpu_handle h, const ax1gpu_newton_opts* opts, ax1gpu_ne
 
 /* ---- building blocks exposed for parity tests and profiling ---- */
 int ax1gpu_spmv(ax1gpu_handle h, const double* x, double* y);
-int ax1gpu_ilu_factor(ax1gpu_handle h, int slab_w);
+int ax1gpu_ilu_factor(ax1gpu_handle h, int slab_w);   /* keeps the handle's current fill level (0 at creation) */
+/* SeqILUn(A, n, 1.0): fill = 0 or 1; also selects the preconditioner of later ax1gpu_solve calls */
+int ax1gpu_ilu_factor_n(ax1gpu_handle h, int slab_w, int fill);
 int ax1gpu_ilu_apply(ax1gpu_handle h, const double* d, double* v);
 int ax1gpu_rownorm(ax1gpu_handle h, double* r); /* scales device Jacobian and r */
 /* run `reps` launches of one named kernel on device-resident data and return the mean device time

@@ -137,7 +137,10 @@ struct LinearSolverResult {  // Dune::PDELab::LinearSolverResult
 template <class U, class M, class EP = DefaultErrorPolicy>
 class SolverBackendShim {
  public:
-  SolverBackendShim(Device& d, unsigned maxiter = 5000, int slab_w = 0) : d_(d), maxiter_(maxiter), slab_w_(slab_w) {}
+  // n = level of fill of SeqILUn as in ISTLBackend_SEQ_BCGS_ILUn(n, w, maxiter, verbose)
+  // (acme2_cyl_setup.hh:797-798 passes n = 1); n < 0 keeps the library default (block ILU0)
+  SolverBackendShim(Device& d, unsigned maxiter = 5000, int slab_w = 0, int n = -1)
+      : d_(d), maxiter_(maxiter), slab_w_(slab_w), n_(n) {}
   double norm(const U& v) const {  // sequential backend: v.two_norm()
     const double* p = VectorAccess<U>::data(v);
     double s = 0;
@@ -149,7 +152,12 @@ class SolverBackendShim {
   void apply(M& A, U& z, U& r, double reduction) {
     EP::library(ax1gpu_set_jacobian(d_.handle(), MatrixAccess<M>::blocks(A)));
     ax1gpu_lin_result lr;
-    EP::library(ax1gpu_solve(d_.handle(), VectorAccess<U>::data(r), reduction, (int)maxiter_, slab_w_,
+    int slab_w = slab_w_;
+    if (n_ >= 0) {  // the backend builds SeqILUn(A, n, w) inside apply
+      EP::library(ax1gpu_ilu_factor_n(d_.handle(), slab_w_, n_));
+      slab_w = 0;
+    }
+    EP::library(ax1gpu_solve(d_.handle(), VectorAccess<U>::data(r), reduction, (int)maxiter_, slab_w,
                              VectorAccess<U>::data(z), &lr));
     res_.converged = lr.converged != 0;
     res_.iterations = (unsigned)lr.iterations;
@@ -161,7 +169,7 @@ class SolverBackendShim {
  private:
   Device& d_;
   unsigned maxiter_;
-  int slab_w_;
+  int slab_w_, n_;
   LinearSolverResult res_;
 };
 
@@ -187,6 +195,7 @@ class NewtonShim {
   void setLinearSolverMaxIterations(unsigned v) { o_.lin_maxit = (int)v; }
   void disableLineSearch(bool v) { o_.disable_line_search = v; }          // :838-839
   void setSlabWidth(int v) { o_.slab_w = v; }
+  void setIluFill(int n) { o_.ilu_fill = n; }  // n of SeqILUn in the linear solver backend (:764-765, :797-798)
   // Ax1Newton::apply(u): the whole damped Newton loop runs on the device; u in/out
   void apply(U& u) {
     ax1gpu_newton_result r;

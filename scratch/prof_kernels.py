@@ -10,7 +10,8 @@ dev.set_time(1.0, 1.0); dev.update_state(); dev.set_uold_dev()
 dev.residual(None, want_r=False)
 dev.jacobian(None, download=False)
 sw = int(sys.argv[2]) if len(sys.argv) > 2 else 128
-dev.ilu_factor(sw)
+fill = int(os.environ.get("AX1_FILL", "0"))
+dev.ilu_factor(sw, fill)
 for name in (sys.argv[3].split(",") if len(sys.argv) > 3 else ("ilu_apply", "spmv", "residual", "jacobian", "ilu_factor", "dot", "axpy")):
     print(name, dev.time_kernel(name, reps=2))
 dev.close()

@@ -174,6 +174,59 @@ def test_ilu0_apply_parity(oracle, axlib, slab_w):
     dev.close()
 
 
+@pytest.mark.parametrize("slab_w,nx", [(3, 8), (5, 9), (7, 20), (100, 8), (16, 40)])
+def test_ilu1_apply_parity(oracle, axlib, slab_w, nx):
+    """block ILU(1) = SeqILUn(A, 1, 1.0), the reference's default preconditioner (acme2_cyl_setup.hh:764-765)."""
+    s = small_setup(nx=nx)
+    dev, P, u0 = _both(oracle, axlib, s)
+    Jo = P.jacobian(u0)
+    dev.set_jacobian(Jo)
+    dev.ilu_factor(slab_w, fill=1)
+    rng = np.random.default_rng(7)
+    d = rng.standard_normal(P.n)
+    vg = dev.ilu_apply(d)
+    vo = P.ilu_apply(Jo, d, ilu_fill=1, slab_w=min(slab_w, s["nx"] + 1))
+    assert np.max(np.abs(vg - vo)) <= 1e-9 * np.max(np.abs(vo)), np.max(np.abs(vg - vo)) / np.max(np.abs(vo))
+    # switching back to ILU0 on the same handle
+    dev.ilu_factor(slab_w, fill=0)
+    vg0 = dev.ilu_apply(d)
+    vo0 = P.ilu_apply(Jo, d, ilu_fill=0, slab_w=min(slab_w, s["nx"] + 1))
+    assert np.max(np.abs(vg0 - vo0)) <= 1e-9 * np.max(np.abs(vo0))
+    dev.close()
+
+
+def test_reference_default_backend_ilu1_global(oracle, axlib):
+    """The reference's sequential default: BiCGStab + ONE global block ILU(1) (ISTLBackend_SEQ_BCGS_ILUn(1, 1.0)).
+    With slab_w >= #vertex columns the device factorisation is the global one: same iteration count,
+    same Newton history as the oracle's unpartitioned ILU(1)."""
+    s = small_setup(nx=20)
+    dev, P, u0 = _both(oracle, axlib, s)
+    Jo = P.jacobian(u0)
+    r = P.residual(u0)
+    dev.set_jacobian(Jo)
+    zg, rg, resg = dev.solve(r, 1e-10, maxit=500, slab_w=64, fill=1)
+    zo, ro, reso = P.solve(Jo, r, 1e-10, maxit=500, ilu_fill=1, slab_w=0)
+    assert resg.converged == 1 and reso.converged == 1
+    assert abs(resg.iterations - reso.iterations) <= 1
+    assert np.max(np.abs(zg - zo)) <= 1e-7 * np.max(np.abs(zo))
+    og = axlib.default_newton_opts(reduction=1e-9, abs_limit=1e-14, min_lin_reduction=1e-10, slab_w=64, ilu_fill=1)
+    oc = oracle.default_newton_opts(reduction=1e-9, abs_limit=1e-14, min_lin_reduction=1e-10, ilu_fill=1, slab_w=0)
+    ug, ng = dev.newton(u0, og)
+    uc, nc = P.newton(u0, oc)
+    assert ng.status == 0 and nc.status == 0
+    assert ng.iterations == nc.iterations and abs(ng.lin_iterations - nc.lin_iterations) <= ng.iterations
+    scale = np.max(np.abs(uc.reshape(-1, 4)), axis=0)
+    err = np.max(np.abs(ug - uc).reshape(-1, 4) / scale, axis=0)
+    assert np.all(err[:3] < 1e-8), err          # concentrations
+    assert err[3] < 5e-7, err                   # potential: attainable accuracy at the residual floor (DESIGN 5)
+    # mirror class with the reference's constructor signature
+    ls = axlib.ISTLBackend_SEQ_BCGS_ILUn(dev, 1, 1.0, 500, 0, slab_w=64)
+    z = np.zeros(P.n); rr = r.copy()
+    ls.apply(Jo, z, rr, 1e-10)
+    assert ls.result().converged == 1 and np.max(np.abs(z - zo)) <= 1e-7 * np.max(np.abs(zo))
+    dev.close()
+
+
 def test_linear_solve_parity(oracle, axlib):
     s = small_setup(nx=8)
     dev, P, u0 = _both(oracle, axlib, s)
