@@ -139,6 +139,7 @@ def lib():
     L.ax1gpu_stream.restype = C.c_void_p
     L.ax1gpu_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p]
     L.ax1gpu_comm_init.argtypes = [H, C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+    L.ax1gpu_comm_mode.argtypes = [H]
     L.ax1host_generate_y.argtypes = [C.c_double] * 6 + [C.c_int, C.c_double, C.c_double, C.c_int, c_double_p, C.c_int]
     L.ax1host_physics_maps.argtypes = [C.POINTER(Grid), C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                        C.c_double, C.c_int, C.c_double, C.POINTER(HostBC), c_ubyte_p, c_double_p,
@@ -470,6 +471,10 @@ class Ax1Gpu:
 
     def comm_init(self, unique_id, rank, nranks, libnccl=None):
         _chk(lib().ax1gpu_comm_init(self.h, (libnccl or nccl_library_path()).encode(), unique_id, rank, nranks))
+
+    def comm_mode(self):
+        """0 single rank, 1 NCCL send/recv + allreduce, 2 NVLink peer windows (p2p.cuh)."""
+        return int(lib().ax1gpu_comm_mode(self.h))
 
 
 def nccl_unique_id(libnccl=None):

@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" surface declared in include/ax1gpu.h.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "ctx.h"
 
@@ -131,8 +132,8 @@ int ax1gpu_create(const ax1gpu_grid* grid, const unsigned char* cell_subdomain, 
     TRY(dev_alloc(&c->d_geff, 4 * (size_t)nx));
     TRY(dev_alloc(&c->d_vrest, 1));
     TRY(dev_alloc(&c->d_vm, nx));
-    TRY(dev_alloc(&c->d_err, 2));
-    if (cudaMemsetAsync(c->d_err, 0, 2 * sizeof(int), st) != cudaSuccess) { ax1gpu_destroy(c); return AX1GPU_ECUDA; }
+    TRY(dev_alloc(&c->d_err, 4));
+    if (cudaMemsetAsync(c->d_err, 0, 4 * sizeof(int), st) != cudaSuccess) { ax1gpu_destroy(c); return AX1GPU_ECUDA; }
     for (int k = 0; k < 3; ++k) c->ch.gbar[k] = c->d_gbar + (size_t)k * nx;
     for (int k = 0; k < 2; ++k) c->ch.ratio[k] = c->d_chstate + (size_t)k * nx;
     for (int k = 0; k < 3; ++k) { c->ch.gate[k] = c->d_chstate + (size_t)(2 + k) * nx; c->ch.gate_new[k] = c->d_chstate + (size_t)(5 + k) * nx; }
@@ -199,6 +200,12 @@ int ax1gpu_destroy(ax1gpu_handle c) {
   if (!c) return AX1GPU_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->p2p.win) {
+    for (int k = 0; k < c->nranks && k < AX1_MAX_RANKS; ++k)
+      if (k != c->rank && c->p2p.peer[k]) cudaIpcCloseMemHandle(c->p2p.peer[k]);
+    cudaFree(c->p2p.win);
+    if (c->p2p.cnt) cudaFree(c->p2p.cnt);
+  }
   if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
   for (void* p : {(void*)c->d_x, (void*)c->d_y, (void*)c->d_nodevol, (void*)c->d_epsm, (void*)c->d_dmask, (void*)c->d_rowptr,
                   (void*)c->d_u, (void*)c->d_uold, (void*)c->d_r0, (void*)c->d_r, (void*)c->d_z, (void*)c->d_uprev, (void*)c->d_A,
@@ -457,6 +464,59 @@ int ax1gpu_nccl_unique_id(const char* libnccl_path, char* id128) {
   return AX1GPU_OK;
 }
 
+}  // extern "C"
+
+// Peer windows: every rank exports one small cudaMalloc'ed window with CUDA IPC; the handles are gathered
+// with the NCCL communicator that already exists, and every rank maps all peers' windows. If any rank
+// cannot map a peer (no NVLink/P2P, AX1_P2P=0), all ranks fall back to the NCCL send/recv + allreduce path.
+static int p2p_setup(ax1gpu_ctx* c) {
+  const char* env = getenv("AX1_P2P");
+  int want = !(env && env[0] == '0') && c->nranks <= AX1_MAX_RANKS;
+  auto& P = c->p2p;
+  P.halo_len = 3 * (size_t)c->g.nvy * 4;
+  const size_t wlen = AX1_P2P_HALO_OFF + 4 * P.halo_len;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  int ok = want;
+  if (ok && cudaMalloc((void**)&P.win, wlen * sizeof(double)) != cudaSuccess) { cudaGetLastError(); ok = 0; P.win = nullptr; }
+  if (ok && cudaMalloc((void**)&P.cnt, 2 * sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  if (ok) {
+    cudaMemsetAsync(P.win, 0, wlen * sizeof(double), c->stream);
+    cudaMemsetAsync(P.cnt, 0, 2 * sizeof(unsigned int), c->stream);
+    if (cudaIpcGetMemHandle(&mine, P.win) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  }
+  // gather the handles (64 B each) through NCCL
+  char *d_in = nullptr, *d_all = nullptr;
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  AX1_CUDA(cudaMalloc((void**)&d_in, hb));
+  AX1_CUDA(cudaMalloc((void**)&d_all, hb * c->nranks));
+  AX1_CUDA(cudaMemcpyAsync(d_in, &mine, hb, cudaMemcpyHostToDevice, c->stream));
+  if (c->nccl.AllGather(d_in, d_all, hb, ncclInt8, c->comm, c->stream) != ncclSuccess) { set_error("ncclAllGather failed"); return AX1GPU_ENCCL; }
+  std::vector<cudaIpcMemHandle_t> all(c->nranks);
+  AX1_CUDA(cudaMemcpyAsync(all.data(), d_all, hb * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+  AX1_CUDA(cudaStreamSynchronize(c->stream));
+  if (ok) {
+    for (int k = 0; k < c->nranks; ++k) {
+      if (k == c->rank) { P.peer[k] = P.win; continue; }
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+      P.peer[k] = (double*)ptr;
+    }
+  }
+  // agree: peer windows are used only if every rank mapped every peer (min over ranks); the all-reduce also
+  // guarantees that every rank's window has been zeroed before anybody writes into it
+  int* d_ok = (int*)d_in;
+  AX1_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (c->nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, c->stream) != ncclSuccess) { set_error("ncclAllReduce failed"); return AX1GPU_ENCCL; }
+  AX1_CUDA(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  AX1_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_in); cudaFree(d_all);
+  P.on = ok != 0;
+  return AX1GPU_OK;
+}
+
+extern "C" {
+
 int ax1gpu_comm_init(ax1gpu_handle c, const char* libnccl_path, const char* id128, int rank, int nranks) {
   AX1_CHECK_H(c);
   cudaSetDevice(c->device);
@@ -474,7 +534,9 @@ int ax1gpu_comm_init(ax1gpu_handle c, const char* libnccl_path, const char* id12
   int rc;
   if ((rc = dev_alloc(&c->d_halo_send, n))) return rc;
   if ((rc = dev_alloc(&c->d_halo_recv, n))) return rc;
-  return AX1GPU_OK;
+  return p2p_setup(c);
 }
+
+int ax1gpu_comm_mode(ax1gpu_handle c) { return c ? (c->nranks > 1 ? (c->p2p.on ? 2 : 1) : 0) : 0; }
 
 }  // extern "C"

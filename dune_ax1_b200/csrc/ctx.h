@@ -52,6 +52,15 @@ struct ax1gpu_ctx {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
   double *d_halo_send = nullptr, *d_halo_recv = nullptr;  // 2 sides x 3 columns x nvy x 4
+  // peer-memory windows over NVLink (p2p.cuh); off: the NCCL send/recv + allreduce path is used
+  struct {
+    bool on = false;
+    double* win = nullptr;                 // own window (cudaMalloc, exported with cudaIpcGetMemHandle)
+    double* peer[AX1_MAX_RANKS] = {};      // mapped windows of all ranks, peer[rank] = win
+    unsigned int* cnt = nullptr;           // local last-CTA counters [2]
+    unsigned long long halo_seq = 0, red_seq = 0;
+    size_t halo_len = 0;                   // doubles per halo slot = 3 * nvy * 4
+  } p2p;
   // accounting
   long long launches = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -184,6 +184,66 @@ __global__ void __launch_bounds__(1024) reduce_final_kernel(const double* partia
   }
 }
 
+// multi-GPU with peer windows: block reduction, one-shot all-reduce over NVLink and the scalar recurrence
+// in ONE launch. Every rank stores its two partial sums into slot [parity][rank] of every peer's window,
+// releases the slot's sequence flag, then acquires the nranks slots of its own window and adds them in
+// rank order -> all ranks obtain bitwise identical sums (they must take identical convergence decisions).
+__global__ void __launch_bounds__(1024) reduce_final_p2p_kernel(const double* partials, int nblocks, double* sums, int op,
+                                                                Scalars* sc, double reduction, double* out, RedP2P rp,
+                                                                int* err) {
+  __shared__ double sh[2][32];
+  double s[2] = {0.0, 0.0};
+  for (int k = threadIdx.x; k < nblocks; k += blockDim.x) { s[0] += partials[k]; s[1] += partials[nblocks + k]; }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+    if (lane == 0) sh[q][w] = s[q];
+  }
+  __syncthreads();
+  if (w == 0) {
+    double t0 = sh[0][lane], t1 = sh[1][lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
+    const size_t slot = AX1_P2P_RED_OFF + (size_t)(rp.seq & 1) * AX1_MAX_RANKS * 8;
+    double a0 = 0.0, a1 = 0.0;
+    bool ok = true;
+    if (lane < rp.nranks) {
+      volatile double* p = rp.peer[lane] + slot + (size_t)rp.rank * 8;  // my slot in rank `lane`'s window
+      p[0] = t0; p[1] = t1;
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<unsigned long long*>(rp.peer[lane] + slot + (size_t)rp.rank * 8 + 4), rp.seq);
+      const double* q = rp.peer[rp.rank] + slot + (size_t)lane * 8;       // rank `lane`'s slot in my window
+      ok = wait_seq(reinterpret_cast<const unsigned long long*>(q + 4), rp.seq);
+      a0 = reinterpret_cast<const volatile double*>(q)[0];
+      a1 = reinterpret_cast<const volatile double*>(q)[1];
+    }
+    if (!ok) atomicExch(err, 1);
+    double r0 = 0.0, r1 = 0.0;
+    for (int k = 0; k < rp.nranks; ++k) { r0 += __shfl_sync(0xffffffffu, a0, k); r1 += __shfl_sync(0xffffffffu, a1, k); }
+    if (lane == 0) {
+      sums[0] = r0; sums[1] = r1;
+      if (op != OP_NONE) scalar_step(op, sc, sums, reduction, out);
+    }
+  }
+}
+
+// receiver side of the halo sum with peer windows: acquire the neighbour's sequence flag, then add the
+// three vertex columns it stored into my window (AddDataHandle)
+__global__ void halo_wait_add_kernel(Dev g, double* v, const double* slot, const unsigned long long* flag,
+                                     unsigned long long seq, int c0, int* err) {
+  __shared__ int ok_sh;
+  if (threadIdx.x == 0) ok_sh = wait_seq(flag, seq) ? 1 : 0;
+  __syncthreads();
+  if (!ok_sh) { if (threadIdx.x == 0) atomicExch(err, 1); return; }
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = 3 * g.nvy * 4;
+  if (t >= n) return;
+  const int k = t & 3, j = (t >> 2) % g.nvy, c = (t >> 2) / g.nvy;
+  v[4 * (size_t)(c0 + c + g.nvx * j) + k] += reinterpret_cast<const volatile double*>(slot)[t];
+}
+
 __global__ void scalar_kernel(int op, Scalars* sc, const double* sums, double reduction, double* out) {
   scalar_step(op, sc, sums, reduction, out);
 }
@@ -220,7 +280,14 @@ static inline Own own_of(const ax1gpu_ctx* c) { return Own{c->own_lo, c->own_hi,
 // partials -> sums (+ allreduce over ranks) -> scalar recurrence `op`
 static int reduce_op_from(ax1gpu_ctx* c, const double* partials, int nblocks, int nsums, int op, double reduction,
                           double* out = nullptr) {
-  if (c->nranks > 1) {
+  if (c->nranks > 1 && c->p2p.on) {
+    RedP2P rp;
+    for (int k = 0; k < AX1_MAX_RANKS; ++k) rp.peer[k] = c->p2p.peer[k];
+    rp.rank = c->rank; rp.nranks = c->nranks; rp.seq = ++c->p2p.red_seq;
+    reduce_final_p2p_kernel<<<1, 1024, 0, c->stream>>>(partials, nblocks, c->d_sums, op, c->d_sc, reduction, out, rp,
+                                                       c->d_err + 2);
+    AX1_LAUNCH_CHECK(c);
+  } else if (c->nranks > 1) {
     reduce_final_kernel<<<1, 1024, 0, c->stream>>>(partials, nblocks, c->d_sums, OP_NONE, c->d_sc, reduction, out);
     AX1_LAUNCH_CHECK(c);
     AX1_NCCL(c, c->nccl.AllReduce(c->d_sums, c->d_sums, nsums, ncclDouble, ncclSum, c->comm, c->stream));
@@ -390,6 +457,42 @@ int drv_factor(ax1gpu_ctx* c, int slab_w, int fill) {
 }
 
 int drv_prec_apply(ax1gpu_ctx* c, const double* d, double* v) {
+  if (c->nranks > 1 && c->p2p.on) {
+    // sweep with fused halo push into the neighbours' windows, then acquire + add what they pushed to me
+    const Dev& g = c->g;
+    const size_t H = c->p2p.halo_len;
+    HaloPush hp{};
+    hp.seq = ++c->p2p.halo_seq;
+    const size_t par = (size_t)(hp.seq & 1);
+    hp.cnt = c->p2p.cnt;
+    halo_contributors(g, c->slab_w, &hp.ncontrib[0], &hp.ncontrib[1]);
+    if (c->left_pb) {   // my left columns -> slot "from the right neighbour" (side 1) of rank-1
+      double* pw = c->p2p.peer[c->rank - 1];
+      hp.dst[0] = pw + AX1_P2P_HALO_OFF + (2 + par) * H;
+      hp.flag[0] = reinterpret_cast<unsigned long long*>(pw + AX1_P2P_FLAG_OFF + 1);
+    }
+    if (c->right_pb) {  // my right columns -> slot "from the left neighbour" (side 0) of rank+1
+      double* pw = c->p2p.peer[c->rank + 1];
+      hp.dst[1] = pw + AX1_P2P_HALO_OFF + (0 + par) * H;
+      hp.flag[1] = reinterpret_cast<unsigned long long*>(pw + AX1_P2P_FLAG_OFF + 0);
+    }
+    if (c->ilu_fill == 1) launch_ilu1_apply(g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream, &hp);
+    else launch_ilu_apply(g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream, &hp);
+    AX1_LAUNCH_CHECK(c);
+    const int n = 3 * g.nvy * 4, bs = 256, nb = (n + bs - 1) / bs;
+    double* w = c->p2p.win;
+    if (c->left_pb) {
+      halo_wait_add_kernel<<<nb, bs, 0, c->stream>>>(g, v, w + AX1_P2P_HALO_OFF + (0 + par) * H,
+          reinterpret_cast<const unsigned long long*>(w + AX1_P2P_FLAG_OFF + 0), hp.seq, 0, c->d_err + 2);
+      AX1_LAUNCH_CHECK(c);
+    }
+    if (c->right_pb) {
+      halo_wait_add_kernel<<<nb, bs, 0, c->stream>>>(g, v, w + AX1_P2P_HALO_OFF + (2 + par) * H,
+          reinterpret_cast<const unsigned long long*>(w + AX1_P2P_FLAG_OFF + 1), hp.seq, g.nvx - 3, c->d_err + 2);
+      AX1_LAUNCH_CHECK(c);
+    }
+    return 0;
+  }
   if (c->ilu_fill == 1) launch_ilu1_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
   else launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
   AX1_LAUNCH_CHECK(c);
@@ -579,9 +682,10 @@ int drv_newton(ax1gpu_ctx* c, const ax1gpu_newton_opts* o, ax1gpu_newton_result*
   res->t_lin_solv = t_lin_ms * 1e-3;
   res->t_elapsed = ev_ms(e3, e2) * 1e-3;
   // channel-kernel error flag (leak ratio outside [0,1], channelset.hh:298-299)
-  int herr = 0;
-  AX1_CUDA(cudaMemcpy(&herr, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (herr) { set_error("Calculated leak channel ratio outside [0,1]"); return AX1GPU_ESTATE; }
+  int herr[3] = {0, 0, 0};
+  AX1_CUDA(cudaMemcpy(herr, c->d_err, 3 * sizeof(int), cudaMemcpyDeviceToHost));
+  if (herr[0]) { set_error("Calculated leak channel ratio outside [0,1]"); return AX1GPU_ESTATE; }
+  if (herr[2]) { set_error("peer-memory exchange timed out (a neighbour rank did not arrive)"); return AX1GPU_ENCCL; }
   return 0;
 }
 

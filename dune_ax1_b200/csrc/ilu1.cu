@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <vector>
 #include "ilu_common.cuh"
+#include "p2p.cuh"
 
 namespace ax1 {
 
@@ -186,11 +187,11 @@ __global__ void __launch_bounds__(256, 1) ilu1_factor_kernel(Dev g, const double
 // v = (LU)^-1 d, forward and backward sweep in one launch; same software pipeline as ilu_apply_kernel
 // (solver.cu): every lane streams its scalar row of the next D levels' blocks into a private
 // shared-memory slot with cp.async, solution values of the last levels go through a small ring.
-template <int D>
+template <int D, bool P2P>
 __global__ void __launch_bounds__(256) ilu1_apply_kernel(Dev g, const double* __restrict__ LF,
                                                          const double* __restrict__ LB, const double* __restrict__ d,
                                                          double* v_out, int slab_w, int nq,
-                                                         const int* __restrict__ lvl_tab) {
+                                                         const int* __restrict__ lvl_tab, HaloPush hp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nt = 4 * nq, tid = threadIdx.x;  // nq = rows a level can hold; threads beyond 4 nq never own a row
   const int q = tid >> 2, r = tid & 3;
@@ -310,11 +311,13 @@ __global__ void __launch_bounds__(256) ilu1_apply_kernel(Dev g, const double* __
       xo += d23.y * __shfl_sync(qmask, acc, qb + 3);
       ring[((size_t)(L & 7) * nq + q) * 4 + r] = xo;
       v_out[4 * (size_t)w.v + r] = xo;
+      if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + w.il, w.j, r, xo);
     }
     __syncthreads();
     issue_bwd(L - D);
   }
   cp_async_wait<0>();
+  if (P2P) halo_push_finish(hp, g.nvx, i0, wc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -368,18 +371,24 @@ void launch_ilu1_factor(const Dev& g, const double* A, double* LU, int slab_w, c
   ilu1_factor_kernel<<<nslab, nt, factor1_smem(g, slab_w), st>>>(g, A, LU, LU + (size_t)g.nv * 96, slab_w,
                                                                  slab1_rows(slab_w), lvl_tab);
 }
-void launch_ilu1_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, const int* lvl_tab,
-                       cudaStream_t st) {
+template <bool P2P>
+static void launch_ilu1_apply_t(const Dev& g, const double* LU, const double* d, double* v, int slab_w,
+                                const int* lvl_tab, const HaloPush& hp, cudaStream_t st) {
   constexpr int D = 2;
   const int nslab = (g.nvx + slab_w - 1) / slab_w;
   const int nt = slab1_threads(slab_w), nq = slab1_rows(slab_w);
   const size_t smem = (size_t)D * 4 * nq * (7 * 32 + 8) + 8 * (size_t)nq * 32 + (size_t)(slab_w + 3 * g.nvy) * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(ilu1_apply_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(ilu1_apply_kernel<D, P2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  ilu1_apply_kernel<D><<<nslab, nt, smem, st>>>(g, LU, LU + (size_t)g.nv * 96, d, v, slab_w, nq, lvl_tab);
+  ilu1_apply_kernel<D, P2P><<<nslab, nt, smem, st>>>(g, LU, LU + (size_t)g.nv * 96, d, v, slab_w, nq, lvl_tab, hp);
+}
+void launch_ilu1_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, const int* lvl_tab,
+                       cudaStream_t st, const HaloPush* hp) {
+  if (hp) launch_ilu1_apply_t<true>(g, LU, d, v, slab_w, lvl_tab, *hp, st);
+  else launch_ilu1_apply_t<false>(g, LU, d, v, slab_w, lvl_tab, HaloPush{}, st);
 }
 
 }  // namespace ax1

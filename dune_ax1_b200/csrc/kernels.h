@@ -1,6 +1,7 @@
 // kernels.h -- launch wrappers shared between the translation units of libax1gpu.
 #pragma once
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace ax1 {
 
@@ -36,14 +37,16 @@ void launch_spmv_dot(const Dev& g, const double* A, const double* x, double* y, 
                      cudaStream_t st);
 void ilu_level_tables(const Dev& g, int slab_w, std::vector<int>& tab);
 void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st);
+// hp != null: multi-GPU with peer windows, the sweep also pushes the halo columns to the neighbours (p2p.cuh)
 void launch_ilu_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, const int* lvl_tab,
-                      cudaStream_t st);
+                      cudaStream_t st, const HaloPush* hp = nullptr);
+void halo_contributors(const Dev& g, int slab_w, int* left, int* right);
 // ilu1.cu: block ILU(1), 13 blocks per row, wavefronts il + 3 j
 int ilu1_max_slab_w(const Dev& g);
 void ilu1_level_tables(const Dev& g, int slab_w, std::vector<int>& tab);
 void launch_ilu1_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st);
 void launch_ilu1_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, const int* lvl_tab,
-                       cudaStream_t st);
+                       cudaStream_t st, const HaloPush* hp = nullptr);
 void launch_rownorm(const Dev& g, double* A, double* r, cudaStream_t st);
 void launch_compact_bcrs(const Dev& g, const double* A9, double* blocks, const int* rowptr, cudaStream_t st);
 void launch_expand_bcrs(const Dev& g, const double* blocks, double* A9, const int* rowptr, int* viol, cudaStream_t st);

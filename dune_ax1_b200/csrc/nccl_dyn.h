@@ -23,6 +23,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -34,7 +35,7 @@ struct NcclApi {
     lib = dlopen(path && path[0] ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) return false;
 #define AX1_SYM(name) *(void**)(&name) = dlsym(lib, "nccl" #name); if (!name) return false;
-    AX1_SYM(GetUniqueId) AX1_SYM(CommInitRank) AX1_SYM(CommDestroy) AX1_SYM(AllReduce) AX1_SYM(Send) AX1_SYM(Recv)
+    AX1_SYM(GetUniqueId) AX1_SYM(CommInitRank) AX1_SYM(CommDestroy) AX1_SYM(AllReduce) AX1_SYM(AllGather) AX1_SYM(Send) AX1_SYM(Recv)
     AX1_SYM(GroupStart) AX1_SYM(GroupEnd) AX1_SYM(GetErrorString)
 #undef AX1_SYM
     return true;

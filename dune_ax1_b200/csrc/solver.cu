@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <vector>
 #include "ilu_common.cuh"
+#include "p2p.cuh"
 #include "reduce.cuh"
 
 namespace ax1 {
@@ -241,10 +242,13 @@ __global__ void __launch_bounds__(256, 1) ilu_factor_kernel(Dev g, const double*
 // factor data, only cp.async.wait_group. The solution values of the last three levels, which the
 // next level depends on, are exchanged through a small shared-memory ring (one __syncthreads per
 // level) instead of an L2 round trip.
-template <int D>
+// P2P: multi-GPU run with peer windows -- the final values of the three vertex columns shared with a
+// neighbour rank are also stored straight into that rank's memory over NVLink (p2p.cuh).
+template <int D, bool P2P>
 __global__ void __launch_bounds__(256) ilu_apply_kernel(Dev g, const double* __restrict__ LF,
                                                         const double* __restrict__ LB, const double* __restrict__ d,
-                                                        double* v_out, int slab_w, const int* __restrict__ lvl_tab) {
+                                                        double* v_out, int slab_w, const int* __restrict__ lvl_tab,
+                                                        HaloPush hp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nt = blockDim.x, tid = threadIdx.x;
   const int q = tid >> 2, r = tid & 3, nq = nt >> 2;
@@ -365,11 +369,13 @@ __global__ void __launch_bounds__(256) ilu_apply_kernel(Dev g, const double* __r
       xo += d23.y * __shfl_sync(qmask, acc, qb + 3);
       ring[((size_t)(L & 3) * nq + q) * 4 + r] = xo;
       v_out[4 * (size_t)w.v + r] = xo;
+      if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + w.il, w.j, r, xo);
     }
     __syncthreads();
     issue_bwd(L - D);
   }
   cp_async_wait<0>();
+  if (P2P) halo_push_finish(hp, g.nvx, i0, wc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -481,30 +487,40 @@ static int ilu_stages() {
   static const int d = getenv("AX1_ILU_STAGES") ? atoi(getenv("AX1_ILU_STAGES")) : 2;
   return d;
 }
-template <int D>
+template <int D, bool P2P>
 static void launch_ilu_apply_t(const Dev& g, const double* LU, const double* d, double* v, int slab_w,
-                               const int* lvl_tab, cudaStream_t st) {
+                               const int* lvl_tab, const HaloPush& hp, cudaStream_t st) {
   const int nslab = (g.nvx + slab_w - 1) / slab_w;
   const int nt = slab_threads(slab_w);
   const size_t smem = (size_t)D * nt * (5 * 32 + 8) + 4 * (size_t)(nt / 4) * 32 + (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(ilu_apply_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(ilu_apply_kernel<D, P2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  ilu_apply_kernel<D><<<nslab, nt, smem, st>>>(g, LU, LU + (size_t)g.nv * 64, d, v, slab_w, lvl_tab);
+  ilu_apply_kernel<D, P2P><<<nslab, nt, smem, st>>>(g, LU, LU + (size_t)g.nv * 64, d, v, slab_w, lvl_tab, hp);
 }
 void launch_ilu_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, const int* lvl_tab,
-                      cudaStream_t st) {
+                      cudaStream_t st, const HaloPush* hp) {
   // the inputs of the preconditioner are already zero on constrained DOFs (see driver.cu)
+  if (hp) { launch_ilu_apply_t<2, true>(g, LU, d, v, slab_w, lvl_tab, *hp, st); return; }
+  const HaloPush none{};
   switch (ilu_stages()) {
-    case 3: launch_ilu_apply_t<3>(g, LU, d, v, slab_w, lvl_tab, st); break;
-    case 5: launch_ilu_apply_t<5>(g, LU, d, v, slab_w, lvl_tab, st); break;
-    case 6: launch_ilu_apply_t<6>(g, LU, d, v, slab_w, lvl_tab, st); break;
-    case 8: launch_ilu_apply_t<8>(g, LU, d, v, slab_w, lvl_tab, st); break;
-    case 4: launch_ilu_apply_t<4>(g, LU, d, v, slab_w, lvl_tab, st); break;
-    default: launch_ilu_apply_t<2>(g, LU, d, v, slab_w, lvl_tab, st); break;
+    case 3: launch_ilu_apply_t<3, false>(g, LU, d, v, slab_w, lvl_tab, none, st); break;
+    case 4: launch_ilu_apply_t<4, false>(g, LU, d, v, slab_w, lvl_tab, none, st); break;
+    default: launch_ilu_apply_t<2, false>(g, LU, d, v, slab_w, lvl_tab, none, st); break;
   }
+}
+// sub-slab CTAs that own part of the left / right three halo vertex columns
+void halo_contributors(const Dev& g, int slab_w, int* left, int* right) {
+  const int nslab = (g.nvx + slab_w - 1) / slab_w;
+  int l = 0, r = 0;
+  for (int b = 0; b < nslab; ++b) {
+    const int i0 = b * slab_w, wc = std::min(slab_w, g.nvx - i0);
+    if (i0 < 3) ++l;
+    if (i0 + wc > g.nvx - 3) ++r;
+  }
+  *left = l; *right = r;
 }
 void launch_rownorm(const Dev& g, double* A, double* r, cudaStream_t st) {
   const int bs = 256;

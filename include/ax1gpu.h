@@ -164,6 +164,10 @@ void* ax1gpu_stream(ax1gpu_handle h);
  * (AddDataHandle halo sum + allreduce, ax1_solverbackend.hh:346-381,413-437). */
 int ax1gpu_nccl_unique_id(const char* libnccl_path, char* id128);
 int ax1gpu_comm_init(ax1gpu_handle h, const char* libnccl_path, const char* id128, int rank, int nranks);
+/* how the two exchange steps run: 0 single rank, 1 NCCL send/recv + allreduce, 2 direct stores into the
+ * neighbours' memory over NVLink (CUDA IPC peer windows; default when every rank can map every peer,
+ * AX1_P2P=0 forces mode 1) */
+int ax1gpu_comm_mode(ax1gpu_handle h);
 
 /* ---- host model: restatement of the reference's host-side Physics precomputations, so that the
  * library can be driven without DUNE (bench, tests, examples). No GPU needed. ---- */

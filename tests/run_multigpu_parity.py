@@ -29,6 +29,8 @@ def main():
     ids = [api.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     dev.comm_init(ids[0], rank, world)
+    mode = dev.comm_mode()
+    want_p2p = os.environ.get("AX1_P2P", "1") != "0"
     dev.set_time(0.0, 1.0); dev.set_uold(s["u0"]); dev.update_state(s["u0"])
     kw = dict(reduction=1e-9, abs_limit=1e-14, min_lin_reduction=1e-10)
     ug, rg = dev.newton(s["u0"], api.default_newton_opts(slab_w=slab_w, **kw))
@@ -36,9 +38,14 @@ def main():
     r0, nrm = dev.residual(s["u0"])
     dev.jacobian(s["u0"], download=False)
     zg, _, lres = dev.solve(r0, 1e-8, maxit=500, slab_w=slab_w)
+    # the reference's default parallel backend: ISTLBackend_OVLP_BCGS_ILUn(multigfs, cc, 1, ...) = one block
+    # ILU(1) per rank (slab_w >= local columns -> a single sub-slab per rank)
+    dev.set_time(0.0, 1.0); dev.set_uold(s["u0"]); dev.update_state(s["u0"])
+    ug1, rg1 = dev.newton(s["u0"], api.default_newton_opts(slab_w=64, ilu_fill=1, **kw))
     gathered = [None] * world
     dist.all_gather_object(gathered, dict(u=ug, z=zg, nrm=nrm, its=rg.iterations, lin=rg.lin_iterations,
-                                          status=rg.status, lit=lres.iterations))
+                                          status=rg.status, lit=lres.iterations, mode=mode, u1=ug1,
+                                          its1=rg1.iterations, lin1=rg1.lin_iterations, status1=rg1.status))
     ok = True
     if rank == 0:
         from oracle import pyoracle as O
@@ -58,6 +65,22 @@ def main():
                   % (r, g["status"], g["its"], res[r].iterations, g["lin"], res[r].lin_iterations, err, g["nrm"]))
             ok &= g["status"] == 0 and g["its"] == res[r].iterations
             ok &= bool(np.all(err[:3] < 1e-8) and err[3] < 5e-7)
+        # ILU(1) per rank, the reference default
+        for r in range(world):
+            probs[r].set_time(0.0, 1.0); probs[r].set_uold(us[r]); probs[r].update_state(us[r])
+        out1, res1, st1 = O.newton_mt(probs, us, O.default_newton_opts(ilu_fill=1, slab_w=0, **kw))
+        assert st1 == 0
+        for r in range(world):
+            g = gathered[r]
+            scale = np.max(np.abs(out1[r].reshape(-1, 4)), axis=0)
+            err = np.max(np.abs(g["u1"] - out1[r]).reshape(-1, 4) / scale, axis=0)
+            print("rank %d ILU(1): status %d its gpu/cpu %d/%d lin %d/%d field err %s"
+                  % (r, g["status1"], g["its1"], res1[r].iterations, g["lin1"], res1[r].lin_iterations, err))
+            ok &= g["status1"] == 0 and g["its1"] == res1[r].iterations
+            ok &= bool(np.all(err[:3] < 1e-8) and err[3] < 5e-7)
+        modes = {g["mode"] for g in gathered}
+        print("comm mode", modes, "(2 = NVLink peer windows, 1 = NCCL)")
+        ok &= modes == ({2} if want_p2p else {1})
         # the masked defect norm is global: identical on every rank
         ok &= len({g["nrm"] for g in gathered}) == 1
         print("MULTIGPU PARITY", "OK" if ok else "FAILED")

@@ -9,13 +9,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_gpu_parity():
+@pytest.mark.parametrize("p2p", ["1", "0"])
+def test_two_gpu_parity(p2p):
+    """p2p=1: halo sum and dot products through NVLink peer windows (p2p.cuh); p2p=0: NCCL send/recv + allreduce."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "run_multigpu_parity.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, AX1_P2P=p2p))
     sys.stdout.write(out.stdout[-3000:])
     sys.stderr.write(out.stderr[-3000:])
     assert out.returncode == 0 and "MULTIGPU PARITY OK" in out.stdout
