@@ -152,15 +152,27 @@ def main():
     ap.add_argument("--slab-w", type=int, default=SLAB_W)
     ap.add_argument("--cpu-nx", type=int, default=2048, help="cell columns of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "myelin"],
+                    help="synthetic: weak scaling, Nx columns PER GPU (headline); myelin: BASELINE config 5, the 48 mm "
+                         "myelinated axon with 48 nodes of Ranvier (7,251 x 180 cells), STRONG scaling over z-slabs")
+    ap.add_argument("--ilu-fill", type=int, default=0, choices=[0, 1])
     args = ap.parse_args()
+    myelin = args.workload == "myelin"
+    if myelin and args.slab_w == SLAB_W:
+        args.slab_w = 32   # few columns per GPU: more, narrower sub-slabs keep the SMs busy
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     nv_full = (args.nx + 1) * 181
     workload = ("synthetic refined r-z tensor grid: Ny=180 (shipped 181-point radial vector) x Nx=%d columns/GPU, "
-                "dx=100 nm, HH channels, implicit Euler dt=1us, %d Newton x %d BiCGStab(ILU0 slab %d) per step"
-                % (args.nx, NEWTON_ITS, KRYLOV_ITS, args.slab_w))
+                "dx=100 nm, HH channels, implicit Euler dt=1us, %d Newton x %d BiCGStab(ILU%d slab %d) per step"
+                % (args.nx, NEWTON_ITS, KRYLOV_ITS, args.ilu_fill, args.slab_w))
+    if myelin:
+        workload = ("myelinated axon 48 mm x 10 mm, 48 nodes of Ranvier (acme2_cyl_par_fiona_myelin_48mmx10mm_48nodes "
+                    "config): 7,251 x 180 cells in total, non-uniform x (100 nm in the nodes ... 10 um in the myelin), "
+                    "implicit Euler dt=1us, %d Newton x %d BiCGStab(ILU%d slab %d) per step"
+                    % (NEWTON_ITS, KRYLOV_ITS, args.ilu_fill, args.slab_w))
 
     if args.impl == "reference":
         if rank != 0:
@@ -198,7 +210,10 @@ def main():
     if world > 1:
         dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
 
-    s = setups.make_setup(args.nx * world, dx=DX, rank=rank, nranks=world, perturbation=1e-3)
+    if myelin:
+        s = setups.make_myelin_setup(rank=rank, nranks=world)
+    else:
+        s = setups.make_setup(args.nx * world, dx=DX, rank=rank, nranks=world, perturbation=1e-3)
     stream = torch.cuda.Stream(device=local_rank)
     dev = setups.make_device(s, device=local_rank, stream=stream.cuda_stream)
     if world > 1:
@@ -206,7 +221,8 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         dev.comm_init(ids[0], rank, world)
     nv = dev.nv
-    opts = api.default_newton_opts(maxit=NEWTON_ITS, lin_maxit=KRYLOV_ITS, fixed_work=1, slab_w=args.slab_w)
+    opts = api.default_newton_opts(maxit=NEWTON_ITS, lin_maxit=KRYLOV_ITS, fixed_work=1, slab_w=args.slab_w,
+                                   ilu_fill=args.ilu_fill)
 
     # pinned host buffers for the e2e leg
     u_host_t = torch.empty(dev.n, dtype=torch.float64, pin_memory=True)
@@ -284,6 +300,8 @@ def main():
         launches = int(lt[0])
     its = NEWTON_ITS * args.steps
     nv_total = nv_full * world
+    if myelin:   # strong scaling: the global grid is fixed
+        nv_total = len(s["xg"]) * 181
     newton_per_s = its / (ms * 1e-3)
     value = 4.0 * nv_total * its / (ms * 1e-3) / 1e9          # whole-job GDOF/s
     e2e_value = 4.0 * nv_total * its / (ms_e2e * 1e-3) / 1e9
@@ -296,33 +314,40 @@ def main():
               "spmv": 2 * KRYLOV_ITS * NEWTON_ITS, "ilu_apply": 2 * KRYLOV_ITS * NEWTON_ITS,
               "dot": 3 * NEWTON_ITS + 1, "axpy": 2 * KRYLOV_ITS * NEWTON_ITS}
     kern = {}
+    bytes_k, bytes_dense = dict(BYTES), dict(BYTES_DENSE)
+    if args.ilu_fill == 1:   # 13 instead of 9 blocks per factor row (ilu1.cu)
+        bytes_k["ilu_factor"], bytes_k["ilu_apply"] = 720 + 1664, 1664 + 64
+        bytes_dense["ilu_factor"], bytes_dense["ilu_apply"] = 1192 + 1664, 1664 + 64
     for name in counts:
         t_ms = dev.time_kernel(name, reps=3)
         kern[name] = {"ms": t_ms, "launches_per_step": counts[name],
-                      "GBps": BYTES[name] * nv / (t_ms * 1e-3) / 1e9,
-                      "GBps_dense_equivalent": BYTES_DENSE[name] * nv / (t_ms * 1e-3) / 1e9,
+                      "GBps": bytes_k[name] * nv / (t_ms * 1e-3) / 1e9,
+                      "GBps_dense_equivalent": bytes_dense[name] * nv / (t_ms * 1e-3) / 1e9,
                       "share_of_step": counts[name] * t_ms / (ms / args.steps)}
     dom = max(kern, key=lambda k: kern[k]["share_of_step"])
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (named workload only)
     traffic = None
-    if args.nx == NX_PER_GPU and args.slab_w == SLAB_W:
+    if args.nx == NX_PER_GPU and args.slab_w == SLAB_W and not myelin and args.ilu_fill == 0:
         traffic = {"ilu_apply": 20.352319e9 + 1.073509e9}.get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kern[dom]["GBps"] / peak, "traffic": traffic,
                 "traffic_source": "profiles/r01_top_kernels_ncu.json", "peak_kind": peak_kind,
-                "algorithmic_bytes_per_launch": BYTES[dom] * nv, "kernels": kern}
+                "algorithmic_bytes_per_launch": bytes_k[dom] * nv, "kernels": kern}
     # whole-step algorithmic traffic (SURVEY 8(d) formula, l = 1 line-search residual, k Krylov its)
-    step_bytes = NEWTON_ITS * (BYTES["jacobian"] + BYTES["ilu_factor"] + 2 * 104 +
-                               KRYLOV_ITS * (2 * BYTES["spmv"] + 2 * 1384 + 416)) * nv
-    step_bytes_dense = NEWTON_ITS * (1184 + 2384 + 2 * 104 + KRYLOV_ITS * (2 * 1256 + 2 * 1384 + 416)) * nv
+    step_bytes = NEWTON_ITS * (bytes_k["jacobian"] + bytes_k["ilu_factor"] + 2 * 104 +
+                               KRYLOV_ITS * (2 * bytes_k["spmv"] + 2 * bytes_k["ilu_apply"] + 416)) * nv
+    step_bytes_dense = NEWTON_ITS * (1184 + bytes_dense["ilu_factor"] + 2 * 104 +
+                                     KRYLOV_ITS * (2 * 1256 + 2 * bytes_dense["ilu_apply"] + 416)) * nv
     roofline["step_frac_of_peak"] = step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak
     roofline["step_frac_of_peak_dense_equivalent"] = step_bytes_dense / (ms / args.steps * 1e-3) / 1e9 / peak
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload, "cells_per_gpu": args.nx * 180, "dof_total": 4 * nv_total,
-                      "l2": "inputs larger than L2 (working set ~46 GB per GPU)", "parallelism": "z-slab x%d" % world},
+           "scaling": "strong" if myelin else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload, "cells_per_gpu": s["nx"] * 180, "dof_total": 4 * nv_total,
+                      "l2": ("working set %.1f GB per GPU" % (nv * (720 + 1664 + 12 * 32) / 1e9)) if myelin else
+                            "inputs larger than L2 (working set ~46 GB per GPU)",
+                      "parallelism": "z-slab x%d" % world, "comm": {0: "none", 1: "nccl", 2: "nvlink peer windows"}[dev.comm_mode()]},
            "newton_steps_per_s": newton_per_s, "newton_iterations_per_step": NEWTON_ITS,
            "krylov_iterations_per_solve": KRYLOV_ITS,
            "last_step": {"defect": last.defect, "first_defect": last.first_defect, "lin_iterations": last.lin_iterations,
@@ -331,7 +356,7 @@ def main():
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * dev.n * 8,
                    "d2h_bytes_per_step": dev.n * 8, "ms_per_step": ms_e2e / args.steps},
            "roofline": roofline}
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not myelin:
         # secondary figure: the paper configuration (square10mm.config, 100 x 180 cells, 73,124 DOF), first 60
         # adaptive time steps of the stimulated run through the restated time loop (latency-bound regime)
         try:
@@ -350,7 +375,7 @@ def main():
             devp.close()
         except Exception as e:  # never lose the headline line because of the secondary figure
             out["paper_config"] = {"error": str(e)}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not myelin:
         threads = os.cpu_count() or 1
         r = cpu_reference(args.cpu_nx, threads, 1, 0)
         out["cpu_baseline"] = {

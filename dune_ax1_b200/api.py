@@ -69,6 +69,13 @@ class LinResult(C.Structure):
                 ("it_half", C.c_double)]
 
 
+class MembraneGroupC(C.Structure):
+    _fields_ = [("start", C.c_double), ("width", C.c_double), ("stride", C.c_double), ("dx", C.c_double),
+                ("smooth_transition", C.c_int), ("geometric_refinement", C.c_int), ("dx_transition", C.c_double),
+                ("n_transition", C.c_int), ("permittivity", C.c_double), ("d_memb", C.c_double),
+                ("g_leak", C.c_double), ("g_nav", C.c_double), ("g_kv", C.c_double)]
+
+
 class HostBC(C.Structure):
     _fields_ = [("top", C.c_int * 2), ("bottom", C.c_int * 2), ("left_cytosol", C.c_int * 2),
                 ("right_cytosol", C.c_int * 2), ("left_debye", C.c_int * 2), ("right_debye", C.c_int * 2),
@@ -145,6 +152,15 @@ def lib():
                                        C.c_double, C.c_int, C.c_double, C.POINTER(HostBC), c_ubyte_p, c_double_p,
                                        c_ubyte_p]
     L.ax1host_slab.argtypes = [C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p]
+    GP = C.POINTER(MembraneGroupC)
+    L.ax1host_group_partition.argtypes = [GP, C.c_int, C.c_int, C.c_double, c_int_p, c_double_p, c_double_p, C.c_int]
+    L.ax1host_generate_x_groups.argtypes = [GP, C.c_int, C.c_int, c_int_p, c_double_p, c_double_p, C.c_double,
+                                            C.c_double, c_double_p, C.c_int]
+    L.ax1host_membrane_arrays.argtypes = [GP, C.c_int, C.c_int, c_int_p, c_double_p, c_double_p, C.c_int, C.c_double,
+                                          C.c_double, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
+                                          c_double_p, c_int_p]
+    L.ax1host_check_processor_boundary.argtypes = [GP, C.c_int, c_int_p, c_double_p, c_double_p, C.c_int, C.c_double,
+                                                   C.c_double, C.c_double]
     L.ax1host_state_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     L.ax1host_state_free.argtypes = [C.c_void_p]
     L.ax1host_state_info.argtypes = [C.c_void_p, c_int_p, c_double_p, c_double_p, c_int_p, c_int_p, c_int_p, c_int_p]
@@ -243,6 +259,68 @@ def physics_maps(x, y, ymemb=500.0, dmemb=5.0, xmin_global=None, xmax_global=Non
         y[-1] if ymax is None else ymax, int(do_volume_scaling), volume_scaling_threshold, C.byref(bc.c),
         cs.ctypes.data_as(c_ubyte_p), _dp(nvol), dm.ctypes.data_as(c_ubyte_p)))
     return cs, nvol, dm
+
+
+class MembraneGroups:
+    """[membrane.<group>] sections of the INI file (myelin / nodes of Ranvier): x partition, grid vector,
+    per-column permittivities and channel densities (host model of Ax1GridGenerator / Physics)."""
+
+    def __init__(self, groups, default_group, xmax, dx_default, smooth_permittivities=True,
+                 default_permittivity=2.0, default_dmemb=5.0):
+        """groups: ordered dict name -> dict(start, width, stride, dx, smoothTransition, geometricRefinement,
+        dx_transition, n_transition, permittivity, d_memb, leak, Nav, Kv) using the INI key names."""
+        self.names = list(groups)
+        self.xmax, self.dx_default = float(xmax), float(dx_default)
+        self.smooth, self.def_perm, self.def_dmemb = int(smooth_permittivities), default_permittivity, default_dmemb
+        self.c = (MembraneGroupC * len(self.names))()
+        for k, n in enumerate(self.names):
+            g = groups[n]
+            c = self.c[k]
+            c.start, c.width, c.stride = g.get("start", -1.0), g.get("width", -1.0), g.get("stride", -1.0)
+            c.dx = g.get("dx", -1.0)
+            c.smooth_transition = int(g.get("smoothTransition", False))
+            c.geometric_refinement = int(g.get("geometricRefinement", False))
+            c.dx_transition, c.n_transition = g.get("dx_transition", -1.0), int(g.get("n_transition", 10))
+            c.permittivity, c.d_memb = g.get("permittivity", -1.0), g.get("d_memb", -1.0)
+            c.g_leak, c.g_nav, c.g_kv = g.get("leak", 0.0), g.get("Nav", 0.0), g.get("Kv", 0.0)
+        self.default = self.names.index(default_group)
+        L = lib()
+        n = L.ax1host_group_partition(self.c, len(self.names), self.default, self.xmax, None, None, None, 0)
+        if n < 0:
+            raise Ax1GpuError(_err())
+        self.ival_group = np.zeros(n, dtype=np.int32)
+        self.ival_start, self.ival_end = np.zeros(n), np.zeros(n)
+        L.ax1host_group_partition(self.c, len(self.names), self.default, self.xmax,
+                                  self.ival_group.ctypes.data_as(c_int_p), _dp(self.ival_start), _dp(self.ival_end), n)
+
+    def _iv(self):
+        return (len(self.ival_group), self.ival_group.ctypes.data_as(c_int_p), _dp(self.ival_start),
+                _dp(self.ival_end))
+
+    def x_vector(self):
+        L = lib()
+        n = L.ax1host_generate_x_groups(self.c, len(self.names), *self._iv(), self.dx_default, self.xmax, None, 0)
+        if n < 0:
+            raise Ax1GpuError(_err())
+        x = np.zeros(n)
+        L.ax1host_generate_x_groups(self.c, len(self.names), *self._iv(), self.dx_default, self.xmax, _dp(x), n)
+        return x
+
+    def membrane_arrays(self, x):
+        """eps_memb, g_leak, g_nav, g_kv, group index of the membrane cell columns of the local grid x."""
+        x = f64(x)
+        nx = len(x) - 1
+        eps, gl, gn, gk = np.zeros(nx), np.zeros(nx), np.zeros(nx), np.zeros(nx)
+        grp = np.zeros(nx, dtype=np.int32)
+        _chk(lib().ax1host_membrane_arrays(self.c, len(self.names), *self._iv(), self.smooth, self.def_perm,
+                                           self.def_dmemb, nx, _dp(x), _dp(eps), _dp(gl), _dp(gn), _dp(gk),
+                                           grp.ctypes.data_as(c_int_p)))
+        return eps, gl, gn, gk, grp
+
+    def check_processor_boundary(self, xmax_rank, forbidden="node_of_ranvier"):
+        fg = self.names.index(forbidden) if forbidden in self.names else -1
+        _chk(lib().ax1host_check_processor_boundary(self.c, *self._iv(), fg, self.dx_default, float(xmax_rank),
+                                                    self.xmax))
 
 
 # ------------------------------------------------------------------------------------------------

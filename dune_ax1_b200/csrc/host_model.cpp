@@ -213,6 +213,216 @@ int ax1host_slab(int nx_global, int nranks, int rank, int* c0, int* c1, int* l0,
   return AX1GPU_OK;
 }
 
+// ---- membrane groups (myelin / nodes of Ranvier) ------------------------------------------------
+// Ax1GridGenerator::setupXPartition (ax1_gridgenerator.hh:1238-1312): intervals of the groups that carry
+// position information (start, width, optional stride), sorted; gaps are filled with the default group.
+int ax1host_group_partition(const ax1host_membrane_group* groups, int ngroups, int default_group, double xmax,
+                            int* ival_group, double* ival_start, double* ival_end, int cap) {
+  if (!groups || ngroups < 1 || default_group < 0 || default_group >= ngroups) { ax1::set_error("bad membrane groups"); return AX1GPU_EINVAL; }
+  struct Ival { int g; double s, e; };
+  std::vector<Ival> iv;
+  for (int g = 0; g < ngroups; ++g) {
+    const double start = groups[g].start, width = groups[g].width, stride = groups[g].stride;
+    if (start > -1 && width > -1) {
+      iv.push_back({g, start, std::min(start + width, xmax)});
+      if (stride > -1) {
+        if (width > stride) { ax1::set_error("membrane group: width > stride"); return AX1GPU_EINVAL; }
+        double xn = start + stride;
+        while (xn < xmax) { iv.push_back({g, xn, std::min(xn + width, xmax)}); xn += stride; }
+      }
+    }
+  }
+  std::sort(iv.begin(), iv.end(), [](const Ival& a, const Ival& b) { return a.s < b.s; });
+  std::vector<Ival> out;
+  double last_end = 0.0;
+  for (const Ival& k : iv) {
+    if (k.s > last_end) out.push_back({default_group, last_end, k.s});
+    out.push_back(k);
+    last_end = k.e;
+  }
+  if (last_end < xmax) out.push_back({default_group, last_end, xmax});
+  last_end = 0.0;
+  for (const Ival& k : out) {  // checkPartition (:1314-1334)
+    if (k.s != last_end) { ax1::set_error("inconsistent membrane group partition"); return AX1GPU_EINVAL; }
+    last_end = k.e;
+  }
+  for (int k = 0; k < (int)out.size() && k < cap; ++k) {
+    if (ival_group) ival_group[k] = out[k].g;
+    if (ival_start) ival_start[k] = out[k].s;
+    if (ival_end) ival_end[k] = out[k].e;
+  }
+  return (int)out.size();
+}
+
+// Ax1GridGenerator::intervalVectorToGridVector (ax1_gridgenerator.hh:1021-1234): every interval is filled
+// with cells of the group's dx; a group with smoothTransition gets n_transition cells of dx_transition next
+// to a different group and (geometricRefinement) a geometric ramp (q = 0.7) between dx_transition and dx.
+int ax1host_generate_x_groups(const ax1host_membrane_group* groups, int ngroups, int nival, const int* ival_group,
+                              const double* ival_start, const double* ival_end, double dx_default, double xmax,
+                              double* out, int cap) {
+  const double q = 0.7;  // qTransition, ax1_gridgenerator.hh:62
+  Axis x;
+  x.p.push_back(0.0);
+  for (int it = 0; it < nival; ++it) {
+    const ax1host_membrane_group& G = groups[ival_group[it]];
+    const double start = ival_start[it], end = ival_end[it], my_width = end - start;
+    double remaining = my_width;
+    const double dx = G.dx > 0 ? G.dx : dx_default;
+    const bool trans_begin = it > 0 && ival_group[it] != ival_group[it - 1];
+    const bool trans_end = it < nival - 1 && ival_group[it] != ival_group[it + 1];
+    bool smooth_begin = false, smooth_end = false;
+    double dxt_l = 0.0, dxt_r = 0.0, geo_l = 0.0, geo_r = 0.0;
+    int nt_l = 0, nt_r = 0;
+    if (trans_begin && G.smooth_transition) {
+      const double last_w = ival_end[it - 1] - ival_start[it - 1];
+      dxt_l = G.dx_transition > 0 ? G.dx_transition : std::min(my_width, last_w);
+      nt_l = std::min(G.n_transition, (int)std::floor(remaining / dxt_l));
+      if (nt_l > 0) {
+        smooth_begin = true;
+        x.uniform_steps(nt_l, dxt_l);
+        remaining -= nt_l * dxt_l;
+      }
+    }
+    if (trans_end && G.smooth_transition) {
+      const double next_w = ival_end[it + 1] - ival_start[it + 1];
+      dxt_r = G.dx_transition > 0 ? G.dx_transition : std::min(my_width, next_w);
+      nt_r = std::min(G.n_transition, (int)std::floor(remaining / dxt_r));
+      if (nt_r > 0) {
+        smooth_end = true;
+        remaining -= nt_r * dxt_r;
+      }
+    }
+    if (G.geometric_refinement && remaining < my_width) {
+      if (smooth_begin) {
+        const int ng = (int)std::ceil(std::fabs(std::log(dxt_l / dx) / std::log(q)));
+        geo_l = dx * (std::pow(q, ng + 1) - 1) / (q - 1);
+      }
+      if (smooth_end) {
+        const int ng = (int)std::ceil(std::fabs(std::log(dxt_r / dx) / std::log(q)));
+        geo_r = dx * (std::pow(q, ng + 1) - 1) / (q - 1);
+      }
+      double rest = remaining - (geo_l + geo_r);
+      if (rest > dx) rest -= (int)std::floor(rest / dx) * dx;
+      if (smooth_begin && smooth_end) { geo_l += 0.5 * rest; geo_r += 0.5 * rest; }
+      else if (smooth_begin) geo_l += rest;
+      else geo_r += rest;
+      if (geo_l + geo_r > remaining) { ax1::set_error("membrane group too narrow for its geometric transition"); return AX1GPU_EINVAL; }
+      remaining -= geo_l + geo_r;
+      if (geo_l > 0.0) x.geometric(dxt_l, dx, x.last() + geo_l, true);
+    }
+    int n_x = 1;
+    double dx_eq = remaining;
+    if (remaining >= dx) { n_x = (int)std::round(remaining / dx); dx_eq = remaining / n_x; }
+    const double eq_range = n_x * dx_eq;
+    if (eq_range > 0) x.uniform_to(n_x, x.last() + eq_range);
+    if (trans_end && nt_r > 0) {
+      if (geo_r > 0.0) {
+        if (std::fabs(geo_r - (end - nt_r * dxt_r - x.last())) > 1e-6) { ax1::set_error("geometric refinement to the right went wrong"); return AX1GPU_EINVAL; }
+        x.geometric(dx, dxt_r, end - nt_r * dxt_r, false);
+      }
+      x.uniform_to(nt_r, end);
+    }
+  }
+  if (std::fabs(x.last() - xmax) > 1e-6) { ax1::set_error("x grid does not end at xmax"); return AX1GPU_EINVAL; }
+  if (out) for (int k = 0; k < (int)x.p.size() && k < cap; ++k) out[k] = x.p[k];
+  return (int)x.p.size();
+}
+
+// Per membrane cell column of a rank: group index (first interval with start < centre < end,
+// ax1_gridgenerator.hh:868-895), channel densities of that group, and the membrane permittivity of
+// Physics::initPermittivities (acme2_cyl_physics.hh:2424-2606) incl. the smooth-step blending
+// x^2 (3 - 2 x) over n_transition * dx_transition next to a group transition.
+int ax1host_membrane_arrays(const ax1host_membrane_group* groups, int ngroups, int nival, const int* ival_group,
+                            const double* ival_start, const double* ival_end, int smooth_permittivities,
+                            double default_permittivity, double default_dmemb, int nx, const double* x,
+                            double* eps_memb, double* g_leak, double* g_nav, double* g_kv, int* cell_group) {
+  if (nival < 1 || nx < 1) { ax1::set_error("bad arguments"); return AX1GPU_EINVAL; }
+  auto eff_perm = [&](int g) {
+    const double perm = groups[g].permittivity > 0 ? groups[g].permittivity : default_permittivity;
+    const double dm = groups[g].d_memb > 0 ? groups[g].d_memb : default_dmemb;
+    return perm * (default_dmemb / dm);
+  };
+  auto width_of = [&](int k) { return ival_end[k] - ival_start[k]; };
+  auto smooth_of = [&](int k) { return smooth_permittivities && groups[ival_group[k]].smooth_transition; };
+  auto dtrans_of = [&](int k, int other) {
+    const ax1host_membrane_group& G = groups[ival_group[k]];
+    const double dxt = G.dx_transition > 0 ? G.dx_transition : std::min(width_of(k), width_of(other));
+    return dxt * G.n_transition;
+  };
+  const double x_start = x[0];
+  int git = 0;
+  while (ival_end[git] < x_start && git != nival - 1) ++git;
+  bool right = x_start + 1e-6 > ival_start[git];
+  double cur = right ? ival_end[git] : ival_start[git];
+  double d_transition = dtrans_of(git, git + 1 != nival ? git + 1 : git);
+  bool smooth = smooth_of(git);
+  if (nival == 1) { d_transition = 0.0; smooth = false; }
+  for (int i = 0; i < nx; ++i) {
+    const double xc = 0.5 * (x[i] + x[i + 1]);
+    int grp = -1;
+    for (int k = 0; k < nival; ++k)
+      if (xc > ival_start[k] && xc < ival_end[k]) { grp = ival_group[k]; break; }
+    if (grp < 0) { ax1::set_error("membrane element could not be assigned to a group"); return AX1GPU_EINVAL; }
+    if (cell_group) cell_group[i] = grp;
+    if (g_leak) g_leak[i] = groups[grp].g_leak;
+    if (g_nav) g_nav[i] = groups[grp].g_nav;
+    if (g_kv) g_kv[i] = groups[grp].g_kv;
+    if (!eps_memb) continue;
+    bool updated = false;
+    if (!right && xc > cur + d_transition && git != nival - 1) {
+      cur = ival_end[git];
+      right = true;
+      updated = true;
+    } else if (right && xc > cur && git != nival - 1) {
+      ++git;
+      smooth = smooth_of(git);
+      if (!smooth && git != nival - 1) { cur = ival_end[git]; right = true; }
+      else { cur = ival_start[git]; right = false; }
+      updated = true;
+    }
+    if (updated) {
+      if (smooth && (right ? (git + 1 != nival) : (git != 0))) d_transition = dtrans_of(git, right ? git + 1 : git - 1);
+      else d_transition = 0.0;
+    }
+    if (smooth && d_transition > 0.0) {
+      const int gl = right ? git : git - 1, gr = right ? git + 1 : git;
+      if (smooth_of(gl) && smooth_of(gr)) { ax1::set_error("only one side of a group transition may have smoothTransition"); return AX1GPU_EINVAL; }
+      const double pl = eff_perm(ival_group[gl]), pr = eff_perm(ival_group[gr]);
+      double xs;
+      if (std::fabs(xc - cur) < d_transition) xs = right ? (xc - (cur - d_transition)) / d_transition : (xc - cur) / d_transition;
+      else xs = right ? 0.0 : 1.0;
+      eps_memb[i] = pl + (pr - pl) * (xs * xs * (3 - 2 * xs));
+    } else {
+      eps_memb[i] = eff_perm(grp);
+    }
+  }
+  return AX1GPU_OK;
+}
+
+// guard of makeMultidomainGrid (ax1_gridgenerator.hh:903-942): an interior processor boundary must not lie
+// inside group `forbidden_group` (node_of_ranvier) nor closer to a group transition than the safety distance
+int ax1host_check_processor_boundary(const ax1host_membrane_group* groups, int nival, const int* ival_group,
+                                     const double* ival_start, const double* ival_end, int forbidden_group,
+                                     double dx_default, double xmax_rank, double xmax_global) {
+  int gb = -1;
+  double nearest = 0.0;
+  for (int k = 0; k < nival; ++k) {
+    if (ival_start[k] < xmax_rank && ival_end[k] > xmax_rank) gb = ival_group[k];
+    if (std::fabs(ival_end[k] - xmax_rank) < std::fabs(nearest - xmax_rank)) nearest = ival_end[k];
+  }
+  if (gb >= 0 && gb == forbidden_group) { ax1::set_error("processor boundary is located at membrane group 'node_of_ranvier'"); return AX1GPU_EINVAL; }
+  double safety = dx_default;
+  if (gb >= 0 && groups[gb].smooth_transition) {
+    const double node_width = forbidden_group >= 0 ? groups[forbidden_group].width : 1.e3;
+    safety = (groups[gb].dx_transition > 0 ? groups[gb].dx_transition : node_width) * groups[gb].n_transition;
+  }
+  if (std::fabs(nearest - xmax_rank) < safety && xmax_rank != xmax_global) {
+    ax1::set_error("processor boundary is located very close to the next membrane group transition");
+    return AX1GPU_EINVAL;
+  }
+  return AX1GPU_OK;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------

@@ -371,10 +371,10 @@ void launch_ilu1_factor(const Dev& g, const double* A, double* LU, int slab_w, c
   ilu1_factor_kernel<<<nslab, nt, factor1_smem(g, slab_w), st>>>(g, A, LU, LU + (size_t)g.nv * 96, slab_w,
                                                                  slab1_rows(slab_w), lvl_tab);
 }
-template <bool P2P>
+int ilu_pick_stages(int nt, int bytes_per_thread_stage);  // solver.cu
+template <int D, bool P2P>
 static void launch_ilu1_apply_t(const Dev& g, const double* LU, const double* d, double* v, int slab_w,
                                 const int* lvl_tab, const HaloPush& hp, cudaStream_t st) {
-  constexpr int D = 2;
   const int nslab = (g.nvx + slab_w - 1) / slab_w;
   const int nt = slab1_threads(slab_w), nq = slab1_rows(slab_w);
   const size_t smem = (size_t)D * 4 * nq * (7 * 32 + 8) + 8 * (size_t)nq * 32 + (size_t)(slab_w + 3 * g.nvy) * sizeof(int);
@@ -385,10 +385,21 @@ static void launch_ilu1_apply_t(const Dev& g, const double* LU, const double* d,
   }
   ilu1_apply_kernel<D, P2P><<<nslab, nt, smem, st>>>(g, LU, LU + (size_t)g.nv * 96, d, v, slab_w, nq, lvl_tab, hp);
 }
+template <bool P2P>
+static void launch_ilu1_apply_d(const Dev& g, const double* LU, const double* d, double* v, int slab_w,
+                                const int* lvl_tab, const HaloPush& hp, cudaStream_t st) {
+  switch (ilu_pick_stages(4 * slab1_rows(slab_w), 7 * 32 + 8)) {
+    case 8: launch_ilu1_apply_t<8, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
+    case 6: launch_ilu1_apply_t<6, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
+    case 4: launch_ilu1_apply_t<4, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
+    case 3: launch_ilu1_apply_t<3, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
+    default: launch_ilu1_apply_t<2, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
+  }
+}
 void launch_ilu1_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, const int* lvl_tab,
                        cudaStream_t st, const HaloPush* hp) {
-  if (hp) launch_ilu1_apply_t<true>(g, LU, d, v, slab_w, lvl_tab, *hp, st);
-  else launch_ilu1_apply_t<false>(g, LU, d, v, slab_w, lvl_tab, HaloPush{}, st);
+  if (hp) launch_ilu1_apply_d<true>(g, LU, d, v, slab_w, lvl_tab, *hp, st);
+  else launch_ilu1_apply_d<false>(g, LU, d, v, slab_w, lvl_tab, HaloPush{}, st);
 }
 
 }  // namespace ax1

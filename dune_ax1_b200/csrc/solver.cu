@@ -483,9 +483,15 @@ void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, co
   }
   ilu_factor_kernel<<<nslab, nt, smem, st>>>(g, A, LU, LU + (size_t)g.nv * 64, slab_w, lvl_tab);
 }
-static int ilu_stages() {
-  static const int d = getenv("AX1_ILU_STAGES") ? atoi(getenv("AX1_ILU_STAGES")) : 2;
-  return d;
+// Depth of the cp.async pipeline of the sweeps. A level is consumed D levels after its loads were issued, so
+// the sweep advances one level per (HBM latency / D) unless bandwidth limits it first. With 256-thread CTAs
+// (sub-slabs of 128 columns) a stage is 43 KB and two stages x two CTAs per SM already saturate HBM; narrow
+// sub-slabs / small grids (paper and myelin configurations) are latency bound and get a deeper pipeline.
+int ilu_pick_stages(int nt, int bytes_per_thread_stage) {
+  static const int env = getenv("AX1_ILU_STAGES") ? atoi(getenv("AX1_ILU_STAGES")) : 0;
+  if (env > 0) return env;
+  const int d = (110 * 1024) / (nt * bytes_per_thread_stage);
+  return d >= 8 ? 8 : (d >= 6 ? 6 : (d >= 4 ? 4 : (d >= 3 ? 3 : 2)));
 }
 template <int D, bool P2P>
 static void launch_ilu_apply_t(const Dev& g, const double* LU, const double* d, double* v, int slab_w,
@@ -500,16 +506,22 @@ static void launch_ilu_apply_t(const Dev& g, const double* LU, const double* d, 
   }
   ilu_apply_kernel<D, P2P><<<nslab, nt, smem, st>>>(g, LU, LU + (size_t)g.nv * 64, d, v, slab_w, lvl_tab, hp);
 }
+template <bool P2P>
+static void launch_ilu_apply_d(const Dev& g, const double* LU, const double* d, double* v, int slab_w,
+                               const int* lvl_tab, const HaloPush& hp, cudaStream_t st) {
+  switch (ilu_pick_stages(slab_threads(slab_w), 5 * 32 + 8)) {
+    case 8: launch_ilu_apply_t<8, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
+    case 6: launch_ilu_apply_t<6, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
+    case 4: launch_ilu_apply_t<4, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
+    case 3: launch_ilu_apply_t<3, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
+    default: launch_ilu_apply_t<2, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
+  }
+}
 void launch_ilu_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, const int* lvl_tab,
                       cudaStream_t st, const HaloPush* hp) {
   // the inputs of the preconditioner are already zero on constrained DOFs (see driver.cu)
-  if (hp) { launch_ilu_apply_t<2, true>(g, LU, d, v, slab_w, lvl_tab, *hp, st); return; }
-  const HaloPush none{};
-  switch (ilu_stages()) {
-    case 3: launch_ilu_apply_t<3, false>(g, LU, d, v, slab_w, lvl_tab, none, st); break;
-    case 4: launch_ilu_apply_t<4, false>(g, LU, d, v, slab_w, lvl_tab, none, st); break;
-    default: launch_ilu_apply_t<2, false>(g, LU, d, v, slab_w, lvl_tab, none, st); break;
-  }
+  if (hp) launch_ilu_apply_d<true>(g, LU, d, v, slab_w, lvl_tab, *hp, st);
+  else launch_ilu_apply_d<false>(g, LU, d, v, slab_w, lvl_tab, HaloPush{}, st);
 }
 // sub-slab CTAs that own part of the left / right three halo vertex columns
 void halo_contributors(const Dev& g, int slab_w, int* left, int* right) {

@@ -93,6 +93,54 @@ def make_setup(nx, dx=None, xmax=None, stimulation=False, hh=True, equilibration
                 right_pb=right_pb, bc=bc, slab=(c0, c1, l0, l1))
 
 
+GOLDEN_MYELIN = os.path.join(_ROOT, "tests", "golden", "yasp_square10mm_myelin.json")
+
+
+def myelin_groups(xmax=48.0e6, node_stride=1000.0e3, node_start=500.0e3, node_width=1.0e3, dx=10.0e3):
+    """[membrane.*] sections of src/config/acme2_cyl_par_fiona_myelin_48mmx10mm_48nodes_...config
+    (docker-compose-myelin.yml): nodes of Ranvier every `node_stride`, myelin (default group) in between."""
+    groups = {
+        "node_of_ranvier": dict(start=node_start, width=node_width, stride=node_stride, permittivity=2.0, dx=100.0,
+                                smoothTransition=False, leak=0.5, Nav=1200.0, Kv=360.0),
+        "myelin": dict(permittivity=6.0, d_memb=500.0, smoothTransition=True, geometricRefinement=True,
+                       dx_transition=100.0, n_transition=10, leak=0.0, Nav=0.0, Kv=0.0),
+    }
+    return api.MembraneGroups(groups, "myelin", xmax, dx, smooth_permittivities=True)
+
+
+def make_myelin_setup(xmax=48.0e6, rank=0, nranks=1, stimulation=True, check_boundaries=True, **param_over):
+    """BASELINE config 5: the myelinated axon (48 mm x 10 mm, 48 nodes of Ranvier by default). Grid vector and
+    membrane arrays from the host model of Ax1GridGenerator / Physics; initial state = the two shipped
+    equilibrium columns (node / myelin, loadMultipleStates = yes, interpolateMultipleStates = no): a vertex
+    column takes the state of the group of the cell column to its right [approximation of the element-wise
+    PDELab interpolation of Ax1CoarseToFineGridTransferGridFunction, acme2_cyl_simloader.hh:257-290]."""
+    mg = myelin_groups(xmax)
+    xg = mg.x_vector()
+    nx = len(xg) - 1
+    y, ucol_node, _ = load_equilibrium_column()
+    y2, ucol_myel, _ = load_equilibrium_column(GOLDEN_MYELIN)
+    assert np.array_equal(y, y2)
+    c0, c1, l0, l1 = api.slab(nx, nranks, rank) if nranks > 1 else (0, nx, 0, nx)
+    if check_boundaries and nranks > 1 and rank < nranks - 1:
+        mg.check_processor_boundary(xg[c1])
+    x = xg[l0:l1 + 1].copy()
+    left_pb, right_pb = rank > 0, rank < nranks - 1
+    nxl = len(x) - 1
+    bc = api.BoundaryConfig()
+    cs, nvol, dm = api.physics_maps(x, y, xmin_global=0.0, xmax_global=xmax, bc=bc, left_pb=left_pb, right_pb=right_pb)
+    eps_memb, g_leak, g_nav, g_kv, grp = mg.membrane_arrays(x)
+    node = mg.names.index("node_of_ranvier")
+    vgrp = np.concatenate([grp, grp[-1:]])                      # vertex column -> group of the cell to its right
+    u0 = np.where((vgrp == node)[None, :, None], ucol_node[:, None, :], ucol_myel[:, None, :]).reshape(-1)
+    # square10mm-type stimulation at the first node (config: position_x = 500e3, I_inj = 1.1e11, t in (20, 3000) us)
+    params = dict(do_stimulation=int(stimulation), tinj_start=20.0, tinj_end=3.0e3, stim_x=500.0e3, stim_y=0.0,
+                  I_inj=1.1e11, do_equilibration=0, t_equilibrium=0.0, dummy_value=1.0)
+    params.update(param_over)
+    return dict(x=x, y=y, nx=nxl, ny=len(y) - 1, xmax=xmax, cell_subdomain=cs, node_volume=nvol, dirichlet=dm,
+                eps_memb=eps_memb, g_leak=g_leak, g_nav=g_nav, g_kv=g_kv, u0=u0, params=params, left_pb=left_pb,
+                right_pb=right_pb, bc=bc, slab=(c0, c1, l0, l1), xg=xg, groups=mg, cell_group=grp)
+
+
 def make_device(s, device=0, stream=None):
     p = api.default_params(**s["params"])
     return api.Ax1Gpu(s["x"], s["y"], s["cell_subdomain"], s["eps_memb"], s["node_volume"], s["dirichlet"], p,

@@ -187,6 +187,33 @@ int ax1host_physics_maps(const ax1gpu_grid* grid, double ymemb, double dmemb, do
  * interior cells [c0,c1) and local cells [l0,l1) incl. one overlap column per interior side. */
 int ax1host_slab(int nx_global, int nranks, int rank, int* c0, int* c1, int* l0, int* l1);
 
+/* ---- membrane groups ([membrane.<group>] sections: myelin / nodes of Ranvier) ---- */
+typedef struct ax1host_membrane_group {
+  double start, width, stride;   /* -1: key absent (a group without position is only used as default group) */
+  double dx;                     /* <= 0: [general] dx                                                      */
+  int smooth_transition, geometric_refinement;
+  double dx_transition;          /* <= 0: min(width of this interval, width of the neighbouring interval)   */
+  int n_transition;              /* default 10                                                              */
+  double permittivity, d_memb;   /* <= 0: membrane default (2.0) / [general] d_memb                         */
+  double g_leak, g_nav, g_kv;    /* channel densities [mS/cm^2]                                             */
+} ax1host_membrane_group;
+/* Ax1GridGenerator::setupXPartition (ax1_gridgenerator.hh:1238-1312); returns the number of intervals */
+int ax1host_group_partition(const ax1host_membrane_group* groups, int ngroups, int default_group, double xmax,
+                            int* ival_group, double* ival_start, double* ival_end, int cap);
+/* Ax1GridGenerator::intervalVectorToGridVector (:1021-1234); returns the number of x points */
+int ax1host_generate_x_groups(const ax1host_membrane_group* groups, int ngroups, int nival, const int* ival_group,
+                              const double* ival_start, const double* ival_end, double dx_default, double xmax,
+                              double* out, int cap);
+/* group index (:868-895), channel densities and Physics::initPermittivities (acme2_cyl_physics.hh:2424-2606)
+ * for the nx membrane cell columns of the local grid x[0..nx] */
+int ax1host_membrane_arrays(const ax1host_membrane_group* groups, int ngroups, int nival, const int* ival_group,
+                            const double* ival_start, const double* ival_end, int smooth_permittivities,
+                            double default_permittivity, double default_dmemb, int nx, const double* x,
+                            double* eps_memb, double* g_leak, double* g_nav, double* g_kv, int* cell_group);
+/* processor-boundary guard of makeMultidomainGrid (:903-942) */
+int ax1host_check_processor_boundary(const ax1host_membrane_group* groups, int nival, const int* ival_group,
+                                     const double* ival_start, const double* ival_end, int forbidden_group,
+                                     double dx_default, double xmax_rank, double xmax_global);
 
 /* ---- simulation-state files ("next" row 8(f)1): Ax1SimulationState ASCII format
  * (dune/ax1/common/ax1_simulationstate.hh:30-57, acme2_cyl_output.hh:937-979) and the x-extrapolation

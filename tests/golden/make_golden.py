@@ -13,7 +13,7 @@ import sys
 
 REF = "/root/reference/src/simulation_states/equilibrium/cyl"
 OUT = os.path.dirname(os.path.abspath(__file__))
-FILES = ["yasp_square10mm_p0.dat", "yasp_square1mm_p0.dat"]
+FILES = ["yasp_square10mm_p0.dat", "yasp_square1mm_p0.dat", "yasp_square10mm_myelin_p0.dat"]
 
 
 def parse(path):
