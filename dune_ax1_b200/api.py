@@ -47,7 +47,8 @@ class NewtonOpts(C.Structure):
         ("reduction", C.c_double), ("abs_limit", C.c_double), ("min_lin_reduction", C.c_double),
         ("fixed_lin_reduction", C.c_int), ("maxit", C.c_int), ("line_search_maxit", C.c_int),
         ("lin_maxit", C.c_int), ("force_iteration", C.c_int), ("disable_line_search", C.c_int),
-        ("slab_w", C.c_int), ("fixed_work", C.c_int), ("ilu_fill", C.c_int),
+        ("slab_w", C.c_int), ("fixed_work", C.c_int), ("ilu_fill", C.c_int), ("amg", C.c_int),
+        ("krylov", C.c_int), ("restart", C.c_int),
     ]
 
 
@@ -129,6 +130,8 @@ def lib():
     L.ax1gpu_set_jacobian.argtypes = [H, c_double_p]
     L.ax1gpu_get_jacobian.argtypes = [H, c_double_p]
     L.ax1gpu_solve.argtypes = [H, c_double_p, C.c_double, C.c_int, C.c_int, c_double_p, C.POINTER(LinResult)]
+    L.ax1gpu_solve_gmres.argtypes = [H, c_double_p, C.c_double, C.c_int, C.c_int, C.c_int, c_double_p,
+                                     C.POINTER(LinResult)]
     L.ax1gpu_newton.argtypes = [H, C.POINTER(NewtonOpts), c_double_p, C.POINTER(NewtonResult)]
     L.ax1gpu_upload_u.argtypes = [H, c_double_p]
     L.ax1gpu_download_u.argtypes = [H, c_double_p]
@@ -137,6 +140,7 @@ def lib():
     L.ax1gpu_spmv.argtypes = [H, c_double_p, c_double_p]
     L.ax1gpu_ilu_factor.argtypes = [H, C.c_int]
     L.ax1gpu_ilu_factor_n.argtypes = [H, C.c_int, C.c_int]
+    L.ax1gpu_set_amg.argtypes = [H, C.c_int, C.c_int]
     L.ax1gpu_ilu_apply.argtypes = [H, c_double_p, c_double_p]
     L.ax1gpu_rownorm.argtypes = [H, c_double_p]
     L.ax1gpu_time_kernel.argtypes = [H, C.c_char_p, C.c_int, c_double_p]
@@ -496,6 +500,10 @@ class Ax1Gpu:
         """SeqILUn(A, n=fill, 1.0) on the device Jacobian; fill < 0 keeps the handle's current level."""
         _chk(lib().ax1gpu_ilu_factor_n(self.h, int(slab_w), int(fill)))
 
+    def set_amg(self, on=True, cx=0):
+        """Preconditioner = one V(1,1) cycle of the x-aggregation AMG (block-ILU smoothers) instead of the ILU alone."""
+        _chk(lib().ax1gpu_set_amg(self.h, int(on), int(cx)))
+
     def ilu_apply(self, d):
         v = np.zeros(self.n)
         _chk(lib().ax1gpu_ilu_apply(self.h, _dp(f64(d)), _dp(v)))
@@ -509,6 +517,18 @@ class Ax1Gpu:
             self.ilu_factor(slab_w, fill)
             slab_w = 0
         _chk(lib().ax1gpu_solve(self.h, _dp(r), float(reduction), int(maxit), int(slab_w), _dp(z), C.byref(res)))
+        return z, r, res
+
+    def solve_gmres(self, r, reduction, restart=100, maxit=5000, slab_w=0, fill=-1):
+        """Dune::RestartedGMResSolver with the handle's preconditioner (ISTLBackend_GMRES_AMG::apply)."""
+        r = f64(r).copy()
+        z = np.zeros(self.n)
+        res = LinResult()
+        if fill >= 0:
+            self.ilu_factor(slab_w, fill)
+            slab_w = 0
+        _chk(lib().ax1gpu_solve_gmres(self.h, _dp(r), float(reduction), int(restart), int(maxit), int(slab_w),
+                                      _dp(z), C.byref(res)))
         return z, r, res
 
     # -- Newton
@@ -628,6 +648,27 @@ class ISTLBackend_SEQ_BCGS_ILUn(ISTLBackend_BCGS_ILU0):
         r[:] = rr
 
 
+class ISTLBackend_GMRES_AMG_ILU0(ISTLBackend_BCGS_ILU0):
+    """LS of the myelin build: ISTLBackend_GMRES_AMG_ILU0(gfs, maxiter, verbose, reuse, usesuperlu)
+    (ax1_solverbackend.hh:279-302, acme2_cyl_setup.hh:749-760): RestartedGMRes(100) preconditioned by one
+    multigrid cycle with ILU0 smoothers. On the device the aggregates are `cx` vertex columns (csrc/amg.cu)."""
+
+    def __init__(self, dev, maxiter=5000, verbose=0, reuse=False, usesuperlu=True, slab_w=0, restart=100, cx=4):
+        super().__init__(dev, maxiter, slab_w, verbose)
+        self.restart, self.cx = int(restart), int(cx)
+
+    def apply(self, A, z, r, reduction):
+        if A is not None:
+            self.dev.set_jacobian(A)
+        self.dev.set_amg(True, self.cx)
+        try:
+            zz, rr, self.res = self.dev.solve_gmres(r, reduction, self.restart, self.maxiter, self.slab_w, fill=0)
+        finally:
+            self.dev.set_amg(False)
+        z[:] = zz
+        r[:] = rr
+
+
 class MembraneFlux:
     """gfMembFlux: implicit membrane flux grid function state (channels)."""
 
@@ -661,6 +702,8 @@ class Ax1Newton:
     def setLinearSolverMaxIterations(self, v): self.opts.lin_maxit = int(v)
     def setSlabWidth(self, v): self.opts.slab_w = int(v)
     def setIluFill(self, n): self.opts.ilu_fill = int(n)
+    def setAmg(self, on): self.opts.amg = int(on)
+    def setKrylov(self, gmres, restart=100): self.opts.krylov, self.opts.restart = int(gmres), int(restart)
 
     def apply(self, u):
         unew, self.res = self.dev.newton(u, self.opts)

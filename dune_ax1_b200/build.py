@@ -16,6 +16,7 @@ UNITS = [
     ("boundary_fd.cu", ["--fmad=false"]),
     ("solver.cu", []),
     ("ilu1.cu", []),
+    ("amg.cu", []),
     ("driver.cu", []),
     ("capi.cu", []),
     ("host_model.cpp", []),

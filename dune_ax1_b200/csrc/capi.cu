@@ -57,7 +57,8 @@ void ax1gpu_params_default(ax1gpu_params* p) {
 void ax1gpu_newton_opts_default(ax1gpu_newton_opts* o) {
   o->reduction = 1e-5; o->abs_limit = 1e-5; o->min_lin_reduction = 1e-5;
   o->fixed_lin_reduction = 0; o->maxit = 50; o->line_search_maxit = 10; o->lin_maxit = 5000;
-  o->force_iteration = 0; o->disable_line_search = 0; o->slab_w = 0; o->fixed_work = 0; o->ilu_fill = 0;
+  o->force_iteration = 0; o->disable_line_search = 0; o->slab_w = 0; o->fixed_work = 0; o->ilu_fill = 0; o->amg = 0;
+  o->krylov = 0; o->restart = 100;
 }
 
 int ax1gpu_sizeof_params(void) { return (int)sizeof(ax1gpu_params); }
@@ -200,6 +201,9 @@ int ax1gpu_destroy(ax1gpu_handle c) {
   if (!c) return AX1GPU_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  drv_amg_free(c);
+  if (c->d_gmV) cudaFree(c->d_gmV);
+  if (c->d_gm) cudaFree(c->d_gm);
   if (c->p2p.win) {
     for (int k = 0; k < c->nranks && k < AX1_MAX_RANKS; ++k)
       if (k != c->rank && c->p2p.peer[k]) cudaIpcCloseMemHandle(c->p2p.peer[k]);
@@ -402,6 +406,20 @@ int ax1gpu_ilu_factor_n(ax1gpu_handle c, int slab_w, int fill) {
   return AX1GPU_OK;
 }
 
+int ax1gpu_set_amg(ax1gpu_handle c, int on, int cx) {
+  AX1_CHECK_H(c);
+  if (cx > 0 && cx != c->amg_cx) {
+    if (cx < 2 || cx > 64) { set_error("amg: columns per aggregate must be in [2, 64]"); return AX1GPU_EINVAL; }
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    drv_amg_free(c);
+    c->amg_cx = cx;
+  }
+  c->amg = on ? 1 : 0;
+  c->factored = false;
+  return AX1GPU_OK;
+}
+
 int ax1gpu_ilu_apply(ax1gpu_handle c, const double* d, double* v) {
   AX1_CHECK_H(c);
   cudaSetDevice(c->device);
@@ -420,6 +438,21 @@ int ax1gpu_solve(ax1gpu_handle c, double* r, double reduction, int maxit, int sl
   if (!c->factored || (slab_w > 0 && slab_w != c->slab_w)) { if ((rc = drv_factor(c, slab_w))) return rc; }
   ax1gpu_lin_result lr{};
   if ((rc = drv_solve(c, c->d_r, c->d_z, reduction, maxit, &lr))) return rc;
+  if (res) *res = lr;
+  if (z) { if ((rc = down(c, z, c->d_z))) return rc; }
+  if (r) { if ((rc = down(c, r, c->d_r))) return rc; }
+  return AX1GPU_OK;
+}
+
+int ax1gpu_solve_gmres(ax1gpu_handle c, double* r, double reduction, int restart, int maxit, int slab_w, double* z,
+                       ax1gpu_lin_result* res) {
+  AX1_CHECK_H(c);
+  cudaSetDevice(c->device);
+  int rc;
+  if (r) { if ((rc = up(c, c->d_r, r))) return rc; }
+  if (!c->factored || (slab_w > 0 && slab_w != c->slab_w)) { if ((rc = drv_factor(c, slab_w))) return rc; }
+  ax1gpu_lin_result lr{};
+  if ((rc = drv_solve_gmres(c, c->d_r, c->d_z, reduction, restart, maxit, &lr))) return rc;
   if (res) *res = lr;
   if (z) { if ((rc = down(c, z, c->d_z))) return rc; }
   if (r) { if ((rc = down(c, r, c->d_r))) return rc; }

@@ -47,6 +47,22 @@ struct ax1gpu_ctx {
   size_t lvl_cap = 0;          // ints allocated for d_lvl
   size_t lu_cap = 0;           // doubles allocated for d_LU (144 per vertex for ILU0, 208 for ILU(1))
   bool factored = false;
+  // aggregation multigrid on top of the ILU smoother (amg.cu); level 0 = (g, d_A, d_LU)
+  struct AmgLevel {
+    ax1::Dev g{};
+    int slab_w = 0;
+    double *A = nullptr, *LU = nullptr, *b = nullptr, *x = nullptr;
+    int* lvl = nullptr;
+  };
+  int amg = 0;                 // 0: ILU only, 1: V(1,1) cycle of x-aggregation AMG with block-ILU smoothers
+  int amg_cx = 4;              // vertex columns per aggregate
+  int amg_slab_w = 0;          // level-0 slab width the hierarchy was built for
+  std::vector<AmgLevel> amg_levels;   // coarse levels 1..L-1
+  double* d_amg_t = nullptr;   // level-0 scratch (defect / smoother output)
+  // restarted GMRES (driver.cu: drv_solve_gmres), allocated by the first GMRES solve
+  double* d_gmV = nullptr;     // Krylov basis, gm_cap + 1 vectors
+  double* d_gm = nullptr;      // Hessenberg matrix, rotations, scalars
+  int gm_cap = 0;              // restart length the buffers hold
   // multi-GPU
   ax1::NcclApi nccl;
   ncclComm_t comm = nullptr;
@@ -74,10 +90,13 @@ int drv_update_state(ax1gpu_ctx* c, const double* d_u);
 int drv_accept_state(ax1gpu_ctx* c);
 int drv_residual(ax1gpu_ctx* c, const double* d_u, double* d_r, double* norm_host);
 int drv_jacobian(ax1gpu_ctx* c, const double* d_u);
-int drv_factor(ax1gpu_ctx* c, int slab_w, int fill = -1);  // fill < 0: keep c->ilu_fill
+int drv_factor(ax1gpu_ctx* c, int slab_w, int fill = -1, int amg = -1);  // < 0: keep the handle's setting
 int drv_prec_apply(ax1gpu_ctx* c, const double* d, double* v);
+void drv_amg_free(ax1gpu_ctx* c);
 int drv_op_apply(ax1gpu_ctx* c, const double* x, double* y);
 int drv_solve(ax1gpu_ctx* c, double* d_rhs, double* d_zout, double reduction, int maxit, ax1gpu_lin_result* res);
+int drv_solve_gmres(ax1gpu_ctx* c, double* d_rhs, double* d_zout, double reduction, int restart, int maxit,
+                    ax1gpu_lin_result* res);
 int drv_newton(ax1gpu_ctx* c, const ax1gpu_newton_opts* o, ax1gpu_newton_result* res);
 int drv_norm(ax1gpu_ctx* c, const double* a, double* out_host);
 int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms);

@@ -117,14 +117,154 @@ __global__ void __launch_bounds__(256) newton_update_kernel(int nv, double* u, c
   }
 }
 
-enum { OP_NONE = -1, OP_NORM0 = 0, OP_H, OP_NORM_A, OP_OMEGA, OP_NORM_B, OP_PLAIN_NORM };
+// ---- restarted GMRES vector kernels (modified Gram-Schmidt) ----
+// w -= gm[GM_SCALE] * vprev (if vprev), then the partial of <w, vk> (vk == nullptr: <w, w>), owner-masked
+__global__ void __launch_bounds__(256) gmres_mgs_kernel(int nv, double* w, const double* __restrict__ vprev,
+                                                        const double* __restrict__ vk, const double* gm,
+                                                        const Scalars* sc, Own own, double* partials) {
+  double s[2] = {0.0, 0.0};
+  if (!sc->done) {
+    const double h = vprev ? gm[1] : 0.0;   // GM_SCALE
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
+      double wv[4];
+      ld4v(w + 4 * (size_t)k, wv);
+      if (vprev) {
+        double pv[4];
+        ld4v(vprev + 4 * (size_t)k, pv);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wv[c] += (-h) * pv[c];
+        st4v(w + 4 * (size_t)k, wv);
+      }
+      if (owned(own, k)) {
+        if (vk) {
+          double kv[4];
+          ld4v(vk + 4 * (size_t)k, kv);
+          s[0] += wv[0] * kv[0]; s[0] += wv[1] * kv[1]; s[0] += wv[2] * kv[2]; s[0] += wv[3] * kv[3];
+        } else {
+          s[0] += wv[0] * wv[0]; s[0] += wv[1] * wv[1]; s[0] += wv[2] * wv[2]; s[0] += wv[3] * wv[3];
+        }
+      }
+    }
+  }
+  block_reduce_store<2>(s, partials);
+}
+// dst = src * gm[GM_SCALE]
+__global__ void __launch_bounds__(256) gmres_scale_kernel(int nv, double* dst, const double* src, const double* gm,
+                                                          const Scalars* sc) {
+  if (sc->done) return;
+  const double a = gm[1];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
+    double v[4];
+    ld4v(src + 4 * (size_t)k, v);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] *= a;
+    st4v(dst + 4 * (size_t)k, v);
+  }
+}
+// RestartedGMResSolver::update: back substitution y = H^-1 s over the cnt columns of this cycle
+__global__ void gmres_ysolve_kernel(double* gm) {
+  const int m = (int)gm[3], cnt = (int)gm[2];
+  const double* H = gm + 8;
+  const double* sv = H + (size_t)(m + 1) * m + 2 * (size_t)m;
+  double* y = gm + 8 + (size_t)(m + 1) * m + 3 * (size_t)m + 1;
+  for (int a = 0; a < cnt; ++a) y[a] = sv[a];
+  for (int a = cnt - 1; a >= 0; --a) {
+    y[a] /= H[(size_t)a * m + a];
+    for (int c = a - 1; c >= 0; --c) y[c] -= H[(size_t)c * m + a] * y[a];
+  }
+}
+// w = sum_{c < cnt} y[c] V_c ; x += w
+__global__ void __launch_bounds__(256) gmres_combine_kernel(int nv, const double* __restrict__ V, size_t ldv,
+                                                            const double* gm, double* w, double* x) {
+  const int m = (int)gm[3], cnt = (int)gm[2];
+  const double* y = gm + 8 + (size_t)(m + 1) * m + 3 * (size_t)m + 1;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = 0; c < cnt; ++c) {
+      double v[4];
+      ld4v(V + (size_t)c * ldv + 4 * (size_t)k, v);
+      const double yc = y[c];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] += yc * v[q];
+    }
+    double xv[4];
+    ld4v(x + 4 * (size_t)k, xv);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) xv[q] += acc[q];
+    st4v(w + 4 * (size_t)k, acc);
+    st4v(x + 4 * (size_t)k, xv);
+  }
+}
 
-// the Krylov scalar recurrences of Dune::BiCGSTABSolver, executed by one thread on the device
-__device__ void scalar_step(int op, Scalars* sc, const double* sums, double reduction, double* out) {
+enum { OP_NONE = -1, OP_NORM0 = 0, OP_H, OP_NORM_A, OP_OMEGA, OP_NORM_B, OP_PLAIN_NORM, OP_G_BETA, OP_G_H, OP_G_NORMW };
+
+// device-resident state of the restarted GMRES (one flat double array `gm`): scalars, then the Hessenberg
+// matrix H[(m+1) x m] (row-major), the Givens rotations cs[m], sn[m], the rotated rhs s[m+1] and y[m]
+enum { GM_BETA = 0, GM_SCALE = 1, GM_CNT = 2, GM_M = 3, GM_H = 8 };
+__host__ __device__ inline size_t gm_len(int m) { return GM_H + (size_t)(m + 1) * m + 4 * (size_t)m + 8; }
+
+// Dune::RestartedGMResSolver::generatePlaneRotation / applyPlaneRotation (dune-istl 2.3 solvers.hh) [ext]
+__device__ inline void gm_generate_rotation(double dx, double dy, double& cs, double& sn) {
+  if (dy == 0.0) { cs = 1.0; sn = 0.0; }
+  else if (fabs(dy) > fabs(dx)) { const double t = dx / dy; sn = 1.0 / sqrt(1.0 + t * t); cs = t * sn; }
+  else { const double t = dy / dx; cs = 1.0 / sqrt(1.0 + t * t); sn = t * cs; }
+}
+__device__ inline void gm_apply_rotation(double& dx, double& dy, double cs, double sn) {
+  const double t = cs * dx + sn * dy;
+  dy = -sn * dx + cs * dy;
+  dx = t;
+}
+
+// the Krylov scalar recurrences of Dune::BiCGSTABSolver / Dune::RestartedGMResSolver, executed by one
+// thread on the device. GMRES ops: out = the gm array, aux = step indices.
+__device__ void scalar_step(int op, Scalars* sc, const double* sums, double reduction, double* out, int aux) {
   const double EPSILON = 1e-80;
   if (op == OP_PLAIN_NORM) { out[0] = sqrt(sums[0]); return; }
   if (sc->done) return;
   switch (op) {
+    case OP_G_BETA: {   // beta = |M^-1 (b - A x)| at the start (aux = 1) / after a restart (aux = 0)
+      double* gm = out;
+      const int m = (int)gm[GM_M];
+      double* sv = gm + GM_H + (size_t)(m + 1) * m + 2 * (size_t)m;
+      const double beta = sqrt(sums[0]);
+      gm[GM_BETA] = beta;
+      if (aux) { sc->norm0 = beta == 0.0 ? 1.0 : beta; sc->it_half = 0.0; sc->converged = 0; sc->breakdown = 0; }
+      sc->norm = beta;
+      if (aux ? beta <= reduction * sc->norm0 : beta < reduction * sc->norm0) { sc->converged = 1; sc->done = 1; break; }
+      gm[GM_SCALE] = 1.0 / beta;
+      gm[GM_CNT] = 0.0;
+      sv[0] = beta;
+      for (int i = 1; i <= m; ++i) sv[i] = 0.0;
+      break;
+    }
+    case OP_G_H: {      // H[k][i] = <w, v_k>, aux = k * 1024 + i
+      double* gm = out;
+      const int m = (int)gm[GM_M], k = aux >> 10, i = aux & 1023;
+      gm[GM_H + (size_t)k * m + i] = sums[0];
+      gm[GM_SCALE] = sums[0];
+      break;
+    }
+    case OP_G_NORMW: {  // H[i+1][i] = |w|, Givens update of column i, residual estimate |s[i+1]|
+      double* gm = out;
+      const int m = (int)gm[GM_M], i = aux;
+      double* H = gm + GM_H;
+      double* cs = H + (size_t)(m + 1) * m;
+      double* sn = cs + m;
+      double* sv = sn + m;
+      const double hn = sqrt(sums[0]);
+      H[(size_t)(i + 1) * m + i] = hn;
+      if (hn == 0.0) { sc->breakdown = 1; sc->done = 1; break; }
+      gm[GM_SCALE] = 1.0 / hn;
+      for (int k = 0; k < i; ++k) gm_apply_rotation(H[(size_t)k * m + i], H[(size_t)(k + 1) * m + i], cs[k], sn[k]);
+      gm_generate_rotation(H[(size_t)i * m + i], H[(size_t)(i + 1) * m + i], cs[i], sn[i]);
+      gm_apply_rotation(H[(size_t)i * m + i], H[(size_t)(i + 1) * m + i], cs[i], sn[i]);
+      gm_apply_rotation(sv[i], sv[i + 1], cs[i], sn[i]);
+      sc->norm = fabs(sv[i + 1]);
+      sc->it_half += 1.0;
+      gm[GM_CNT] = (double)(i + 1);
+      if (sc->norm < reduction * sc->norm0) { sc->converged = 1; sc->done = 1; }
+      break;
+    }
     case OP_NORM0:
       sc->norm = sc->norm0 = sqrt(sums[0]);
       sc->rho = sc->alpha = sc->omega = 1.0;
@@ -161,7 +301,7 @@ __device__ void scalar_step(int op, Scalars* sc, const double* sums, double redu
 
 // partials -> sums (fixed order) and, on one GPU, the scalar recurrence in the same launch
 __global__ void __launch_bounds__(1024) reduce_final_kernel(const double* partials, int nblocks, double* sums, int op,
-                                                            Scalars* sc, double reduction, double* out) {
+                                                            Scalars* sc, double reduction, double* out, int aux) {
   __shared__ double sh[2][32];
   double s[2] = {0.0, 0.0};
   for (int k = threadIdx.x; k < nblocks; k += blockDim.x) { s[0] += partials[k]; s[1] += partials[nblocks + k]; }
@@ -179,7 +319,7 @@ __global__ void __launch_bounds__(1024) reduce_final_kernel(const double* partia
     for (int o = 16; o > 0; o >>= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
     if (lane == 0) {
       sums[0] = t0; sums[1] = t1;
-      if (op != OP_NONE) scalar_step(op, sc, sums, reduction, out);
+      if (op != OP_NONE) scalar_step(op, sc, sums, reduction, out, aux);
     }
   }
 }
@@ -190,7 +330,7 @@ __global__ void __launch_bounds__(1024) reduce_final_kernel(const double* partia
 // rank order -> all ranks obtain bitwise identical sums (they must take identical convergence decisions).
 __global__ void __launch_bounds__(1024) reduce_final_p2p_kernel(const double* partials, int nblocks, double* sums, int op,
                                                                 Scalars* sc, double reduction, double* out, RedP2P rp,
-                                                                int* err) {
+                                                                int* err, int aux) {
   __shared__ double sh[2][32];
   double s[2] = {0.0, 0.0};
   for (int k = threadIdx.x; k < nblocks; k += blockDim.x) { s[0] += partials[k]; s[1] += partials[nblocks + k]; }
@@ -224,7 +364,7 @@ __global__ void __launch_bounds__(1024) reduce_final_p2p_kernel(const double* pa
     for (int k = 0; k < rp.nranks; ++k) { r0 += __shfl_sync(0xffffffffu, a0, k); r1 += __shfl_sync(0xffffffffu, a1, k); }
     if (lane == 0) {
       sums[0] = r0; sums[1] = r1;
-      if (op != OP_NONE) scalar_step(op, sc, sums, reduction, out);
+      if (op != OP_NONE) scalar_step(op, sc, sums, reduction, out, aux);
     }
   }
 }
@@ -244,8 +384,8 @@ __global__ void halo_wait_add_kernel(Dev g, double* v, const double* slot, const
   v[4 * (size_t)(c0 + c + g.nvx * j) + k] += reinterpret_cast<const volatile double*>(slot)[t];
 }
 
-__global__ void scalar_kernel(int op, Scalars* sc, const double* sums, double reduction, double* out) {
-  scalar_step(op, sc, sums, reduction, out);
+__global__ void scalar_kernel(int op, Scalars* sc, const double* sums, double reduction, double* out, int aux) {
+  scalar_step(op, sc, sums, reduction, out, aux);
 }
 
 // halo pack / unpack-add of 3 vertex columns per processor-boundary side
@@ -279,28 +419,29 @@ static inline Own own_of(const ax1gpu_ctx* c) { return Own{c->own_lo, c->own_hi,
 
 // partials -> sums (+ allreduce over ranks) -> scalar recurrence `op`
 static int reduce_op_from(ax1gpu_ctx* c, const double* partials, int nblocks, int nsums, int op, double reduction,
-                          double* out = nullptr) {
+                          double* out = nullptr, int aux = 0) {
   if (c->nranks > 1 && c->p2p.on) {
     RedP2P rp;
     for (int k = 0; k < AX1_MAX_RANKS; ++k) rp.peer[k] = c->p2p.peer[k];
     rp.rank = c->rank; rp.nranks = c->nranks; rp.seq = ++c->p2p.red_seq;
     reduce_final_p2p_kernel<<<1, 1024, 0, c->stream>>>(partials, nblocks, c->d_sums, op, c->d_sc, reduction, out, rp,
-                                                       c->d_err + 2);
+                                                       c->d_err + 2, aux);
     AX1_LAUNCH_CHECK(c);
   } else if (c->nranks > 1) {
-    reduce_final_kernel<<<1, 1024, 0, c->stream>>>(partials, nblocks, c->d_sums, OP_NONE, c->d_sc, reduction, out);
+    reduce_final_kernel<<<1, 1024, 0, c->stream>>>(partials, nblocks, c->d_sums, OP_NONE, c->d_sc, reduction, out, aux);
     AX1_LAUNCH_CHECK(c);
     AX1_NCCL(c, c->nccl.AllReduce(c->d_sums, c->d_sums, nsums, ncclDouble, ncclSum, c->comm, c->stream));
-    scalar_kernel<<<1, 1, 0, c->stream>>>(op, c->d_sc, c->d_sums, reduction, out);
+    scalar_kernel<<<1, 1, 0, c->stream>>>(op, c->d_sc, c->d_sums, reduction, out, aux);
     AX1_LAUNCH_CHECK(c);
   } else {
-    reduce_final_kernel<<<1, 1024, 0, c->stream>>>(partials, nblocks, c->d_sums, op, c->d_sc, reduction, out);
+    reduce_final_kernel<<<1, 1024, 0, c->stream>>>(partials, nblocks, c->d_sums, op, c->d_sc, reduction, out, aux);
     AX1_LAUNCH_CHECK(c);
   }
   return 0;
 }
-static int reduce_op(ax1gpu_ctx* c, int nblocks, int nsums, int op, double reduction, double* out = nullptr) {
-  return reduce_op_from(c, c->d_partials, nblocks, nsums, op, reduction, out);
+static int reduce_op(ax1gpu_ctx* c, int nblocks, int nsums, int op, double reduction, double* out = nullptr,
+                     int aux = 0) {
+  return reduce_op_from(c, c->d_partials, nblocks, nsums, op, reduction, out, aux);
 }
 
 static int halo_add(ax1gpu_ctx* c, double* v) {
@@ -446,52 +587,185 @@ static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill) {
   return ensure_level_tables(c);
 }
 
-int drv_factor(ax1gpu_ctx* c, int slab_w, int fill) {
+// ---- aggregation multigrid (see amg.cu) ------------------------------------------------------
+static void amg_free(ax1gpu_ctx* c) {
+  for (auto& L : c->amg_levels) {
+    cudaFree(L.A); cudaFree(L.LU); cudaFree(L.b); cudaFree(L.x); cudaFree(L.lvl);
+  }
+  c->amg_levels.clear();
+}
+void drv_amg_free(ax1gpu_ctx* c) {
+  amg_free(c);
+  if (c->d_amg_t) { cudaFree(c->d_amg_t); c->d_amg_t = nullptr; }
+}
+
+// allocate the hierarchy: nvx -> ceil(nvx / cx) -> ... until a level has at most 2 cx vertex columns
+static int amg_allocate(ax1gpu_ctx* c) {
+  if (!c->amg_levels.empty() && c->amg_slab_w == c->slab_w) return 0;
+  AX1_CUDA(cudaStreamSynchronize(c->stream));
+  amg_free(c);
+  if (!c->d_amg_t) AX1_CUDA(cudaMalloc((void**)&c->d_amg_t, 4 * (size_t)c->g.nv * sizeof(double)));
+  int nvx = c->g.nvx;
+  while (nvx > 2 * c->amg_cx) {
+    ax1gpu_ctx::AmgLevel L;
+    nvx = (nvx + c->amg_cx - 1) / c->amg_cx;
+    L.g = c->g;
+    L.g.nx = nvx - 1; L.g.nvx = nvx; L.g.nv = nvx * c->g.nvy;
+    L.g.dmask = nullptr;
+    L.slab_w = std::min(c->slab_w, nvx);
+    const size_t nv = L.g.nv;
+    AX1_CUDA(cudaMalloc((void**)&L.A, nv * AX1_ROW * sizeof(double)));
+    AX1_CUDA(cudaMalloc((void**)&L.LU, nv * 144 * sizeof(double)));
+    AX1_CUDA(cudaMalloc((void**)&L.b, 4 * nv * sizeof(double)));
+    AX1_CUDA(cudaMalloc((void**)&L.x, 4 * nv * sizeof(double)));
+    std::vector<int> tab;
+    ilu_level_tables(L.g, L.slab_w, tab);
+    AX1_CUDA(cudaMalloc((void**)&L.lvl, tab.size() * sizeof(int)));
+    AX1_CUDA(cudaMemcpy(L.lvl, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+    c->amg_levels.push_back(L);
+  }
+  c->amg_slab_w = c->slab_w;
+  return 0;
+}
+
+// Galerkin coarse operators + their ILU0 factors (after the level-0 factorisation)
+static int amg_setup(ax1gpu_ctx* c) {
+  int rc = amg_allocate(c);
+  if (rc) return rc;
+  const double* Af = c->d_A;
+  int nvx_f = c->g.nvx;
+  const uint8_t* mask = c->g.dmask;
+  for (auto& L : c->amg_levels) {
+    launch_galerkin_x(nvx_f, L.g.nvx, c->g.nvy, c->amg_cx, Af, L.A, mask, c->stream);
+    AX1_LAUNCH_CHECK(c);
+    launch_ilu_factor(L.g, L.A, L.LU, L.slab_w, L.lvl, c->stream);
+    AX1_LAUNCH_CHECK(c);
+    Af = L.A; nvx_f = L.g.nvx; mask = nullptr;
+  }
+  return 0;
+}
+
+static int smoother0(ax1gpu_ctx* c, const double* d, double* v) {  // level-0 smoother: block ILU(fill)
+  if (c->ilu_fill == 1) launch_ilu1_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
+  else launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
+  AX1_LAUNCH_CHECK(c);
+  return 0;
+}
+
+// v = V(1,1)-cycle applied to d (zero initial guess on every level). Level 0 is (g, d_A, d_LU); level l >= 1
+// is amg_levels[l-1]. Scratch of level-0 size serves every level: d_amg_t = defect, d_tmp = smoother output.
+static int amg_vcycle(ax1gpu_ctx* c, const double* d, double* v) {
+  const int nl = (int)c->amg_levels.size();
+  const int cx = c->amg_cx, nvy = c->g.nvy;
+  struct View { Dev g; const double* A; const double* b; double* x; const uint8_t* mask; };
+  auto view = [&](int l) -> View {
+    if (l == 0) return View{c->g, c->d_A, d, v, c->g.dmask};
+    auto& L = c->amg_levels[l - 1];
+    return View{L.g, L.A, L.b, L.x, nullptr};
+  };
+  auto smooth = [&](int l, const double* rhs, double* out) -> int {
+    if (l == 0) return smoother0(c, rhs, out);
+    auto& L = c->amg_levels[l - 1];
+    launch_ilu_apply(L.g, L.LU, rhs, out, L.slab_w, L.lvl, c->stream);
+    AX1_LAUNCH_CHECK(c);
+    return 0;
+  };
+  int rc;
+  if ((rc = smooth(0, d, v))) return rc;                       // pre-smoothing from zero
+  for (int l = 0; l < nl; ++l) {                               // down
+    const View F = view(l);
+    auto& C = c->amg_levels[l];
+    launch_spmv_residual(F.g, F.A, F.x, F.b, c->d_amg_t, 0, c->stream);
+    AX1_LAUNCH_CHECK(c);
+    launch_restrict_x(F.g.nvx, C.g.nvx, nvy, cx, c->d_amg_t, C.b, F.mask, c->stream);
+    AX1_LAUNCH_CHECK(c);
+    if ((rc = smooth(l + 1, C.b, C.x))) return rc;
+  }
+  for (int l = nl - 1; l >= 0; --l) {                          // up
+    const View F = view(l);
+    auto& C = c->amg_levels[l];
+    launch_prolong_add_x(F.g.nvx, C.g.nvx, nvy, cx, C.x, F.x, F.mask, c->stream);
+    AX1_LAUNCH_CHECK(c);
+    launch_spmv_residual(F.g, F.A, F.x, F.b, c->d_amg_t, 0, c->stream);
+    AX1_LAUNCH_CHECK(c);
+    if ((rc = smooth(l, c->d_amg_t, c->d_tmp))) return rc;      // post-smoothing
+    launch_vec_add(4 * F.g.nv, F.x, c->d_tmp, c->stream);
+    AX1_LAUNCH_CHECK(c);
+  }
+  return 0;
+}
+
+int drv_factor(ax1gpu_ctx* c, int slab_w, int fill, int amg) {
   int rc = select_preconditioner(c, slab_w, fill);
   if (rc) return rc;
+  if (amg >= 0) c->amg = amg ? 1 : 0;
   if (c->ilu_fill == 1) launch_ilu1_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);
   else launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);
   AX1_LAUNCH_CHECK(c);
+  if (c->amg && (rc = amg_setup(c))) return rc;
   c->factored = true;
   return 0;
 }
 
-int drv_prec_apply(ax1gpu_ctx* c, const double* d, double* v) {
-  if (c->nranks > 1 && c->p2p.on) {
-    // sweep with fused halo push into the neighbours' windows, then acquire + add what they pushed to me
-    const Dev& g = c->g;
-    const size_t H = c->p2p.halo_len;
-    HaloPush hp{};
-    hp.seq = ++c->p2p.halo_seq;
-    const size_t par = (size_t)(hp.seq & 1);
-    hp.cnt = c->p2p.cnt;
-    halo_contributors(g, c->slab_w, &hp.ncontrib[0], &hp.ncontrib[1]);
-    if (c->left_pb) {   // my left columns -> slot "from the right neighbour" (side 1) of rank-1
-      double* pw = c->p2p.peer[c->rank - 1];
-      hp.dst[0] = pw + AX1_P2P_HALO_OFF + (2 + par) * H;
-      hp.flag[0] = reinterpret_cast<unsigned long long*>(pw + AX1_P2P_FLAG_OFF + 1);
-    }
-    if (c->right_pb) {  // my right columns -> slot "from the left neighbour" (side 0) of rank+1
-      double* pw = c->p2p.peer[c->rank + 1];
-      hp.dst[1] = pw + AX1_P2P_HALO_OFF + (0 + par) * H;
-      hp.flag[1] = reinterpret_cast<unsigned long long*>(pw + AX1_P2P_FLAG_OFF + 0);
-    }
-    if (c->ilu_fill == 1) launch_ilu1_apply(g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream, &hp);
-    else launch_ilu_apply(g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream, &hp);
+// HaloPush descriptor of the next halo exchange through the peer windows
+static HaloPush next_halo_push(ax1gpu_ctx* c) {
+  const size_t H = c->p2p.halo_len;
+  HaloPush hp{};
+  hp.seq = ++c->p2p.halo_seq;
+  const size_t par = (size_t)(hp.seq & 1);
+  hp.cnt = c->p2p.cnt;
+  halo_contributors(c->g, c->slab_w, &hp.ncontrib[0], &hp.ncontrib[1]);
+  if (c->left_pb) {   // my left columns -> slot "from the right neighbour" (side 1) of rank-1
+    double* pw = c->p2p.peer[c->rank - 1];
+    hp.dst[0] = pw + AX1_P2P_HALO_OFF + (2 + par) * H;
+    hp.flag[0] = reinterpret_cast<unsigned long long*>(pw + AX1_P2P_FLAG_OFF + 1);
+  }
+  if (c->right_pb) {  // my right columns -> slot "from the left neighbour" (side 0) of rank+1
+    double* pw = c->p2p.peer[c->rank + 1];
+    hp.dst[1] = pw + AX1_P2P_HALO_OFF + (0 + par) * H;
+    hp.flag[1] = reinterpret_cast<unsigned long long*>(pw + AX1_P2P_FLAG_OFF + 0);
+  }
+  return hp;
+}
+static int halo_wait_add(ax1gpu_ctx* c, double* v, unsigned long long seq) {
+  const Dev& g = c->g;
+  const size_t H = c->p2p.halo_len, par = (size_t)(seq & 1);
+  const int n = 3 * g.nvy * 4, bs = 256, nb = (n + bs - 1) / bs;
+  double* w = c->p2p.win;
+  if (c->left_pb) {
+    halo_wait_add_kernel<<<nb, bs, 0, c->stream>>>(g, v, w + AX1_P2P_HALO_OFF + (0 + par) * H,
+        reinterpret_cast<const unsigned long long*>(w + AX1_P2P_FLAG_OFF + 0), seq, 0, c->d_err + 2);
     AX1_LAUNCH_CHECK(c);
-    const int n = 3 * g.nvy * 4, bs = 256, nb = (n + bs - 1) / bs;
-    double* w = c->p2p.win;
-    if (c->left_pb) {
-      halo_wait_add_kernel<<<nb, bs, 0, c->stream>>>(g, v, w + AX1_P2P_HALO_OFF + (0 + par) * H,
-          reinterpret_cast<const unsigned long long*>(w + AX1_P2P_FLAG_OFF + 0), hp.seq, 0, c->d_err + 2);
+  }
+  if (c->right_pb) {
+    halo_wait_add_kernel<<<nb, bs, 0, c->stream>>>(g, v, w + AX1_P2P_HALO_OFF + (2 + par) * H,
+        reinterpret_cast<const unsigned long long*>(w + AX1_P2P_FLAG_OFF + 1), seq, g.nvx - 3, c->d_err + 2);
+    AX1_LAUNCH_CHECK(c);
+  }
+  return 0;
+}
+
+int drv_prec_apply(ax1gpu_ctx* c, const double* d, double* v) {
+  const bool p2p = c->nranks > 1 && c->p2p.on;
+  if (c->amg) {
+    // per-rank multigrid cycle (the rank-local matrix incl. its overlap), then the additive halo sum
+    int rc = amg_vcycle(c, d, v);
+    if (rc) return rc;
+    if (p2p) {
+      const HaloPush hp = next_halo_push(c);
+      launch_halo_push(c->g, v, hp, c->stream);
       AX1_LAUNCH_CHECK(c);
+      return halo_wait_add(c, v, hp.seq);
     }
-    if (c->right_pb) {
-      halo_wait_add_kernel<<<nb, bs, 0, c->stream>>>(g, v, w + AX1_P2P_HALO_OFF + (2 + par) * H,
-          reinterpret_cast<const unsigned long long*>(w + AX1_P2P_FLAG_OFF + 1), hp.seq, g.nvx - 3, c->d_err + 2);
-      AX1_LAUNCH_CHECK(c);
-    }
-    return 0;
+    return halo_add(c, v);
+  }
+  if (p2p) {
+    // sweep with fused halo push into the neighbours' windows, then acquire + add what they pushed to me
+    const HaloPush hp = next_halo_push(c);
+    if (c->ilu_fill == 1) launch_ilu1_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream, &hp);
+    else launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream, &hp);
+    AX1_LAUNCH_CHECK(c);
+    return halo_wait_add(c, v, hp.seq);
   }
   if (c->ilu_fill == 1) launch_ilu1_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
   else launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
@@ -569,6 +843,101 @@ int drv_solve(ax1gpu_ctx* c, double* r, double* x, double reduction, int maxit, 
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Restarted GMRES on A z = rhs from z = 0: Dune::RestartedGMResSolver (dune-istl 2.3 solvers.hh) as driven by
+// ISTLBackend_GMRES_AMG (dune/ax1/common/ax1_solverbackend.hh:196-213: restart 100, recalcDefect = false) [ext]:
+// left preconditioning, modified Gram-Schmidt, Givens rotations, convergence on the preconditioned residual.
+// The Hessenberg matrix, rotations and convergence flag live on the device; the host polls the flag.
+int drv_solve_gmres(ax1gpu_ctx* c, double* b, double* x, double reduction, int restart, int maxit,
+                    ax1gpu_lin_result* res) {
+  const int nv = c->g.nv;
+  const size_t len = 4 * (size_t)nv, bytes = len * sizeof(double);
+  const Own own = own_of(c);
+  const int G = vec_grid(c);
+  const int zc = c->nranks > 1;
+  int rc;
+  int m = restart <= 0 ? 100 : restart;
+  if (m > 1000) { set_error("gmres: restart must be <= 1000"); return AX1GPU_EINVAL; }
+  if (m > maxit && maxit > 0) m = maxit;
+  if (m > c->gm_cap) {
+    AX1_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->d_gmV) { cudaFree(c->d_gmV); c->d_gmV = nullptr; }
+    if (c->d_gm) { cudaFree(c->d_gm); c->d_gm = nullptr; }
+    c->gm_cap = 0;
+    AX1_CUDA(cudaMalloc((void**)&c->d_gmV, (size_t)(m + 1) * bytes));
+    AX1_CUDA(cudaMalloc((void**)&c->d_gm, gm_len(m) * sizeof(double)));
+    c->gm_cap = m;
+  }
+  if (!c->factored) { rc = drv_factor(c, c->slab_w); if (rc) return rc; }
+  double* V = c->d_gmV;
+  double* gm = c->d_gm;
+  double* w = c->d_p;
+  auto Vk = [&](int k) { return V + (size_t)k * len; };
+  AX1_CUDA(cudaMemsetAsync(x, 0, bytes, c->stream));
+  AX1_CUDA(cudaMemsetAsync(c->d_sc, 0, sizeof(Scalars), c->stream));
+  AX1_CUDA(cudaMemsetAsync(gm, 0, gm_len(m) * sizeof(double), c->stream));
+  c->h_pin[0] = (double)m;
+  AX1_CUDA(cudaMemcpyAsync(gm + GM_M, c->h_pin, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  // b - A*0 = b ; v0 = M^-1 b ; beta = |v0|
+  if ((rc = drv_prec_apply(c, b, Vk(0)))) return rc;
+  gmres_mgs_kernel<<<G, 256, 0, c->stream>>>(nv, Vk(0), nullptr, nullptr, gm, c->d_sc, own, c->d_partials);
+  AX1_LAUNCH_CHECK(c);
+  if ((rc = reduce_op(c, G, 1, OP_G_BETA, reduction, gm, 1))) return rc;
+  if ((rc = poll_scalars(c))) return rc;
+  int j = 1;
+  bool stop = c->h_sc->done != 0;
+  while (j <= maxit && !stop) {
+    gmres_scale_kernel<<<G, 256, 0, c->stream>>>(nv, Vk(0), Vk(0), gm, c->d_sc);
+    AX1_LAUNCH_CHECK(c);
+    for (int i = 0; i < m && j <= maxit; ++i, ++j) {
+      launch_spmv(c->g, c->d_A, Vk(i), Vk(i + 1), zc, c->stream);      // v[i+1] as temporary
+      AX1_LAUNCH_CHECK(c);
+      if ((rc = drv_prec_apply(c, Vk(i + 1), w))) return rc;
+      for (int k = 0; k <= i; ++k) {
+        gmres_mgs_kernel<<<G, 256, 0, c->stream>>>(nv, w, k ? Vk(k - 1) : nullptr, Vk(k), gm, c->d_sc, own, c->d_partials);
+        AX1_LAUNCH_CHECK(c);
+        if ((rc = reduce_op(c, G, 1, OP_G_H, reduction, gm, (k << 10) | i))) return rc;
+      }
+      gmres_mgs_kernel<<<G, 256, 0, c->stream>>>(nv, w, Vk(i), nullptr, gm, c->d_sc, own, c->d_partials);
+      AX1_LAUNCH_CHECK(c);
+      if ((rc = reduce_op(c, G, 1, OP_G_NORMW, reduction, gm, i))) return rc;
+      gmres_scale_kernel<<<G, 256, 0, c->stream>>>(nv, Vk(i + 1), w, gm, c->d_sc);
+      AX1_LAUNCH_CHECK(c);
+      if (reduction > 0.0 && (j & 3) == 0) {
+        if ((rc = poll_scalars(c))) return rc;
+        if (c->h_sc->done) { ++j; break; }
+      }
+    }
+    // x += sum_c y_c v_c over the steps this cycle completed (count kept on the device)
+    gmres_ysolve_kernel<<<1, 1, 0, c->stream>>>(gm);
+    AX1_LAUNCH_CHECK(c);
+    gmres_combine_kernel<<<G, 256, 0, c->stream>>>(nv, V, len, gm, w, x);
+    AX1_LAUNCH_CHECK(c);
+    // b -= A w (ISTL keeps the defect in b)
+    launch_spmv_residual(c->g, c->d_A, w, b, c->d_t, zc, c->stream);
+    AX1_LAUNCH_CHECK(c);
+    AX1_CUDA(cudaMemcpyAsync(b, c->d_t, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if ((rc = poll_scalars(c))) return rc;
+    if (c->h_sc->done) break;
+    if (j > maxit) break;
+    if ((rc = drv_prec_apply(c, b, Vk(0)))) return rc;
+    gmres_mgs_kernel<<<G, 256, 0, c->stream>>>(nv, Vk(0), nullptr, nullptr, gm, c->d_sc, own, c->d_partials);
+    AX1_LAUNCH_CHECK(c);
+    if ((rc = reduce_op(c, G, 1, OP_G_BETA, reduction, gm, 0))) return rc;
+    if ((rc = poll_scalars(c))) return rc;
+    stop = c->h_sc->done != 0;
+  }
+  if ((rc = poll_scalars(c))) return rc;
+  const Scalars& s = *c->h_sc;
+  if (s.breakdown) { set_error("breakdown in GMRes - |w| == 0.0"); res->converged = 0; return AX1GPU_ESTATE; }
+  res->converged = s.converged;
+  res->it_half = s.it_half;
+  res->iterations = (int)s.it_half;
+  res->reduction = s.norm0 > 0 ? s.norm / s.norm0 : 0.0;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 static float ev_ms(cudaEvent_t a, cudaEvent_t b) {
   float ms = 0.f;
@@ -625,8 +994,11 @@ int drv_newton(ax1gpu_ctx* c, const ax1gpu_newton_opts* o, ax1gpu_newton_result*
     AX1_CUDA(cudaEventRecord(e1, c->stream));
     // linear solve (ILU0 re-factorised every Newton iteration, like SeqILUn in the backend's apply)
     ax1gpu_lin_result lr{};
-    if ((rc = drv_factor(c, o->slab_w, o->ilu_fill))) return rc;
-    rc = drv_solve(c, c->d_r, c->d_z, o->fixed_work ? 0.0 : linear_reduction, o->lin_maxit, &lr);
+    if ((rc = drv_factor(c, o->slab_w, o->ilu_fill, o->amg))) return rc;
+    if (o->krylov == 1)
+      rc = drv_solve_gmres(c, c->d_r, c->d_z, o->fixed_work ? 0.0 : linear_reduction, o->restart, o->lin_maxit, &lr);
+    else
+      rc = drv_solve(c, c->d_r, c->d_z, o->fixed_work ? 0.0 : linear_reduction, o->lin_maxit, &lr);
     AX1_CUDA(cudaEventRecord(e2, c->stream));
     AX1_CUDA(cudaEventSynchronize(e2));
     t_asm_ms += ev_ms(e0, e1);

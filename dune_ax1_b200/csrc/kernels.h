@@ -30,6 +30,8 @@ struct Scalars {  // device-resident Krylov scalars
   int done, converged, breakdown, pad;
 };
 void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int zero_constrained, cudaStream_t st);
+void launch_spmv_residual(const Dev& g, const double* A, const double* x, const double* b, double* r,
+                          int zero_constrained, cudaStream_t st);
 int spmv_blocks(const Dev& g);
 // SpMV with fused dot products: dot_mode 1: partial <w, y>; 2: partial <y, w> and <y, y>; one partial per block
 void launch_spmv_dot(const Dev& g, const double* A, const double* x, double* y, int zero_constrained, int dot_mode,
@@ -47,6 +49,16 @@ void ilu1_level_tables(const Dev& g, int slab_w, std::vector<int>& tab);
 void launch_ilu1_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st);
 void launch_ilu1_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, const int* lvl_tab,
                        cudaStream_t st, const HaloPush* hp = nullptr);
+// amg.cu: x-aggregation multigrid (piecewise-constant aggregates of cx vertex columns, Galerkin coarse
+// operators in the same 9-slot arrow format) -- transfer kernels; the cycle itself is in driver.cu
+void launch_galerkin_x(int nvx_f, int nvx_c, int nvy, int cx, const double* Af, double* Ac, const uint8_t* dmask_f,
+                       cudaStream_t st);
+void launch_restrict_x(int nvx_f, int nvx_c, int nvy, int cx, const double* rf, double* bc, const uint8_t* dmask_f,
+                       cudaStream_t st);
+void launch_prolong_add_x(int nvx_f, int nvx_c, int nvy, int cx, const double* xc, double* xf, const uint8_t* dmask_f,
+                          cudaStream_t st);
+void launch_vec_add(int n, double* x, const double* t, cudaStream_t st);   // x += t
+void launch_halo_push(const Dev& g, const double* v, const HaloPush& hp, cudaStream_t st);
 void launch_rownorm(const Dev& g, double* A, double* r, cudaStream_t st);
 void launch_compact_bcrs(const Dev& g, const double* A9, double* blocks, const int* rowptr, cudaStream_t st);
 void launch_expand_bcrs(const Dev& g, const double* blocks, double* A9, const int* rowptr, int* viol, cudaStream_t st);

@@ -20,6 +20,7 @@ namespace ax1 {
 
 // ------------------------------------------------------------------------------------------
 // y = A x ; 4 lanes per block row, lane r = scalar row r.
+// DOT = 3: residual mode y = w - A x (multigrid defect), no reduction.
 // DOT = 1: also partial <w, y> (BiCGStab h = <rt, v>);  DOT = 2: partial <y, w> and <y, y>
 // (omega = <t, r> / <t, t>): the SpMV result is reduced while it is still in registers.
 template <int DOT>
@@ -29,7 +30,7 @@ __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restri
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int v = (int)(t >> 2), r = (int)(t & 3);
   double s[2] = {0.0, 0.0};
-  const bool active = (v < g.nv) && !(DOT && sc && sc->done);
+  const bool active = (v < g.nv) && !(DOT && DOT != 3 && sc && sc->done);
   if (active) {
     const int i = v % g.nvx, j = v / g.nvx;
     const double* Arow = A + (size_t)v * AX1_ROW;
@@ -53,9 +54,10 @@ __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restri
       acc += (r == 3 ? b2.x : 0.0) * xv[2];
       acc += (r == 3 ? b2.y : 0.0) * xv[3];
     }
+    if (DOT == 3) acc = __ldg(w + 4 * (size_t)v + r) - acc;
     if (zero_con && ((g.dmask[v] >> r) & 1)) acc = 0.0;
     y[4 * (size_t)v + r] = acc;
-    if (DOT) {
+    if (DOT == 1 || DOT == 2) {
       if (!own.masked || (i >= own.lo && i <= own.hi)) {
         const double wv = __ldg(w + 4 * (size_t)v + r);
         s[0] = acc * wv;
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restri
       }
     }
   }
-  if (DOT) block_reduce_store<2>(s, partials);
+  if (DOT == 1 || DOT == 2) block_reduce_store<2>(s, partials);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -436,6 +438,11 @@ __global__ void bcrs_copy_kernel(Dev g, double* A9, double* blocks, const int* _
 int spmv_blocks(const Dev& g) { return (int)((4LL * g.nv + 255) / 256); }
 void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int zero_con, cudaStream_t st) {
   spmv_kernel<0><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, nullptr, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
+}
+// r = b - A x
+void launch_spmv_residual(const Dev& g, const double* A, const double* x, const double* b, double* r, int zero_con,
+                          cudaStream_t st) {
+  spmv_kernel<3><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, r, zero_con, b, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
 }
 void launch_spmv_dot(const Dev& g, const double* A, const double* x, double* y, int zero_con, int dot_mode,
                      const double* w, int own_lo, int own_hi, int masked, const Scalars* sc, double* partials,

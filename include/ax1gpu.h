@@ -79,6 +79,12 @@ typedef struct ax1gpu_newton_opts {
   int fixed_work;  /* benchmark mode: exactly maxit Newton x lin_maxit BiCGStab iterations     */
   int ilu_fill;    /* n of SeqILUn: 0 = block ILU0, 1 = block ILU(1) (reference default,
                       acme2_cyl_setup.hh:764-765: ISTLBackend_OVLP_BCGS_ILUn(multigfs,cc,1,...))  */
+  int amg;         /* 1: multigrid preconditioner (x-aggregation AMG, V(1,1), block-ILU smoothers) instead of
+                      the plain ILU -- the device counterpart of ISTLBackend_GMRES_AMG_ILU0's Dune::Amg::AMG
+                      (ax1_solverbackend.hh:73-302, selected by the myelin build acme2_cyl_setup.hh:749-760)   */
+  int krylov;      /* 0: Dune::BiCGSTABSolver (default backends), 1: Dune::RestartedGMResSolver as in
+                      ISTLBackend_GMRES_AMG::apply (ax1_solverbackend.hh:196-213)                               */
+  int restart;     /* GMRES restart length (reference: 100, ax1_solverbackend.hh:201)                          */
 } ax1gpu_newton_opts;
 
 typedef struct ax1gpu_newton_result { /* PDELab NewtonResult + ax1_newton.hh:600-607 */
@@ -137,6 +143,11 @@ int ax1gpu_get_jacobian(ax1gpu_handle h, double* blocks);
  * the final linear residual as ISTL does. */
 int ax1gpu_solve(ax1gpu_handle h, double* r, double reduction, int maxit, int slab_w, double* z,
                  ax1gpu_lin_result* res);
+/* LS::apply of ISTLBackend_GMRES_AMG (ax1_solverbackend.hh:166-213): left-preconditioned restarted GMRES
+ * (modified Gram-Schmidt, Givens rotations, convergence on the preconditioned residual) with the handle's
+ * current preconditioner (ILU, or the multigrid cycle after ax1gpu_set_amg); arguments as ax1gpu_solve. */
+int ax1gpu_solve_gmres(ax1gpu_handle h, double* r, double reduction, int restart, int maxit, int slab_w, double* z,
+                       ax1gpu_lin_result* res);
 /* Ax1Newton::apply(u): u in/out. */
 int ax1gpu_newton(ax1gpu_handle h, const ax1gpu_newton_opts* opts, double* u, ax1gpu_newton_result* res);
 
@@ -151,6 +162,11 @@ int ax1gpu_spmv(ax1gpu_handle h, const double* x, double* y);
 int ax1gpu_ilu_factor(ax1gpu_handle h, int slab_w);   /* keeps the handle's current fill level (0 at creation) */
 /* SeqILUn(A, n, 1.0): fill = 0 or 1; also selects the preconditioner of later ax1gpu_solve calls */
 int ax1gpu_ilu_factor_n(ax1gpu_handle h, int slab_w, int fill);
+/* switch the preconditioner of ax1gpu_ilu_factor / ax1gpu_ilu_apply / ax1gpu_solve between the ILU alone
+ * (on = 0) and one V(1,1) cycle of the aggregation multigrid with `cx` vertex columns per aggregate
+ * (cx <= 0: keep, default 4); the hierarchy is rebuilt by the next factorisation */
+int ax1gpu_set_amg(ax1gpu_handle h, int on, int cx);
+/* one application of the current preconditioner (ILU sweep or AMG cycle) incl. the halo sum */
 int ax1gpu_ilu_apply(ax1gpu_handle h, const double* d, double* v);
 int ax1gpu_rownorm(ax1gpu_handle h, double* r); /* scales device Jacobian and r */
 /* run `reps` launches of one named kernel on device-resident data and return the mean device time

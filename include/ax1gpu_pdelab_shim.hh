@@ -173,6 +173,43 @@ class SolverBackendShim {
   LinearSolverResult res_;
 };
 
+// LS of the myelin build: ISTLBackend_GMRES_AMG_ILU0(gfs, maxiter, verbose, reuse, usesuperlu)
+// (ax1_solverbackend.hh:279-302; instantiated at acme2_cyl_setup.hh:749-760) -- RestartedGMRes(100)
+// preconditioned by one multigrid cycle with ILU0 smoothers
+template <class U, class M, class EP = DefaultErrorPolicy>
+class GMResAMGBackendShim {
+ public:
+  GMResAMGBackendShim(Device& d, unsigned maxiter = 5000, int slab_w = 0, int restart = 100, int columns_per_aggregate = 4)
+      : d_(d), maxiter_(maxiter), slab_w_(slab_w), restart_(restart), cx_(columns_per_aggregate) {}
+  double norm(const U& v) const {
+    const double* p = VectorAccess<U>::data(v);
+    double s = 0;
+    for (std::size_t k = 0; k < VectorAccess<U>::size(v); ++k) s += p[k] * p[k];
+    return std::sqrt(s);
+  }
+  void apply(M& A, U& z, U& r, double reduction) {
+    EP::library(ax1gpu_set_jacobian(d_.handle(), MatrixAccess<M>::blocks(A)));
+    EP::library(ax1gpu_set_amg(d_.handle(), 1, cx_));
+    EP::library(ax1gpu_ilu_factor_n(d_.handle(), slab_w_, 0));   // smoother SeqILU0 + Galerkin hierarchy
+    ax1gpu_lin_result lr;
+    const int rc = ax1gpu_solve_gmres(d_.handle(), VectorAccess<U>::data(r), reduction, restart_, (int)maxiter_, 0,
+                                      VectorAccess<U>::data(z), &lr);
+    ax1gpu_set_amg(d_.handle(), 0, 0);
+    EP::library(rc);
+    res_.converged = lr.converged != 0;
+    res_.iterations = (unsigned)lr.iterations;
+    res_.reduction = lr.reduction;
+    res_.conv_rate = lr.iterations > 0 ? std::pow(lr.reduction, 1.0 / lr.iterations) : 0.0;
+  }
+  const LinearSolverResult& result() const { return res_; }
+
+ private:
+  Device& d_;
+  unsigned maxiter_;
+  int slab_w_, restart_, cx_;
+  LinearSolverResult res_;
+};
+
 // ---- PDESOLVER -----------------------------------------------------------------------------------
 struct NewtonResult {  // Dune::PDELab::NewtonResult + the keys Ax1Newton copies to diagnostics.dat
   bool converged = false;
@@ -196,6 +233,8 @@ class NewtonShim {
   void disableLineSearch(bool v) { o_.disable_line_search = v; }          // :838-839
   void setSlabWidth(int v) { o_.slab_w = v; }
   void setIluFill(int n) { o_.ilu_fill = n; }  // n of SeqILUn in the linear solver backend (:764-765, :797-798)
+  void setAmg(bool on) { o_.amg = on; }        // AMG(ILU0) preconditioner of the myelin build (:749-760)
+  void setGMRes(bool on, int restart = 100) { o_.krylov = on; o_.restart = restart; }  // ax1_solverbackend.hh:201-204
   // Ax1Newton::apply(u): the whole damped Newton loop runs on the device; u in/out
   void apply(U& u) {
     ax1gpu_newton_result r;

@@ -35,6 +35,10 @@ typedef struct ax1o_newton_opts {
   int fixed_lin_reduction, maxit, line_search_maxit, lin_maxit;
   int force_iteration, disable_line_search;
   int ilu_fill, slab_w, fixed_work;
+  int krylov;   /* 0 BiCGSTABSolver, 1 RestartedGMResSolver (ISTLBackend_GMRES_AMG, ax1_solverbackend.hh:196-213) */
+  int restart;  /* GMRES restart length (reference: 100) */
+  int amg;      /* 1: x-aggregation multigrid V(1,1) with block-ILU smoothers instead of the ILU alone */
+  int amg_cx;   /* vertex columns per aggregate (<= 0: 4) */
 } ax1o_newton_opts;
 
 typedef struct ax1o_newton_result {
@@ -94,6 +98,13 @@ int ax1o_ilu_num_blocks(const ax1o_problem* p, int ilu_fill, int slab_w);
 /* BiCGStab(ILU) solve A z = r from z = 0; r is overwritten by the final residual */
 int ax1o_solve(const ax1o_problem* p, const double* vals, double* r, double* z, double reduction,
                int maxit, int ilu_fill, int slab_w, ax1o_lin_result* res);
+/* general Krylov solve: krylov 0 BiCGStab / 1 restarted GMRES; amg 0 ILU(fill) / 1 multigrid cycle */
+int ax1o_solve_ex(const ax1o_problem* p, const double* vals, double* r, double* z, double reduction,
+                  int maxit, int ilu_fill, int slab_w, int krylov, int restart, int amg, int amg_cx,
+                  ax1o_lin_result* res);
+/* one application of the multigrid cycle to d */
+int ax1o_amg_apply(const ax1o_problem* p, const double* vals, int ilu_fill, int slab_w, int amg_cx,
+                   const double* d, double* v);
 int ax1o_newton(ax1o_problem* p, double* u, const ax1o_newton_opts* o, ax1o_newton_result* res);
 
 /* overlapping multi-rank emulation: one thread per rank (stand-in for MPI ranks) */

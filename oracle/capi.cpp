@@ -38,6 +38,7 @@ void ax1o_newton_opts_default(ax1o_newton_opts* o) {
   o->fixed_lin_reduction = 0; o->maxit = 50; o->line_search_maxit = 10; o->lin_maxit = 5000;
   o->force_iteration = 0; o->disable_line_search = 0;
   o->ilu_fill = 1; o->slab_w = 0; o->fixed_work = 0;
+  o->krylov = 0; o->restart = 100; o->amg = 0; o->amg_cx = 4;
 }
 
 int ax1o_sizeof_config(void) { return (int)sizeof(ax1o_config); }
@@ -184,6 +185,37 @@ int ax1o_solve(const ax1o_problem* h, const double* vals, double* r, double* z, 
   LinResult lr;
   bicgstab(h->p, A, M, z, r, reduction, maxit, nullptr, lr);
   *res = lr;
+  return 0;
+  AX1O_CATCH(1)
+}
+
+int ax1o_solve_ex(const ax1o_problem* h, const double* vals, double* r, double* z, double reduction, int maxit,
+                  int ilu_fill, int slab_w, int krylov, int restart, int amg, int amg_cx, ax1o_lin_result* res) {
+  AX1O_TRY
+  BCRS A; load(h->p, vals, A);
+  ILU M; AMGx H; Prec prec;
+  if (amg) {
+    amg_build(h->p, A, ilu_fill, slab_w, amg_cx, H);
+    prec = [&H](const double* d, double* v) { amg_vcycle(H, d, v); };
+  } else {
+    ilu_factor(h->p, A, ilu_fill, slab_w, M);
+    prec = [&M](const double* d, double* v) { ilu_apply(M, d, v); };
+  }
+  std::memset(z, 0, 4 * (size_t)h->p.nv * sizeof(double));
+  LinResult lr;
+  if (krylov == 1) gmres(h->p, A, prec, z, r, reduction, restart, maxit, nullptr, lr);
+  else bicgstab(h->p, A, prec, z, r, reduction, maxit, nullptr, lr);
+  *res = lr;
+  return 0;
+  AX1O_CATCH(1)
+}
+
+int ax1o_amg_apply(const ax1o_problem* h, const double* vals, int ilu_fill, int slab_w, int amg_cx, const double* d,
+                   double* v) {
+  AX1O_TRY
+  BCRS A; load(h->p, vals, A);
+  AMGx H; amg_build(h->p, A, ilu_fill, slab_w, amg_cx, H);
+  amg_vcycle(H, d, v);
   return 0;
   AX1O_CATCH(1)
 }

@@ -13,6 +13,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <vector>
 #include <string>
 #include "ax1_oracle.h"
@@ -108,6 +109,7 @@ struct ILU {
 // sub-slab additive-Schwarz decomposition inside one rank: vertex columns grouped into slabs of
 // width slab_w (<=0: one slab = plain ILU on the local matrix as the reference does)
 void ilu_factor(const Problem& p, const BCRS& A, int fill_level, int slab_w, ILU& f);
+void ilu_factor_nvx(int nvx, const BCRS& A, int fill_level, int slab_w, ILU& f);  // vertex v lies in column v % nvx
 void ilu_apply(const ILU& f, const double* d, double* v);
 void spmv(const BCRS& A, const double* x, double* y);
 
@@ -118,9 +120,39 @@ struct Comm {  // collectives for the overlapping multi-rank path (identity for 
   double (*allreduce_sum)(void* ctx, int rank, double local) = nullptr;
   int rank = 0;
 };
+using Prec = std::function<void(const double* d, double* v)>;  // rank-local v = M^-1 d
 void bicgstab(const Problem& p, const BCRS& A, const ILU& M, double* x, double* b, double reduction,
               int maxit, const Comm* comm, LinResult& res);
+void bicgstab(const Problem& p, const BCRS& A, const Prec& M, double* x, double* b, double reduction,
+              int maxit, const Comm* comm, LinResult& res);
+void zero_constrained(const Problem& p, double* v);
+void op_apply(const Problem& p, const BCRS& A, const double* x, double* y, const Comm* comm);
+void prec_apply(const Problem& p, const Prec& M, const double* d, double* v, std::vector<double>& dd,
+                const Comm* comm);
 double masked_dot(const Problem& p, const double* a, const double* b, const Comm* comm);
+
+// ---- gmres_amg.cpp
+// Dune::RestartedGMResSolver (dune-istl 2.3 solvers.hh) as driven by ISTLBackend_GMRES_AMG
+// (dune/ax1/common/ax1_solverbackend.hh:196-213: restart = 100, recalcDefect = false)          [ext]
+void gmres(const Problem& p, const BCRS& A, const Prec& M, double* x, double* b, double reduction,
+           int restart, int maxit, const Comm* comm, LinResult& res);
+// x-aggregation multigrid with block-ILU smoothers: the CHECKER of the device cycle (csrc/amg.cu).
+// Dune::Amg's greedy aggregation [ext, dune-istl aggregates.hh] is not in /root/reference and is not
+// reproducible bit for bit; a preconditioner changes iteration counts only, never converged answers.
+struct AMGx {
+  int cx = 4, nvy = 0;
+  struct Level {
+    int nvx = 0;
+    BCRS A;            // level 0 holds a copy of the fine matrix
+    ILU M;
+    std::vector<double> b, x;
+  };
+  std::vector<Level> lv;
+  std::vector<uint8_t> mask;   // fine-level constrained DOFs (bit c of vertex v)
+  std::vector<double> t, s;
+};
+void amg_build(const Problem& p, const BCRS& A, int fill_level, int slab_w, int cx, AMGx& H);
+void amg_vcycle(AMGx& H, const double* d, double* v);
 
 struct NewtonOpts : ax1o_newton_opts {
   NewtonOpts() { ax1o_newton_opts_default(this); }

@@ -46,6 +46,7 @@ class NewtonOpts(C.Structure):
         ("fixed_lin_reduction", C.c_int), ("maxit", C.c_int), ("line_search_maxit", C.c_int),
         ("lin_maxit", C.c_int), ("force_iteration", C.c_int), ("disable_line_search", C.c_int),
         ("ilu_fill", C.c_int), ("slab_w", C.c_int), ("fixed_work", C.c_int),
+        ("krylov", C.c_int), ("restart", C.c_int), ("amg", C.c_int), ("amg_cx", C.c_int),
     ]
 
 
@@ -119,6 +120,9 @@ def lib():
     L.ax1o_ilu_num_blocks.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ax1o_solve.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_int,
                              C.c_int, C.c_int, C.POINTER(LinResult)]
+    L.ax1o_solve_ex.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_int,
+                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(LinResult)]
+    L.ax1o_amg_apply.argtypes = [C.c_void_p, c_double_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p]
     L.ax1o_newton.argtypes = [C.c_void_p, c_double_p, C.POINTER(NewtonOpts), C.POINTER(NewtonResult)]
     L.ax1o_newton_ext.argtypes = [C.c_void_p, c_double_p, C.POINTER(NewtonOpts),
                                   C.POINTER(NewtonResult), C.c_int, HALO_FN, ALLREDUCE_FN, C.c_void_p]
@@ -291,6 +295,23 @@ class Problem:
                             C.byref(res)):
             raise RuntimeError(lib().ax1o_last_error().decode())
         return z, r, res
+
+    def solve_ex(self, vals, r, reduction, maxit=5000, ilu_fill=0, slab_w=0, krylov=0, restart=100, amg=0,
+                 amg_cx=4):
+        """krylov 0 = BiCGStab, 1 = RestartedGMRes(restart); amg 1 = multigrid cycle as preconditioner."""
+        r = f64(r).copy()
+        z = np.zeros(self.n)
+        res = LinResult()
+        if lib().ax1o_solve_ex(self.h, _dp(f64(vals)), _dp(r), _dp(z), reduction, maxit, ilu_fill, slab_w,
+                               krylov, restart, amg, amg_cx, C.byref(res)):
+            raise RuntimeError(lib().ax1o_last_error().decode())
+        return z, r, res
+
+    def amg_apply(self, vals, d, ilu_fill=0, slab_w=0, amg_cx=4):
+        v = np.zeros(self.n)
+        if lib().ax1o_amg_apply(self.h, _dp(f64(vals)), ilu_fill, slab_w, amg_cx, _dp(f64(d)), _dp(v)):
+            raise RuntimeError(lib().ax1o_last_error().decode())
+        return v
 
     def newton(self, u, opts=None):
         u = f64(u).copy()

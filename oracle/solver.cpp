@@ -67,8 +67,11 @@ void mat4_invert(double* M) {  // Gauss-Jordan with partial pivoting (FieldMatri
 // then bilu0_decomposition on the enlarged pattern. slab_w > 0 first drops all blocks that couple
 // vertex columns of different sub-slabs (our many-slabs-per-rank reading of additive Schwarz).
 void ilu_factor(const Problem& p, const BCRS& A, int n_fill, int slab_w, ILU& f) {
+  ilu_factor_nvx(p.nvx, A, n_fill, slab_w, f);
+}
+void ilu_factor_nvx(int nvx, const BCRS& A, int n_fill, int slab_w, ILU& f) {
   const int N = A.n;
-  auto slab_of = [&](int v) { return slab_w > 0 ? (v % p.nvx) / slab_w : 0; };
+  auto slab_of = [&](int v) { return slab_w > 0 ? (v % nvx) / slab_w : 0; };
   BCRS& LU = f.LU;
   LU.n = N;
   LU.rowptr.assign(N + 1, 0);
@@ -177,8 +180,6 @@ double masked_dot(const Problem& p, const double* a, const double* b, const Comm
   return comm->allreduce_sum(comm->ctx, comm->rank, s);
 }
 
-namespace {
-
 void zero_constrained(const Problem& p, double* v) {
   for (int k = 0; k < p.nv; ++k)
     if (p.dirichlet[k])
@@ -191,18 +192,22 @@ void op_apply(const Problem& p, const BCRS& A, const double* x, double* y, const
   if (comm) zero_constrained(p, y);  // OverlappingOperator::apply
 }
 
-void prec_apply(const Problem& p, const ILU& M, const double* d, double* v, std::vector<double>& dd,
+// OverlappingWrappedPreconditioner::apply around any rank-local preconditioner
+void prec_apply(const Problem& p, const Prec& M, const double* d, double* v, std::vector<double>& dd,
                 const Comm* comm) {
-  if (!comm) { ilu_apply(M, d, v); return; }
-  dd.assign(d, d + 4 * (size_t)p.nv);         // OverlappingWrappedPreconditioner::apply
+  if (!comm) { M(d, v); return; }
+  dd.assign(d, d + 4 * (size_t)p.nv);
   zero_constrained(p, dd.data());
-  ilu_apply(M, dd.data(), v);
+  M(dd.data(), v);
   comm->halo_add(comm->ctx, comm->rank, v);
 }
 
-}  // namespace
-
 void bicgstab(const Problem& p, const BCRS& A, const ILU& M, double* x, double* b, double reduction,
+              int maxit, const Comm* comm, LinResult& res) {
+  bicgstab(p, A, Prec([&M](const double* d, double* v) { ilu_apply(M, d, v); }), x, b, reduction, maxit, comm, res);
+}
+
+void bicgstab(const Problem& p, const BCRS& A, const Prec& M, double* x, double* b, double reduction,
               int maxit, const Comm* comm, LinResult& res) {
   const size_t n = 4 * (size_t)p.nv;
   const double EPSILON = 1e-80;
@@ -272,6 +277,7 @@ void newton(Problem& p, double* u, const NewtonOpts& o, const Comm* comm, Newton
   BCRS A;
   build_pattern(p, A);
   ILU M;
+  AMGx H;
   res = NewtonResult();
   auto t_start = clk::now();
   auto defect = [&]() -> bool {  // false on NaN
@@ -313,8 +319,16 @@ void newton(Problem& p, double* u, const NewtonOpts& o, const Comm* comm, Newton
     std::fill(z.begin(), z.end(), 0.0);
     LinResult lr;
     try {
-      ilu_factor(p, A, o.ilu_fill, o.slab_w, M);
-      bicgstab(p, A, M, z.data(), r.data(), linear_reduction, o.lin_maxit, comm, lr);
+      Prec prec;
+      if (o.amg) {
+        amg_build(p, A, o.ilu_fill, o.slab_w, o.amg_cx, H);
+        prec = [&H](const double* d, double* v) { amg_vcycle(H, d, v); };
+      } else {
+        ilu_factor(p, A, o.ilu_fill, o.slab_w, M);
+        prec = [&M](const double* d, double* v) { ilu_apply(M, d, v); };
+      }
+      if (o.krylov == 1) gmres(p, A, prec, z.data(), r.data(), linear_reduction, o.restart, o.lin_maxit, comm, lr);
+      else bicgstab(p, A, prec, z.data(), r.data(), linear_reduction, o.lin_maxit, comm, lr);
     } catch (std::exception&) {
       res.t_lin_solv += secs(t1, clk::now());
       res.status = NEWTON_LINSOLVE_FAILED;

@@ -491,3 +491,92 @@ def test_myelin_config_parity(oracle, axlib):
     vm_g, vm_c = dev.membrane_potential(ug), P.membrane_potential(uc)
     assert np.max(np.abs(vm_g - vm_c)) < 1e-2      # mV
     dev.close()
+
+
+# ---- second linear solver backend of the reference: RestartedGMRes(100) + AMG(ILU0) (myelin build) ----
+@pytest.mark.parametrize("nx,slab_w,cx,fill", [(40, 8, 4, 0), (37, 5, 3, 0), (64, 16, 4, 1), (20, 100, 2, 0)])
+def test_amg_cycle_parity(oracle, axlib, nx, slab_w, cx, fill):
+    """One V(1,1) cycle of the x-aggregation multigrid (Galerkin coarse operators, block-ILU smoothers on every
+    level) against its CPU restatement: 1e-9 of the result's magnitude."""
+    s = small_setup(nx=nx, dx=100.0)
+    dev, P, u0 = _both(oracle, axlib, s)
+    Jo = P.jacobian(u0)
+    dev.set_jacobian(Jo)
+    dev.set_amg(True, cx)
+    dev.ilu_factor(slab_w, fill=fill)
+    rng = np.random.default_rng(11)
+    d = rng.standard_normal(P.n)
+    vg = dev.ilu_apply(d)
+    vo = P.amg_apply(Jo, d, ilu_fill=fill, slab_w=min(slab_w, s["nx"] + 1), amg_cx=cx)
+    assert np.max(np.abs(vg - vo)) <= 1e-9 * np.max(np.abs(vo)), np.max(np.abs(vg - vo)) / np.max(np.abs(vo))
+    # switching the multigrid off again gives the plain ILU
+    dev.set_amg(False)
+    dev.ilu_factor(slab_w, fill=fill)
+    v1 = dev.ilu_apply(d)
+    vo1 = P.ilu_apply(Jo, d, ilu_fill=fill, slab_w=min(slab_w, s["nx"] + 1))
+    assert np.max(np.abs(v1 - vo1)) <= 1e-9 * np.max(np.abs(vo1))
+    dev.close()
+
+
+@pytest.mark.parametrize("restart,red", [(100, 1e-10), (9, 1e-6)])
+def test_gmres_parity(oracle, axlib, restart, red):
+    """Dune::RestartedGMResSolver on the device against the oracle's restatement, same ILU0 preconditioner:
+    equal iteration counts (+-1), solution within 1e-7, incl. the restart path."""
+    s = small_setup(nx=12)
+    dev, P, u0 = _both(oracle, axlib, s)
+    Jo = P.jacobian(u0)
+    r = P.residual(u0)
+    dev.set_jacobian(Jo)
+    zg, rg, resg = dev.solve_gmres(r, red, restart=restart, maxit=600, slab_w=4, fill=0)
+    zo, ro, reso = P.solve_ex(Jo, r, red, maxit=600, ilu_fill=0, slab_w=4, krylov=1, restart=restart)
+    assert resg.converged == 1 and reso.converged == 1
+    assert abs(resg.iterations - reso.iterations) <= 1, (resg.iterations, reso.iterations)
+    assert np.max(np.abs(zg - zo)) <= max(1e-7, 10 * red) * np.max(np.abs(zo))
+    # b holds the final defect b - A z (ISTL keeps the defect in b)
+    assert np.max(np.abs(rg - (r - P.spmv(Jo, zg)))) <= 1e-9 * np.max(np.abs(r))
+    # the BiCGStab backend reaches the same solution
+    zb, _, resb = dev.solve(r, 1e-12, maxit=600, slab_w=4, fill=0)
+    # (ill-conditioned system: two solvers that both reduce their residual norm by 1e-10 agree to ~1e-6)
+    assert resb.converged == 1 and np.max(np.abs(zg - zb)) <= max(1e-5, 1e3 * red) * np.max(np.abs(zb))
+    # maxit exhausted -> not converged, no error
+    zq, _, resq = dev.solve_gmres(r, 1e-30, restart=restart, maxit=9, slab_w=4, fill=0)
+    assert resq.converged == 0 and resq.iterations == 9
+    dev.close()
+
+
+def test_gmres_amg_backend_and_newton(oracle, axlib):
+    """ISTLBackend_GMRES_AMG_ILU0 mirror class (ax1_solverbackend.hh:279-302) and a Newton step that uses it."""
+    s = small_setup(nx=48, dx=100.0)
+    dev, P, u0 = _both(oracle, axlib, s)
+    Jo = P.jacobian(u0)
+    r = P.residual(u0)
+    ls = axlib.ISTLBackend_GMRES_AMG_ILU0(dev, 500, 0, slab_w=8, restart=100, cx=4)
+    z = np.zeros(P.n); rr = r.copy()
+    ls.apply(Jo, z, rr, 1e-8)
+    zo, ro, reso = P.solve_ex(Jo, r, 1e-8, maxit=500, ilu_fill=0, slab_w=8, krylov=1, restart=100, amg=1, amg_cx=4)
+    assert ls.result().converged == 1 and reso.converged == 1
+    assert abs(ls.result().iterations - reso.iterations) <= 2, (ls.result().iterations, reso.iterations)
+    assert np.linalg.norm(r - P.spmv(Jo, z)) <= 1e-6 * np.linalg.norm(r)
+    assert np.max(np.abs(z - zo)) <= 1e-6 * np.max(np.abs(zo))
+    # the multigrid cycle pays: far fewer BiCGStab iterations than with the ILU alone (fine axial grid)
+    dev.set_jacobian(Jo)
+    _, _, res_ilu = dev.solve(r, 1e-8, maxit=2000, slab_w=8, fill=0)
+    dev.set_amg(True, 4)
+    _, _, res_amg = dev.solve(r, 1e-8, maxit=2000, slab_w=8, fill=0)
+    dev.set_amg(False)
+    assert res_ilu.converged == 1 and res_amg.converged == 1
+    assert res_amg.iterations * 3 < res_ilu.iterations, (res_amg.iterations, res_ilu.iterations)
+    # Newton with GMRES + AMG converges to the oracle's fields
+    og = axlib.default_newton_opts(reduction=1e-8, abs_limit=1e-14, min_lin_reduction=1e-6, slab_w=8, amg=1,
+                                   krylov=1, restart=100, lin_maxit=500)
+    oc = oracle.default_newton_opts(reduction=1e-8, abs_limit=1e-14, min_lin_reduction=1e-6, ilu_fill=0, slab_w=8,
+                                    amg=1, amg_cx=4, krylov=1, restart=100, lin_maxit=500)
+    ug, ng = dev.newton(u0, og)
+    uc, nc = P.newton(u0, oc)
+    assert ng.status == 0 and nc.status == 0
+    assert ng.iterations == nc.iterations
+    scale = np.max(np.abs(uc.reshape(-1, 4)), axis=0)
+    err = np.max(np.abs(ug - uc).reshape(-1, 4) / scale, axis=0)
+    assert np.all(err[:3] < 1e-8), err
+    assert err[3] < 5e-7, err
+    dev.close()
