@@ -39,6 +39,8 @@ class Params(C.Structure):
         ("membrane_active", C.c_int), ("automatic_channel_init", C.c_int),
         ("channel_resting_potential", C.c_double), ("use_rownorm_preconditioner", C.c_int),
         ("leak_ratio_na", C.c_double), ("leak_ratio_k", C.c_double),
+        ("use_elec_jacobian_volume", C.c_int), ("use_memb_jacobian_volume", C.c_int),
+        ("use_time_jacobian_volume", C.c_int),
     ]
 
 

@@ -94,6 +94,10 @@ __global__ void __launch_bounds__(128, 4) jacobian_kernel(Dev g, const double* _
       const int ka = 1 - a, kb = 1 - b;
       const bool memb = (cj == g.jm);
       if (memb && !potrow) continue;  // membrane cells carry the potential only
+      // operators whose volume Jacobian is taken by forward differences are left to jacobian_volume_fd_kernel
+      const bool opA = !(g.fd_mask & (memb ? 2 : 1));   // spatial operator of this cell: analytic?
+      const bool timeA = !(g.fd_mask & 4);
+      if (potrow ? !opA : (!opA && !timeA)) continue;
       const double x0 = g.x[ci], x1 = g.x[ci + 1], y0 = g.y[cj], y1 = g.y[cj + 1];
       const double hx = x1 - x0, hy = y1 - y0, ihx = 1.0 / hx, ihy = 1.0 / hy;
       const int v0 = ci + g.nvx * cj;
@@ -128,9 +132,9 @@ __global__ void __launch_bounds__(128, 4) jacobian_kernel(Dev g, const double* _
             for (int m = 0; m < 4; ++m) { gpx += pot[m] * gx[m]; gpy += pot[m] * gy[m]; uk += own[m] * phi[m]; }
             const double Wdt = g.dt * W;
             const double bk = -Dz * (gpx * gx[k] + gpy * gy[k]);  // b . grad psi_k
-            alpha = Wdt * Di;
-            beta = W * phi[k] - Wdt * bk;
-            gamma = Wdt * uk * Dz;
+            alpha = opA ? Wdt * Di : 0.0;
+            beta = (timeA ? W * phi[k] : 0.0) - (opA ? Wdt * bk : 0.0);
+            gamma = opA ? Wdt * uk * Dz : 0.0;
           }
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {

@@ -1,4 +1,5 @@
-// boundary_fd.cu -- finite-difference Jacobian of the membrane-interface boundary term.
+// boundary_fd.cu -- finite-difference Jacobians: the membrane-interface boundary term (always) and the
+// volume terms of the operators configured without analytic jacobian_volume (the reference's default).
 //
 // The reference has no jacobian_boundary: PDELab's NumericalJacobianBoundary differentiates
 // alpha_boundary (acme2_cyl_operator_fully_coupled.hh:29-36, 676-926) with
@@ -56,6 +57,82 @@ __global__ void jacobian_boundary_fd_kernel(Dev g, const double* __restrict__ u,
         }
       }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// PDELab NumericalJacobianVolume (formula: stuff/idefault_patch.dat:14-23) for the local operators that run
+// without an analytic jacobian_volume -- the reference's DEFAULT (use{Elec,Memb,Time}OperatorJacobianVolume
+// = no): per cell, J_ij += (alpha_i(u + delta e_j) - alpha_i(u)) / delta over the 16 local coefficients in
+// the order Na0-3, K0-3, Cl0-3, pot0-3, separately for the spatial operator (weight dt inside alpha) and the
+// time operator. Row-owner form: one thread per vertex row evaluates its own test function in the <= 4
+// cells around it and ADDS to the blocks the analytic kernel left out. Row con_j of alpha does not read the
+// other species, so those differences are exactly zero and the arrow shape of the blocks is kept.
+__global__ void __launch_bounds__(128) jacobian_volume_fd_kernel(Dev g, const double* __restrict__ u, double* A) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= g.nv) return;
+  const int i = v % g.nvx, j = v / g.nvx;
+  const uint8_t rmask = g.dmask[v];
+  const double vs = g.do_volume_scaling ? 1. / g.node_vol[v] : 1.0;
+  const double fd_eps = 1e-7;
+  double* Arow = A + (size_t)v * AX1_ROW;
+  for (int b = 0; b < 2; ++b)
+    for (int a = 0; a < 2; ++a) {
+      const int ci = i - 1 + a, cj = j - 1 + b;
+      if (ci < 0 || ci >= g.nx || cj < 0 || cj >= g.ny) continue;
+      const int ka = 1 - a, kb = 1 - b, k = ka + 2 * kb;
+      const bool memb = (cj == g.jm);
+      if (memb ? !(g.fd_mask & 2) : !(g.fd_mask & 5)) continue;
+      CellCtx c;
+      load_cell(g, u, ci, cj, c);
+      if (memb) {
+        double down = 0.0;
+        memb_volume_row(g, c, k, vs, down);
+        for (int m = 0; m < 4; ++m) {
+          const int lc = 12 + m;
+          const double orig = c.xl[lc];
+          const double delta = fd_eps * (1.0 + fabs(orig));
+          c.xl[lc] += delta;
+          double up = 0.0;
+          memb_volume_row(g, c, k, vs, up);
+          c.xl[lc] = orig;
+          const int s = ((m >> 1) - kb + 1) * 3 + ((m & 1) - ka + 1);
+          if (!((rmask >> 3) & 1)) Arow[s * AX1_BLK + 9] += (up - down) / delta;
+        }
+        continue;
+      }
+      for (int part = 0; part < 2; ++part) {     // 0: spatial operator, 1: time operator
+        if (!(g.fd_mask & (part ? 4 : 1))) continue;
+        const double wm = part ? 1.0 : 0.0;
+        const bool spatial = part == 0;
+        double down[4] = {0.0, 0.0, 0.0, 0.0};
+        elec_volume_row(g, c, k, vs, wm, spatial, down);
+        const int ncomp = part ? 3 : 4;           // the time operator lives on the concentrations only
+        for (int comp = 0; comp < ncomp; ++comp)
+          for (int m = 0; m < 4; ++m) {
+            const int lc = comp * 4 + m;
+            const double orig = c.xl[lc];
+            const double delta = fd_eps * (1.0 + fabs(orig));
+            c.xl[lc] += delta;
+            double up[4] = {0.0, 0.0, 0.0, 0.0};
+            elec_volume_row(g, c, k, vs, wm, spatial, up);
+            c.xl[lc] = orig;
+            const int s = ((m >> 1) - kb + 1) * 3 + ((m & 1) - ka + 1);
+            double* blk = Arow + s * AX1_BLK;
+            for (int r = 0; r < 3; ++r) {
+              if ((rmask >> r) & 1) continue;
+              if (comp == r) blk[2 * r] += (up[r] - down[r]) / delta;
+              else if (comp == 3) blk[2 * r + 1] += (up[r] - down[r]) / delta;
+            }
+            if (spatial && !((rmask >> 3) & 1)) blk[6 + comp] += (up[3] - down[3]) / delta;
+          }
+      }
+    }
+}
+
+void launch_jacobian_volume_fd(const Dev& g, const double* u, double* A, cudaStream_t st) {
+  if (!g.fd_mask) return;
+  const int bs = 128;
+  jacobian_volume_fd_kernel<<<(g.nv + bs - 1) / bs, bs, 0, st>>>(g, u, A);
 }
 
 void launch_jacobian_boundary_fd(const Dev& g, const double* u, double* A, cudaStream_t st) {

@@ -43,6 +43,9 @@ struct Dev {
   int equil;                  // do_equilibration && time < t_equilibrium (host evaluated)
   double dummy_value;
   double dt;
+  // volume Jacobian by forward differences instead of the analytic blocks: bit 0 electrolyte operator,
+  // bit 1 membrane operator, bit 2 time operator (the use*OperatorJacobianVolume = no default of the reference)
+  int fd_mask;
 };
 
 // Matrix layout: 9 stencil slots per vertex row, slot s = (dj+1)*3 + (di+1). Within a 4x4 block the

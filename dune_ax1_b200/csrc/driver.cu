@@ -473,6 +473,8 @@ int drv_refresh_dev(ax1gpu_ctx* c) {
   const double t_lop = c->time + c->dt;  // OneStepMethod sets the LOP time to t+dt
   g.stim_on = p.do_stimulation && (t_lop > p.tinj_start && t_lop < p.tinj_end);
   g.equil = p.do_equilibration && c->time < p.t_equilibrium;
+  g.fd_mask = (p.use_elec_jacobian_volume ? 0 : 1) | (p.use_memb_jacobian_volume ? 0 : 2) |
+              (p.use_time_jacobian_volume ? 0 : 4);
   return 0;
 }
 
@@ -538,6 +540,10 @@ int drv_jacobian(ax1gpu_ctx* c, const double* d_u) {
   drv_refresh_dev(c);
   launch_jacobian_volume(c->g, d_u, c->d_A, c->stream);
   AX1_LAUNCH_CHECK(c);
+  if (c->g.fd_mask) {   // NumericalJacobianVolume for the operators configured without jacobian_volume
+    launch_jacobian_volume_fd(c->g, d_u, c->d_A, c->stream);
+    AX1_LAUNCH_CHECK(c);
+  }
   if (c->prm.membrane_active) {
     launch_jacobian_boundary_fd(c->g, d_u, c->d_A, c->stream);
     AX1_LAUNCH_CHECK(c);

@@ -23,6 +23,7 @@ void launch_channel_accept(int nx, const ChannelDev& ch, cudaStream_t st);
 void launch_memb_pot(const Dev& g, const double* u, double* vm, cudaStream_t st);
 // boundary_fd.cu (compiled with --fmad=false)
 void launch_jacobian_boundary_fd(const Dev& g, const double* u, double* A, cudaStream_t st);
+void launch_jacobian_volume_fd(const Dev& g, const double* u, double* A, cudaStream_t st);  // adds the g.fd_mask parts
 
 // solver.cu
 struct Scalars {  // device-resident Krylov scalars

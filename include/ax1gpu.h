@@ -69,6 +69,11 @@ typedef struct ax1gpu_params {
   double channel_resting_potential;
   int use_rownorm_preconditioner; /* rownorm_preconditioner.hh:65-155                           */
   double leak_ratio_na, leak_ratio_k; /* [equilibration] Na_leak / K_leak                       */
+  /* [general] useElecOperatorJacobianVolume / useMembOperatorJacobianVolume / useTimeOperatorJacobianVolume
+   * (acme2_cyl_operator_fully_coupled.hh:79, convectiondiffusionfem.hh:78, acme2_cyl_toperator.hh:51):
+   * 1 = the operator's analytic jacobian_volume, 0 = PDELab's NumericalJacobianVolume (forward difference,
+   * delta = 1e-7 (1 + |u_j|)), which is the reference's default. ax1gpu_params_default sets all three to 1. */
+  int use_elec_jacobian_volume, use_memb_jacobian_volume, use_time_jacobian_volume;
 } ax1gpu_params;
 
 typedef struct ax1gpu_newton_opts {

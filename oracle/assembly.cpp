@@ -405,7 +405,7 @@ void jacobian(const Problem& p, const double* u, BCRS& A) {
       bool memb = p.cell_sub[p.cid(i, j)] == MEMBRANE;
       if (memb) {
         double m[16] = {0};
-        if (p.cfg.analytic_volume_jacobian) {
+        if (p.cfg.analytic_volume_jacobian & 2) {
           memb_jacobian_volume(p, c, p.dt, m);
         } else {
           double down[4] = {0}, xp[4];
@@ -425,7 +425,7 @@ void jacobian(const Problem& p, const double* u, BCRS& A) {
       }
       {  // spatial volume term, weight dt
         double m[256] = {0};
-        if (p.cfg.analytic_volume_jacobian) {
+        if (p.cfg.analytic_volume_jacobian & 1) {
           elec_jacobian_volume(p, c, xl, p.dt, m);
         } else {
           double down[16] = {0}, xp[16];
@@ -444,7 +444,7 @@ void jacobian(const Problem& p, const double* u, BCRS& A) {
       }
       {  // mass term, weight 1
         double m[144] = {0};
-        if (p.cfg.analytic_volume_jacobian) {
+        if (p.cfg.analytic_volume_jacobian & 4) {
           time_jacobian_volume(c, 1.0, m);
         } else {
           double down[12] = {0}, xp[12];

@@ -26,6 +26,8 @@ typedef struct ax1o_config {
   double t_equilibrium, dummy_value;
   int membrane_active, automatic_channel_init;
   double channel_resting_potential;
+  /* bit 0/1/2 = use{Elec,Memb,Time}OperatorJacobianVolume (analytic jacobian_volume; a cleared bit means
+   * PDELab's NumericalJacobianVolume, the reference default); 7 = all analytic, 0 = all finite differences */
   int analytic_volume_jacobian, use_rownorm_preconditioner;
   double leak_ratio_na, leak_ratio_k;
 } ax1o_config;

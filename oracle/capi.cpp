@@ -29,7 +29,7 @@ void ax1o_config_default(ax1o_config* c) {
   c->top_dirichlet[0] = c->top_dirichlet[1] = 1;
   c->dummy_value = 1.0;
   c->membrane_active = 1; c->automatic_channel_init = 1; c->channel_resting_potential = -65.0;
-  c->analytic_volume_jacobian = 1;
+  c->analytic_volume_jacobian = 7;
   c->leak_ratio_na = 0.13; c->leak_ratio_k = 0.87;
 }
 

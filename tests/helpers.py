@@ -5,7 +5,10 @@ from dune_ax1_b200 import setups
 
 
 def oracle_problem(O, s, analytic=1, **cfg_over):
+    """analytic: 1 = all three operators with analytic jacobian_volume, 0 = all by finite differences (reference
+    default), otherwise a bit mask (1 elec, 2 memb, 4 time operator analytic)."""
     p = s["params"]
+    analytic = 7 if analytic == 1 else int(analytic)
     bc = s["bc"].c
     cfg = O.default_config(
         xmin_global=0.0, xmax_global=s["xmax"], ymin=float(s["y"][0]), ymax=float(s["y"][-1]),

@@ -580,3 +580,47 @@ def test_gmres_amg_backend_and_newton(oracle, axlib):
     assert np.all(err[:3] < 1e-8), err
     assert err[3] < 5e-7, err
     dev.close()
+
+
+# ---- the reference's DEFAULT Jacobian: PDELab NumericalJacobianVolume (use*OperatorJacobianVolume = no) ----
+@pytest.mark.parametrize("mask", [0, 6, 3])
+def test_fd_volume_jacobian_parity(oracle, axlib, mask):
+    """Forward-difference volume Jacobian on the device against the oracle's restatement of PDELab's
+    NumericalJacobianVolume. mask: bit 0/1/2 = elec/memb/time operator analytic (0 = everything by FD).
+    Tolerance 1e-6 of the scalar-row scale: the difference quotient amplifies last-bit differences by 1/delta."""
+    s = small_setup(nx=6, stimulation=True)
+    s["params"].update(use_elec_jacobian_volume=mask & 1, use_memb_jacobian_volume=(mask >> 1) & 1,
+                       use_time_jacobian_volume=(mask >> 2) & 1)
+    dev, P, u0 = _both(oracle, axlib, s, t=30.0, analytic=mask)
+    rng = np.random.default_rng(17)
+    u = u0 * (1.0 + 1e-4 * rng.standard_normal(u0.shape))
+    Jg = dev.jacobian(u).reshape(-1, 4, 4)
+    Jo = P.jacobian(u).reshape(-1, 4, 4)
+    rowptr, _ = P.pattern()
+    rows = np.repeat(np.arange(P.nv), np.diff(rowptr))
+    scale = np.zeros((P.nv, 4))
+    np.maximum.at(scale, rows, np.max(np.abs(Jo), axis=2))
+    err = np.abs(Jg - Jo) / (scale[rows][:, :, None] + 1e-300)
+    assert err.max() < 1e-6, err.max()
+    # FD keeps the structure: constrained rows are unit rows, species do not couple directly
+    assert np.all(Jg[:, 0, 1] == 0.0) and np.all(Jg[:, 1, 2] == 0.0) and np.all(Jg[:, 2, 0] == 0.0)
+    dev.close()
+
+
+def test_newton_with_fd_jacobian(oracle, axlib):
+    """A Newton step in the reference's default mode (all volume Jacobians by finite differences) follows the
+    oracle in the same mode: same iteration count, fields within 1e-8."""
+    s = small_setup(nx=6)
+    s["params"].update(use_elec_jacobian_volume=0, use_memb_jacobian_volume=0, use_time_jacobian_volume=0)
+    dev, P, u0 = _both(oracle, axlib, s, analytic=0)
+    og = axlib.default_newton_opts(reduction=1e-9, abs_limit=1e-14, min_lin_reduction=1e-10, slab_w=4)
+    oc = oracle.default_newton_opts(reduction=1e-9, abs_limit=1e-14, min_lin_reduction=1e-10, ilu_fill=0, slab_w=4)
+    ug, rg = dev.newton(u0, og)
+    uc, rc = P.newton(u0, oc)
+    assert rg.status == 0 and rc.status == 0
+    assert rg.iterations == rc.iterations
+    scale = np.max(np.abs(uc.reshape(-1, 4)), axis=0)
+    err = np.max(np.abs(ug - uc).reshape(-1, 4) / scale, axis=0)
+    assert np.all(err[:3] < 1e-8), err
+    assert err[3] < 5e-7, err
+    dev.close()
