@@ -67,6 +67,27 @@ class NewtonResult(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class TimeLoopOpts(C.Structure):
+    _fields_ = [("dtstart", C.c_double), ("max_dt", C.c_double), ("min_dt", C.c_double), ("max_dt_ap", C.c_double),
+                ("vm_ap_threshold", C.c_double), ("lower_limit", C.c_int), ("upper_limit", C.c_int),
+                ("max_restarts", C.c_int), ("adaptive", C.c_int)]
+
+
+class TimeLoopState(C.Structure):
+    _fields_ = [("time", C.c_double), ("dt", C.c_double), ("its", C.c_int), ("last_its", C.c_int), ("steps", C.c_int)]
+
+
+class StepResult(C.Structure):
+    _fields_ = [("time", C.c_double), ("dt", C.c_double), ("newton_iterations", C.c_int),
+                ("lin_iterations", C.c_int), ("restarts", C.c_int), ("newton_status", C.c_int),
+                ("vm_min", C.c_double), ("vm_max", C.c_double), ("defect", C.c_double),
+                ("first_defect", C.c_double), ("t_assembler", C.c_double), ("t_lin_solv", C.c_double)]
+
+    @property
+    def iterations(self):
+        return self.newton_iterations
+
+
 class LinResult(C.Structure):
     _fields_ = [("converged", C.c_int), ("iterations", C.c_int), ("reduction", C.c_double),
                 ("it_half", C.c_double)]
@@ -139,6 +160,12 @@ def lib():
     L.ax1gpu_download_u.argtypes = [H, c_double_p]
     L.ax1gpu_set_uold_dev.argtypes = [H]
     L.ax1gpu_newton_dev.argtypes = [H, C.POINTER(NewtonOpts), C.POINTER(NewtonResult)]
+    L.ax1gpu_timeloop_opts_default.argtypes = [C.POINTER(TimeLoopOpts)]
+    L.ax1gpu_timeloop_opts_default.restype = None
+    L.ax1gpu_time_step.argtypes = [H, C.POINTER(TimeLoopOpts), C.POINTER(NewtonOpts), C.POINTER(TimeLoopState),
+                                   C.POINTER(StepResult)]
+    L.ax1gpu_membrane_potential_range.argtypes = [H, c_double_p, c_double_p]
+    L.ax1gpu_membrane_potential_dev.argtypes = [H, c_double_p]
     L.ax1gpu_spmv.argtypes = [H, c_double_p, c_double_p]
     L.ax1gpu_ilu_factor.argtypes = [H, C.c_int]
     L.ax1gpu_ilu_factor_n.argtypes = [H, C.c_int, C.c_int]
@@ -540,6 +567,22 @@ class Ax1Gpu:
         res = NewtonResult()
         _chk(lib().ax1gpu_newton(self.h, C.byref(opts), _dp(u), C.byref(res)))
         return u, res
+
+    def time_step(self, tl_opts, newton_opts, state):
+        """One adaptive time step on the device-resident iterate (ax1gpu_time_step); state is updated in place."""
+        res = StepResult()
+        _chk(lib().ax1gpu_time_step(self.h, C.byref(tl_opts), C.byref(newton_opts), C.byref(state), C.byref(res)))
+        return res
+
+    def membrane_potential_range(self):
+        lo, hi = C.c_double(), C.c_double()
+        _chk(lib().ax1gpu_membrane_potential_range(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def membrane_potential_dev(self):
+        vm = np.zeros(self.nx)
+        _chk(lib().ax1gpu_membrane_potential_dev(self.h, _dp(vm)))
+        return vm
 
     def upload_u(self, u):
         _chk(lib().ax1gpu_upload_u(self.h, _dp(f64(u))))

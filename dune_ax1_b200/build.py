@@ -18,6 +18,7 @@ UNITS = [
     ("ilu1.cu", []),
     ("amg.cu", []),
     ("driver.cu", []),
+    ("timeloop.cu", []),
     ("capi.cu", []),
     ("host_model.cpp", []),
 ]

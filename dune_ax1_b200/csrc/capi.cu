@@ -480,6 +480,37 @@ int ax1gpu_newton(ax1gpu_handle c, const ax1gpu_newton_opts* opts, double* u, ax
   return down(c, u, c->d_u);
 }
 
+void ax1gpu_timeloop_opts_default(ax1gpu_timeloop_opts* o) {
+  // [timeStepping] defaults of acme2_cyl_parametertree.hh (seconds) over the default time_scale 1e-6
+  o->dtstart = 1.0; o->max_dt = 50.0; o->min_dt = 0.05; o->max_dt_ap = 10.0; o->vm_ap_threshold = -50.0;
+  o->lower_limit = 3; o->upper_limit = 5; o->max_restarts = 3; o->adaptive = 1;
+}
+
+int ax1gpu_time_step(ax1gpu_handle c, const ax1gpu_timeloop_opts* opts, const ax1gpu_newton_opts* newton,
+                     ax1gpu_timeloop_state* state, ax1gpu_step_result* res) {
+  AX1_CHECK_H(c);
+  if (!state || !res) { set_error("time_step: state and res must not be NULL"); return AX1GPU_EINVAL; }
+  cudaSetDevice(c->device);
+  ax1gpu_timeloop_opts o;
+  if (opts) o = *opts; else ax1gpu_timeloop_opts_default(&o);
+  ax1gpu_newton_opts no;
+  if (newton) no = *newton; else ax1gpu_newton_opts_default(&no);
+  return drv_time_step(c, &o, &no, state, res);
+}
+
+int ax1gpu_membrane_potential_range(ax1gpu_handle c, double* vm_min, double* vm_max) {
+  AX1_CHECK_H(c);
+  cudaSetDevice(c->device);
+  double lo = 0, hi = 0;
+  int rc = drv_vm_minmax(c, &lo, &hi);
+  if (rc) return rc;
+  if (vm_min) *vm_min = lo;
+  if (vm_max) *vm_max = hi;
+  return AX1GPU_OK;
+}
+
+int ax1gpu_membrane_potential_dev(ax1gpu_handle c, double* vm) { return ax1gpu_membrane_potential(c, nullptr, vm); }
+
 int ax1gpu_time_kernel(ax1gpu_handle c, const char* name, int reps, double* ms) {
   AX1_CHECK_H(c);
   cudaSetDevice(c->device);

@@ -98,6 +98,10 @@ int drv_solve(ax1gpu_ctx* c, double* d_rhs, double* d_zout, double reduction, in
 int drv_solve_gmres(ax1gpu_ctx* c, double* d_rhs, double* d_zout, double reduction, int restart, int maxit,
                     ax1gpu_lin_result* res);
 int drv_newton(ax1gpu_ctx* c, const ax1gpu_newton_opts* o, ax1gpu_newton_result* res);
+// timeloop.cu
+int drv_vm_minmax(ax1gpu_ctx* c, double* vmin, double* vmax);
+int drv_time_step(ax1gpu_ctx* c, const ax1gpu_timeloop_opts* o, const ax1gpu_newton_opts* no, ax1gpu_timeloop_state* s,
+                  ax1gpu_step_result* out);
 int drv_norm(ax1gpu_ctx* c, const double* a, double* out_host);
 int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms);
 }  // namespace ax1

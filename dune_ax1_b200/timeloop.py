@@ -83,3 +83,49 @@ class TimeLoop:
             if vm_every and n % vm_every == 0:
                 vms.append((self.time, self.dev.membrane_potential(self.u)))
         return vms
+
+
+class DeviceTimeLoop:
+    """The same loop run by the library itself (ax1gpu_time_step, csrc/timeloop.cu): iterate, previous step and
+    channel state stay in HBM, only the step result (Newton statistics, min / max V_m) comes back per step."""
+
+    def __init__(self, dev, u0, dtstart=1.0, time0=0.0, newton_opts=None, max_dt=50.0, min_dt=0.05, max_dt_ap=10.0,
+                 lower_limit=3, upper_limit=5, max_restarts=3, adaptive=True):
+        from . import api
+        self.dev = dev
+        self.opts = newton_opts or api.default_newton_opts()
+        self.tl = api.TimeLoopOpts()
+        api.lib().ax1gpu_timeloop_opts_default(self.tl)
+        self.tl.dtstart, self.tl.max_dt, self.tl.min_dt, self.tl.max_dt_ap = dtstart, max_dt, min_dt, max_dt_ap
+        self.tl.lower_limit, self.tl.upper_limit = lower_limit, upper_limit
+        self.tl.max_restarts, self.tl.adaptive = max_restarts, int(adaptive)
+        self.state = api.TimeLoopState(time=float(time0), dt=float(dtstart), its=0, last_its=0, steps=0)
+        dev.upload_u(u0)
+        self.trace = []
+
+    @property
+    def time(self):
+        return self.state.time
+
+    @property
+    def dt(self):
+        return self.state.dt
+
+    @property
+    def u(self):
+        return self.dev.download_u()
+
+    def step(self):
+        res = self.dev.time_step(self.tl, self.opts, self.state)
+        if res.newton_status != 0:
+            raise NewtonFailure("Newton failed %d times at t=%g (status %d)" % (res.restarts, res.time,
+                                                                               res.newton_status))
+        self.trace.append((res.time, res.dt, res.newton_iterations, res.restarts, res.vm_min, res.vm_max))
+        return res
+
+    def run(self, tend, max_steps=10 ** 9):
+        n = 0
+        while self.state.time < tend - 1e-8 and n < max_steps:
+            self.step()
+            n += 1
+        return n

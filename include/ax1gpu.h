@@ -162,6 +162,39 @@ int ax1gpu_download_u(ax1gpu_handle h, double* u);
 int ax1gpu_set_uold_dev(ax1gpu_handle h); /* uold := device iterate */
 int ax1gpu_newton_dev(ax1gpu_handle h, const ax1gpu_newton_opts* opts, ax1gpu_newton_result* res);
 
+/* ---- the caller of the path with all state resident on the device ----
+ * One adaptive time step of Acme2CylSimulation::run (acme2_cyl_simulation.hh:255-439 dt control, :457/:589/
+ * :916-927 updateState -> solver.apply -> uold = unew -> acceptTimeStep, :593-638 halve-and-retry). Times in
+ * the units of the grid operator (micro seconds with the default time_scale). */
+typedef struct ax1gpu_timeloop_opts {
+  double dtstart;                 /* command line dt0; re-used when the stimulation starts (:262-266)        */
+  double max_dt, min_dt;          /* [timeStepping] maxTimeStep / minTimeStep, already divided by time_scale */
+  double max_dt_ap;               /* maxTimeStepAP / time_scale (:378-383)                                   */
+  double vm_ap_threshold;         /* -50 mV                                                                  */
+  int lower_limit, upper_limit;   /* timeStepLowerLimitNewtonIt (3) / timeStepUpperLimitNewtonIt (5)         */
+  int max_restarts;               /* maxNumberNewtonRestarts                                                 */
+  int adaptive;                   /* useAdaptiveTimeStep                                                     */
+} ax1gpu_timeloop_opts;
+typedef struct ax1gpu_timeloop_state { /* carried by the caller between steps */
+  double time, dt;
+  int its, last_its, steps;
+} ax1gpu_timeloop_state;
+typedef struct ax1gpu_step_result {
+  double time, dt;                /* time reached and the step that was accepted                             */
+  int newton_iterations, lin_iterations, restarts;
+  int newton_status;              /* != 0: the step failed max_restarts + 1 times; iterate reset to uold     */
+  double vm_min, vm_max;          /* membrane potential extrema [mV] over all ranks after the step           */
+  double defect, first_defect, t_assembler, t_lin_solv;
+} ax1gpu_step_result;
+void ax1gpu_timeloop_opts_default(ax1gpu_timeloop_opts* o);
+/* advances the device-resident iterate (ax1gpu_upload_u / ax1gpu_download_u) by one time step */
+int ax1gpu_time_step(ax1gpu_handle h, const ax1gpu_timeloop_opts* opts, const ax1gpu_newton_opts* newton,
+                     ax1gpu_timeloop_state* state, ax1gpu_step_result* res);
+/* min / max of the membrane potential [mV] of the device iterate (all ranks) */
+int ax1gpu_membrane_potential_range(ax1gpu_handle h, double* vm_min, double* vm_max);
+/* membrane potential [mV] per membrane column of the device iterate */
+int ax1gpu_membrane_potential_dev(ax1gpu_handle h, double* vm_mV);
+
 /* ---- building blocks exposed for parity tests and profiling ---- */
 int ax1gpu_spmv(ax1gpu_handle h, const double* x, double* y);
 int ax1gpu_ilu_factor(ax1gpu_handle h, int slab_w);   /* keeps the handle's current fill level (0 at creation) */

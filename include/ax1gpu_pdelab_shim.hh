@@ -255,4 +255,39 @@ class NewtonShim {
   NewtonResult res_;
 };
 
+// ---- time loop -----------------------------------------------------------------------------------
+// The body of the while(time < tend) loop of Acme2CylSimulation::run (acme2_cyl_simulation.hh:236-932)
+// executed by the library with the solution vectors resident on the device: dt control (:255-439),
+// updateState -> solver.apply -> uold = unew -> acceptTimeStep (:457, :589, :916-927), halve-and-retry on a
+// NewtonError (:593-638). u is uploaded once (load) and read back only when the caller wants output (store).
+template <class U, class EP = DefaultErrorPolicy>
+class TimeLoopShim {
+ public:
+  TimeLoopShim(Device& d, double time0, double dtstart) : d_(d) {
+    ax1gpu_timeloop_opts_default(&tl_);
+    ax1gpu_newton_opts_default(&no_);
+    tl_.dtstart = dtstart;
+    st_.time = time0; st_.dt = dtstart; st_.its = st_.last_its = st_.steps = 0;
+  }
+  ax1gpu_timeloop_opts& options() { return tl_; }        // [timeStepping] keys
+  ax1gpu_newton_opts& newtonOptions() { return no_; }    // [solver] keys
+  void load(const U& u) { EP::library(ax1gpu_upload_u(d_.handle(), VectorAccess<U>::data(u))); }
+  void store(U& u) const { EP::library(ax1gpu_download_u(d_.handle(), VectorAccess<U>::data(u))); }
+  double time() const { return st_.time; }
+  double dt() const { return st_.dt; }
+  // one accepted time step; throws the NewtonError of the last attempt when all restarts failed
+  const ax1gpu_step_result& step() {
+    EP::library(ax1gpu_time_step(d_.handle(), &tl_, &no_, &st_, &res_));
+    EP::newton(res_.newton_status);
+    return res_;
+  }
+
+ private:
+  Device& d_;
+  ax1gpu_timeloop_opts tl_;
+  ax1gpu_newton_opts no_;
+  ax1gpu_timeloop_state st_;
+  ax1gpu_step_result res_;
+};
+
 }  // namespace ax1gpu

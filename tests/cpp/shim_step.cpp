@@ -44,6 +44,21 @@ int main(int argc, char** argv) {
     pdesolver.setReduction(1e-9); pdesolver.setAbsoluteLimit(1e-14); pdesolver.setMinLinearReduction(1e-10);
     pdesolver.setSlabWidth(hdr[2]);
     const double time = 0.0, dt = 1.0;
+    if (hdr[3] == 2) {
+      // the same step through the library's own time loop (state stays on the device)
+      ax1gpu::TimeLoopShim<U> loop(dev, time, dt);
+      ax1gpu_newton_opts& no = loop.newtonOptions();
+      no.reduction = 1e-9; no.abs_limit = 1e-14; no.min_lin_reduction = 1e-10; no.slab_w = hdr[2];
+      loop.load(u);
+      const ax1gpu_step_result& sr = loop.step();
+      loop.store(u);
+      std::printf("time %.3f dt %.3f newton its %d lin its %d vm [%.4f, %.4f]\n", sr.time, sr.dt, sr.newton_iterations,
+                  sr.lin_iterations, sr.vm_min, sr.vm_max);
+      FILE* o = std::fopen(argv[2], "wb");
+      std::fwrite(u.data(), sizeof(double), u.size(), o);
+      std::fclose(o);
+      return 0;
+    }
     U uold = u;
     gfMembFlux.updateState(time, dt, uold);
     igo.preStep(time, dt, uold);

@@ -28,13 +28,14 @@ def test_shim_compiles_without_dune(axlib, tmp_path):
 
 
 @pytest.mark.gpu
-def test_shim_time_step_matches_oracle(oracle, axlib, tmp_path):
+@pytest.mark.parametrize("mode", [1, 2])   # 1: IGO / LS / PDESOLVER seam, 2: TimeLoopShim (ax1gpu_time_step)
+def test_shim_time_step_matches_oracle(oracle, axlib, tmp_path, mode):
     exe = _build(tmp_path)
     s = small_setup(nx=6)
     slab_w = 4
     blob = str(tmp_path / "problem.bin")
     with open(blob, "wb") as f:
-        f.write(struct.pack("4i", s["nx"], s["ny"], slab_w, 1))
+        f.write(struct.pack("4i", s["nx"], s["ny"], slab_w, mode))
         for a, dt in ((s["x"], "f8"), (s["y"], "f8"), (s["cell_subdomain"], "u1"), (s["eps_memb"], "f8"),
                       (s["node_volume"], "f8"), (s["dirichlet"], "u1"), (s["g_leak"], "f8"), (s["g_nav"], "f8"),
                       (s["g_kv"], "f8"), (s["u0"], "f8")):

@@ -37,3 +37,51 @@ def test_action_potential_upstroke_matches_oracle(oracle, axlib):
     sg, _ = dev.channel_state()
     assert np.max(np.abs(sg - P.channel_state())) < 1e-8  # gating variables m, h, n and leak ratios
     dev.close()
+
+
+def test_device_resident_time_loop_matches_host_loop(oracle, axlib):
+    """ax1gpu_time_step (the time loop inside the library, state resident in HBM) takes exactly the steps of the
+    host-side TimeLoop that hands u back and forth every step: same dt sequence, same Newton counts, same fields."""
+    from dune_ax1_b200 import setups
+    from dune_ax1_b200.timeloop import DeviceTimeLoop, TimeLoop
+    s = setups.make_setup(12, dx=100.0e3, stimulation=True, perturbation=0.0)
+    kw = dict(reduction=1e-8, abs_limit=20.0, min_lin_reduction=1e-8, maxit=50)
+    d1, d2 = setups.make_device(s), setups.make_device(s)
+    t1 = TimeLoop(d1, s["u0"], newton_opts=axlib.default_newton_opts(slab_w=128, **kw), dtstart=1.0, do_stimulation=True,
+                  lower_limit=10, upper_limit=30)
+    t2 = DeviceTimeLoop(d2, s["u0"], newton_opts=axlib.default_newton_opts(slab_w=128, **kw), dtstart=1.0,
+                        lower_limit=10, upper_limit=30)
+    while t1.time < 120.0:
+        t1.step()
+        r = t2.step()
+        a, b = t1.trace[-1], t2.trace[-1]
+        assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2], (a, b)
+        assert abs(a[4] - b[4]) < 1e-9 and abs(a[5] - b[5]) < 1e-9
+    assert np.array_equal(t1.u, t2.u)
+    lo, hi = d2.membrane_potential_range()
+    vm = d2.membrane_potential_dev()
+    assert lo == vm.min() and hi == vm.max() and hi > -50.0
+    d1.close(); d2.close()
+
+
+def test_time_step_restart_on_newton_failure(axlib):
+    """Newton failure -> dt / 2 and retry from uold (acme2_cyl_simulation.hh:593-638); exhausting the restarts
+    reports the status and leaves the iterate at uold."""
+    from dune_ax1_b200 import setups
+    s = setups.make_setup(8, dx=100.0e3, stimulation=True, perturbation=0.0)
+    dev = setups.make_device(s)
+    dev.upload_u(s["u0"])
+    tl = axlib.TimeLoopOpts()
+    axlib.lib().ax1gpu_timeloop_opts_default(tl)
+    tl.max_restarts = 2
+    st = axlib.TimeLoopState(time=0.0, dt=1.0, its=0, last_its=0, steps=0)
+    # a Newton solver that may not iterate at all cannot converge: every attempt fails
+    bad = axlib.default_newton_opts(maxit=0, reduction=1e-30, abs_limit=1e-300)
+    r = dev.time_step(tl, bad, st)
+    assert r.newton_status == 1 and r.restarts == 3 and st.steps == 0 and st.time == 0.0
+    assert st.dt == 0.25                                   # halved twice before giving up
+    assert np.array_equal(dev.download_u(), s["u0"])
+    good = axlib.default_newton_opts(slab_w=128)
+    r = dev.time_step(tl, good, st)
+    assert r.newton_status == 0 and st.steps == 1 and st.time == 0.25
+    dev.close()
