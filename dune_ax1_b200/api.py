@@ -41,6 +41,7 @@ class Params(C.Structure):
         ("leak_ratio_na", C.c_double), ("leak_ratio_k", C.c_double),
         ("use_elec_jacobian_volume", C.c_int), ("use_memb_jacobian_volume", C.c_int),
         ("use_time_jacobian_volume", C.c_int),
+        ("do_memb_flux_stimulation", C.c_int), ("memb_flux_ion", C.c_int), ("memb_flux_inj", C.c_double),
     ]
 
 

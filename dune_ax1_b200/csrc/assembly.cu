@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(128) residual_kernel(Dev g, const double* __re
         if (mode == 0) memb_volume_row(g, c, k, vs, out[3]);
       } else {
         elec_volume_row(g, c, k, vs, mode == 0 ? 1.0 : -1.0, mode == 0, out);
-        if (mode == 0 && g.membrane_active && ((cj == g.jm - 1 && b == 0) || (cj == g.jm + 1 && b == 1))) {
+        if (mode == 0 && (g.membrane_active || g.fstim_on) && ((cj == g.jm - 1 && b == 0) || (cj == g.jm + 1 && b == 1))) {
           // our vertex lies on the membrane interface face of this cell
           FaceCtx f;
           make_face(g, u, c, f);

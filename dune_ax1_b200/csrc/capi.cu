@@ -53,6 +53,7 @@ void ax1gpu_params_default(ax1gpu_params* p) {
   p->membrane_active = 1; p->automatic_channel_init = 1; p->channel_resting_potential = -65.0;
   p->leak_ratio_na = 0.13; p->leak_ratio_k = 0.87;
   p->use_elec_jacobian_volume = p->use_memb_jacobian_volume = p->use_time_jacobian_volume = 1;
+  p->do_memb_flux_stimulation = 0; p->memb_flux_ion = 2; p->memb_flux_inj = 0.0;
 }
 
 void ax1gpu_newton_opts_default(ax1gpu_newton_opts* o) {

@@ -46,6 +46,9 @@ struct Dev {
   // volume Jacobian by forward differences instead of the analytic blocks: bit 0 electrolyte operator,
   // bit 1 membrane operator, bit 2 time operator (the use*OperatorJacobianVolume = no default of the reference)
   int fd_mask;
+  // trans-membrane flux stimulation (host evaluated per LOP time): species, and memb_flux_inj times the cosine ramp
+  int fstim_on, fstim_ion;
+  double fstim_amp, fstim_inj;
 };
 
 // Matrix layout: 9 stencil slots per vertex row, slot s = (dj+1)*3 + (di+1). Within a 4x4 block the

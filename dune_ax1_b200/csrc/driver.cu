@@ -473,6 +473,13 @@ int drv_refresh_dev(ax1gpu_ctx* c) {
   const double t_lop = c->time + c->dt;  // OneStepMethod sets the LOP time to t+dt
   g.stim_on = p.do_stimulation && (t_lop > p.tinj_start && t_lop < p.tinj_end);
   g.equil = p.do_equilibration && c->time < p.t_equilibrium;
+  g.fstim_on = p.do_memb_flux_stimulation && (t_lop > p.tinj_start && t_lop < p.tinj_end);
+  g.fstim_ion = p.memb_flux_ion;
+  g.fstim_inj = p.memb_flux_inj;
+  {
+    const double t_rel = (t_lop - p.tinj_start) / p.tinj_end;
+    g.fstim_amp = g.fstim_on ? 0.5 * (1 - std::cos(2 * con_pi * t_rel)) : 0.0;   // times memb_flux_inj / |face| on the device
+  }
   g.fd_mask = (p.use_elec_jacobian_volume ? 0 : 1) | (p.use_memb_jacobian_volume ? 0 : 2) |
               (p.use_time_jacobian_volume ? 0 : 4);
   return 0;

@@ -143,7 +143,7 @@ __device__ __forceinline__ void memb_volume_row(const Dev& g, const CellCtx& c, 
 // Returns j_species * (A_ext / A_this) for the three species (Cl has no channel -> 0).
 __device__ __forceinline__ void membrane_flux(const Dev& g, int ci, bool from_cytosol, double uPot,
                                               const double uCon[3], double pot2, const double con2[3],
-                                              double surfaceScale, double jout[3]) {
+                                              double surfaceScale, double stimFlux, double jout[3]) {
   const int ySign = from_cytosol ? -1 : 1;
   const double n_y = from_cytosol ? 1.0 : -1.0;
   double potJump = pot2;
@@ -161,6 +161,7 @@ __device__ __forceinline__ void membrane_flux(const Dev& g, int ci, bool from_cy
       if (j == CL) continue;
       const int ch = j + 2 * kk;      // 0 Na_leak, 1 K_leak, 2 Nav, 3 Kv
       double conductance = (g.equil && kk == 1) ? 0.0 : g.geff[(size_t)ch * g.nx + ci];
+      if (!g.membrane_active) conductance = 0.0;
       double C = (10 * conductance) / (con_e * valence * con_mol);
       if (g.equil) C *= g.dummy_value;
       C *= g.time_scale / g.length_scale;
@@ -172,6 +173,7 @@ __device__ __forceinline__ void membrane_flux(const Dev& g, int ci, bool from_cy
       total += flux;
     }
     double yj = total * n_y;
+    if (j == g.fstim_ion) yj += stimFlux;   // default_nernst_planck_parameters.hh:439-475
     yj *= surfaceScale;
     jout[j] = yj;
   }
@@ -180,6 +182,7 @@ __device__ __forceinline__ void membrane_flux(const Dev& g, int ci, bool from_cy
 struct FaceCtx {
   bool from_cytosol;
   double eta, y_this, surfaceScale, factor;  // factor = 0.5 * 2 pi y L
+  double stimFlux;                           // flux stimulation of this face (0 if none)
   double pot2, con2[3];
 };
 
@@ -192,6 +195,13 @@ __device__ __forceinline__ void make_face(const Dev& g, const double* u, const C
   const double ext_surface = (con_pi * (y_es + y_es)) * c.hx;
   f.surfaceScale = ext_surface / my_surface;
   f.factor = 0.5 * ((2 * con_pi * f.y_this) * c.hx);
+  f.stimFlux = 0.0;
+  if (g.fstim_on && (g.x[c.ci] - 1e-6 < g.stim_x && g.x[c.ci + 1] + 1e-6 > g.stim_x)) {
+    double sf = g.fstim_inj / my_surface;
+    sf *= g.fstim_amp;
+    sf *= f.from_cytosol ? 1.0 : -1.0;
+    f.stimFlux = sf;
+  }
   const int jopp = f.from_cytosol ? g.jm + 1 : g.jm;
   const double* ua = u + 4 * (size_t)(c.ci + g.nvx * jopp);
   double a0, a1, a2, a3, b0, b1, b2, b3;
@@ -220,7 +230,7 @@ __device__ __forceinline__ void elec_boundary_row(const Dev& g, const FaceCtx& f
       uCon[j] = t;
     }
     double jf[3];
-    membrane_flux(g, ci, f.from_cytosol, uPot, uCon, f.pot2, f.con2, f.surfaceScale, jf);
+    membrane_flux(g, ci, f.from_cytosol, uPot, uCon, f.pot2, f.con2, f.surfaceScale, f.stimFlux, jf);
 #pragma unroll
     for (int j = 0; j < 3; ++j) out[j] += g.dt * (jf[j] * phi[k] * f.factor * vs);
   }

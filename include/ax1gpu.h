@@ -74,6 +74,11 @@ typedef struct ax1gpu_params {
    * 1 = the operator's analytic jacobian_volume, 0 = PDELab's NumericalJacobianVolume (forward difference,
    * delta = 1e-7 (1 + |u_j|)), which is the reference's default. ax1gpu_params_default sets all three to 1. */
   int use_elec_jacobian_volume, use_memb_jacobian_volume, use_time_jacobian_volume;
+  /* [stimulation] memb_flux_stimulation, memb_flux_ion (0 Na, 1 K, 2 Cl; default Cl), memb_flux_inj: cosine-
+   * ramped flux 0.5 (1 - cos(2 pi (t - tinj_start) / tinj_end)) memb_flux_inj / |face| added to one species on
+   * the membrane-interface faces above stim_x (default_nernst_planck_parameters.hh:439-475)              */
+  int do_memb_flux_stimulation, memb_flux_ion;
+  double memb_flux_inj;
 } ax1gpu_params;
 
 typedef struct ax1gpu_newton_opts {

@@ -174,7 +174,21 @@ void time_alpha_volume(const Cell& c, const double* xcon, double weight, double*
 void elec_alpha_boundary(const Problem& p, const Cell& c, const double* xl, const double* uglob,
                          double weight, double* r, double* ra = nullptr) {
   const Config& g = p.cfg;
-  if (!g.membrane_active) return;  // passive membrane: y = 0 (flux*normal*scale accumulates zeros)
+  // [stimulation] memb_flux_stimulation (default_nernst_planck_parameters.hh:439-475): time = LOP time t+dt
+  double stimFlux = 0.0;
+  {
+    const double t = p.time + p.dt;
+    if (g.do_memb_flux_stimulation && (t > g.tinj_start && t < g.tinj_end) &&
+        (p.x[c.i] - 1e-6 < g.stim_x && p.x[c.i + 1] + 1e-6 > g.stim_x)) {
+      const double y_face = (c.j == p.jm - 1) ? p.y[p.jm] : p.y[p.jm + 1];
+      stimFlux = g.memb_flux_inj / ((con_pi * (y_face + y_face)) * c.hx);   // / igeo.volume()
+      const double t_rel = (t - g.tinj_start) / g.tinj_end;
+      stimFlux *= 0.5 * (1 - std::cos(2 * con_pi * t_rel));
+      stimFlux *= (c.j == p.jm - 1) ? 1.0 : -1.0;                            // centerUnitOuterNormal()[1]
+    }
+  }
+  // passive membrane: channel flux y = 0 (flux*normal*scale accumulates zeros)
+  if (!g.membrane_active && stimFlux == 0.0) return;
   const bool from_cytosol = (c.j == p.jm - 1);
   const double eta = from_cytosol ? 1.0 : 0.0;
   const double y_this = from_cytosol ? p.y[p.jm] : p.y[p.jm + 1];
@@ -219,6 +233,7 @@ void elec_alpha_boundary(const Problem& p, const Cell& c, const double* xl, cons
         if (species_of[k] != j) continue;
         bool leak = k < 2;
         double conductance = (equil && !leak) ? 0.0 : eff_conductance_new(p, k, c.i);
+        if (!g.membrane_active) conductance = 0.0;
         double C = (10 * conductance) / (con_e * valence * con_mol);
         if (equil) C *= g.dummy_value;
         C *= g.time_scale / g.length_scale;
@@ -231,8 +246,10 @@ void elec_alpha_boundary(const Problem& p, const Cell& c, const double* xl, cons
         absFlux += std::fabs(C * C1) * (std::fabs(pot2) + std::fabs(uPot)) + std::fabs(diffTerm);
       }
       double yj = totalFlux * n_y;
+      if (j == g.memb_flux_ion) yj += stimFlux;
       yj *= surfaceScaleFactor;
       for (int k = 0; k < 4; ++k) r[4 * j + k] += weight * (yj * phi[k] * factor * c.vs[k]);
+      if (j == g.memb_flux_ion) absFlux += std::fabs(stimFlux);
       if (ra) for (int k = 0; k < 4; ++k) ra[4 * j + k] += std::fabs(weight * (absFlux * surfaceScaleFactor * phi[k] * factor * c.vs[k]));
     }
   }

@@ -30,6 +30,10 @@ typedef struct ax1o_config {
    * PDELab's NumericalJacobianVolume, the reference default); 7 = all analytic, 0 = all finite differences */
   int analytic_volume_jacobian, use_rownorm_preconditioner;
   double leak_ratio_na, leak_ratio_k;
+  /* [stimulation] memb_flux_stimulation / memb_flux_ion / memb_flux_inj: cosine-ramped trans-membrane flux
+   * added to one species on the interface faces above stim_x (default_nernst_planck_parameters.hh:439-475) */
+  int do_memb_flux_stimulation, memb_flux_ion;
+  double memb_flux_inj;
 } ax1o_config;
 
 typedef struct ax1o_newton_opts {

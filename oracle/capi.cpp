@@ -31,6 +31,7 @@ void ax1o_config_default(ax1o_config* c) {
   c->membrane_active = 1; c->automatic_channel_init = 1; c->channel_resting_potential = -65.0;
   c->analytic_volume_jacobian = 7;
   c->leak_ratio_na = 0.13; c->leak_ratio_k = 0.87;
+  c->do_memb_flux_stimulation = 0; c->memb_flux_ion = 2 /* Cl */; c->memb_flux_inj = 0.0;
 }
 
 void ax1o_newton_opts_default(ax1o_newton_opts* o) {

@@ -37,6 +37,7 @@ class Config(C.Structure):
         ("channel_resting_potential", C.c_double),
         ("analytic_volume_jacobian", C.c_int), ("use_rownorm_preconditioner", C.c_int),
         ("leak_ratio_na", C.c_double), ("leak_ratio_k", C.c_double),
+        ("do_memb_flux_stimulation", C.c_int), ("memb_flux_ion", C.c_int), ("memb_flux_inj", C.c_double),
     ]
 
 

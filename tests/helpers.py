@@ -22,7 +22,9 @@ def oracle_problem(O, s, analytic=1, **cfg_over):
         debye_layer_width=bc.debye_layer_width,
         use_rownorm_preconditioner=p.get("use_rownorm_preconditioner", 0), membrane_active=p.get("membrane_active", 1),
         automatic_channel_init=p.get("automatic_channel_init", 1),
-        channel_resting_potential=p.get("channel_resting_potential", -65.0), **cfg_over)
+        channel_resting_potential=p.get("channel_resting_potential", -65.0),
+        do_memb_flux_stimulation=p.get("do_memb_flux_stimulation", 0), memb_flux_ion=p.get("memb_flux_ion", 2),
+        memb_flux_inj=p.get("memb_flux_inj", 0.0), **cfg_over)
     return O.Problem(cfg, s["x"], s["y"], left_pb=s["left_pb"], right_pb=s["right_pb"], eps_memb=s["eps_memb"],
                      g_leak=s["g_leak"], g_nav=s["g_nav"], g_kv=s["g_kv"])
 

@@ -624,3 +624,34 @@ def test_newton_with_fd_jacobian(oracle, axlib):
     assert np.all(err[:3] < 1e-8), err
     assert err[3] < 5e-7, err
     dev.close()
+
+
+@pytest.mark.parametrize("ion,active", [(0, 1), (2, 1), (1, 0)])
+def test_membrane_flux_stimulation(oracle, axlib, ion, active):
+    """[stimulation] memb_flux_stimulation (default_nernst_planck_parameters.hh:439-475): cosine-ramped flux of one
+    species through the interface faces above stim_x, also with a passive membrane. Residual 1e-12, Newton 1e-8."""
+    s = small_setup(nx=6)
+    s["params"].update(do_memb_flux_stimulation=1, memb_flux_ion=ion, memb_flux_inj=3.0e5, tinj_start=20.0,
+                       tinj_end=2000.0, stim_x=250.0e3, membrane_active=active)
+    dev, P, u0 = _both(oracle, axlib, s, t=400.0, dt=2.0)
+    r_g, _ = dev.residual(u0)
+    r_o, a_o = P.residual(u0, with_abs=True)
+    assert np.max(np.abs(r_g - r_o) / (a_o + 1e-300)) < 1e-12
+    # the stimulation really acts: switching it off changes the rows of the two interface vertex rows
+    s2 = small_setup(nx=6)
+    s2["params"].update(membrane_active=active)
+    dev2, P2, _ = _both(oracle, axlib, s2, t=400.0, dt=2.0)
+    r_0, _ = dev2.residual(u0)
+    changed = np.nonzero(np.abs(r_g - r_0).reshape(-1, 4).max(axis=1) > 0)[0]
+    nvx = s["nx"] + 1
+    assert len(changed) > 0 and set(changed // nvx) <= {P.jm, P.jm + 1}
+    assert np.all(np.abs(r_g - r_0).reshape(-1, 4)[:, [c for c in range(4) if c != ion]] == 0.0)
+    og = axlib.default_newton_opts(reduction=1e-9, abs_limit=1e-14, min_lin_reduction=1e-10, slab_w=4)
+    oc = oracle.default_newton_opts(reduction=1e-9, abs_limit=1e-14, min_lin_reduction=1e-10, ilu_fill=0, slab_w=4)
+    ug, rg = dev.newton(u0, og)
+    uc, rc = P.newton(u0, oc)
+    assert rg.status == 0 and rc.status == 0 and rg.iterations == rc.iterations
+    scale = np.max(np.abs(uc.reshape(-1, 4)), axis=0)
+    err = np.max(np.abs(ug - uc).reshape(-1, 4) / scale, axis=0)
+    assert np.all(err[:3] < 1e-8) and err[3] < 5e-7, err
+    dev.close(); dev2.close()
