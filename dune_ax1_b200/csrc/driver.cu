@@ -582,7 +582,14 @@ static int ensure_level_tables(ax1gpu_ctx* c) {
 static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill) {
   if (fill < 0) fill = c->ilu_fill;
   if (fill > 1) { set_error("block ILU(n) is implemented on the device for n = 0 and n = 1"); return AX1GPU_EINVAL; }
-  if (slab_w <= 0) slab_w = c->slab_w > 0 ? c->slab_w : 128;
+  if (slab_w <= 0) {
+    // library default: 128 columns per sub-slab when that still gives >= 2 CTAs per SM, otherwise narrower
+    // slabs (>= 16 columns = one warp per CTA) -- small grids are bound by the sweep's per-level latency, and
+    // more, narrower slabs shorten the wavefront count and keep more SMs busy
+    int w = (c->g.nvx + 295) / 296;
+    w = ((w + 15) / 16) * 16;
+    slab_w = c->slab_w > 0 ? c->slab_w : std::min(128, std::max(16, w));
+  }
   // one quad per wavefront row with <= 256-thread CTAs: levels are ceil(w/2) (ILU0) / ceil(w/3) (ILU(1)) rows wide
   const int wmax = fill == 1 ? ilu1_max_slab_w(c->g) : 128;
   if (slab_w > wmax) slab_w = wmax;

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256, 1) ilu1_factor_kernel(Dev g, const double
   issue(1);
   for (int L = 0; L < nlev; ++L) {
     cp_async_wait<1>();
-    __syncthreads();  // staged row of this level and the ring rows of level L-1 are visible
+    cta_sync();  // staged row of this level and the ring rows of level L-1 are visible
     const Row1 w = level_row1(g, L, nlev, i0, wc, q);
     double row[13][4];
     if (w.v >= 0) {
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256, 1) ilu1_factor_kernel(Dev g, const double
 #pragma unroll
       for (int k = 6; k < 13; ++k) st4(LB + p * 112 + (k - 6) * 16 + r * 4, row[k]);
     }
-    __syncthreads();  // every read of ring slot L&3 (it held level L-4) is done
+    cta_sync();  // every read of ring slot L&3 (it held level L-4) is done
     if (w.v >= 0) {
       double* kr = ring + ((size_t)(L & 3) * nq + q) * AX1_RING1_ROW;
 #pragma unroll
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256) ilu1_apply_kernel(Dev g, const double* __
       ring[((size_t)(L & 7) * nq + q) * 4 + r] = acc;
       v_out[4 * (size_t)w.v + r] = acc;
     }
-    __syncthreads();
+    cta_sync();
     issue_fwd(L + D);
   }
   cp_async_wait<0>();
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(256) ilu1_apply_kernel(Dev g, const double* __
       v_out[4 * (size_t)w.v + r] = xo;
       if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + w.il, w.j, r, xo);
     }
-    __syncthreads();
+    cta_sync();
     issue_bwd(L - D);
   }
   cp_async_wait<0>();

@@ -51,6 +51,13 @@ __device__ __forceinline__ void invert4(double a[4][4], double inv[4][4]) {
   }
 }
 
+// per-level barrier of the sweeps: a sub-slab of <= 16 vertex columns is swept by a single warp, which only
+// needs warp-level ordering of its shared-memory ring (latency-bound small grids: paper / myelin / AMG coarse levels)
+__device__ __forceinline__ void cta_sync() {
+  if (blockDim.x == 32) __syncwarp();
+  else __syncthreads();
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256, 1) ilu_factor_kernel(Dev g, const double*
   issue(1);
   for (int L = 0; L < nlev; ++L) {
     cp_async_wait<1>();
-    __syncthreads();  // staged row of this level and the ring rows of level L-1 are visible
+    cta_sync();  // staged row of this level and the ring rows of level L-1 are visible
     const LevelRow w = level_row(g, L, nlev, i0, wc, q);
     double row[9][4];
     if (w.v >= 0) {
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256, 1) ilu_factor_kernel(Dev g, const double*
 #pragma unroll
       for (int s = 4; s < 9; ++s) st4(LB + p * 80 + (s - 4) * 16 + r * 4, row[s]);
     }
-    __syncthreads();  // every read of ring slot L%3 (it held level L-3) is done
+    cta_sync();  // every read of ring slot L%3 (it held level L-3) is done
     if (w.v >= 0) {
       double* kr = ring + ((size_t)(L % 3) * nq + q) * AX1_RING_ROW;
 #pragma unroll
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) ilu_apply_kernel(Dev g, const double* __r
       ring[((size_t)(L & 3) * nq + q) * 4 + r] = acc;
       v_out[4 * (size_t)w.v + r] = acc;
     }
-    __syncthreads();
+    cta_sync();
     issue_fwd(L + D);
   }
   cp_async_wait<0>();
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256) ilu_apply_kernel(Dev g, const double* __r
       v_out[4 * (size_t)w.v + r] = xo;
       if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + w.il, w.j, r, xo);
     }
-    __syncthreads();
+    cta_sync();
     issue_bwd(L - D);
   }
   cp_async_wait<0>();
