@@ -381,6 +381,153 @@ __global__ void __launch_bounds__(256) ilu_apply_kernel(Dev g, const double* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// The same sweeps with the factor staged by bulk TMA. The packed layout stores the rows of a wavefront level
+// contiguously, so ONE cp.async.bulk issued by one thread brings a whole level (rows x 512 B forward, rows x 640 B
+// backward) into a shared-memory stage and completes on that stage's mbarrier; the other threads issue nothing
+// for the factor. Together with three further changes this halves the instructions on the per-level critical
+// path, which is what bounds the sweeps on small grids (paper / myelin configurations, multigrid coarse levels):
+//  * quad q owns the vertex-column pair (2q, 2q+1) of the sub-slab for the whole sweep (column 2q + (L & 1) at
+//    level L), so the ring of recent solution values is indexed by column and no neighbour needs lev_jlo;
+//  * blocks of non-existent neighbours are stored as zeros by the factorisation and the ring is zero-initialised
+//    and padded by one quad on either side, so the four block-row x vector products run without predicates;
+//  * the level's barrier is a __syncwarp when the sub-slab is swept by a single warp (cta_sync).
+template <int D, bool P2P>
+__global__ void __launch_bounds__(256) ilu_apply_tma_kernel(Dev g, const double* __restrict__ LF,
+                                                            const double* __restrict__ LB, const double* __restrict__ d,
+                                                            double* v_out, int slab_w, const int* __restrict__ lvl_tab,
+                                                            HaloPush hp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int nt = blockDim.x, tid = threadIdx.x;
+  const int q = tid >> 2, r = tid & 3, nq = nt >> 2;
+  double* stage = reinterpret_cast<double*>(smem_raw);               // [D][nq * 80]
+  double* stageR = stage + (size_t)D * nq * 80;                       // [D][nt]
+  double* ring = stageR + (size_t)D * nt;                             // [4][nq + 2][4]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + 4 * (size_t)(nq + 2) * 4);   // [D]
+  int* lvl_sh = reinterpret_cast<int*>(bars + D);
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) mbar_init(&bars[k], 1);
+    mbar_init_fence();
+  }
+  for (int k = tid; k < 4 * (nq + 2) * 4; k += nt) ring[k] = 0.0;
+  const SlabGeom sg = slab_geom(g, slab_w, lvl_tab, lvl_sh);          // ends with __syncthreads
+  const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
+  const int rstride = (nq + 2) * 4;
+
+  // row of this quad at level L: column il = 2q + (L & 1), j = (L - il) / 2
+  auto my_row = [&](int L, int& il, int& j) -> bool {
+    il = 2 * q + (L & 1);
+    const int tj = L - il;
+    j = tj >> 1;
+    return il < wc && tj >= 0 && j < g.nvy;
+  };
+
+  // ---------------- forward: y = L^-1 d ----------------
+  auto issue_fwd = [&](int L) {
+    if (L < nlev) {
+      const int st = L % D;
+      if (tid == 0) {
+        const unsigned bytes = (unsigned)(sg.lvl[L + 1] - sg.lvl[L]) * 512u;
+        mbar_arrive_expect_tx(&bars[st], bytes);
+        bulk_g2s(stage + (size_t)st * nq * 80, LF + (sg.row_off + (size_t)sg.lvl[L]) * 64, bytes, &bars[st]);
+      }
+      int il, j;
+      if (my_row(L, il, j)) cp_async8(stageR + st * nt + tid, d + 4 * (size_t)(i0 + il + g.nvx * j) + r);
+    }
+    cp_async_commit();
+  };
+  for (int L = 0; L < D; ++L) issue_fwd(L);
+  for (int L = 0; L < nlev; ++L) {
+    const int st = L % D;
+    cp_async_wait<D - 1>();
+    mbar_wait(&bars[st], (unsigned)(L / D) & 1u);
+    int il, j;
+    if (my_row(L, il, j)) {
+      const double* lrow = stage + ((size_t)st * nq * 80) + (size_t)(j - lev_jlo(L, wc)) * 64 + r * 4;
+      double acc = stageR[st * nt + tid];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int di = s % 3 - 1, dj = s / 3 - 1;
+        const double2 l01 = *reinterpret_cast<const double2*>(lrow + s * 16);
+        const double2 l23 = *reinterpret_cast<const double2*>(lrow + s * 16 + 2);
+        const int Ln = L + di + 2 * dj;
+        const double* yp = ring + (Ln & 3) * rstride + (((il + di) >> 1) + 1) * 4;
+        const double2 y01 = *reinterpret_cast<const double2*>(yp);
+        const double2 y23 = *reinterpret_cast<const double2*>(yp + 2);
+        double t = l01.x * y01.x;
+        t += l01.y * y01.y;
+        t += l23.x * y23.x;
+        t += l23.y * y23.y;
+        acc -= t;
+      }
+      ring[(L & 3) * rstride + (q + 1) * 4 + r] = acc;
+      v_out[4 * (size_t)(i0 + il + g.nvx * j) + r] = acc;
+    }
+    cta_sync();
+    issue_fwd(L + D);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---------------- backward: x = U^-1 y ----------------
+  // pipeline step k = nlev + (nlev - 1 - L) continues the forward numbering (stage k % D, phase (k / D) & 1)
+  auto issue_bwd = [&](int L) {
+    if (L >= 0) {
+      const int k = 2 * nlev - 1 - L, st = k % D;
+      if (tid == 0) {
+        const unsigned bytes = (unsigned)(sg.lvl[L + 1] - sg.lvl[L]) * 640u;
+        mbar_arrive_expect_tx(&bars[st], bytes);
+        bulk_g2s(stage + (size_t)st * nq * 80, LB + (sg.row_off + (size_t)sg.lvl[L]) * 80, bytes, &bars[st]);
+      }
+      int il, j;
+      if (my_row(L, il, j)) cp_async8(stageR + st * nt + tid, v_out + 4 * (size_t)(i0 + il + g.nvx * j) + r);
+    }
+    cp_async_commit();
+  };
+  for (int k = 0; k < D; ++k) issue_bwd(nlev - 1 - k);
+  for (int L = nlev - 1; L >= 0; --L) {
+    const int k = 2 * nlev - 1 - L, st = k % D;
+    cp_async_wait<D - 1>();
+    mbar_wait(&bars[st], (unsigned)(k / D) & 1u);
+    int il, j;
+    if (my_row(L, il, j)) {
+      const double* urow = stage + ((size_t)st * nq * 80) + (size_t)(j - lev_jlo(L, wc)) * 80 + r * 4;
+      double acc = stageR[st * nt + tid];
+#pragma unroll
+      for (int s = 5; s < 9; ++s) {
+        const int di = s % 3 - 1, dj = s / 3 - 1;
+        const double2 u01 = *reinterpret_cast<const double2*>(urow + (s - 4) * 16);
+        const double2 u23 = *reinterpret_cast<const double2*>(urow + (s - 4) * 16 + 2);
+        const int Ln = L + di + 2 * dj;
+        const double* xp = ring + (Ln & 3) * rstride + (((il + di) >> 1) + 1) * 4;
+        const double2 x01 = *reinterpret_cast<const double2*>(xp);
+        const double2 x23 = *reinterpret_cast<const double2*>(xp + 2);
+        double t = u01.x * x01.x;
+        t += u01.y * x01.y;
+        t += u23.x * x23.x;
+        t += u23.y * x23.y;
+        acc -= t;
+      }
+      const double2 d01 = *reinterpret_cast<const double2*>(urow);
+      const double2 d23 = *reinterpret_cast<const double2*>(urow + 2);
+      const unsigned qmask = 0xFu << (tid & 28);
+      const int qb = tid & 28;
+      double xo = d01.x * __shfl_sync(qmask, acc, qb + 0);
+      xo += d01.y * __shfl_sync(qmask, acc, qb + 1);
+      xo += d23.x * __shfl_sync(qmask, acc, qb + 2);
+      xo += d23.y * __shfl_sync(qmask, acc, qb + 3);
+      ring[(L & 3) * rstride + (q + 1) * 4 + r] = xo;
+      v_out[4 * (size_t)(i0 + il + g.nvx * j) + r] = xo;
+      if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + il, j, r, xo);
+    }
+    cta_sync();
+    issue_bwd(L - D);
+  }
+  cp_async_wait<0>();
+  if (P2P) halo_push_finish(hp, g.nvx, i0, wc);
+}
+
+// ------------------------------------------------------------------------------------------
 __global__ void rownorm_kernel(Dev g, double* A, double* rv) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int v = (int)(t >> 2), r = (int)(t & 3);
@@ -500,11 +647,28 @@ int ilu_pick_stages(int nt, int bytes_per_thread_stage) {
   const int d = (110 * 1024) / (nt * bytes_per_thread_stage);
   return d >= 8 ? 8 : (d >= 6 ? 6 : (d >= 4 ? 4 : (d >= 3 ? 3 : 2)));
 }
+// AX1_ILU_TMA=0 selects the cp.async (LDGSTS) sweeps instead of the bulk-TMA ones
+static bool ilu_use_tma() {
+  static const int v = getenv("AX1_ILU_TMA") ? atoi(getenv("AX1_ILU_TMA")) : 1;
+  return v != 0;
+}
 template <int D, bool P2P>
 static void launch_ilu_apply_t(const Dev& g, const double* LU, const double* d, double* v, int slab_w,
                                const int* lvl_tab, const HaloPush& hp, cudaStream_t st) {
   const int nslab = (g.nvx + slab_w - 1) / slab_w;
   const int nt = slab_threads(slab_w);
+  if (ilu_use_tma()) {
+    const int nq = nt / 4;
+    const size_t smem_t = (size_t)D * nq * 640 + (size_t)D * nt * 8 + 4 * (size_t)(nq + 2) * 32 + (size_t)D * 8 +
+                          (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
+    static bool attr_t = false;
+    if (!attr_t) {
+      cudaFuncSetAttribute(ilu_apply_tma_kernel<D, P2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      attr_t = true;
+    }
+    ilu_apply_tma_kernel<D, P2P><<<nslab, nt, smem_t, st>>>(g, LU, LU + (size_t)g.nv * 64, d, v, slab_w, lvl_tab, hp);
+    return;
+  }
   const size_t smem = (size_t)D * nt * (5 * 32 + 8) + 4 * (size_t)(nt / 4) * 32 + (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {
