@@ -381,149 +381,168 @@ __global__ void __launch_bounds__(256) ilu_apply_kernel(Dev g, const double* __r
 }
 
 // ------------------------------------------------------------------------------------------
-// The same sweeps with the factor staged by bulk TMA. The packed layout stores the rows of a wavefront level
-// contiguously, so ONE cp.async.bulk issued by one thread brings a whole level (rows x 512 B forward, rows x 640 B
-// backward) into a shared-memory stage and completes on that stage's mbarrier; the other threads issue nothing
-// for the factor. Together with three further changes this halves the instructions on the per-level critical
-// path, which is what bounds the sweeps on small grids (paper / myelin configurations, multigrid coarse levels):
+// The same sweeps as a warp-specialised bulk-TMA pipeline. The packed layout stores the rows of a wavefront
+// level contiguously, so ONE cp.async.bulk brings a whole level of the factor (rows x 512 B forward, rows x 640 B
+// backward) into a shared-memory stage. A dedicated producer warp issues it, gathers the level's right-hand side
+// with cp.async, and lets both complete on the stage's `full` mbarrier; the consumer warps only wait on that
+// barrier, multiply, and hand the stage back through an `empty` mbarrier. What bounds the sweeps on small grids
+// (paper / myelin configurations, multigrid coarse levels) is the instruction count on the per-level critical
+// path of the consumers; besides moving all load issue off that path:
 //  * quad q owns the vertex-column pair (2q, 2q+1) of the sub-slab for the whole sweep (column 2q + (L & 1) at
 //    level L), so the ring of recent solution values is indexed by column and no neighbour needs lev_jlo;
 //  * blocks of non-existent neighbours are stored as zeros by the factorisation and the ring is zero-initialised
 //    and padded by one quad on either side, so the four block-row x vector products run without predicates;
-//  * the level's barrier is a __syncwarp when the sub-slab is swept by a single warp (cta_sync).
+//  * the level barrier is a __syncwarp when the sub-slab is swept by a single consumer warp.
+// Pipeline step k: forward level L = k, backward level L = 2 nlev - 1 - k; stage k % D, use number k / D.
 template <int D, bool P2P>
-__global__ void __launch_bounds__(256) ilu_apply_tma_kernel(Dev g, const double* __restrict__ LF,
+__global__ void __launch_bounds__(288) ilu_apply_tma_kernel(Dev g, const double* __restrict__ LF,
                                                             const double* __restrict__ LB, const double* __restrict__ d,
                                                             double* v_out, int slab_w, const int* __restrict__ lvl_tab,
                                                             HaloPush hp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int nt = blockDim.x, tid = threadIdx.x;
-  const int q = tid >> 2, r = tid & 3, nq = nt >> 2;
+  const int tid = threadIdx.x;
+  const int nt = blockDim.x - 32;                                     // consumer threads; the last warp produces
+  const int nq = nt >> 2;
   double* stage = reinterpret_cast<double*>(smem_raw);               // [D][nq * 80]
   double* stageR = stage + (size_t)D * nq * 80;                       // [D][nt]
   double* ring = stageR + (size_t)D * nt;                             // [4][nq + 2][4]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + 4 * (size_t)(nq + 2) * 4);   // [D]
-  int* lvl_sh = reinterpret_cast<int*>(bars + D);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + 4 * (size_t)(nq + 2) * 4);   // [D]
+  unsigned long long* empty = full + D;                                                                 // [D]
+  int* lvl_sh = reinterpret_cast<int*>(empty + D);
   if (tid == 0) {
 #pragma unroll
-    for (int k = 0; k < D; ++k) mbar_init(&bars[k], 1);
+    for (int k = 0; k < D; ++k) { mbar_init(&full[k], 33); mbar_init(&empty[k], (unsigned)(blockDim.x - 32) >> 5); }
     mbar_init_fence();
   }
-  for (int k = tid; k < 4 * (nq + 2) * 4; k += nt) ring[k] = 0.0;
+  for (int k = tid; k < 4 * (nq + 2) * 4; k += blockDim.x) ring[k] = 0.0;
   const SlabGeom sg = slab_geom(g, slab_w, lvl_tab, lvl_sh);          // ends with __syncthreads
   const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
-  const int rstride = (nq + 2) * 4;
+  const bool producer = tid >= nt;
 
-  // row of this quad at level L: column il = 2q + (L & 1), j = (L - il) / 2
-  auto my_row = [&](int L, int& il, int& j) -> bool {
-    il = 2 * q + (L & 1);
-    const int tj = L - il;
-    j = tj >> 1;
-    return il < wc && tj >= 0 && j < g.nvy;
-  };
-
-  // ---------------- forward: y = L^-1 d ----------------
-  auto issue_fwd = [&](int L) {
-    if (L < nlev) {
+  if (producer) {
+    const int lane = tid - nt;
+    auto produce = [&](int k) {
+      const int st = k % D, use = k / D;
+      if (use > 0) mbar_wait(&empty[st], (unsigned)(use - 1) & 1u);
+      const bool fwd = k < nlev;
+      const int L = fwd ? k : 2 * nlev - 1 - k;
+      if (lane == 0) {                                                // the level's factor rows: one bulk copy
+        const unsigned rows = (unsigned)(sg.lvl[L + 1] - sg.lvl[L]);
+        const unsigned bytes = rows * (fwd ? 512u : 640u);
+        mbar_arrive_expect_tx(&full[st], bytes);
+        const double* gsrc = fwd ? LF + (sg.row_off + (size_t)sg.lvl[L]) * 64 : LB + (sg.row_off + (size_t)sg.lvl[L]) * 80;
+        bulk_g2s(stage + (size_t)st * nq * 80, gsrc, bytes, &full[st]);
+      }
+      const double* src = fwd ? d : v_out;                            // backward: the forward result y
+      for (int t = lane; t < nt; t += 32) {                           // the level's right-hand side values
+        const int il = 2 * (t >> 2) + (L & 1), tj = L - il, j = tj >> 1;
+        if (il < wc && tj >= 0 && j < g.nvy)
+          cp_async8(stageR + st * nt + t, src + 4 * (size_t)(i0 + il + g.nvx * j) + (t & 3));
+      }
+      cp_async_mbar_arrive_noinc(&full[st]);
+    };
+    for (int k = 0; k < nlev; ++k) produce(k);
+    __syncthreads();          // the consumers' forward results are in global memory
+    for (int k = nlev; k < 2 * nlev; ++k) produce(k);
+  } else {
+    const int q = tid >> 2, r = tid & 3;
+    const int rstride = (nq + 2) * 4;
+    // a consumer warp hands the stage back as soon as its operands are in registers (mbarrier.arrive releases the
+    // warp's prior shared-memory reads); the level barrier only orders the ring of solution values
+    auto release_stage = [&](int st) {
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+    };
+    auto level_done = [&]() {
+      if (nt == 32) __syncwarp();
+      else named_bar_sync(1, nt);
+    };
+    // ---------------- forward: y = L^-1 d ----------------
+    for (int L = 0; L < nlev; ++L) {
       const int st = L % D;
-      if (tid == 0) {
-        const unsigned bytes = (unsigned)(sg.lvl[L + 1] - sg.lvl[L]) * 512u;
-        mbar_arrive_expect_tx(&bars[st], bytes);
-        bulk_g2s(stage + (size_t)st * nq * 80, LF + (sg.row_off + (size_t)sg.lvl[L]) * 64, bytes, &bars[st]);
-      }
-      int il, j;
-      if (my_row(L, il, j)) cp_async8(stageR + st * nt + tid, d + 4 * (size_t)(i0 + il + g.nvx * j) + r);
-    }
-    cp_async_commit();
-  };
-  for (int L = 0; L < D; ++L) issue_fwd(L);
-  for (int L = 0; L < nlev; ++L) {
-    const int st = L % D;
-    cp_async_wait<D - 1>();
-    mbar_wait(&bars[st], (unsigned)(L / D) & 1u);
-    int il, j;
-    if (my_row(L, il, j)) {
-      const double* lrow = stage + ((size_t)st * nq * 80) + (size_t)(j - lev_jlo(L, wc)) * 64 + r * 4;
-      double acc = stageR[st * nt + tid];
+      mbar_wait(&full[st], (unsigned)(L / D) & 1u);
+      const int il = 2 * q + (L & 1), tj = L - il, j = tj >> 1;
+      const bool act = il < wc && tj >= 0 && j < g.nvy;
+      double2 lv[4][2], yv[4][2];
+      double acc = 0.0;
+      if (act) {
+        const double* lrow = stage + ((size_t)st * nq * 80) + (size_t)(j - lev_jlo(L, wc)) * 64 + r * 4;
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int di = s % 3 - 1, dj = s / 3 - 1;
-        const double2 l01 = *reinterpret_cast<const double2*>(lrow + s * 16);
-        const double2 l23 = *reinterpret_cast<const double2*>(lrow + s * 16 + 2);
-        const int Ln = L + di + 2 * dj;
-        const double* yp = ring + (Ln & 3) * rstride + (((il + di) >> 1) + 1) * 4;
-        const double2 y01 = *reinterpret_cast<const double2*>(yp);
-        const double2 y23 = *reinterpret_cast<const double2*>(yp + 2);
-        double t = l01.x * y01.x;
-        t += l01.y * y01.y;
-        t += l23.x * y23.x;
-        t += l23.y * y23.y;
-        acc -= t;
+        for (int s = 0; s < 4; ++s) {
+          const int di = s % 3 - 1, dj = s / 3 - 1;
+          const int Ln = L + di + 2 * dj;
+          const double* yp = ring + (Ln & 3) * rstride + (((il + di) >> 1) + 1) * 4;
+          lv[s][0] = *reinterpret_cast<const double2*>(lrow + s * 16);
+          lv[s][1] = *reinterpret_cast<const double2*>(lrow + s * 16 + 2);
+          yv[s][0] = *reinterpret_cast<const double2*>(yp);
+          yv[s][1] = *reinterpret_cast<const double2*>(yp + 2);
+        }
+        acc = stageR[st * nt + tid];
       }
-      ring[(L & 3) * rstride + (q + 1) * 4 + r] = acc;
-      v_out[4 * (size_t)(i0 + il + g.nvx * j) + r] = acc;
+      release_stage(st);
+      if (act) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          double t = lv[s][0].x * yv[s][0].x;
+          t += lv[s][0].y * yv[s][0].y;
+          t += lv[s][1].x * yv[s][1].x;
+          t += lv[s][1].y * yv[s][1].y;
+          acc -= t;
+        }
+        ring[(L & 3) * rstride + (q + 1) * 4 + r] = acc;
+        v_out[4 * (size_t)(i0 + il + g.nvx * j) + r] = acc;
+      }
+      level_done();
     }
-    cta_sync();
-    issue_fwd(L + D);
-  }
-  cp_async_wait<0>();
-  __syncthreads();
-
-  // ---------------- backward: x = U^-1 y ----------------
-  // pipeline step k = nlev + (nlev - 1 - L) continues the forward numbering (stage k % D, phase (k / D) & 1)
-  auto issue_bwd = [&](int L) {
-    if (L >= 0) {
+    __syncthreads();
+    // ---------------- backward: x = U^-1 y ----------------
+    for (int L = nlev - 1; L >= 0; --L) {
       const int k = 2 * nlev - 1 - L, st = k % D;
-      if (tid == 0) {
-        const unsigned bytes = (unsigned)(sg.lvl[L + 1] - sg.lvl[L]) * 640u;
-        mbar_arrive_expect_tx(&bars[st], bytes);
-        bulk_g2s(stage + (size_t)st * nq * 80, LB + (sg.row_off + (size_t)sg.lvl[L]) * 80, bytes, &bars[st]);
-      }
-      int il, j;
-      if (my_row(L, il, j)) cp_async8(stageR + st * nt + tid, v_out + 4 * (size_t)(i0 + il + g.nvx * j) + r);
-    }
-    cp_async_commit();
-  };
-  for (int k = 0; k < D; ++k) issue_bwd(nlev - 1 - k);
-  for (int L = nlev - 1; L >= 0; --L) {
-    const int k = 2 * nlev - 1 - L, st = k % D;
-    cp_async_wait<D - 1>();
-    mbar_wait(&bars[st], (unsigned)(k / D) & 1u);
-    int il, j;
-    if (my_row(L, il, j)) {
-      const double* urow = stage + ((size_t)st * nq * 80) + (size_t)(j - lev_jlo(L, wc)) * 80 + r * 4;
-      double acc = stageR[st * nt + tid];
+      mbar_wait(&full[st], (unsigned)(k / D) & 1u);
+      const int il = 2 * q + (L & 1), tj = L - il, j = tj >> 1;
+      const bool act = il < wc && tj >= 0 && j < g.nvy;
+      double2 uv[5][2], xv[4][2];
+      double acc = 0.0;
+      if (act) {
+        const double* urow = stage + ((size_t)st * nq * 80) + (size_t)(j - lev_jlo(L, wc)) * 80 + r * 4;
 #pragma unroll
-      for (int s = 5; s < 9; ++s) {
-        const int di = s % 3 - 1, dj = s / 3 - 1;
-        const double2 u01 = *reinterpret_cast<const double2*>(urow + (s - 4) * 16);
-        const double2 u23 = *reinterpret_cast<const double2*>(urow + (s - 4) * 16 + 2);
-        const int Ln = L + di + 2 * dj;
-        const double* xp = ring + (Ln & 3) * rstride + (((il + di) >> 1) + 1) * 4;
-        const double2 x01 = *reinterpret_cast<const double2*>(xp);
-        const double2 x23 = *reinterpret_cast<const double2*>(xp + 2);
-        double t = u01.x * x01.x;
-        t += u01.y * x01.y;
-        t += u23.x * x23.x;
-        t += u23.y * x23.y;
-        acc -= t;
+        for (int s = 4; s < 9; ++s) {
+          uv[s - 4][0] = *reinterpret_cast<const double2*>(urow + (s - 4) * 16);
+          uv[s - 4][1] = *reinterpret_cast<const double2*>(urow + (s - 4) * 16 + 2);
+          if (s > 4) {
+            const int di = s % 3 - 1, dj = s / 3 - 1;
+            const int Ln = L + di + 2 * dj;
+            const double* xp = ring + (Ln & 3) * rstride + (((il + di) >> 1) + 1) * 4;
+            xv[s - 5][0] = *reinterpret_cast<const double2*>(xp);
+            xv[s - 5][1] = *reinterpret_cast<const double2*>(xp + 2);
+          }
+        }
+        acc = stageR[st * nt + tid];
       }
-      const double2 d01 = *reinterpret_cast<const double2*>(urow);
-      const double2 d23 = *reinterpret_cast<const double2*>(urow + 2);
-      const unsigned qmask = 0xFu << (tid & 28);
-      const int qb = tid & 28;
-      double xo = d01.x * __shfl_sync(qmask, acc, qb + 0);
-      xo += d01.y * __shfl_sync(qmask, acc, qb + 1);
-      xo += d23.x * __shfl_sync(qmask, acc, qb + 2);
-      xo += d23.y * __shfl_sync(qmask, acc, qb + 3);
-      ring[(L & 3) * rstride + (q + 1) * 4 + r] = xo;
-      v_out[4 * (size_t)(i0 + il + g.nvx * j) + r] = xo;
-      if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + il, j, r, xo);
+      release_stage(st);
+      if (act) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          double t = uv[s + 1][0].x * xv[s][0].x;
+          t += uv[s + 1][0].y * xv[s][0].y;
+          t += uv[s + 1][1].x * xv[s][1].x;
+          t += uv[s + 1][1].y * xv[s][1].y;
+          acc -= t;
+        }
+        // x_r = sum_c Dinv[r][c] * acc_c : exchange acc within the quad
+        const unsigned qmask = 0xFu << (tid & 28);
+        const int qb = tid & 28;
+        double xo = uv[0][0].x * __shfl_sync(qmask, acc, qb + 0);
+        xo += uv[0][0].y * __shfl_sync(qmask, acc, qb + 1);
+        xo += uv[0][1].x * __shfl_sync(qmask, acc, qb + 2);
+        xo += uv[0][1].y * __shfl_sync(qmask, acc, qb + 3);
+        ring[(L & 3) * rstride + (q + 1) * 4 + r] = xo;
+        v_out[4 * (size_t)(i0 + il + g.nvx * j) + r] = xo;
+        if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + il, j, r, xo);
+      }
+      level_done();
     }
-    cta_sync();
-    issue_bwd(L - D);
   }
-  cp_async_wait<0>();
   if (P2P) halo_push_finish(hp, g.nvx, i0, wc);
 }
 
@@ -659,14 +678,14 @@ static void launch_ilu_apply_t(const Dev& g, const double* LU, const double* d, 
   const int nt = slab_threads(slab_w);
   if (ilu_use_tma()) {
     const int nq = nt / 4;
-    const size_t smem_t = (size_t)D * nq * 640 + (size_t)D * nt * 8 + 4 * (size_t)(nq + 2) * 32 + (size_t)D * 8 +
+    const size_t smem_t = (size_t)D * nq * 640 + (size_t)D * nt * 8 + 4 * (size_t)(nq + 2) * 32 + (size_t)D * 16 +
                           (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
     static bool attr_t = false;
     if (!attr_t) {
       cudaFuncSetAttribute(ilu_apply_tma_kernel<D, P2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       attr_t = true;
     }
-    ilu_apply_tma_kernel<D, P2P><<<nslab, nt, smem_t, st>>>(g, LU, LU + (size_t)g.nv * 64, d, v, slab_w, lvl_tab, hp);
+    ilu_apply_tma_kernel<D, P2P><<<nslab, nt + 32, smem_t, st>>>(g, LU, LU + (size_t)g.nv * 64, d, v, slab_w, lvl_tab, hp);
     return;
   }
   const size_t smem = (size_t)D * nt * (5 * 32 + 8) + 4 * (size_t)(nt / 4) * 32 + (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
