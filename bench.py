@@ -158,11 +158,11 @@ def main():
     ap.add_argument("--ilu-fill", type=int, default=0, choices=[0, 1])
     args = ap.parse_args()
     myelin = args.workload == "myelin"
-    if myelin and args.slab_w == SLAB_W:
-        args.slab_w = 32   # few columns per GPU: more, narrower sub-slabs keep the SMs busy
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if myelin and args.slab_w == SLAB_W:
+        args.slab_w = 32 if world <= 2 else 16   # few columns per GPU: more, narrower sub-slabs keep the SMs busy
+
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     nv_full = (args.nx + 1) * 181
     workload = ("synthetic refined r-z tensor grid: Ny=180 (shipped 181-point radial vector) x Nx=%d columns/GPU, "
