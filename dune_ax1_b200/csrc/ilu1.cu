@@ -321,6 +321,161 @@ __global__ void __launch_bounds__(256) ilu1_apply_kernel(Dev g, const double* __
 }
 
 // ------------------------------------------------------------------------------------------
+// The same sweeps as a warp-specialised bulk-TMA pipeline (see ilu_apply_tma_kernel in solver.cu for the
+// scheme): a producer warp brings each wavefront level of the packed factor (rows x 768 B forward, rows x 896 B
+// backward) into a shared-memory stage with one cp.async.bulk and gathers the level's right-hand side; consumer
+// quad q owns the column triple (3q, 3q+1, 3q+2) of the sub-slab (column 3q + L mod 3 at level L), the ring of
+// recent solution values is indexed by column triple and zero-padded, blocks of absent neighbours are zeros.
+template <int D, bool P2P>
+__global__ void __launch_bounds__(288) ilu1_apply_tma_kernel(Dev g, const double* __restrict__ LF,
+                                                             const double* __restrict__ LB, const double* __restrict__ d,
+                                                             double* v_out, int slab_w, const int* __restrict__ lvl_tab,
+                                                             HaloPush hp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int nt = blockDim.x - 32;                                     // consumer threads; the last warp produces
+  const int nq = nt >> 2;
+  double* stage = reinterpret_cast<double*>(smem_raw);               // [D][nq * 112]
+  double* stageR = stage + (size_t)D * nq * 112;                      // [D][nt]
+  double* ring = stageR + (size_t)D * nt;                             // [8][nq + 2][4]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + 8 * (size_t)(nq + 2) * 4);   // [D]
+  unsigned long long* empty = full + D;                                                                 // [D]
+  int* lvl_sh = reinterpret_cast<int*>(empty + D);
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) { mbar_init(&full[k], 33); mbar_init(&empty[k], (unsigned)nt >> 5); }
+    mbar_init_fence();
+  }
+  for (int k = tid; k < 8 * (nq + 2) * 4; k += blockDim.x) ring[k] = 0.0;
+  const Slab1 sg = slab1_geom(g, slab_w, lvl_tab, lvl_sh);            // ends with __syncthreads
+  const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
+
+  if (tid >= nt) {
+    const int lane = tid - nt;
+    auto produce = [&](int k) {
+      const int st = k % D, use = k / D;
+      if (use > 0) mbar_wait(&empty[st], (unsigned)(use - 1) & 1u);
+      const bool fwd = k < nlev;
+      const int L = fwd ? k : 2 * nlev - 1 - k;
+      if (lane == 0) {
+        const unsigned rows = (unsigned)(sg.lvl[L + 1] - sg.lvl[L]);
+        const unsigned bytes = rows * (fwd ? 768u : 896u);
+        mbar_arrive_expect_tx(&full[st], bytes);
+        const double* gsrc = fwd ? LF + (sg.row_off + (size_t)sg.lvl[L]) * 96 : LB + (sg.row_off + (size_t)sg.lvl[L]) * 112;
+        bulk_g2s(stage + (size_t)st * nq * 112, gsrc, bytes, &full[st]);
+      }
+      const double* src = fwd ? d : v_out;
+      const int m3 = L % 3;
+      for (int t = lane; t < nt; t += 32) {
+        const int il = 3 * (t >> 2) + m3, tj = L - il, j = tj / 3;
+        if (il < wc && tj >= 0 && j < g.nvy)
+          cp_async8(stageR + st * nt + t, src + 4 * (size_t)(i0 + il + g.nvx * j) + (t & 3));
+      }
+      cp_async_mbar_arrive_noinc(&full[st]);
+    };
+    for (int k = 0; k < nlev; ++k) produce(k);
+    __syncthreads();          // the consumers' forward results are in global memory
+    for (int k = nlev; k < 2 * nlev; ++k) produce(k);
+  } else {
+    const int q = tid >> 2, r = tid & 3;
+    const int rstride = (nq + 2) * 4;
+    auto release_stage = [&](int st) {
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+    };
+    auto level_done = [&]() {
+      if (nt == 32) __syncwarp();
+      else named_bar_sync(1, nt);
+    };
+    // ---------------- forward: y = L^-1 d ----------------
+    for (int L = 0; L < nlev; ++L) {
+      const int st = L % D;
+      mbar_wait(&full[st], (unsigned)(L / D) & 1u);
+      const int il = 3 * q + L % 3, tj = L - il, j = tj / 3;
+      const bool act = il < wc && tj >= 0 && j < g.nvy;
+      double2 lv[6][2], yv[6][2];
+      double acc = 0.0;
+      if (act) {
+        const double* lrow = stage + ((size_t)st * nq * 112) + (size_t)(j - lev1_jlo(L, wc)) * 96 + r * 4;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int di = P1_DI(k), dj = P1_DJ(k);
+          const int Ln = L + di + 3 * dj;
+          const double* yp = ring + (Ln & 7) * rstride + ((il + di + 3) / 3) * 4;
+          lv[k][0] = *reinterpret_cast<const double2*>(lrow + k * 16);
+          lv[k][1] = *reinterpret_cast<const double2*>(lrow + k * 16 + 2);
+          yv[k][0] = *reinterpret_cast<const double2*>(yp);
+          yv[k][1] = *reinterpret_cast<const double2*>(yp + 2);
+        }
+        acc = stageR[st * nt + tid];
+      }
+      release_stage(st);
+      if (act) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          double t = lv[k][0].x * yv[k][0].x;
+          t += lv[k][0].y * yv[k][0].y;
+          t += lv[k][1].x * yv[k][1].x;
+          t += lv[k][1].y * yv[k][1].y;
+          acc -= t;
+        }
+        ring[(L & 7) * rstride + (q + 1) * 4 + r] = acc;
+        v_out[4 * (size_t)(i0 + il + g.nvx * j) + r] = acc;
+      }
+      level_done();
+    }
+    __syncthreads();
+    // ---------------- backward: x = U^-1 y ----------------
+    for (int L = nlev - 1; L >= 0; --L) {
+      const int k = 2 * nlev - 1 - L, st = k % D;
+      mbar_wait(&full[st], (unsigned)(k / D) & 1u);
+      const int il = 3 * q + L % 3, tj = L - il, j = tj / 3;
+      const bool act = il < wc && tj >= 0 && j < g.nvy;
+      double2 uv[7][2], xv[6][2];
+      double acc = 0.0;
+      if (act) {
+        const double* urow = stage + ((size_t)st * nq * 112) + (size_t)(j - lev1_jlo(L, wc)) * 112 + r * 4;
+#pragma unroll
+        for (int p = 6; p < 13; ++p) {
+          uv[p - 6][0] = *reinterpret_cast<const double2*>(urow + (p - 6) * 16);
+          uv[p - 6][1] = *reinterpret_cast<const double2*>(urow + (p - 6) * 16 + 2);
+          if (p > 6) {
+            const int di = P1_DI(p), dj = P1_DJ(p);
+            const int Ln = L + di + 3 * dj;
+            const double* xp = ring + (Ln & 7) * rstride + ((il + di + 3) / 3) * 4;
+            xv[p - 7][0] = *reinterpret_cast<const double2*>(xp);
+            xv[p - 7][1] = *reinterpret_cast<const double2*>(xp + 2);
+          }
+        }
+        acc = stageR[st * nt + tid];
+      }
+      release_stage(st);
+      if (act) {
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          double t = uv[p + 1][0].x * xv[p][0].x;
+          t += uv[p + 1][0].y * xv[p][0].y;
+          t += uv[p + 1][1].x * xv[p][1].x;
+          t += uv[p + 1][1].y * xv[p][1].y;
+          acc -= t;
+        }
+        const unsigned qmask = 0xFu << (tid & 28);
+        const int qb = tid & 28;
+        double xo = uv[0][0].x * __shfl_sync(qmask, acc, qb + 0);
+        xo += uv[0][0].y * __shfl_sync(qmask, acc, qb + 1);
+        xo += uv[0][1].x * __shfl_sync(qmask, acc, qb + 2);
+        xo += uv[0][1].y * __shfl_sync(qmask, acc, qb + 3);
+        ring[(L & 7) * rstride + (q + 1) * 4 + r] = xo;
+        v_out[4 * (size_t)(i0 + il + g.nvx * j) + r] = xo;
+        if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + il, j, r, xo);
+      }
+      level_done();
+    }
+  }
+  if (P2P) halo_push_finish(hp, g.nvx, i0, wc);
+}
+
+// ------------------------------------------------------------------------------------------
 // one quad per wavefront row: a level of a slab of width w has at most ceil(w/3) rows
 static int slab1_threads(int slab_w) {
   int rows = (slab_w + 2) / 3;
@@ -377,6 +532,23 @@ static void launch_ilu1_apply_t(const Dev& g, const double* LU, const double* d,
                                 const int* lvl_tab, const HaloPush& hp, cudaStream_t st) {
   const int nslab = (g.nvx + slab_w - 1) / slab_w;
   const int nt = slab1_threads(slab_w), nq = slab1_rows(slab_w);
+  static const int use_tma = getenv("AX1_ILU_TMA") ? atoi(getenv("AX1_ILU_TMA")) : 1;
+  // narrow sub-slabs (latency-bound small grids) take the warp-specialised TMA pipeline; at 128+ columns the sweep
+  // is bandwidth-bound and the cp.async kernel below measured faster for ILU(1) (5.6 vs 7.0 ms at 16.9 M vertices)
+  if (use_tma && nt <= 64) {
+    const int nqc = nt / 4;
+    const size_t smem_t = (size_t)D * nqc * 896 + (size_t)D * nt * 8 + 8 * (size_t)(nqc + 2) * 32 + (size_t)D * 16 +
+                          (size_t)(slab_w + 3 * g.nvy) * sizeof(int);
+    if (smem_t <= 227 * 1024) {
+      static bool attr_t = false;
+      if (!attr_t) {
+        cudaFuncSetAttribute(ilu1_apply_tma_kernel<D, P2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_t = true;
+      }
+      ilu1_apply_tma_kernel<D, P2P><<<nslab, nt + 32, smem_t, st>>>(g, LU, LU + (size_t)g.nv * 96, d, v, slab_w, lvl_tab, hp);
+      return;
+    }
+  }
   const size_t smem = (size_t)D * 4 * nq * (7 * 32 + 8) + 8 * (size_t)nq * 32 + (size_t)(slab_w + 3 * g.nvy) * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {
