@@ -586,9 +586,10 @@ static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill) {
     // library default: 128 columns per sub-slab when that still gives >= 2 CTAs per SM, otherwise narrower
     // slabs (>= 16 columns = one warp per CTA) -- small grids are bound by the sweep's per-level latency, and
     // more, narrower slabs shorten the wavefront count and keep more SMs busy
+    const int gran = fill == 1 ? 24 : 16;   // columns one warp sweeps: 8 rows per level = w/2 (ILU0) or w/3 (ILU(1))
     int w = (c->g.nvx + 295) / 296;
-    w = ((w + 15) / 16) * 16;
-    slab_w = c->slab_w > 0 ? c->slab_w : std::min(128, std::max(16, w));
+    w = ((w + gran - 1) / gran) * gran;
+    slab_w = c->slab_w > 0 ? c->slab_w : std::min(128, std::max(gran, w));
   }
   // one quad per wavefront row with <= 256-thread CTAs: levels are ceil(w/2) (ILU0) / ceil(w/3) (ILU(1)) rows wide
   const int wmax = fill == 1 ? ilu1_max_slab_w(c->g) : 128;

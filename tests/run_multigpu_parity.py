@@ -42,8 +42,16 @@ def main():
     # ILU(1) per rank (slab_w >= local columns -> a single sub-slab per rank)
     dev.set_time(0.0, 1.0); dev.set_uold(s["u0"]); dev.update_state(s["u0"])
     ug1, rg1 = dev.newton(s["u0"], api.default_newton_opts(slab_w=64, ilu_fill=1, **kw))
+    # second backend: restarted GMRES preconditioned by the per-rank multigrid cycle + additive halo sum
+    # (ISTLBackend_GMRES_AMG_ILU0, ax1_solverbackend.hh:73-302)
+    dev.set_time(0.0, 1.0); dev.set_uold(s["u0"]); dev.update_state(s["u0"])
+    kw2 = dict(reduction=1e-8, abs_limit=1e-14, min_lin_reduction=1e-6, lin_maxit=500)
+    dev.set_amg(True, 2)       # 2 columns per aggregate: the 7-8 local columns give one coarse level
+    ug2, rg2 = dev.newton(s["u0"], api.default_newton_opts(slab_w=slab_w, amg=1, krylov=1, restart=100, **kw2))
+    dev.set_amg(False)
     gathered = [None] * world
-    dist.all_gather_object(gathered, dict(u=ug, z=zg, nrm=nrm, its=rg.iterations, lin=rg.lin_iterations,
+    dist.all_gather_object(gathered, dict(u2=ug2, its2=rg2.iterations, lin2=rg2.lin_iterations, status2=rg2.status,
+                                          u=ug, z=zg, nrm=nrm, its=rg.iterations, lin=rg.lin_iterations,
                                           status=rg.status, lit=lres.iterations, mode=mode, u1=ug1,
                                           its1=rg1.iterations, lin1=rg1.lin_iterations, status1=rg1.status))
     ok = True
@@ -77,6 +85,20 @@ def main():
             print("rank %d ILU(1): status %d its gpu/cpu %d/%d lin %d/%d field err %s"
                   % (r, g["status1"], g["its1"], res1[r].iterations, g["lin1"], res1[r].lin_iterations, err))
             ok &= g["status1"] == 0 and g["its1"] == res1[r].iterations
+            ok &= bool(np.all(err[:3] < 1e-8) and err[3] < 5e-7)
+        # GMRES + multigrid
+        for r in range(world):
+            probs[r].set_time(0.0, 1.0); probs[r].set_uold(us[r]); probs[r].update_state(us[r])
+        out2, res2, st2 = O.newton_mt(probs, us, O.default_newton_opts(ilu_fill=0, slab_w=slab_w, amg=1, amg_cx=2,
+                                                                      krylov=1, restart=100, **kw2))
+        assert st2 == 0
+        for r in range(world):
+            g = gathered[r]
+            scale = np.max(np.abs(out2[r].reshape(-1, 4)), axis=0)
+            err = np.max(np.abs(g["u2"] - out2[r]).reshape(-1, 4) / scale, axis=0)
+            print("rank %d GMRES+AMG: status %d its gpu/cpu %d/%d lin %d/%d field err %s"
+                  % (r, g["status2"], g["its2"], res2[r].iterations, g["lin2"], res2[r].lin_iterations, err))
+            ok &= g["status2"] == 0 and g["its2"] == res2[r].iterations
             ok &= bool(np.all(err[:3] < 1e-8) and err[3] < 5e-7)
         modes = {g["mode"] for g in gathered}
         print("comm mode", modes, "(2 = NVLink peer windows, 1 = NCCL)")
