@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(256) ilu_apply_kernel(Dev g, const double* __r
 //  * the level barrier is a __syncwarp when the sub-slab is swept by a single consumer warp.
 // Pipeline step k: forward level L = k, backward level L = 2 nlev - 1 - k; stage k % D, use number k / D.
 template <int D, bool P2P>
-__global__ void __launch_bounds__(288) ilu_apply_tma_kernel(Dev g, const double* __restrict__ LF,
+__global__ void __launch_bounds__(160) ilu_apply_tma_kernel(Dev g, const double* __restrict__ LF,
                                                             const double* __restrict__ LB, const double* __restrict__ d,
                                                             double* v_out, int slab_w, const int* __restrict__ lvl_tab,
                                                             HaloPush hp) {
@@ -445,41 +445,55 @@ __global__ void __launch_bounds__(288) ilu_apply_tma_kernel(Dev g, const double*
     __syncthreads();          // the consumers' forward results are in global memory
     for (int k = nlev; k < 2 * nlev; ++k) produce(k);
   } else {
+    // Consumers. Everything that does not change from level to level is computed here once; inside the loops the
+    // level index only advances a handful of running values (stage, phase, ring slots, row index, row pointers).
     const int q = tid >> 2, r = tid & 3;
     const int rstride = (nq + 2) * 4;
-    // a consumer warp hands the stage back as soon as its operands are in registers (mbarrier.arrive releases the
-    // warp's prior shared-memory reads); the level barrier only orders the ring of solution values
-    auto release_stage = [&](int st) {
-      __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(&empty[st]);
-    };
-    auto level_done = [&]() {
-      if (nt == 32) __syncwarp();
-      else named_bar_sync(1, nt);
-    };
+    const unsigned full0 = smem_u32(full), empty0 = smem_u32(empty);
+    const bool lane0 = (tid & 31) == 0, one_warp = nt == 32;
+    const bool okE = 2 * q < wc, okO = 2 * q + 1 < wc;                 // my column at even / odd levels exists
+    const int capE = ((wc + 1) >> 1) - 1, capO = (wc >> 1) - 1;        // row index in the stage: min(m, cap) - q
+    const double* stage_r = stage + r * 4;
+    const double* rhs_t = stageR + tid;
+    double* ring_own = ring + (q + 1) * 4 + r;
+    const double* ring_q = ring + (q + 1) * 4;
+    double* vE = v_out + 4 * (size_t)(i0 + 2 * q) + r;               // my even column; the odd one is 4 doubles on
+    const size_t vstride = 4 * (size_t)g.nvx;
+    const size_t stage_stride = (size_t)nq * 80;
+    // ring neighbour quads (relative to my own slot q + 1) per level parity: column il + di lives in quad (il + di) >> 1
+    //   forward  s = 0..3: di = -1, 0, +1, -1      backward s = 5..8: di = +1, -1, 0, +1
+    //   forward  {-4, 0, 0, -4} (even) {0, 0, 4, 0} (odd);  backward {0, -4, 0, 0} (even) {4, 0, 0, 4} (odd)
+    int st = 0;
+    unsigned ph = 0;
+    int so0 = 0, so1 = 3 * rstride, so2 = 2 * rstride, so3 = rstride;  // ring slot offsets of levels L, L-1, L-2, L-3
+
     // ---------------- forward: y = L^-1 d ----------------
     for (int L = 0; L < nlev; ++L) {
-      const int st = L % D;
-      mbar_wait(&full[st], (unsigned)(L / D) & 1u);
-      const int il = 2 * q + (L & 1), tj = L - il, j = tj >> 1;
-      const bool act = il < wc && tj >= 0 && j < g.nvy;
+      const int b = L & 1, m = L >> 1, j = m - q;
+      mbar_wait_a(full0 + 8u * st, ph);
+      const bool act = (b ? okO : okE) && (unsigned)j < (unsigned)g.nvy;
       double2 lv[4][2], yv[4][2];
       double acc = 0.0;
       if (act) {
-        const double* lrow = stage + ((size_t)st * nq * 80) + (size_t)(j - lev_jlo(L, wc)) * 64 + r * 4;
+        const double* lrow = stage_r + (size_t)st * stage_stride + (size_t)(min(m, b ? capO : capE) - q) * 64;
+        const double* y0 = ring_q + so3 + (b ? 0 : -4);   // (-1,-1): level L-3
+        const double* y1 = ring_q + so2;                   // ( 0,-1): level L-2
+        const double* y2 = ring_q + so1 + (b ? 4 : 0);    // (+1,-1): level L-1
+        const double* y3 = ring_q + so1 + (b ? 0 : -4);   // (-1, 0): level L-1
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          const int di = s % 3 - 1, dj = s / 3 - 1;
-          const int Ln = L + di + 2 * dj;
-          const double* yp = ring + (Ln & 3) * rstride + (((il + di) >> 1) + 1) * 4;
           lv[s][0] = *reinterpret_cast<const double2*>(lrow + s * 16);
           lv[s][1] = *reinterpret_cast<const double2*>(lrow + s * 16 + 2);
-          yv[s][0] = *reinterpret_cast<const double2*>(yp);
-          yv[s][1] = *reinterpret_cast<const double2*>(yp + 2);
         }
-        acc = stageR[st * nt + tid];
+        yv[0][0] = *reinterpret_cast<const double2*>(y0); yv[0][1] = *reinterpret_cast<const double2*>(y0 + 2);
+        yv[1][0] = *reinterpret_cast<const double2*>(y1); yv[1][1] = *reinterpret_cast<const double2*>(y1 + 2);
+        yv[2][0] = *reinterpret_cast<const double2*>(y2); yv[2][1] = *reinterpret_cast<const double2*>(y2 + 2);
+        yv[3][0] = *reinterpret_cast<const double2*>(y3); yv[3][1] = *reinterpret_cast<const double2*>(y3 + 2);
+        acc = rhs_t[st * nt];
       }
-      release_stage(st);
+      // hand the stage back as soon as the operands are in registers (mbarrier.arrive releases the warp's reads)
+      __syncwarp();
+      if (lane0) mbar_arrive_a(empty0 + 8u * st);
       if (act) {
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
@@ -489,37 +503,47 @@ __global__ void __launch_bounds__(288) ilu_apply_tma_kernel(Dev g, const double*
           t += lv[s][1].y * yv[s][1].y;
           acc -= t;
         }
-        ring[(L & 3) * rstride + (q + 1) * 4 + r] = acc;
-        v_out[4 * (size_t)(i0 + il + g.nvx * j) + r] = acc;
+        ring_own[so0] = acc;
+        vE[vstride * (size_t)j + 4 * b] = acc;
       }
-      level_done();
+      if (one_warp) __syncwarp();
+      else named_bar_sync(1, nt);
+      if (++st == D) { st = 0; ph ^= 1u; }
+      { const int t = so3; so3 = so2; so2 = so1; so1 = so0; so0 = t; }
     }
     __syncthreads();
     // ---------------- backward: x = U^-1 y ----------------
+    // slot offsets now refer to levels L, L+1, L+2, L+3: before the loop so0 is the slot of level nlev (= nlev & 3)
+    int su0, su1, su2, su3;
+    {
+      const int top = nlev - 1;
+      su0 = (top & 3) * rstride; su1 = ((top + 1) & 3) * rstride; su2 = ((top + 2) & 3) * rstride; su3 = ((top + 3) & 3) * rstride;
+    }
     for (int L = nlev - 1; L >= 0; --L) {
-      const int k = 2 * nlev - 1 - L, st = k % D;
-      mbar_wait(&full[st], (unsigned)(k / D) & 1u);
-      const int il = 2 * q + (L & 1), tj = L - il, j = tj >> 1;
-      const bool act = il < wc && tj >= 0 && j < g.nvy;
+      const int b = L & 1, m = L >> 1, j = m - q;
+      mbar_wait_a(full0 + 8u * st, ph);
+      const bool act = (b ? okO : okE) && (unsigned)j < (unsigned)g.nvy;
       double2 uv[5][2], xv[4][2];
       double acc = 0.0;
       if (act) {
-        const double* urow = stage + ((size_t)st * nq * 80) + (size_t)(j - lev_jlo(L, wc)) * 80 + r * 4;
+        const double* urow = stage_r + (size_t)st * stage_stride + (size_t)(min(m, b ? capO : capE) - q) * 80;
+        const double* x0 = ring_q + su1 + (b ? 4 : 0);    // (+1, 0): level L+1
+        const double* x1 = ring_q + su1 + (b ? 0 : -4);   // (-1,+1): level L+1
+        const double* x2 = ring_q + su2;                   // ( 0,+1): level L+2
+        const double* x3 = ring_q + su3 + (b ? 4 : 0);    // (+1,+1): level L+3
 #pragma unroll
-        for (int s = 4; s < 9; ++s) {
-          uv[s - 4][0] = *reinterpret_cast<const double2*>(urow + (s - 4) * 16);
-          uv[s - 4][1] = *reinterpret_cast<const double2*>(urow + (s - 4) * 16 + 2);
-          if (s > 4) {
-            const int di = s % 3 - 1, dj = s / 3 - 1;
-            const int Ln = L + di + 2 * dj;
-            const double* xp = ring + (Ln & 3) * rstride + (((il + di) >> 1) + 1) * 4;
-            xv[s - 5][0] = *reinterpret_cast<const double2*>(xp);
-            xv[s - 5][1] = *reinterpret_cast<const double2*>(xp + 2);
-          }
+        for (int s = 0; s < 5; ++s) {
+          uv[s][0] = *reinterpret_cast<const double2*>(urow + s * 16);
+          uv[s][1] = *reinterpret_cast<const double2*>(urow + s * 16 + 2);
         }
-        acc = stageR[st * nt + tid];
+        xv[0][0] = *reinterpret_cast<const double2*>(x0); xv[0][1] = *reinterpret_cast<const double2*>(x0 + 2);
+        xv[1][0] = *reinterpret_cast<const double2*>(x1); xv[1][1] = *reinterpret_cast<const double2*>(x1 + 2);
+        xv[2][0] = *reinterpret_cast<const double2*>(x2); xv[2][1] = *reinterpret_cast<const double2*>(x2 + 2);
+        xv[3][0] = *reinterpret_cast<const double2*>(x3); xv[3][1] = *reinterpret_cast<const double2*>(x3 + 2);
+        acc = rhs_t[st * nt];
       }
-      release_stage(st);
+      __syncwarp();
+      if (lane0) mbar_arrive_a(empty0 + 8u * st);
       if (act) {
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
@@ -536,11 +560,14 @@ __global__ void __launch_bounds__(288) ilu_apply_tma_kernel(Dev g, const double*
         xo += uv[0][0].y * __shfl_sync(qmask, acc, qb + 1);
         xo += uv[0][1].x * __shfl_sync(qmask, acc, qb + 2);
         xo += uv[0][1].y * __shfl_sync(qmask, acc, qb + 3);
-        ring[(L & 3) * rstride + (q + 1) * 4 + r] = xo;
-        v_out[4 * (size_t)(i0 + il + g.nvx * j) + r] = xo;
-        if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + il, j, r, xo);
+        ring_own[su0] = xo;
+        vE[vstride * (size_t)j + 4 * b] = xo;
+        if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + 2 * q + b, j, r, xo);
       }
-      level_done();
+      if (one_warp) __syncwarp();
+      else named_bar_sync(1, nt);
+      if (++st == D) { st = 0; ph ^= 1u; }
+      { const int t = su3; su3 = su2; su2 = su1; su1 = su0; su0 = t; }
     }
   }
   if (P2P) halo_push_finish(hp, g.nvx, i0, wc);
@@ -676,7 +703,10 @@ static void launch_ilu_apply_t(const Dev& g, const double* LU, const double* d, 
                                const int* lvl_tab, const HaloPush& hp, cudaStream_t st) {
   const int nslab = (g.nvx + slab_w - 1) / slab_w;
   const int nt = slab_threads(slab_w);
-  if (ilu_use_tma()) {
+  // Sub-slabs of up to 64 columns (small grids: the sweep is bound by per-level latency) take the warp-specialised
+  // TMA pipeline; at 128 columns the sweep is bandwidth-bound, both kernels reach the same ~0.94 of the copy peak
+  // (3.7-3.9 ms at 16.9 M vertices) and the cp.async kernel needs fewer registers for its 2 CTAs per SM.
+  if (ilu_use_tma() && nt <= 128) {
     const int nq = nt / 4;
     const size_t smem_t = (size_t)D * nq * 640 + (size_t)D * nt * 8 + 4 * (size_t)(nq + 2) * 32 + (size_t)D * 16 +
                           (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
