@@ -655,3 +655,22 @@ def test_membrane_flux_stimulation(oracle, axlib, ion, active):
     err = np.max(np.abs(ug - uc).reshape(-1, 4) / scale, axis=0)
     assert np.all(err[:3] < 1e-8) and err[3] < 5e-7, err
     dev.close(); dev2.close()
+
+
+@pytest.mark.parametrize("nx,slab_w,fill", [(1, 1, 0), (2, 1, 0), (3, 2, 0), (17, 16, 0), (33, 17, 0), (40, 31, 0),
+                                            (70, 64, 0), (70, 65, 0), (150, 128, 0), (2, 1, 1), (25, 24, 1),
+                                            (50, 23, 1), (70, 48, 1), (70, 49, 1)])
+def test_ilu_apply_ragged_sizes(oracle, axlib, nx, slab_w, fill):
+    """Sweeps on ragged sizes: one-column sub-slabs, a narrower last sub-slab, widths on either side of the
+    kernel-selection thresholds (one warp / warp-specialised TMA pipeline / cp.async kernel)."""
+    s = small_setup(nx=nx, dx=100.0)
+    dev, P, u0 = _both(oracle, axlib, s)
+    Jo = P.jacobian(u0)
+    dev.set_jacobian(Jo)
+    dev.ilu_factor(slab_w, fill=fill)
+    rng = np.random.default_rng(nx * 131 + slab_w)
+    d = rng.standard_normal(P.n)
+    vg = dev.ilu_apply(d)
+    vo = P.ilu_apply(Jo, d, ilu_fill=fill, slab_w=min(slab_w, s["nx"] + 1))
+    assert np.max(np.abs(vg - vo)) <= 1e-9 * np.max(np.abs(vo)), np.max(np.abs(vg - vo)) / np.max(np.abs(vo))
+    dev.close()
