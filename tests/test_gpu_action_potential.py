@@ -85,3 +85,40 @@ def test_time_step_restart_on_newton_failure(axlib):
     r = dev.time_step(tl, good, st)
     assert r.newton_status == 0 and st.steps == 1 and st.time == 0.25
     dev.close()
+
+
+def test_reference_test_config_equilibration_steps(oracle, axlib):
+    """BASELINE configs[0]: test/acme2_cyl_par.config of the reference -- 100 um x 1 mm cylinder, dx = 10 um, the
+    91-point radial vector of yasp_square1mm, closed cell (Neumann sides, Dirichlet top), equilibration mode (leak
+    channels only, dummy_value = 10, dtEquilibrium = 10 us), newtonReduction 1e-6 / newtonAbsLimit 1e-3 -- with the
+    one change SURVEY D3 records as necessary to run it with acme2_cyl_par at all: a single membrane element layer
+    (the file's nMembraneElements = 5 needs the non-blocked acme2_cyl_par_mme build). A few adaptive time steps from
+    the shipped 1 mm equilibrium column on the device and on the oracle, through the library's own time loop, at
+    dt = dtEquilibrium. Newton tolerances are tightened to just above the rounding floor of the residual (~1.2 on this
+    grid) so that both sides stop for the same reason and can be compared to 1e-8."""
+    import json, os
+    from dune_ax1_b200 import setups
+    from dune_ax1_b200.timeloop import DeviceTimeLoop, TimeLoop
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    y, ucol, _ = setups.load_equilibrium_column(os.path.join(root, "tests", "golden", "yasp_square1mm.json"))
+    s = setups.make_setup(10, dx=10.0e3, y=y, ucol=ucol, equilibration=True, perturbation=1e-4)
+    dev = setups.make_device(s)
+    P = oracle_problem(oracle, s)
+    kw = dict(reduction=1e-12, abs_limit=5.0, min_lin_reduction=1e-8, maxit=50)
+    og = axlib.default_newton_opts(slab_w=128, **kw)
+    oc = oracle.default_newton_opts(ilu_fill=0, slab_w=0, **kw)
+    ctl = dict(dtstart=10.0, lower_limit=10, upper_limit=30, max_restarts=2, adaptive=False)
+    tg = DeviceTimeLoop(dev, s["u0"], newton_opts=og, **ctl)
+    tc = TimeLoop(P, s["u0"], newton_opts=oc, **ctl)
+    for _ in range(4):
+        rg = tg.step()
+        rc = tc.step()
+        assert abs(tg.time - tc.time) < 1e-12 and rg.newton_iterations == rc.iterations
+    ug, uc = tg.u, tc.u
+    scale = np.max(np.abs(uc.reshape(-1, 4)), axis=0)
+    err = np.max(np.abs(ug - uc).reshape(-1, 4) / scale, axis=0)
+    assert np.all(err[:3] < 1e-8) and err[3] < 5e-7, err
+    # equilibration relaxes the perturbation: the state stays a resting state
+    vm = dev.membrane_potential_dev()
+    assert np.all(np.abs(vm - (-65.0)) < 2.0)
+    dev.close()
