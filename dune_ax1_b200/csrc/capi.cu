@@ -144,7 +144,8 @@ int ax1gpu_create(const ax1gpu_grid* grid, const unsigned char* cell_subdomain, 
   }
   c->nred_blocks = 148 * 8;
   TRY(dev_alloc(&c->d_partials, 2 * (size_t)c->nred_blocks));
-  TRY(dev_alloc(&c->d_spartials, 2 * (size_t)((4 * nv + 255) / 256)));
+  // + 2 x 512 doubles behind the SpMV partials: second-stage partials of the two-stage reduction (driver.cu)
+  TRY(dev_alloc(&c->d_spartials, 2 * (size_t)((4 * nv + 255) / 256) + 1024));
   TRY(dev_alloc(&c->d_sums, 8));
   TRY(dev_alloc(&c->d_sc, 1));
   if (cudaMallocHost((void**)&c->h_sc, sizeof(Scalars)) != cudaSuccess ||

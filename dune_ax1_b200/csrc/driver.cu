@@ -417,9 +417,28 @@ static inline Own own_of(const ax1gpu_ctx* c) { return Own{c->own_lo, c->own_hi,
     }                                                                                 \
   } while (0)
 
+// first stage of the reduction of many block partials (the dot products fused into the SpMV leave one partial per
+// 64 block rows: 263 k at the named workload, which a single block took 135 us to add up): 512 blocks add a fixed
+// contiguous chunk each -- the summation order stays fixed, so results stay bitwise reproducible
+#define AX1_RED2 512
+__global__ void __launch_bounds__(256) reduce_stage_kernel(const double* __restrict__ partials, int nblocks, double* out) {
+  const int chunk = (nblocks + AX1_RED2 - 1) / AX1_RED2;
+  const int lo = blockIdx.x * chunk, hi = min(nblocks, lo + chunk);
+  double s[2] = {0.0, 0.0};
+  for (int k = lo + threadIdx.x; k < hi; k += blockDim.x) { s[0] += partials[k]; s[1] += partials[nblocks + k]; }
+  block_reduce_store<2>(s, out);
+}
+
 // partials -> sums (+ allreduce over ranks) -> scalar recurrence `op`
 static int reduce_op_from(ax1gpu_ctx* c, const double* partials, int nblocks, int nsums, int op, double reduction,
                           double* out = nullptr, int aux = 0) {
+  if (nblocks > 8 * AX1_RED2 && partials == c->d_spartials) {
+    double* p2 = c->d_spartials + 2 * (size_t)spmv_blocks(c->g);
+    reduce_stage_kernel<<<AX1_RED2, 256, 0, c->stream>>>(partials, nblocks, p2);
+    AX1_LAUNCH_CHECK(c);
+    partials = p2;
+    nblocks = AX1_RED2;
+  }
   if (c->nranks > 1 && c->p2p.on) {
     RedP2P rp;
     for (int k = 0; k < AX1_MAX_RANKS; ++k) rp.peer[k] = c->p2p.peer[k];
