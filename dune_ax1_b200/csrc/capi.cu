@@ -80,6 +80,12 @@ int ax1gpu_create(const ax1gpu_grid* grid, const unsigned char* cell_subdomain, 
   if (ax1gpu_device_count() <= 0) { set_error("no CUDA device: libax1gpu has no CPU fallback"); return AX1GPU_ENODEVICE; }
   const int nx = grid->nx, ny = grid->ny;
   if (nx < 1 || ny < 3) { set_error("grid too small"); return AX1GPU_EINVAL; }
+  if (!grid->x || !grid->y) { set_error("null argument"); return AX1GPU_EINVAL; }
+  for (int i = 0; i < nx; ++i)
+    if (!(grid->x[i + 1] > grid->x[i])) { set_error("x coordinates must be strictly increasing"); return AX1GPU_EINVAL; }
+  for (int j = 0; j < ny; ++j)
+    if (!(grid->y[j + 1] > grid->y[j])) { set_error("y coordinates must be strictly increasing"); return AX1GPU_EINVAL; }
+  if (!(grid->y[0] >= 0.0)) { set_error("radial coordinates must be non-negative"); return AX1GPU_EINVAL; }
   // the membrane must be exactly one full cell row (nMembraneElements = 1, numberMembranes = 1)
   int jm = -1;
   for (int j = 0; j < ny; ++j) {

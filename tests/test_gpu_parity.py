@@ -674,3 +674,41 @@ def test_ilu_apply_ragged_sizes(oracle, axlib, nx, slab_w, fill):
     vo = P.ilu_apply(Jo, d, ilu_fill=fill, slab_w=min(slab_w, s["nx"] + 1))
     assert np.max(np.abs(vg - vo)) <= 1e-9 * np.max(np.abs(vo)), np.max(np.abs(vg - vo)) / np.max(np.abs(vo))
     dev.close()
+
+
+def test_error_behaviour(oracle, axlib):
+    """Errors come back as status codes + message (never as a crash or an exception across the C boundary), and a
+    Newton solve that meets NaNs reports NewtonDefectError's status like PDELab's NewtonSolver::defect."""
+    from dune_ax1_b200 import setups
+    s = small_setup(nx=6)
+    # invalid grids / maps
+    bad = dict(s); bad["x"] = s["x"][::-1].copy()
+    with pytest.raises(axlib.Ax1GpuError, match="strictly increasing"):
+        setups.make_device(bad)
+    bad = dict(s); cs = s["cell_subdomain"].copy().reshape(s["ny"], s["nx"]); jm = int(np.nonzero(cs[:, 0] == 2)[0][0])
+    cs[jm + 1, :] = 2; bad["cell_subdomain"] = cs.reshape(-1)
+    with pytest.raises(axlib.Ax1GpuError, match="one membrane cell layer"):
+        setups.make_device(bad)
+    dev = setups.make_device(s)
+    u0 = s["u0"]
+    dev.set_time(0.0, 1.0); dev.set_uold(u0); dev.update_state(u0)
+    dev.jacobian(u0, download=False)
+    with pytest.raises(axlib.Ax1GpuError, match="n = 0 and n = 1"):
+        dev.ilu_factor(4, fill=2)
+    with pytest.raises(axlib.Ax1GpuError, match="aggregate"):
+        dev.set_amg(True, 1000)
+    r, _ = dev.residual(u0)
+    with pytest.raises(axlib.Ax1GpuError, match="restart"):
+        dev.solve_gmres(r, 1e-3, restart=5000, maxit=10000)
+    # a handle survives errors: the same solve with valid arguments works
+    z, _, res = dev.solve_gmres(r, 1e-6, restart=30, maxit=200, slab_w=4, fill=0)
+    assert res.converged == 1
+    # NaN in the iterate -> Newton stops with the defect-error status, no exception, no hang
+    ub = u0.copy(); ub[5] = np.nan
+    un, nres = dev.newton(ub, axlib.default_newton_opts(slab_w=4))
+    assert nres.status == 3 and nres.iterations == 0
+    # negative concentration -> log of a negative ratio in the membrane flux -> NaN defect during the line search
+    # is retried with smaller steps, never accepted
+    dev.close()
+    with pytest.raises(axlib.Ax1GpuError):
+        dev.residual(u0)        # closed handle
