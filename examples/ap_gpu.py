@@ -8,10 +8,11 @@ nx = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 tend = float(sys.argv[2]) if len(sys.argv) > 2 else 3000.0
 slab_w = int(sys.argv[4]) if len(sys.argv) > 4 else 128
 fill = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+krylov = int(sys.argv[6]) if len(sys.argv) > 6 else 0    # 1: restarted GMRES instead of BiCGStab
 native = int(sys.argv[3]) if len(sys.argv) > 3 else 1   # 1: time loop inside the library (state resident in HBM)
 s = setups.make_setup(nx, dx=100e3, stimulation=True, perturbation=0.0)
 dev = setups.make_device(s)
-opts = api.default_newton_opts(reduction=1e-5, abs_limit=1e-5, min_lin_reduction=1e-5, maxit=50, slab_w=slab_w, ilu_fill=fill)
+opts = api.default_newton_opts(reduction=1e-5, abs_limit=1e-5, min_lin_reduction=1e-5, maxit=50, slab_w=slab_w, ilu_fill=fill, krylov=krylov, restart=50)
 if native:
     tl = DeviceTimeLoop(dev, s["u0"], dtstart=1.0, newton_opts=opts, lower_limit=10, upper_limit=30)
 else:
