@@ -69,6 +69,9 @@ int ax1o_generate_y(double ymin, double ymax, double ymemb, double dmemb, double
                     double dy_cell_min, int n_dy_cell_min, double dy, double dy_min, int n_dy_min,
                     double* out, int cap);
 
+/* one GridVector primitive appended to a vector holding `start` (ops: oracle/ref_driver.cpp) */
+int ax1o_gridvector(int op, double start, int n, double a, double b, double c, double* out, int cap);
+
 ax1o_problem* ax1o_create(const ax1o_config* cfg, int nx, int ny, const double* x, const double* y,
                           int left_proc_boundary, int right_proc_boundary, const double* eps_memb,
                           const double* g_leak, const double* g_nav, const double* g_kv);

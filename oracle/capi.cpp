@@ -55,6 +55,14 @@ int ax1o_generate_y(double ymin, double ymax, double ymemb, double dmemb, double
   AX1O_CATCH(-1)
 }
 
+int ax1o_gridvector(int op, double start, int n, double a, double b, double c, double* out, int cap) {
+  AX1O_TRY
+  std::vector<double> g = gridvector_op(op, start, n, a, b, c);
+  for (int i = 0; i < (int)g.size() && i < cap; ++i) out[i] = g[i];
+  return (int)g.size();
+  AX1O_CATCH(-1)
+}
+
 ax1o_problem* ax1o_create(const ax1o_config* cfg, int nx, int ny, const double* x, const double* y,
                           int left_pb, int right_pb, const double* eps_memb, const double* g_leak,
                           const double* g_nav, const double* g_kv) {

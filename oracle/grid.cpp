@@ -111,6 +111,23 @@ std::vector<double> generate_y(double ymin, double ymax, double ymemb, double dm
   return y;
 }
 
+// the GridVector primitives on their own (checked against the reference's compiled ax1_gridvector.hh through
+// oracle/_ref, tests/test_reference_pins.py); op numbers as in oracle/ref_driver.cpp
+std::vector<double> gridvector_op(int op, double start, int n, double a, double b, double c) {
+  GV g;
+  g.push_back(start);
+  switch (op) {
+    case 0: g.equidistant_n_h(n, a); break;
+    case 1: g.equidistant_n_xend(n, a); break;
+    case 6: g.geometric_n_h0_xend(n, a, b); break;
+    case 7: g.geometric_n_hend_xend(n, a, b); break;
+    case 8: g.geometric_h0_hend_xend(a, b, c, 0); break;
+    case 9: g.geometric_h0_hend_xend(a, b, c, 1); break;
+    default: throw std::runtime_error("gridvector_op: primitive not restated");
+  }
+  return g;
+}
+
 // refineXDirection branch of generateTensorGrid (ax1_gridgenerator.hh:536-547)
 std::vector<double> equidistant_x(double xmin, double xmax, double dx) {
   GV x;

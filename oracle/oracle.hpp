@@ -5,11 +5,13 @@
 // the product: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load it. The product path (dune_ax1_b200/) never calls into oracle/.
 //
-// PARITY STATUS: "parity unpinned" at the hot-path boundary. The reference cannot be built here
-// (needs DUNE 2.3 + MPI + autotools) and its own tests hold no golden vector for
-// residual/Jacobian/solve. What pins this oracle: the shipped equilibrium state files
-// (tests/golden/, see tests/test_oracle_golden.py) -- grid vector bit-exact, channel steady
-// states, steady-state residual cancellation.
+// PARITY STATUS: "parity unpinned" at the hot-path boundary. The reference application cannot be built
+// here (needs DUNE 2.3 + MPI + autotools) and its own tests hold no golden vector for
+// residual/Jacobian/solve. What pins this oracle: (1) the shipped equilibrium state files
+// (tests/golden/, tests/test_oracle_golden.py) -- grid vector bit-exact, channel steady states,
+// steady-state residual cancellation; (2) the parts of the reference that compile without DUNE
+// (oracle/_ref from ax1_gridvector.hh, channel.hh, channelset.hh, electrolyte.hh,
+// acme2_cyl_geometrywrapper.hh; tests/test_reference_pins.py).
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -86,6 +88,7 @@ std::vector<double> generate_y(double ymin, double ymax, double ymemb, double dm
                                double dy_cell_min, int n_dy_cell_min, double dy, double dy_min,
                                int n_dy_min);
 std::vector<double> equidistant_x(double xmin, double xmax, double dx);
+std::vector<double> gridvector_op(int op, double start, int n, double a, double b, double c);
 
 // ---- model.cpp
 void setup_problem(Problem& p);           // tags, node volumes, constraints, constants

@@ -75,6 +75,32 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_int, C.c_double)
 _lib = None
 
 
+_REF_LIB = os.path.join(_HERE, "_ref", "libax1ref.so")
+
+
+def build_ref(reference="/root/reference"):
+    """Compile oracle/_ref/libax1ref.so from the reference's own headers (grid-vector primitives, HH channel
+    classes) where they lie under `reference`; returns None when the reference tree is not there (GPU box)."""
+    if not os.path.isdir(os.path.join(reference, "dune", "ax1")):
+        return _REF_LIB if os.path.exists(_REF_LIB) else None
+    subprocess.check_call(["make", "-C", _HERE, "_ref", "REFERENCE=" + reference], stdout=subprocess.DEVNULL)
+    return _REF_LIB
+
+
+def ref_lib():
+    """ctypes handle of oracle/_ref/libax1ref.so, or None if it was not built."""
+    if not os.path.exists(_REF_LIB):
+        return None
+    R = C.CDLL(_REF_LIB)
+    R.ax1ref_gridvector.argtypes = [C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, c_double_p, C.c_int]
+    R.ax1ref_cyl_geometry.argtypes = [C.c_int] + [C.c_double] * 6 + [c_double_p]
+    R.ax1ref_cyl_geometry.restype = None
+    R.ax1ref_electrolyte.argtypes = [C.c_double] * 4 + [c_double_p]
+    R.ax1ref_electrolyte.restype = None
+    R.ax1ref_channelset.argtypes = [C.c_double] * 7 + [c_double_p, C.c_int, c_double_p]
+    return R
+
+
 def build(force=False):
     """Compile oracle/libax1oracle.so (g++ only; building the checker is not using it)."""
     if force or not os.path.exists(_LIB) or any(
@@ -97,6 +123,7 @@ def lib():
     L.ax1o_create.argtypes = [C.POINTER(Config), C.c_int, C.c_int, c_double_p, c_double_p, C.c_int,
                               C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]
     L.ax1o_destroy.argtypes = [C.c_void_p]
+    L.ax1o_gridvector.argtypes = [C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, c_double_p, C.c_int]
     L.ax1o_generate_y.argtypes = [C.c_double] * 6 + [C.c_int, C.c_double, C.c_double, C.c_int,
                                                       c_double_p, C.c_int]
     for name in ("ax1o_num_vertices", "ax1o_membrane_row"):

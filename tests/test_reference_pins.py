@@ -1,0 +1,142 @@
+"""Pins of the oracle against the REFERENCE'S OWN COMPILED CODE (oracle/_ref/libax1ref.so, built by
+`make -C oracle _ref` from /root/reference/dune/ax1/{common/ax1_gridvector.hh, channels/channel.hh,
+channels/channelset.hh} against the stand-in headers of oracle/ref_stubs): the GridVector primitives behind the
+grid generator, and the Hodgkin-Huxley channel set (steady-state initialisation, leak re-balancing, backward-Euler
+gating step, effective conductances) -- SURVEY row a10. The product's host model is held to the same numbers.
+CPU only; skipped where the reference tree is absent and no prebuilt library travelled along."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import oracle_problem, small_setup
+
+
+@pytest.fixture(scope="module")
+def ref(oracle):
+    oracle.build_ref()
+    R = oracle.ref_lib()
+    if R is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    return R
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+GRID_CASES = [
+    (0, 0.0, 17, 0.5, 0.0, 0.0),                 # equidistant_n_h
+    (0, 494.5, 10, 0.5, 0.0, 0.0),
+    (1, 505.0, 7, 1.0e4, 0.0, 0.0),              # equidistant_n_xend
+    (1, 0.0, 100, 1.0e7, 0.0, 0.0),              # the paper's x vector
+    (6, 0.0, 12, 100.0, 495.0, 0.0),             # geometric_n_h0_xend (Newton iteration for q)
+    (7, 510.0, 15, 1.0e5, 3.0e5, 0.0),           # geometric_n_hend_xend
+    (8, 0.0, 0, 100.0, 0.5, 495.0),              # geometric_h0_hend_xend, h0 guaranteed (towards the membrane)
+    (9, 510.0, 0, 0.5, 1.0e5, 4.0e5),            # hend guaranteed (away from the membrane)
+    (8, 300.0, 0, 10.0, 0.5, 495.0),
+]
+
+
+@pytest.mark.parametrize("case", GRID_CASES)
+def test_gridvector_primitives_bit_exact(oracle, ref, case):
+    op, start, n, a, b, c = case
+    out_r, out_o = np.zeros(4096), np.zeros(4096)
+    nr = ref.ax1ref_gridvector(op, start, n, a, b, c, _dp(out_r), 4096)
+    no = oracle.lib().ax1o_gridvector(op, start, n, a, b, c, _dp(out_o), 4096)
+    assert nr > 1 and nr == no
+    assert np.array_equal(out_r[:nr], out_o[:no])
+
+
+@pytest.mark.parametrize("gbar,v_init", [((0.5, 120.0, 36.0), -65.0), ((0.5, 1200.0, 360.0), -64.9076),
+                                         ((0.3, 40.0, 90.0), -70.0)])
+def test_channel_set_against_reference_classes(oracle, ref, gbar, v_init):
+    """DynamicChannelSet with [Na_leak, K_leak, Nav, Kv]: initChannels at v_init, then backward-Euler gating steps
+    through a depolarisation. The oracle is driven through its public API on a one-column problem whose membrane
+    potential is set to the same values."""
+    g_leak, g_nav, g_kv = gbar
+    dt_us = 10.0
+    v_steps = np.array([-60.0, -40.0, -10.0, 20.0, 35.0, 10.0, -30.0, -70.0, -75.0, v_init])
+    out = np.zeros(9 * (len(v_steps) + 1))
+    rc = ref.ax1ref_channelset(g_leak, g_nav, g_kv, 0.13, 0.87, v_init, dt_us * 1e-6, _dp(v_steps), len(v_steps), _dp(out))
+    assert rc == 0
+    want = out.reshape(-1, 9)
+
+    s = small_setup(nx=1, perturbation=0.0)
+    s["g_leak"][:], s["g_nav"][:], s["g_kv"][:] = g_leak, g_nav, g_kv
+    P = oracle_problem(oracle, s)
+    kT_e_mV = P.constants()["kT_e"] * 1e3
+    nvx, jm = s["nx"] + 1, P.jm
+
+    def state_with_vm(v_mV):
+        u = s["u0"].reshape(-1, nvx, 4).copy()
+        u[jm, :, 3] = v_mV / kT_e_mV          # cytosol-side membrane vertices
+        u[jm + 1, :, 3] = 0.0                 # extracellular side
+        assert abs(P.membrane_potential(u.reshape(-1))[0] - v_mV) < 1e-12 * max(1.0, abs(v_mV))
+        return u.reshape(-1)
+
+    def check(stage, got5):
+        w = want[stage]
+        assert np.max(np.abs(got5 - w[:5]) / np.abs(w[:5])) < 1e-14, (stage, got5, w[:5])
+        # effective conductances as the flux kernel forms them from the same state
+        geff = np.array([g_leak * got5[0], g_leak * got5[1], g_nav * got5[2] ** 3 * got5[3], g_kv * got5[4] ** 4])
+        assert np.max(np.abs(geff - w[5:]) / (np.abs(w[5:]) + 1e-300)) < 1e-13
+
+    t = 0.0
+    P.set_time(t, dt_us)
+    P.update_state(state_with_vm(v_init))      # initChannels (steady state, v_rest := v_init, leak re-balancing)
+    assert abs(P.v_rest() - v_init) < 1e-12
+    check(0, P.channel_state(new=True))
+    P.accept_state()
+    for k, v in enumerate(v_steps):
+        P.set_time(t, dt_us)
+        P.update_state(state_with_vm(v))       # backward-Euler step from the accepted state
+        check(k + 1, P.channel_state(new=True))
+        P.accept_state()
+        t += dt_us
+    # the shipped channelStates vector (m, h, n at rest) is the reference's own steady state too
+    if v_init == -65.0:
+        assert abs(want[0][2] - 0.052932485257249577) < 1e-15 and abs(want[0][4] - 0.31767691406069742) < 1e-15
+
+
+def test_poisson_constant_against_reference_electrolyte(oracle, ref):
+    """Electrolyte(eps = 80, T = 279.45 K, stdCon = N_A, lengthScale = 1e-9) as default_config.hh builds it."""
+    out = np.zeros(2)
+    ref.ax1ref_electrolyte(80.0, 279.45, 6.02214129e23, 1e-9, _dp(out))
+    P = oracle_problem(oracle, small_setup(nx=1))
+    assert P.constants()["PC"] == out[0]
+    assert abs(out[0] - 0.4525173207) < 1e-9
+
+
+def test_node_volumes_against_reference_cylinder_geometry(oracle, axlib, ref):
+    """Acme2CylGeometry::volume() = pi (r_last + r_first) * vol2D of the reference (acme2_cyl_geometrywrapper.hh:64-72)
+    is what Physics::calcNodeVolumes divides: node volume = min over the adjacent cells of V_cell / V_reference, with
+    V_reference the first cell above the scaling threshold. Checked for the oracle's and the product host model's maps."""
+    s = small_setup(nx=4)
+    P = oracle_problem(oracle, s)
+    _, nvol_o, _ = P.maps()
+    x, y = s["x"], s["y"]
+    nx, ny = s["nx"], s["ny"]
+
+    def vol(i, j):
+        out = np.zeros(2)
+        ref.ax1ref_cyl_geometry(2, x[i], y[j], x[i + 1], y[j + 1], 0.5, 0.5, _dp(out))
+        assert out[0] == 2 * np.pi * (y[j] + 0.5 * (y[j + 1] - y[j])) * ((x[i + 1] - x[i]) * (y[j + 1] - y[j])) or \
+            abs(out[0] / (2 * np.pi * 0.5 * (y[j] + y[j + 1]) * (x[i + 1] - x[i]) * (y[j + 1] - y[j])) - 1) < 1e-15
+        return out[1]
+
+    y_start = 500.0 + 5.0 + 500.0                     # y_memb + d_memb + cellWidth (physics.hh:2286-2397)
+    j0 = int(np.nonzero(0.5 * (y[:-1] + y[1:]) > y_start)[0][0])
+    v_ref = vol(0, j0)
+    nvx = nx + 1
+    for (i, j) in ((2, ny), (0, ny), (nx, ny - 3), (1, j0 + 5), (3, j0 + 1)):
+        cells = [(ci, cj) for ci in (i - 1, i) for cj in (j - 1, j) if 0 <= ci < nx and 0 <= cj < ny
+                 and 0.5 * (y[cj] + y[cj + 1]) > y_start]
+        want = min(vol(ci, cj) / v_ref for (ci, cj) in cells)
+        assert nvol_o[i + nvx * j] == want, (i, j)
+        assert s["node_volume"][i + nvx * j] == want, (i, j)     # product host model (ax1host_physics_maps)
+    assert np.all(nvol_o[: nvx * j0] == 1.0)
+    # a membrane-interface face: the wrapped edge volume is the cylinder surface 2 pi r L
+    out = np.zeros(2)
+    ref.ax1ref_cyl_geometry(1, x[1], 505.0, x[2], 505.0, 0.5, 0.0, _dp(out))
+    assert out[1] == (np.pi * (505.0 + 505.0)) * (x[2] - x[1])
