@@ -11,6 +11,7 @@
 //   constraints       rows of constrained DOFs -> unit rows; their COLUMNS are kept (PDELab's default,
 //                     non-symmetric etadd) -- the overlapping operator needs the front-vertex columns [ext]
 #include "oracle.hpp"
+#include <stdexcept>
 #include <algorithm>
 #include <cstring>
 
@@ -345,6 +346,44 @@ inline void gather(const Cell& c, const double* u, double* xl) {
 inline bool is_interface_cell(const Problem& p, int j) { return j == p.jm - 1 || j == p.jm + 1; }
 
 }  // namespace
+
+// one local kernel on cell (i, j) with given local coefficients xl[16] (comp * 4 + vertex, comp = Na, K, Cl, pot):
+// which = 0 elec spatial alpha_volume, 1 time-operator alpha_volume (mass), 2 membrane Poisson alpha_volume,
+// 3 elec alpha_boundary on the membrane-interface face (uglob supplies the opposite side). weight as the
+// one-step method passes it (dt for the spatial operator, 1 for the time operator). out[16] is overwritten.
+// Used by tests/test_reference_pins.py to compare with the reference's own local operators (oracle/_ref).
+void cell_kernel(const Problem& p, int i, int j, int which, const double* xl, const double* uglob, double weight,
+                 double* out) {
+  Cell c = make_cell(p, i, j);
+  for (int k = 0; k < 16; ++k) out[k] = 0.0;
+  switch (which) {
+    case 0: elec_alpha_volume(p, c, xl, weight, out); break;
+    case 1: time_alpha_volume(c, xl, weight, out); break;
+    case 2: memb_alpha_volume(p, c, xl + 12, weight, out + 12); break;
+    case 3: elec_alpha_boundary(p, c, xl, uglob, weight, out); break;
+    default: throw std::runtime_error("cell_kernel: unknown kernel");
+  }
+}
+
+// local Jacobian of one kernel as a 16 x 16 matrix (row = comp_i * 4 + vertex_i, column = comp_j * 4 + vertex_j):
+// which = 0 elec spatial (analytic), 1 time operator (analytic), 2 membrane Poisson (analytic)
+void cell_jacobian(const Problem& p, int i, int j, int which, const double* xl, double weight, double* out256) {
+  Cell c = make_cell(p, i, j);
+  for (int k = 0; k < 256; ++k) out256[k] = 0.0;
+  if (which == 0) {
+    elec_jacobian_volume(p, c, xl, weight, out256);
+  } else if (which == 1) {
+    double m[144] = {0};
+    time_jacobian_volume(c, weight, m);
+    for (int a = 0; a < 12; ++a) for (int b = 0; b < 12; ++b) out256[a * 16 + b] = m[a * 12 + b];
+  } else if (which == 2) {
+    double m[16] = {0};
+    memb_jacobian_volume(p, c, weight, m);
+    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) out256[(12 + a) * 16 + 12 + b] = m[a * 4 + b];
+  } else {
+    throw std::runtime_error("cell_jacobian: unknown kernel");
+  }
+}
 
 void set_uold(Problem& p, const double* uold) {
   p.uold.assign(uold, uold + 4 * (size_t)p.nv);

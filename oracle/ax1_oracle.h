@@ -96,6 +96,12 @@ void ax1o_set_channel_state(ax1o_problem* p, const double* s, double v_rest, int
 double ax1o_get_v_rest(const ax1o_problem* p);
 void ax1o_membrane_potential(const ax1o_problem* p, const double* u, double* vm_mV);
 
+/* one local kernel of cell (i, j) on given local coefficients xl[16] (comp*4 + vertex): which = 0 elec spatial
+ * alpha_volume, 1 time operator, 2 membrane Poisson, 3 membrane-interface alpha_boundary (u supplies the other side) */
+int ax1o_cell_kernel(const ax1o_problem* p, int i, int j, int which, const double* xl, const double* u, double weight,
+                     double* out16);
+/* analytic local Jacobian (16 x 16, row/column = comp*4 + vertex): which = 0 elec spatial, 1 time operator, 2 membrane */
+int ax1o_cell_jacobian(const ax1o_problem* p, int i, int j, int which, const double* xl, double weight, double* out256);
 int ax1o_residual(const ax1o_problem* p, const double* u, double* r, double* abs_terms);
 int ax1o_jacobian(const ax1o_problem* p, const double* u, double* vals /* BCRS order */);
 void ax1o_rownorm(const ax1o_problem* p, double* vals, double* r);

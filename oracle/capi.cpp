@@ -137,6 +137,15 @@ void ax1o_set_channel_state(ax1o_problem* h, const double* s, double v_rest, int
 double ax1o_get_v_rest(const ax1o_problem* h) { return h->p.v_rest; }
 void ax1o_membrane_potential(const ax1o_problem* h, const double* u, double* vm) { membrane_potential_mV(h->p, u, vm); }
 
+int ax1o_cell_kernel(const ax1o_problem* h, int i, int j, int which, const double* xl, const double* u, double weight,
+                     double* out16) {
+  AX1O_TRY cell_kernel(h->p, i, j, which, xl, u, weight, out16); return 0; AX1O_CATCH(1)
+}
+
+int ax1o_cell_jacobian(const ax1o_problem* h, int i, int j, int which, const double* xl, double weight, double* out256) {
+  AX1O_TRY cell_jacobian(h->p, i, j, which, xl, weight, out256); return 0; AX1O_CATCH(1)
+}
+
 int ax1o_residual(const ax1o_problem* h, const double* u, double* r, double* abs_terms) {
   AX1O_TRY residual(h->p, u, r, abs_terms); return 0; AX1O_CATCH(1)
 }

@@ -103,6 +103,9 @@ void set_uold(Problem& p, const double* uold);    // r0 = -M(uold)
 void residual(const Problem& p, const double* u, double* r, double* abs_terms = nullptr);
 void jacobian(const Problem& p, const double* u, BCRS& A);
 void rownorm_scale(BCRS& A, double* r);           // rownorm_preconditioner.hh:65-155
+void cell_jacobian(const Problem& p, int i, int j, int which, const double* xl, double weight, double* out256);
+void cell_kernel(const Problem& p, int i, int j, int which, const double* xl, const double* uglob, double weight,
+                 double* out);
 
 // ---- solver.cpp
 struct ILU {

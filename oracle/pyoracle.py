@@ -87,6 +87,17 @@ def build_ref(reference="/root/reference"):
     return _REF_LIB
 
 
+def ref_operator_lib():
+    """ctypes handle of oracle/_ref/libax1refop.so (the reference's local operators on single cells), or None."""
+    path = os.path.join(_HERE, "_ref", "libax1refop.so")
+    if not os.path.exists(path):
+        return None
+    R = C.CDLL(path)
+    R.ax1ref_local_operator.argtypes = [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p, c_double_p,
+                                        C.c_int, c_double_p, c_double_p]
+    return R
+
+
 def ref_lib():
     """ctypes handle of oracle/_ref/libax1ref.so, or None if it was not built."""
     if not os.path.exists(_REF_LIB):
@@ -140,6 +151,8 @@ def lib():
     L.ax1o_get_v_rest.argtypes = [C.c_void_p]
     L.ax1o_get_v_rest.restype = C.c_double
     L.ax1o_membrane_potential.argtypes = [C.c_void_p, c_double_p, c_double_p]
+    L.ax1o_cell_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, C.c_double, c_double_p]
+    L.ax1o_cell_jacobian.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, C.c_double, c_double_p]
     L.ax1o_residual.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
     L.ax1o_jacobian.argtypes = [C.c_void_p, c_double_p, c_double_p]
     L.ax1o_rownorm.argtypes = [C.c_void_p, c_double_p, c_double_p]
@@ -283,6 +296,19 @@ class Problem:
         vm = np.zeros(self.nx)
         lib().ax1o_membrane_potential(self.h, _dp(f64(u)), _dp(vm))
         return vm
+
+    def cell_kernel(self, i, j, which, xl, u=None, weight=1.0):
+        out = np.zeros(16)
+        uu = f64(u) if u is not None else None
+        if lib().ax1o_cell_kernel(self.h, int(i), int(j), int(which), _dp(f64(xl)), _dp(uu), float(weight), _dp(out)):
+            raise RuntimeError(lib().ax1o_last_error().decode())
+        return out
+
+    def cell_jacobian(self, i, j, which, xl, weight=1.0):
+        out = np.zeros(256)
+        if lib().ax1o_cell_jacobian(self.h, int(i), int(j), int(which), _dp(f64(xl)), float(weight), _dp(out)):
+            raise RuntimeError(lib().ax1o_last_error().decode())
+        return out.reshape(16, 16)
 
     def residual(self, u, with_abs=False):
         r = np.zeros(self.n)

@@ -1,0 +1,379 @@
+// oracle/ref_operator_driver.cpp -- TEST INFRASTRUCTURE ONLY.
+// Runs the reference's OWN local operators and parameter classes on single cells, compiled FROM /root/reference
+// (never copied) against the stand-ins of oracle/ref_stubs for the DUNE interfaces they are templated on:
+//   dune/ax1/acme2_cyl/operator/acme2_cyl_operator_fully_coupled.hh          Acme2CylOperatorFullyCoupled::alpha_volume
+//   dune/ax1/acme2_cyl/configurations/default/default_poisson_parameters.hh  DefaultPoissonParameters::A, b, c, f
+//   dune/ax1/acme2_cyl/configurations/default/default_nernst_planck_parameters.hh  DefaultNernstPlanckParameters::A, b, c, f
+//   dune/ax1/acme2_cyl/operator/acme2_cyl_toperator.hh                       NernstPlanckTimeLocalOperator::alpha_volume
+//   dune/ax1/acme2_cyl/operator/convectiondiffusionfem.hh                    ConvectionDiffusionFEM::alpha_volume (membrane)
+//   ... and the analytic jacobian_volume of the three operators
+//   dune/ax1/common/power_parameters.hh, dune/ax1/acme2_cyl/common/acme2_cyl_geometrywrapper.hh
+// What is stood in for: the grid (one axis-aligned cell), the Q1 local function space tree, quadrature, and a
+// "Physics" object that hands back the coefficients the test chooses (permittivity, diffusion coefficients,
+// valences, node volumes, scales) -- i.e. the look-ups, not the arithmetic. Built into oracle/_ref/libax1refop.so.
+#define USE_CYLINDER_COORDS 1
+#define AX1_USE_JACOBIAN_METHODS_IN_OPERATOR 1   // as in the reference's build flags (src/Makefile.am)
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <dune_standins.hh>
+
+// the reference's printing / comparison helpers live in dune/ax1/common/tools.hh, which needs DUNE; the two
+// comparisons the parameter classes call are restated here (tools.hh:1006-1044)
+struct Tools {
+  template <class T, int size>
+  static bool lessOrEqualThan(const Dune::FieldVector<T, size>& v1, const Dune::FieldVector<T, size>& v2, T eps = 0.0) {
+    bool result = true;
+    for (int i = 0; i < size; i++) result = result && v1[i] - eps <= v2[i];
+    return result;
+  }
+  template <class T, int size>
+  static bool greaterOrEqualThan(const Dune::FieldVector<T, size>& v1, const Dune::FieldVector<T, size>& v2, T eps = 0.0) {
+    bool result = true;
+    for (int i = 0; i < size; i++) result = result && v1[i] + eps >= v2[i];
+    return result;
+  }
+};
+
+// ---- configuration stand-in (the reference's Acme2CylParameters wraps a Dune::ParameterTree): look-ups only
+struct Tree {
+  std::map<std::string, double> num;
+  std::map<std::string, std::string> str;
+  double get(const std::string& k, double def) const { auto it = num.find(k); return it == num.end() ? def : it->second; }
+  bool get(const std::string& k, bool def) const { auto it = num.find(k); return it == num.end() ? def : it->second != 0.0; }
+  int get(const std::string& k, int def) const { auto it = num.find(k); return it == num.end() ? def : (int)it->second; }
+  std::string get(const std::string& k, const std::string& def) const { auto it = str.find(k); return it == str.end() ? def : it->second; }
+  std::string get(const std::string& k, const char* def) const { return get(k, std::string(def)); }
+};
+struct Acme2CylParameters {
+  Tree general, boundary, stimulation, solution_ex, solution_in, equilibration, membrane;
+  bool stim = false, volscale = true;
+  double t0 = 0, t1 = 0, pot_scale = 1.0;
+  double xmin = 0, xmax = 1, ymin = 0, ymax = 1, ymemb = 500.0, dmemb = 5.0;
+#define AX1_BC(name) bool name() const { return false; }
+  AX1_BC(isTopBoundaryDirichlet_Potential) AX1_BC(isBottomBoundaryDirichlet_Potential)
+  AX1_BC(isLeftCytosolBoundaryDirichlet_Potential) AX1_BC(isRightCytosolBoundaryDirichlet_Potential)
+  AX1_BC(isLeftDebyeBoundaryDirichlet_Potential) AX1_BC(isRightDebyeBoundaryDirichlet_Potential)
+  AX1_BC(isLeftExtracellularBoundaryDirichlet_Potential) AX1_BC(isRightExtracellularBoundaryDirichlet_Potential)
+  AX1_BC(isMembraneBoundaryNeumann_Potential)
+  AX1_BC(isTopBoundaryDirichlet_Concentration) AX1_BC(isBottomBoundaryDirichlet_Concentration)
+  AX1_BC(isLeftCytosolBoundaryDirichlet_Concentration) AX1_BC(isRightCytosolBoundaryDirichlet_Concentration)
+  AX1_BC(isLeftDebyeBoundaryDirichlet_Concentration) AX1_BC(isRightDebyeBoundaryDirichlet_Concentration)
+  AX1_BC(isLeftExtracellularBoundaryDirichlet_Concentration) AX1_BC(isRightExtracellularBoundaryDirichlet_Concentration)
+#undef AX1_BC
+  std::vector<double> yMemb() const { return std::vector<double>(1, ymemb); }
+  double dMemb() const { return dmemb; }
+  bool useMembrane() const { return true; }
+  double xMin() const { return xmin; }
+  double xMax() const { return xmax; }
+  double yMin() const { return ymin; }
+  double yMax() const { return ymax; }
+  int nMembranes() const { return 1; }
+  bool doStimulation() const { return stim; }
+  double tInj_start() const { return t0; }
+  double tInj_end() const { return t1; }
+  double getPotentialResidualScalingFactor() const { return pot_scale; }
+  bool doVolumeScaling() const { return volscale; }
+  bool useMori() const { return false; }
+};
+
+#include <dune/ax1/common/constants.hh>
+#include <dune/ax1/common/power_parameters.hh>
+#include <dune/ax1/acme2_cyl/common/acme2_cyl_geometrywrapper.hh>
+#include <dune/ax1/acme2_cyl/configurations/default/default_poisson_parameters.hh>
+#include <dune/ax1/acme2_cyl/configurations/default/default_nernst_planck_parameters.hh>
+#include <dune/ax1/acme2_cyl/operator/acme2_cyl_operator_fully_coupled.hh>
+#include <dune/ax1/acme2_cyl/operator/acme2_cyl_toperator.hh>
+#include <dune/ax1/acme2_cyl/operator/convectiondiffusionfem.hh>
+
+namespace {
+
+typedef Dune::FieldVector<double, 2> Coord;
+
+// ---- grid stand-ins: one axis-aligned cell ----------------------------------------------------
+struct CellGeo {
+  typedef double ctype;
+  static const int dimension = 2, dimensionworld = 2, mydimension = 2, coorddimension = 2;
+  double x0, x1, y0, y1;
+  Dune::GeometryType type() const { return Dune::GeometryType(2); }
+  int corners() const { return 4; }
+  Coord corner(int i) const { Coord c; c[0] = (i & 1) ? x1 : x0; c[1] = (i & 2) ? y1 : y0; return c; }
+  Coord global(const Coord& l) const { Coord g; g[0] = x0 + l[0] * (x1 - x0); g[1] = y0 + l[1] * (y1 - y0); return g; }
+  Coord center() const { Coord l(0.5); return global(l); }
+  double volume() const { return (x1 - x0) * (y1 - y0); }
+  double integrationElement(const Coord&) const { return (x1 - x0) * (y1 - y0); }
+  Dune::FieldMatrix<double, 2, 2> jacobianInverseTransposed(const Coord&) const {
+    Dune::FieldMatrix<double, 2, 2> m(0.0);
+    m[0][0] = 1.0 / (x1 - x0); m[1][1] = 1.0 / (y1 - y0);
+    return m;
+  }
+};
+struct Entity {
+  typedef CellGeo Geometry;
+  CellGeo geo;
+  int index, subdomain;
+  const CellGeo& geometry() const { return geo; }
+};
+struct Intersection {};
+struct GV {
+  enum { dimension = 2, dimensionworld = 2 };
+  typedef double ctype;
+  template <int c> struct Codim { typedef ::Entity Entity; };
+  typedef ::Intersection Intersection;
+  struct Traits { struct Grid { enum { dimension = 2 }; }; };
+  typedef GV GridViewType;
+};
+struct ElementGeometry {
+  typedef ::Entity Entity;
+  typedef CellGeo Geometry;
+  const ::Entity* e;
+  const ::Entity& entity() const { return *e; }
+  const CellGeo& geometry() const { return e->geo; }
+};
+
+// ---- Physics stand-in: look-ups only ---------------------------------------------------------------
+struct Physics {
+  typedef double FieldType;
+  typedef GV GridView;
+  Acme2CylParameters prm;
+  double PC = 0, time_scale = 1e-6, length_scale = 1e-9, eps = 80.0, D[3] = {0, 0, 0};
+  int z[3] = {1, 1, -1};
+  std::vector<std::pair<Coord, double> > nodevol;     // node volume by vertex position
+  const Acme2CylParameters& getParams() const { return prm; }
+  double getPoissonConstant() const { return PC; }
+  double convertFrom_mV(double v) const { return v; }
+  int getElementIndex(const Entity& e) const { return e.index; }
+  double getPermittivity(const Entity&) const { return eps; }
+  bool isMembrane(const Entity& e) const { return e.subdomain == MEMBRANE; }
+  int getValence(int j) const { return z[j]; }
+  double getDiffCoeff(int j, int) const { return D[j]; }
+  double getTimeScale() const { return time_scale; }
+  double getLengthScale() const { return length_scale; }
+  int numOfSpecies() const { return 3; }
+  double getNodeVolume(const Coord& x) const {
+    for (auto& nv : nodevol)
+      if (std::fabs(nv.first[0] - x[0]) < 1e-6 && std::fabs(nv.first[1] - x[1]) < 1e-6) return nv.second;
+    DUNE_THROW(Dune::Exception, "no node volume for this position");
+  }
+};
+struct InitialGF {
+  struct Traits { typedef Dune::FieldVector<double, 3> RangeType; typedef Coord DomainType; };
+  void setTime(double) {}
+  void evaluateGlobal(const Coord&, Traits::RangeType&) const {}
+};
+struct NoFlux {   // membrane flux grid function: not reached by the volume terms
+  void setTime(double) {}
+  template <class... A> void updateState(A...) {}
+  template <class... A> void updateChannels(A...) {}
+  template <class... A> void updateFlux(A...) {}
+  template <class... A> void acceptTimeStep(A...) {}
+};
+
+// ---- Q1 local function space tree: [ power<3>(con) , pot ] -----------------------------------------
+struct Q1Basis {
+  struct Traits {
+    typedef double DomainFieldType;
+    typedef double RangeFieldType;
+    typedef Coord DomainType;
+    typedef Dune::FieldVector<double, 1> RangeType;
+    typedef Dune::FieldMatrix<double, 1, 2> JacobianType;
+  };
+  unsigned int order() const { return 1; }
+  unsigned int size() const { return 4; }
+  void evaluateFunction(const Coord& x, std::vector<Traits::RangeType>& out) const {
+    out.resize(4);
+    out[0] = (1 - x[0]) * (1 - x[1]); out[1] = x[0] * (1 - x[1]); out[2] = (1 - x[0]) * x[1]; out[3] = x[0] * x[1];
+  }
+  void evaluateJacobian(const Coord& x, std::vector<Traits::JacobianType>& out) const {
+    out.resize(4);
+    out[0][0][0] = -(1 - x[1]); out[0][0][1] = -(1 - x[0]);
+    out[1][0][0] = (1 - x[1]);  out[1][0][1] = -x[0];
+    out[2][0][0] = -x[1];       out[2][0][1] = (1 - x[0]);
+    out[3][0][0] = x[1];        out[3][0][1] = x[0];
+  }
+};
+struct Q1Interpolation {
+  template <class F, class C>
+  void interpolate(const F& f, std::vector<C>& out) const {
+    out.resize(4);
+    for (int i = 0; i < 4; ++i) {
+      Coord x; x[0] = (i & 1) ? 1.0 : 0.0; x[1] = (i & 2) ? 1.0 : 0.0;
+      C y;
+      f.evaluate(x, y);
+      out[i] = y;
+    }
+  }
+};
+struct Q1FE {
+  struct Traits { typedef Q1Basis LocalBasisType; typedef Q1Interpolation LocalInterpolationType; };
+  Q1Basis b; Q1Interpolation ip;
+  const Q1Basis& localBasis() const { return b; }
+  const Q1Interpolation& localInterpolation() const { return ip; }
+};
+struct FEM { struct Traits { typedef Q1FE FiniteElementType; }; };
+struct Leaf {
+  struct Traits { typedef Q1FE FiniteElementType; typedef std::size_t SizeType; };
+  int comp; Q1FE fe;
+  std::size_t size() const { return 4; }
+  const Q1FE& finiteElement() const { return fe; }
+};
+struct ConSpace {
+  struct Traits { typedef std::size_t SizeType; };
+  template <int k> struct Child { typedef Leaf Type; };
+  Leaf c[3];
+  const Leaf& child(int j) const { return c[j]; }
+};
+struct Root {
+  ConSpace con; Leaf pot;
+  template <int k, int dummy = 0> struct Child { typedef ConSpace Type; };
+  template <int dummy> struct Child<1, dummy> { typedef Leaf Type; };
+  template <int k> const typename Child<k>::Type& child() const;
+};
+template <> const ConSpace& Root::child<0>() const { return con; }
+template <> const Leaf& Root::child<1>() const { return pot; }
+struct XView {
+  const double* v;
+  double operator()(const Leaf& l, std::size_t i) const { return v[l.comp * 4 + i]; }
+};
+struct RView {
+  double* v;
+  void accumulate(const Leaf& l, std::size_t i, double val) { v[l.comp * 4 + i] += val; }
+};
+
+struct MView {   // local matrix, row = test DOF, column = trial DOF
+  double* m;
+  void accumulate(const Leaf& lv, std::size_t i, const Leaf& lu, std::size_t j, double val) {
+    m[(lv.comp * 4 + i) * 16 + lu.comp * 4 + j] += val;
+  }
+};
+
+typedef DefaultPoissonParameters<GV, double, Physics> ParamPot;
+typedef DefaultNernstPlanckParameters<GV, double, Physics, InitialGF, NoFlux, NoFlux> ParamNP;
+typedef PowerParameters<ParamNP, 3> ParamCon;
+typedef Acme2CylOperatorFullyCoupled<ParamCon, ParamPot, FEM, FEM> LopElec;
+typedef NernstPlanckTimeLocalOperator<Physics, FEM> LopTime;
+typedef Dune::PDELab::ConvectionDiffusionFEM<ParamPot, FEM> LopMemb;
+
+// everything one call needs, built from the flat argument arrays
+struct Setup {
+  Physics ph;
+  Entity e;
+  GV gv;
+  InitialGF igf;
+  NoFlux nf;
+  Root lfs;
+  Setup(const double* cell, const double* phys, const int* valence, const double* nodevol4, int do_volume_scaling,
+        const double* stim, int subdomain) {
+    ph.eps = phys[0]; ph.D[0] = phys[1]; ph.D[1] = phys[2]; ph.D[2] = phys[3]; ph.PC = phys[4];
+    ph.prm.pot_scale = phys[5]; ph.time_scale = phys[6];
+    for (int j = 0; j < 3; ++j) ph.z[j] = valence[j];
+    ph.prm.volscale = do_volume_scaling != 0;
+    ph.prm.stim = stim[0] != 0.0; ph.prm.t0 = stim[2]; ph.prm.t1 = stim[3];
+    ph.prm.stimulation.num["position_x"] = stim[4]; ph.prm.stimulation.num["position_y"] = stim[5];
+    ph.prm.stimulation.num["I_inj"] = stim[6];
+    ph.prm.general.num["useElecOperatorJacobianVolume"] = 1;
+    ph.prm.general.num["useMembOperatorJacobianVolume"] = 1;
+    ph.prm.general.num["useTimeOperatorJacobianVolume"] = 1;
+    e.geo.x0 = cell[0]; e.geo.x1 = cell[1]; e.geo.y0 = cell[2]; e.geo.y1 = cell[3];
+    e.index = 0; e.subdomain = subdomain;
+    for (int i = 0; i < 4; ++i) ph.nodevol.push_back(std::make_pair(e.geo.corner(i), nodevol4[i]));
+    for (int j = 0; j < 3; ++j) lfs.con.c[j].comp = j;
+    lfs.pot.comp = 3;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// Acme2CylOperatorFullyCoupled::alpha_volume on one electrolyte cell.
+//   cell  = {x0, x1, y0, y1}
+//   xl    = 16 local coefficients, comp * 4 + vertex, comp = Na, K, Cl, pot, vertices x fastest
+//   phys  = {eps, D_Na, D_K, D_Cl, poisson constant, potential residual scale, time scale}
+//   nodevol4 = node volumes of the 4 vertices (used when do_volume_scaling)
+//   stim  = {doStimulation, LOP time, t_inj_start, t_inj_end, position_x, position_y, I_inj}
+// out16 = the residual contributions r (not weighted by dt), same layout as xl
+int ax1ref_elec_alpha_volume(const double* cell, const double* xl, const double* phys, const int* valence,
+                             const double* nodevol4, int do_volume_scaling, const double* stim, double* out16) {
+  try {
+    Physics ph;
+    ph.eps = phys[0]; ph.D[0] = phys[1]; ph.D[1] = phys[2]; ph.D[2] = phys[3]; ph.PC = phys[4];
+    ph.prm.pot_scale = phys[5]; ph.time_scale = phys[6];
+    for (int j = 0; j < 3; ++j) ph.z[j] = valence[j];
+    ph.prm.volscale = do_volume_scaling != 0;
+    ph.prm.stim = stim[0] != 0.0; ph.prm.t0 = stim[2]; ph.prm.t1 = stim[3];
+    ph.prm.stimulation.num["position_x"] = stim[4]; ph.prm.stimulation.num["position_y"] = stim[5];
+    ph.prm.stimulation.num["I_inj"] = stim[6];
+    Entity e;
+    e.geo.x0 = cell[0]; e.geo.x1 = cell[1]; e.geo.y0 = cell[2]; e.geo.y1 = cell[3];
+    e.index = 0; e.subdomain = ES;
+    for (int i = 0; i < 4; ++i) ph.nodevol.push_back(std::make_pair(e.geo.corner(i), nodevol4[i]));
+    GV gv;
+    InitialGF igf; NoFlux nf;
+    ParamPot paramPot(gv, ph);
+    ParamCon paramCon;
+    for (int j = 0; j < 3; ++j)
+      paramCon.push_back(Dune::shared_ptr<ParamNP>(new ParamNP(j, gv, ph, igf, nf, nf, 0.0)));
+    LopElec lop(paramCon, paramPot, 4);
+    lop.setTime(stim[1]);
+    Root lfs;
+    for (int j = 0; j < 3; ++j) lfs.con.c[j].comp = j;
+    lfs.pot.comp = 3;
+    XView x{xl};
+    for (int k = 0; k < 16; ++k) out16[k] = 0.0;
+    RView r{out16};
+    ElementGeometry eg{&e};
+    lop.alpha_volume(eg, lfs, x, lfs, r);
+    return 0;
+  } catch (std::exception&) {
+    return 1;
+  }
+}
+
+// which = 0: Acme2CylOperatorFullyCoupled (electrolyte cell), 1: NernstPlanckTimeLocalOperator, 2: ConvectionDiffusionFEM
+// with DefaultPoissonParameters on a membrane cell (phys[0] = membrane permittivity).
+// jac = 0: alpha_volume into out[0..15]; jac = 1: the operator's analytic jacobian_volume into out[0..255]
+// (row = test DOF, column = trial DOF, DOF = comp * 4 + vertex). Arguments as ax1ref_elec_alpha_volume.
+int ax1ref_local_operator(int which, int jac, const double* cell, const double* xl, const double* phys,
+                          const int* valence, const double* nodevol4, int do_volume_scaling, const double* stim,
+                          double* out) {
+  try {
+    Setup S(cell, phys, valence, nodevol4, do_volume_scaling, stim, which == 2 ? MEMBRANE : ES);
+    ParamPot paramPot(S.gv, S.ph);
+    ParamCon paramCon;
+    for (int j = 0; j < 3; ++j)
+      paramCon.push_back(Dune::shared_ptr<ParamNP>(new ParamNP(j, S.gv, S.ph, S.igf, S.nf, S.nf, 0.0)));
+    XView x{xl};
+    ElementGeometry eg{&S.e};
+    const int n = jac ? 256 : 16;
+    for (int k = 0; k < n; ++k) out[k] = 0.0;
+    RView r{out};
+    MView m{out};
+    if (which == 0) {
+      LopElec lop(paramCon, paramPot, 4);
+      lop.setTime(stim[1]);
+      if (jac) lop.jacobian_volume(eg, S.lfs, x, S.lfs, m);
+      else lop.alpha_volume(eg, S.lfs, x, S.lfs, r);
+    } else if (which == 1) {
+      LopTime lop(S.ph);
+      if (jac) lop.jacobian_volume(eg, S.lfs.con, x, S.lfs.con, m);
+      else lop.alpha_volume(eg, S.lfs.con, x, S.lfs.con, r);
+    } else if (which == 2) {
+      LopMemb lop(paramPot, 4);
+      if (jac) lop.jacobian_volume(eg, S.lfs.pot, x, S.lfs.pot, m);
+      else lop.alpha_volume(eg, S.lfs.pot, x, S.lfs.pot, r);
+    } else {
+      return 2;
+    }
+    return 0;
+  } catch (std::exception&) {
+    return 1;
+  }
+}
+
+}  // extern "C"

@@ -1,17 +1,67 @@
-// stand-in (see ../../README.md): fixed-size vector with the few members the channel headers touch
+// stand-in (see ../../README.md): fixed-size vector / matrix with the members the reference headers touch
 #pragma once
+#include <cmath>
 #include <cstddef>
 namespace Dune {
 template <class T, int N>
 class FieldVector {
  public:
+  typedef T value_type;
   FieldVector() { for (int i = 0; i < N; ++i) d_[i] = T(); }
   FieldVector(const T& v) { for (int i = 0; i < N; ++i) d_[i] = v; }
   T& operator[](std::size_t i) { return d_[i]; }
   const T& operator[](std::size_t i) const { return d_[i]; }
   FieldVector& operator=(const T& v) { for (int i = 0; i < N; ++i) d_[i] = v; return *this; }
+  FieldVector& operator+=(const FieldVector& o) { for (int i = 0; i < N; ++i) d_[i] += o.d_[i]; return *this; }
+  FieldVector& operator-=(const FieldVector& o) { for (int i = 0; i < N; ++i) d_[i] -= o.d_[i]; return *this; }
+  FieldVector& operator*=(const T& a) { for (int i = 0; i < N; ++i) d_[i] *= a; return *this; }
+  FieldVector& operator/=(const T& a) { for (int i = 0; i < N; ++i) d_[i] /= a; return *this; }
+  FieldVector& axpy(const T& a, const FieldVector& x) { for (int i = 0; i < N; ++i) d_[i] += a * x.d_[i]; return *this; }
+  T operator*(const FieldVector& o) const { T s = T(); for (int i = 0; i < N; ++i) s += d_[i] * o.d_[i]; return s; }
+  T two_norm() const { T s = T(); for (int i = 0; i < N; ++i) s += d_[i] * d_[i]; return std::sqrt(s); }
   static constexpr int size() { return N; }
+  T* begin() { return d_; }
+  T* end() { return d_ + N; }
+  const T* begin() const { return d_; }
+  const T* end() const { return d_ + N; }
  private:
   T d_[N];
+};
+// a vector of length one converts to its entry (dune-common does the same)
+template <class T>
+class FieldVector<T, 1> {
+ public:
+  typedef T value_type;
+  FieldVector() : d_(T()) {}
+  FieldVector(const T& v) : d_(v) {}
+  T& operator[](std::size_t) { return d_; }
+  const T& operator[](std::size_t) const { return d_; }
+  FieldVector& operator=(const T& v) { d_ = v; return *this; }
+  FieldVector& operator+=(const T& v) { d_ += v; return *this; }
+  FieldVector& operator-=(const T& v) { d_ -= v; return *this; }
+  FieldVector& operator*=(const T& v) { d_ *= v; return *this; }
+  operator T&() { return d_; }
+  operator const T&() const { return d_; }
+  static constexpr int size() { return 1; }
+ private:
+  T d_;
+};
+template <class T, int N, int M>
+class FieldMatrix {
+ public:
+  FieldMatrix() {}
+  FieldMatrix(const T& v) { for (int i = 0; i < N; ++i) r_[i] = v; }
+  FieldVector<T, M>& operator[](std::size_t i) { return r_[i]; }
+  const FieldVector<T, M>& operator[](std::size_t i) const { return r_[i]; }
+  template <class X, class Y>
+  void mv(const X& x, Y& y) const {                       // y = A x
+    for (int i = 0; i < N; ++i) { y[i] = T(); for (int j = 0; j < M; ++j) y[i] += r_[i][j] * x[j]; }
+  }
+  template <class X, class Y>
+  void umv(const X& x, Y& y) const {                      // y += A x
+    for (int i = 0; i < N; ++i) for (int j = 0; j < M; ++j) y[i] += r_[i][j] * x[j];
+  }
+ private:
+  FieldVector<T, M> r_[N];
 };
 }  // namespace Dune

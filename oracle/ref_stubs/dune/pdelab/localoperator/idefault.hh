@@ -1,0 +1,3 @@
+// stand-in (see ../../../README.md)
+#pragma once
+#include <dune_standins.hh>

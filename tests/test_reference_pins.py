@@ -140,3 +140,88 @@ def test_node_volumes_against_reference_cylinder_geometry(oracle, axlib, ref):
     out = np.zeros(2)
     ref.ax1ref_cyl_geometry(1, x[1], 505.0, x[2], 505.0, 0.5, 0.0, _dp(out))
     assert out[1] == (np.pi * (505.0 + 505.0)) * (x[2] - x[1])
+
+
+# ---- the reference's own local operators and parameter classes on single cells -------------------------------------
+@pytest.fixture(scope="module")
+def refop(oracle):
+    oracle.build_ref()
+    R = oracle.ref_operator_lib()
+    if R is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    return R
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class _CellRunner:
+    """Feeds one cell of an oracle problem to the reference operators (oracle/ref_operator_driver.cpp)."""
+
+    def __init__(self, oracle, refop, s, t, dt, stim):
+        self.P = oracle_problem(oracle, s)
+        self.P.set_time(t, dt); self.P.set_uold(s["u0"]); self.P.update_state(s["u0"])
+        self.R, self.s = refop, s
+        self.cst = self.P.constants()
+        _, self.nvol, _ = self.P.maps()
+        self.nvx = s["nx"] + 1
+        self.stim = np.array([1.0 if stim else 0.0, t + dt, s["params"]["tinj_start"], s["params"]["tinj_end"],
+                              s["params"]["stim_x"], s["params"]["stim_y"], s["params"]["I_inj"]])
+
+    def verts(self, i, j):
+        n = self.nvx
+        return [i + n * j, i + 1 + n * j, i + n * (j + 1), i + 1 + n * (j + 1)]
+
+    def local(self, i, j, rng):
+        u0 = self.s["u0"]
+        xl = np.array([[u0[4 * v + c] for v in self.verts(i, j)] for c in range(4)]).reshape(-1)
+        return xl * (1.0 + 1e-2 * rng.standard_normal(16))
+
+    def ref(self, which, jac, i, j, xl, eps):
+        x, y = self.s["x"], self.s["y"]
+        cell = np.array([x[i], x[i + 1], y[j], y[j + 1]])
+        D = self.cst["D"]
+        phys = np.array([eps, D[0], D[1], D[2], self.cst["PC"], 1.0, 1e-6])
+        val = np.array([1, 1, -1], dtype=np.int32)
+        nv4 = np.array([self.nvol[v] for v in self.verts(i, j)])
+        out = np.zeros(256 if jac else 16)
+        rc = self.R.ax1ref_local_operator(which, jac, _dp(cell), _dp(np.ascontiguousarray(xl)), _dp(phys), _ip(val),
+                                          _dp(nv4), 1, _dp(self.stim), _dp(out))
+        assert rc == 0
+        return out
+
+
+def test_volume_operators_against_reference_local_operators(oracle, refop):
+    """Acme2CylOperatorFullyCoupled::alpha_volume / jacobian_volume with the reference's DefaultPoissonParameters and
+    DefaultNernstPlanckParameters (A, b, c, f incl. the Na injection source), NernstPlanckTimeLocalOperator and
+    ConvectionDiffusionFEM (membrane Poisson), all compiled from /root/reference, evaluated cell by cell on perturbed
+    local coefficients of the shipped equilibrium state: rows a1, a3, a5, a6, a7, a8, a12 and the node-volume scaling
+    of a13. The oracle's kernels agree to rounding (1e-14 of the largest entry of the same scalar row)."""
+    s = small_setup(nx=4, stimulation=True)
+    run = _CellRunner(oracle, refop, s, t=29.0, dt=1.0, stim=True)     # LOP time 30 us: injection is on
+    P, jm = run.P, run.P.jm
+    rng = np.random.default_rng(1)
+    cells = [(1, 0), (0, 3), (2, jm - 1), (3, jm + 1), (1, jm + 9), (0, 100), (3, s["ny"] - 1), (2, jm - 12)]
+    assert s["x"][1] <= s["params"]["stim_x"] <= s["x"][2]              # cell (1, 0) holds the injection point
+    for (i, j) in cells:
+        xl = run.local(i, j, rng)
+        for which in (0, 1):
+            a, b = run.ref(which, 0, i, j, xl, 80.0), P.cell_kernel(i, j, which, xl, weight=1.0)
+            scale = np.abs(b).reshape(4, 4).max(axis=1, keepdims=True) + 1e-300
+            assert np.max(np.abs(a - b).reshape(4, 4) / scale) < 1e-14, (i, j, which)
+            A, B = run.ref(which, 1, i, j, xl, 80.0).reshape(16, 16), P.cell_jacobian(i, j, which, xl, weight=1.0)
+            scale = np.abs(B).max(axis=1, keepdims=True) + 1e-300
+            assert np.max(np.abs(A - B) / scale) < 1e-14, (i, j, which)
+            assert np.abs(B).max() > 0
+    # the injection source really is in the compared numbers
+    xl = run.local(1, 0, rng)
+    run_off = _CellRunner(oracle, refop, small_setup(nx=4, stimulation=False), t=29.0, dt=1.0, stim=False)
+    assert np.max(np.abs(run.ref(0, 0, 1, 0, xl, 80.0) - run_off.ref(0, 0, 1, 0, xl, 80.0))[:4]) > 0
+    # membrane cell: Poisson with the membrane permittivity
+    for i in range(s["nx"]):
+        xl = run.local(i, jm, rng)
+        a, b = run.ref(2, 0, i, jm, xl, 2.0), P.cell_kernel(i, jm, 2, xl, weight=1.0)
+        assert np.max(np.abs(a - b)) < 1e-14 * np.max(np.abs(b)) and np.all(a[:12] == 0.0)
+        A, B = run.ref(2, 1, i, jm, xl, 2.0).reshape(16, 16), P.cell_jacobian(i, jm, 2, xl, weight=1.0)
+        assert np.max(np.abs(A - B)) < 1e-14 * np.max(np.abs(B))
