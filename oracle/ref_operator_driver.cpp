@@ -7,6 +7,9 @@
 //   dune/ax1/acme2_cyl/operator/acme2_cyl_toperator.hh                       NernstPlanckTimeLocalOperator::alpha_volume
 //   dune/ax1/acme2_cyl/operator/convectiondiffusionfem.hh                    ConvectionDiffusionFEM::alpha_volume (membrane)
 //   ... and the analytic jacobian_volume of the three operators
+//   Acme2CylOperatorFullyCoupled::alpha_boundary on a membrane-interface face, with DefaultNernstPlanckParameters::
+//   bctype / j (surface scaling, flux stimulation) and dune/ax1/common/membranefluxgridfunction_implicit.hh
+//   MembraneFluxGridFunctionImplicit::evaluate over the reference's DynamicChannelSet (channel flux arithmetic)
 //   dune/ax1/common/power_parameters.hh, dune/ax1/acme2_cyl/common/acme2_cyl_geometrywrapper.hh
 // What is stood in for: the grid (one axis-aligned cell), the Q1 local function space tree, quadrature, and a
 // "Physics" object that hands back the coefficients the test chooses (permittivity, diffusion coefficients,
@@ -80,6 +83,14 @@ struct Acme2CylParameters {
   double getPotentialResidualScalingFactor() const { return pot_scale; }
   bool doVolumeScaling() const { return volscale; }
   bool useMori() const { return false; }
+  bool equil = false;
+  bool doEquilibration() const { return equil; }
+  std::vector<bool> isMembraneActive() const { return std::vector<bool>(1, true); }
+};
+
+struct Output {   // printing helper of the reference (dune/ax1/common/output.hh needs DUNE); used by channelset.hh
+  template <class V>
+  static void printVector(const V&) {}
 };
 
 #include <dune/ax1/common/constants.hh>
@@ -88,6 +99,14 @@ struct Acme2CylParameters {
 #include <dune/ax1/acme2_cyl/configurations/default/default_poisson_parameters.hh>
 #include <dune/ax1/acme2_cyl/configurations/default/default_nernst_planck_parameters.hh>
 #include <dune/ax1/acme2_cyl/operator/acme2_cyl_operator_fully_coupled.hh>
+#include <dune/ax1/channels/channel.hh>
+#include <dune/ax1/channels/channelset.hh>
+#include <dune/ax1/common/electrolyte.hh>
+// The flux class keeps its clock (`time`) private and sets it in updateState(time, dt), which also walks all
+// membrane intersections of the grid; the driver sets the clock directly instead.
+#define private public
+#include <dune/ax1/common/membranefluxgridfunction_implicit.hh>
+#undef private
 #include <dune/ax1/acme2_cyl/operator/acme2_cyl_toperator.hh>
 #include <dune/ax1/acme2_cyl/operator/convectiondiffusionfem.hh>
 
@@ -119,13 +138,65 @@ struct Entity {
   int index, subdomain;
   const CellGeo& geometry() const { return geo; }
 };
-struct Intersection {};
+// a membrane-interface face of the cell: the edge y = const between (x0, y) and (x1, y)
+struct FaceGeo {
+  typedef double ctype;
+  static const int dimension = 2, dimensionworld = 2, mydimension = 1, coorddimension = 2;
+  typedef Dune::FieldVector<double, 1> Local;
+  double x0, x1, y;
+  Dune::GeometryType type() const { return Dune::GeometryType(1); }
+  int corners() const { return 2; }
+  Coord corner(int i) const { Coord c; c[0] = i ? x1 : x0; c[1] = y; return c; }
+  Coord global(const Local& l) const { Coord g; g[0] = x0 + l[0] * (x1 - x0); g[1] = y; return g; }
+  Coord center() const { Coord g; g[0] = 0.5 * (x0 + x1); g[1] = y; return g; }
+  double volume() const { return x1 - x0; }
+  double integrationElement(const Local&) const { return x1 - x0; }
+};
+struct FaceInInside {   // the face in the local coordinates of the inside cell: its top (eta = 1) or bottom (eta = 0) edge
+  double eta;
+  Dune::GeometryType type() const { return Dune::GeometryType(1); }
+  Coord global(const Dune::FieldVector<double, 1>& l) const { Coord g; g[0] = l[0]; g[1] = eta; return g; }
+  Coord center() const { Coord g; g[0] = 0.5; g[1] = eta; return g; }
+};
+struct Intersection {
+  typedef FaceGeo Geometry;
+  typedef FaceInInside LocalGeometry;
+  typedef ::Entity Entity;
+  typedef const ::Entity* EntityPointer;
+  FaceGeo geo;
+  FaceInInside gii;
+  const ::Entity* in;
+  double ny;                          // outer normal (0, ny)
+  // what the Physics look-ups return for this face (the test computes them as the grid-bound code would)
+  double y_opposite, pot_opposite, con_opposite[3], ext_surface;
+  int index;
+  const FaceGeo& geometry() const { return geo; }
+  const FaceInInside& geometryInInside() const { return gii; }
+  const ::Entity* inside() const { return in; }
+  Coord centerUnitOuterNormal() const { Coord n; n[0] = 0.0; n[1] = ny; return n; }
+  Coord unitOuterNormal(const Dune::FieldVector<double, 1>&) const { return centerUnitOuterNormal(); }
+};
+struct IntersectionGeometry {       // PDELab's IntersectionGeometry wrapper
+  typedef FaceGeo Geometry;
+  typedef FaceInInside LocalGeometry;
+  typedef ::Entity Entity;
+  typedef const ::Entity* EntityPointer;
+  typedef double ctype;
+  enum { dimension = 2, dimensionworld = 2 };
+  const ::Intersection* is;
+  const ::Intersection& intersection() const { return *is; }
+  const ::Entity* inside() const { return is->in; }
+  const FaceGeo& geometry() const { return is->geo; }
+  const FaceInInside& geometryInInside() const { return is->gii; }
+  Coord unitOuterNormal(const Dune::FieldVector<double, 1>& x) const { return is->unitOuterNormal(x); }
+};
 struct GV {
   enum { dimension = 2, dimensionworld = 2 };
   typedef double ctype;
   template <int c> struct Codim { typedef ::Entity Entity; };
   typedef ::Intersection Intersection;
-  struct Traits { struct Grid { enum { dimension = 2 }; }; };
+  struct Grid { enum { dimension = 2 }; typedef double ctype; };
+  struct Traits { typedef GV::Grid Grid; };
   typedef GV GridViewType;
 };
 struct ElementGeometry {
@@ -137,9 +208,58 @@ struct ElementGeometry {
 };
 
 // ---- Physics stand-in: look-ups only ---------------------------------------------------------------
+struct ChVec : std::vector<double> {   // vector type of the channel templates
+  ChVec() {}
+  explicit ChVec(int n) : std::vector<double>((size_t)n) {}
+  ChVec& operator=(double v) { std::fill(begin(), end(), v); return *this; }
+};
 struct Physics {
   typedef double FieldType;
   typedef GV GridView;
+  typedef DynamicChannelSet<double, ChVec> ChannelSet;
+  typedef const Intersection* ElementIntersectionIterator;
+  ChannelSet channels;
+  Electrolyte<double> electro = Electrolyte<double>(80.0, 279.45, con_mol, 1e-9);
+  ChannelSet& getChannelSet() { return channels; }
+  const Electrolyte<double>& getElectrolyte() const { return electro; }
+  // membrane look-ups of acme2_cyl_physics.hh (they need the grid's interface maps): answered from the numbers the
+  // test put on the face. Restated: getMembranePotentialJump :666-721, getMembraneConcentrationRatio :927-1013
+  bool isMembraneInterface(const Intersection&) const { return true; }
+  int getMembraneIndex(const Intersection&) const { return 0; }
+  int getMembraneNumber(const Intersection&) const { return 0; }
+  ElementIntersectionIterator getPrimaryMembraneIntersection(const Intersection& is) const { return &is; }
+  int getIntersectionIndex(const Intersection& is) const { return is.index; }
+  double getMembraneSurfaceArea(const Intersection& is) const { return is.ext_surface; }
+  template <class DGF>
+  void getMembranePotentialJump(const Intersection& is, DGF&, typename DGF::Traits::RangeType& potJump,
+                                const typename DGF::Traits::RangeType& uPotInside) const {
+    typename DGF::Traits::RangeType pot1(uPotInside), pot2(is.pot_opposite);
+    potJump = pot2;
+    potJump -= pot1;
+    const int ySign = Dune::sign(is.geo.y - is.y_opposite);
+    potJump *= ySign;
+  }
+  template <class DGF>
+  void getMembraneConcentrationRatio(const Intersection& is, DGF&, typename DGF::Traits::RangeType& conRatio,
+                                     const typename DGF::Traits::RangeType& uConInside) const {
+    typename DGF::Traits::RangeType con1(uConInside), con2;
+    for (int j = 0; j < 3; ++j) con2[j] = is.con_opposite[j];
+    conRatio = 0.0;
+    const int ySign = Dune::sign(is.geo.y - is.y_opposite);
+    if (ySign > 0) { conRatio = con2; for (int j = 0; j < 3; ++j) conRatio[j] /= con1[j]; }
+    if (ySign < 0) { conRatio = con1; for (int j = 0; j < 3; ++j) conRatio[j] /= con2[j]; }
+  }
+  // the explicit-flux overloads (values of the last time step on both sides) are not reached with
+  // fullyImplicitMembraneFlux = yes
+  template <class DGF>
+  void getMembranePotentialJump(const Intersection&, DGF&, typename DGF::Traits::RangeType&) const {
+    DUNE_THROW(Dune::NotImplemented, "explicit membrane flux");
+  }
+  template <class DGF>
+  void getMembraneConcentrationRatio(const Intersection&, DGF&, typename DGF::Traits::RangeType&) const {
+    DUNE_THROW(Dune::NotImplemented, "explicit membrane flux");
+  }
+  template <class V> V convertTo_mV(const V& v) const { return v; }   // only feeds debug output
   Acme2CylParameters prm;
   double PC = 0, time_scale = 1e-6, length_scale = 1e-9, eps = 80.0, D[3] = {0, 0, 0};
   int z[3] = {1, 1, -1};
@@ -230,6 +350,7 @@ struct ConSpace {
 };
 struct Root {
   ConSpace con; Leaf pot;
+  std::size_t size() const { return 16; }
   template <int k, int dummy = 0> struct Child { typedef ConSpace Type; };
   template <int dummy> struct Child<1, dummy> { typedef Leaf Type; };
   template <int k> const typename Child<k>::Type& child() const;
@@ -252,8 +373,35 @@ struct MView {   // local matrix, row = test DOF, column = trial DOF
   }
 };
 
+// discrete grid functions / solution container: the flux class constructs them but, in the implicit branch, only hands
+// them to the Physics look-ups above
+struct DGFBase { DGFBase(int, int) {} };
+struct DGFCon {
+  struct Traits { typedef GV GridViewType; typedef double RangeFieldType; typedef Dune::FieldVector<double, 3> RangeType; typedef Coord DomainType; };
+  typedef DGFBase BASE_DGF;
+  GV gv;
+  DGFCon() {}
+  DGFCon(const GV&, DGFBase&, Physics&) {}
+  const GV& getGridView() const { return gv; }
+};
+struct DGFPot {
+  struct Traits { typedef GV GridViewType; typedef double RangeFieldType; typedef Dune::FieldVector<double, 1> RangeType; typedef Coord DomainType; };
+  DGFPot() {}
+  DGFPot(int, int) {}
+};
+struct SolutionContainer {
+  typedef int U;
+  int zero = 0;
+  int getGfsPot() const { return 0; }
+  int getGfsCon() const { return 0; }
+  const int* getSolutionPotNew() const { return &zero; }
+  const int* getSolutionConNew() const { return &zero; }
+  const int* getSolutionConOld() const { return &zero; }
+};
+typedef MembraneFluxGridFunctionImplicit<DGFCon, DGFPot, Physics, SolutionContainer> MembFlux;
+
 typedef DefaultPoissonParameters<GV, double, Physics> ParamPot;
-typedef DefaultNernstPlanckParameters<GV, double, Physics, InitialGF, NoFlux, NoFlux> ParamNP;
+typedef DefaultNernstPlanckParameters<GV, double, Physics, InitialGF, MembFlux, NoFlux> ParamNP;
 typedef PowerParameters<ParamNP, 3> ParamCon;
 typedef Acme2CylOperatorFullyCoupled<ParamCon, ParamPot, FEM, FEM> LopElec;
 typedef NernstPlanckTimeLocalOperator<Physics, FEM> LopTime;
@@ -267,6 +415,10 @@ struct Setup {
   InitialGF igf;
   NoFlux nf;
   Root lfs;
+  DGFCon dgfCon;
+  DGFPot dgfPot;
+  SolutionContainer sol;
+  Dune::shared_ptr<MembFlux> flux;
   Setup(const double* cell, const double* phys, const int* valence, const double* nodevol4, int do_volume_scaling,
         const double* stim, int subdomain) {
     ph.eps = phys[0]; ph.D[0] = phys[1]; ph.D[1] = phys[2]; ph.D[2] = phys[3]; ph.PC = phys[4];
@@ -284,6 +436,8 @@ struct Setup {
     for (int i = 0; i < 4; ++i) ph.nodevol.push_back(std::make_pair(e.geo.corner(i), nodevol4[i]));
     for (int j = 0; j < 3; ++j) lfs.con.c[j].comp = j;
     lfs.pot.comp = 3;
+    ph.prm.boundary.num["fullyImplicitMembraneFlux"] = 1;
+    flux.reset(new MembFlux(dgfCon, dgfPot, ph, sol, 0.0));
   }
 };
 
@@ -291,50 +445,13 @@ struct Setup {
 
 extern "C" {
 
-// Acme2CylOperatorFullyCoupled::alpha_volume on one electrolyte cell.
+// argument conventions of all entry points:
 //   cell  = {x0, x1, y0, y1}
 //   xl    = 16 local coefficients, comp * 4 + vertex, comp = Na, K, Cl, pot, vertices x fastest
 //   phys  = {eps, D_Na, D_K, D_Cl, poisson constant, potential residual scale, time scale}
 //   nodevol4 = node volumes of the 4 vertices (used when do_volume_scaling)
 //   stim  = {doStimulation, LOP time, t_inj_start, t_inj_end, position_x, position_y, I_inj}
-// out16 = the residual contributions r (not weighted by dt), same layout as xl
-int ax1ref_elec_alpha_volume(const double* cell, const double* xl, const double* phys, const int* valence,
-                             const double* nodevol4, int do_volume_scaling, const double* stim, double* out16) {
-  try {
-    Physics ph;
-    ph.eps = phys[0]; ph.D[0] = phys[1]; ph.D[1] = phys[2]; ph.D[2] = phys[3]; ph.PC = phys[4];
-    ph.prm.pot_scale = phys[5]; ph.time_scale = phys[6];
-    for (int j = 0; j < 3; ++j) ph.z[j] = valence[j];
-    ph.prm.volscale = do_volume_scaling != 0;
-    ph.prm.stim = stim[0] != 0.0; ph.prm.t0 = stim[2]; ph.prm.t1 = stim[3];
-    ph.prm.stimulation.num["position_x"] = stim[4]; ph.prm.stimulation.num["position_y"] = stim[5];
-    ph.prm.stimulation.num["I_inj"] = stim[6];
-    Entity e;
-    e.geo.x0 = cell[0]; e.geo.x1 = cell[1]; e.geo.y0 = cell[2]; e.geo.y1 = cell[3];
-    e.index = 0; e.subdomain = ES;
-    for (int i = 0; i < 4; ++i) ph.nodevol.push_back(std::make_pair(e.geo.corner(i), nodevol4[i]));
-    GV gv;
-    InitialGF igf; NoFlux nf;
-    ParamPot paramPot(gv, ph);
-    ParamCon paramCon;
-    for (int j = 0; j < 3; ++j)
-      paramCon.push_back(Dune::shared_ptr<ParamNP>(new ParamNP(j, gv, ph, igf, nf, nf, 0.0)));
-    LopElec lop(paramCon, paramPot, 4);
-    lop.setTime(stim[1]);
-    Root lfs;
-    for (int j = 0; j < 3; ++j) lfs.con.c[j].comp = j;
-    lfs.pot.comp = 3;
-    XView x{xl};
-    for (int k = 0; k < 16; ++k) out16[k] = 0.0;
-    RView r{out16};
-    ElementGeometry eg{&e};
-    lop.alpha_volume(eg, lfs, x, lfs, r);
-    return 0;
-  } catch (std::exception&) {
-    return 1;
-  }
-}
-
+//   results are the operator's contributions (not weighted by dt), DOF = comp * 4 + vertex
 // which = 0: Acme2CylOperatorFullyCoupled (electrolyte cell), 1: NernstPlanckTimeLocalOperator, 2: ConvectionDiffusionFEM
 // with DefaultPoissonParameters on a membrane cell (phys[0] = membrane permittivity).
 // jac = 0: alpha_volume into out[0..15]; jac = 1: the operator's analytic jacobian_volume into out[0..255]
@@ -347,7 +464,7 @@ int ax1ref_local_operator(int which, int jac, const double* cell, const double* 
     ParamPot paramPot(S.gv, S.ph);
     ParamCon paramCon;
     for (int j = 0; j < 3; ++j)
-      paramCon.push_back(Dune::shared_ptr<ParamNP>(new ParamNP(j, S.gv, S.ph, S.igf, S.nf, S.nf, 0.0)));
+      paramCon.push_back(Dune::shared_ptr<ParamNP>(new ParamNP(j, S.gv, S.ph, S.igf, *S.flux, S.nf, 0.0)));
     XView x{xl};
     ElementGeometry eg{&S.e};
     const int n = jac ? 256 : 16;
@@ -370,6 +487,72 @@ int ax1ref_local_operator(int which, int jac, const double* cell, const double* 
     } else {
       return 2;
     }
+    return 0;
+  } catch (std::exception&) {
+    return 1;
+  }
+}
+
+// Acme2CylOperatorFullyCoupled::alpha_boundary on the membrane-interface face of an electrolyte cell
+// (from_cytosol: the face is the cell's top edge and the membrane lies above it; otherwise its bottom edge).
+//   memb  = {y of the opposite interface, potential and Na, K, Cl at the opposite face centre, extracellular
+//            membrane surface 2 pi r L of this column}
+//   geff  = new effective conductances of the channel set [Na_leak, K_leak, Nav, Kv] of this membrane element
+//   equil = {doEquilibration, flux-GF time, tEquilibrium, dummy_value}
+//   fstim = {memb_flux_stimulation, ion (0 Na, 1 K, 2 Cl), memb_flux_inj}   (time window and position_x from `stim`)
+int ax1ref_elec_alpha_boundary(const double* cell, int from_cytosol, const double* xl, const double* phys,
+                               const int* valence, const double* nodevol4, int do_volume_scaling, const double* stim,
+                               const double* memb, const double* geff, const double* equil, const double* fstim,
+                               double temperature, double* out16) {
+  try {
+    Setup S(cell, phys, valence, nodevol4, do_volume_scaling, stim, from_cytosol ? CYTOSOL : ES);
+    S.ph.electro = Electrolyte<double>(80.0, temperature, con_mol, 1e-9);
+    S.ph.prm.equil = equil[0] != 0.0;
+    S.ph.prm.general.num["dummy_value"] = equil[3];
+    S.ph.prm.stimulation.num["memb_flux_stimulation"] = fstim[0];
+    S.ph.prm.stimulation.str["memb_flux_ion"] = fstim[1] == 0 ? "Na" : (fstim[1] == 1 ? "K" : "Cl");
+    S.ph.prm.stimulation.num["memb_flux_inj"] = fstim[2];
+    // channel set of this membrane element with the given effective conductances: leak channels g * ratio with
+    // ratio 1, voltage-gated channels gbar * prod(gates^exponent) with all gates 1
+    typedef Physics::ChannelSet CS;
+    CS& cs = S.ph.channels;
+    cs.addChannel(Dune::shared_ptr<Channel<double, ChVec> >(new LeakChannel<double, ChVec>(Na)));
+    cs.addChannel(Dune::shared_ptr<Channel<double, ChVec> >(new LeakChannel<double, ChVec>(K)));
+    cs.addChannel(Dune::shared_ptr<Channel<double, ChVec> >(new NavChannel<double, ChVec>()));
+    cs.addChannel(Dune::shared_ptr<Channel<double, ChVec> >(new KvChannel<double, ChVec>()));
+    const int elem = 7;
+    cs.addMembraneElement(elem);
+    cs.resize();
+    for (int k = 0; k < cs.size(); ++k) cs.getChannelPtr(k)->init();
+    ChVec ones(1); ones = 1.0;
+    for (int k = 0; k < 4; ++k) {
+      cs.setConductance(k, elem, geff[k]);
+      if (k < 2) cs.setRatio(k, elem, 1.0);
+      else for (int g = 0; g < cs.getChannel(k).numGatingParticles(); ++g) cs.getChannelPtr(k)->setGatingParticle(g, ones);
+    }
+    // the flux class: a new object sees the channel set above; its clock decides the equilibration branch
+    S.flux.reset(new MembFlux(S.dgfCon, S.dgfPot, S.ph, S.sol, equil[2]));
+    S.flux->time = equil[1];
+    ParamPot paramPot(S.gv, S.ph);
+    ParamCon paramCon;
+    for (int j = 0; j < 3; ++j)
+      paramCon.push_back(Dune::shared_ptr<ParamNP>(new ParamNP(j, S.gv, S.ph, S.igf, *S.flux, S.nf, equil[2])));
+    LopElec lop(paramCon, paramPot, 4);
+    lop.setTime(stim[1]);
+    Intersection is;
+    is.geo.x0 = cell[0]; is.geo.x1 = cell[1]; is.geo.y = from_cytosol ? cell[3] : cell[2];
+    is.gii.eta = from_cytosol ? 1.0 : 0.0;
+    is.in = &S.e;
+    is.ny = from_cytosol ? 1.0 : -1.0;
+    is.y_opposite = memb[0]; is.pot_opposite = memb[1];
+    for (int j = 0; j < 3; ++j) is.con_opposite[j] = memb[2 + j];
+    is.ext_surface = memb[5];
+    is.index = elem;
+    IntersectionGeometry ig{&is};
+    XView x{xl};
+    for (int k = 0; k < 16; ++k) out16[k] = 0.0;
+    RView r{out16};
+    lop.alpha_boundary(ig, S.lfs, x, S.lfs, r);
     return 0;
   } catch (std::exception&) {
     return 1;

@@ -10,4 +10,6 @@ class Ax1ParallelDebugStream {
   template <class T>
   Ax1ParallelDebugStream& operator<<(const T&) { return *this; }
   Ax1ParallelDebugStream& operator<<(std::ostream& (*)(std::ostream&)) { return *this; }
+  void push(bool) {}
+  void pop() {}
 };

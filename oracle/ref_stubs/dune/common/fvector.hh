@@ -7,6 +7,7 @@ template <class T, int N>
 class FieldVector {
  public:
   typedef T value_type;
+  enum { dimension = N };
   FieldVector() { for (int i = 0; i < N; ++i) d_[i] = T(); }
   FieldVector(const T& v) { for (int i = 0; i < N; ++i) d_[i] = v; }
   T& operator[](std::size_t i) { return d_[i]; }
@@ -32,6 +33,7 @@ template <class T>
 class FieldVector<T, 1> {
  public:
   typedef T value_type;
+  enum { dimension = 1 };
   FieldVector() : d_(T()) {}
   FieldVector(const T& v) : d_(v) {}
   T& operator[](std::size_t) { return d_; }

@@ -1,4 +1,4 @@
 // stand-in (see ../../README.md)
 #pragma once
 #include <memory>
-namespace Dune { using std::shared_ptr; }
+namespace Dune { using std::shared_ptr; using std::make_shared; }

@@ -59,6 +59,8 @@ template <class ct, int dim>
 struct ReferenceElement {
   FieldVector<ct, dim> position(int, int) const { return FieldVector<ct, dim>(0.5); }   // centre of the cube
 };
+template <class T> int sign(const T& v) { return (v > T(0)) - (v < T(0)); }
+
 template <class ct, int dim>
 struct ReferenceElements {
   static const ReferenceElement<ct, dim>& general(const GeometryType&) { static ReferenceElement<ct, dim> r; return r; }
@@ -89,6 +91,22 @@ class InstationaryLocalOperatorDefaultMethods {
 };
 template <class LB>
 class LocalBasisCache {};
+
+// boundary grid functions (the membrane flux class derives from these)
+template <class GV, class RF, int m, class R>
+struct IntersectionGridFunctionTraits {
+  typedef GV GridViewType;
+  typedef typename GV::ctype DomainFieldType;
+  enum { dimDomain = GV::dimension - 1 };
+  typedef Dune::FieldVector<DomainFieldType, GV::dimension - 1> DomainType;
+  typedef RF RangeFieldType;
+  enum { dimRange = m };
+  typedef R RangeType;
+};
+template <class T, class Imp>
+struct IntersectionGridFunctionBase {
+  typedef T Traits;
+};
 
 struct ConvectionDiffusionBoundaryConditions {
   enum Type { Dirichlet = 1, Neumann = -1, Outflow = -2, None = -3 };

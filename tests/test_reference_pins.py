@@ -225,3 +225,63 @@ def test_volume_operators_against_reference_local_operators(oracle, refop):
         assert np.max(np.abs(a - b)) < 1e-14 * np.max(np.abs(b)) and np.all(a[:12] == 0.0)
         A, B = run.ref(2, 1, i, jm, xl, 2.0).reshape(16, 16), P.cell_jacobian(i, jm, 2, xl, weight=1.0)
         assert np.max(np.abs(A - B)) < 1e-14 * np.max(np.abs(B))
+
+
+@pytest.mark.parametrize("variant", ["hh", "equilibration", "flux_stimulation"])
+def test_membrane_boundary_term_against_reference_operator_and_flux_class(oracle, refop, variant):
+    """Acme2CylOperatorFullyCoupled::alpha_boundary on membrane-interface faces, with the reference's
+    DefaultNernstPlanckParameters::bctype / j (surface scaling A_ext / A_this, cosine-ramped flux stimulation) and
+    MembraneFluxGridFunctionImplicit::evaluate over its DynamicChannelSet (reversal potentials, drift and diffusion
+    terms per channel, equilibration: leak only x dummy_value) -- rows a2, a7, a9. The Physics look-ups that need the
+    grid's interface maps (potential jump, concentration ratio, membrane surface) are answered from the opposite-side
+    face-centre values the test computes from the same iterate. The oracle's boundary kernel agrees to rounding."""
+    kw = dict(equilibration=(variant == "equilibration"))
+    s = small_setup(nx=4, **kw)
+    if variant == "flux_stimulation":
+        s["params"].update(do_memb_flux_stimulation=1, memb_flux_ion=0, memb_flux_inj=3.0e5, tinj_start=20.0,
+                           tinj_end=2000.0, stim_x=250.0e3)
+    P = oracle_problem(oracle, s)
+    u0, t, dt = s["u0"], 399.0, 1.0
+    P.set_time(t, dt); P.set_uold(u0); P.update_state(u0); P.accept_state()
+    P.update_state(u0 * (1.0 + 1e-3))                 # a gating step away from the steady state
+    cst = P.constants()
+    _, nvol, _ = P.maps()
+    nvx, x, y, jm = s["nx"] + 1, s["x"], s["y"], P.jm
+    rng = np.random.default_rng(3)
+    u = u0 * (1.0 + 1e-2 * rng.standard_normal(u0.shape))
+    st = P.channel_state(new=True).reshape(5, -1)
+    p = s["params"]
+    changed = 0
+    for (i, from_cyt) in ((0, 1), (2, 1), (2, 0), (3, 0), (1, 1), (1, 0)):
+        j = jm - 1 if from_cyt else jm + 1
+        vs = [i + nvx * j, i + 1 + nvx * j, i + nvx * (j + 1), i + 1 + nvx * (j + 1)]
+        xl = np.array([[u[4 * v + c] for v in vs] for c in range(4)]).reshape(-1)
+        jopp = jm + 1 if from_cyt else jm
+        ua, ub = u[4 * (i + nvx * jopp):][:4], u[4 * (i + 1 + nvx * jopp):][:4]
+        opp = 0.5 * ua + 0.5 * ub                      # Q1 value at the centre of the opposite interface face
+        memb = np.array([y[jopp], opp[3], opp[0], opp[1], opp[2], (np.pi * (y[jm + 1] + y[jm + 1])) * (x[i + 1] - x[i])])
+        gl, gn, gk = s["g_leak"][i], s["g_nav"][i], s["g_kv"][i]
+        geff = np.array([gl * st[0, i], gl * st[1, i], gn * st[2, i] ** 3 * st[3, i], gk * st[4, i] ** 4])
+        equil = np.array([p["do_equilibration"], t, p["t_equilibrium"], p["dummy_value"]], dtype=np.float64)
+        fst = np.array([p.get("do_memb_flux_stimulation", 0), p.get("memb_flux_ion", 2), p.get("memb_flux_inj", 0.0)],
+                       dtype=np.float64)
+        stim = np.array([0, t + dt, p["tinj_start"], p["tinj_end"], p["stim_x"], p["stim_y"], p["I_inj"]], dtype=np.float64)
+        cell = np.array([x[i], x[i + 1], y[j], y[j + 1]])
+        phys = np.array([80.0, cst["D"][0], cst["D"][1], cst["D"][2], cst["PC"], 1.0, 1e-6])
+        val = np.array([1, 1, -1], dtype=np.int32)
+        nv4 = np.array([nvol[v] for v in vs])
+        out = np.zeros(16)
+        rc = refop.ax1ref_elec_alpha_boundary(_dp(cell), from_cyt, _dp(np.ascontiguousarray(xl)), _dp(phys), _ip(val),
+                                              _dp(nv4), 1, _dp(stim), _dp(memb), _dp(geff), _dp(equil), _dp(fst),
+                                              279.45, _dp(out))
+        assert rc == 0
+        mine = P.cell_kernel(i, j, 3, xl, u=u, weight=1.0)
+        assert np.max(np.abs(mine)) > 0 and np.all(mine[8:] == 0.0)        # Cl has no channel, potential: Neumann 0
+        assert np.max(np.abs(out - mine)) <= 1e-14 * np.max(np.abs(mine)), (i, from_cyt)
+        if variant == "flux_stimulation":
+            s0 = dict(s); s0["params"] = dict(p, do_memb_flux_stimulation=0)
+            P0 = oracle_problem(oracle, s0)
+            P0.set_time(t, dt); P0.set_uold(u0); P0.update_state(u0); P0.accept_state(); P0.update_state(u0 * (1.0 + 1e-3))
+            changed += int(np.any(P0.cell_kernel(i, j, 3, xl, u=u, weight=1.0) != mine))
+    if variant == "flux_stimulation":
+        assert changed == 2          # exactly the two faces above position_x = 250 um (column 2, both sides)
