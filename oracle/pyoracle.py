@@ -95,6 +95,7 @@ def ref_operator_lib():
     R = C.CDLL(path)
     R.ax1ref_local_operator.argtypes = [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p, c_double_p,
                                         C.c_int, c_double_p, c_double_p]
+    R.ax1ref_rownorm.argtypes = [C.c_int, c_int_p, c_int_p, c_double_p, c_double_p]
     R.ax1ref_elec_alpha_boundary.argtypes = [c_double_p, C.c_int, c_double_p, c_double_p, c_int_p, c_double_p, C.c_int,
                                              c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double,
                                              c_double_p]

@@ -10,6 +10,7 @@
 //   Acme2CylOperatorFullyCoupled::alpha_boundary on a membrane-interface face, with DefaultNernstPlanckParameters::
 //   bctype / j (surface scaling, flux stimulation) and dune/ax1/common/membranefluxgridfunction_implicit.hh
 //   MembraneFluxGridFunctionImplicit::evaluate over the reference's DynamicChannelSet (channel flux arithmetic)
+//   dune/ax1/common/rownorm_preconditioner.hh                                RowNormPreconditioner on a block CSR matrix
 //   dune/ax1/common/power_parameters.hh, dune/ax1/acme2_cyl/common/acme2_cyl_geometrywrapper.hh
 // What is stood in for: the grid (one axis-aligned cell), the Q1 local function space tree, quadrature, and a
 // "Physics" object that hands back the coefficients the test chooses (permittivity, diffusion coefficients,
@@ -109,6 +110,8 @@ struct Output {   // printing helper of the reference (dune/ax1/common/output.hh
 #undef private
 #include <dune/ax1/acme2_cyl/operator/acme2_cyl_toperator.hh>
 #include <dune/ax1/acme2_cyl/operator/convectiondiffusionfem.hh>
+#include <istl_standins.hh>
+#include <dune/ax1/common/rownorm_preconditioner.hh>
 
 namespace {
 
@@ -193,7 +196,9 @@ struct IntersectionGeometry {       // PDELab's IntersectionGeometry wrapper
 struct GV {
   enum { dimension = 2, dimensionworld = 2 };
   typedef double ctype;
-  template <int c> struct Codim { typedef ::Entity Entity; };
+  typedef int IndexSet;
+  typedef int IntersectionIterator;
+  template <int c> struct Codim { typedef ::Entity Entity; typedef const ::Entity* Iterator; };
   typedef ::Intersection Intersection;
   struct Grid { enum { dimension = 2 }; typedef double ctype; };
   struct Traits { typedef GV::Grid Grid; };
@@ -553,6 +558,35 @@ int ax1ref_elec_alpha_boundary(const double* cell, int from_cytosol, const doubl
     for (int k = 0; k < 16; ++k) out16[k] = 0.0;
     RView r{out16};
     lop.alpha_boundary(ig, S.lfs, x, S.lfs, r);
+    return 0;
+  } catch (std::exception&) {
+    return 1;
+  }
+}
+
+// RowNormPreconditioner<GV, 4>(A, b) (rownorm_preconditioner.hh:65-155) on a block CSR matrix with 4 x 4 blocks given
+// as rowptr / col / vals (16 doubles per block, row-major) and the right-hand side r (4 per block row); in place.
+int ax1ref_rownorm(int n, const int* rowptr, const int* col, double* vals, double* r) {
+  try {
+    typedef Dune::FieldMatrix<double, 4, 4> Block;
+    Dune::BCRSMatrix<Block> A;
+    Dune::BlockVector<Dune::FieldVector<double, 4> > b;
+    A.rows.resize(n); b.resize(n);
+    for (int i = 0; i < n; ++i) {
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        Block B;
+        for (int a = 0; a < 4; ++a) for (int c = 0; c < 4; ++c) B[a][c] = vals[16 * (size_t)k + 4 * a + c];
+        A.rows[i].cols.push_back(col[k]);
+        A.rows[i].blocks.push_back(B);
+      }
+      for (int a = 0; a < 4; ++a) b[i][a] = r[4 * (size_t)i + a];
+    }
+    { RowNormPreconditioner<GV, 4> prec(A, b); }
+    for (int i = 0; i < n; ++i) {
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+        for (int a = 0; a < 4; ++a) for (int c = 0; c < 4; ++c) vals[16 * (size_t)k + 4 * a + c] = A.rows[i].blocks[k - rowptr[i]][a][c];
+      for (int a = 0; a < 4; ++a) r[4 * (size_t)i + a] = b[i][a];
+    }
     return 0;
   } catch (std::exception&) {
     return 1;

@@ -3,6 +3,21 @@
 #include <cmath>
 #include <cstddef>
 namespace Dune {
+// iterator over the entries / rows of a small dense container that knows its position (dune's index())
+template <class C, class T>
+class IndexedIterator {
+ public:
+  IndexedIterator(C* c, std::size_t i) : c_(c), i_(i) {}
+  T& operator*() const { return (*c_)[i_]; }
+  T* operator->() const { return &(*c_)[i_]; }
+  std::size_t index() const { return i_; }
+  IndexedIterator& operator++() { ++i_; return *this; }
+  bool operator!=(const IndexedIterator& o) const { return i_ != o.i_; }
+  bool operator==(const IndexedIterator& o) const { return i_ == o.i_; }
+ private:
+  C* c_;
+  std::size_t i_;
+};
 template <class T, int N>
 class FieldVector {
  public:
@@ -20,11 +35,11 @@ class FieldVector {
   FieldVector& axpy(const T& a, const FieldVector& x) { for (int i = 0; i < N; ++i) d_[i] += a * x.d_[i]; return *this; }
   T operator*(const FieldVector& o) const { T s = T(); for (int i = 0; i < N; ++i) s += d_[i] * o.d_[i]; return s; }
   T two_norm() const { T s = T(); for (int i = 0; i < N; ++i) s += d_[i] * d_[i]; return std::sqrt(s); }
+  T infinity_norm() const { T m = T(); for (int i = 0; i < N; ++i) m = std::fabs(d_[i]) > m ? std::fabs(d_[i]) : m; return m; }
   static constexpr int size() { return N; }
-  T* begin() { return d_; }
-  T* end() { return d_ + N; }
-  const T* begin() const { return d_; }
-  const T* end() const { return d_ + N; }
+  typedef IndexedIterator<FieldVector, T> Iterator;
+  Iterator begin() { return Iterator(this, 0); }
+  Iterator end() { return Iterator(this, N); }
  private:
   T d_[N];
 };
@@ -55,6 +70,10 @@ class FieldMatrix {
   FieldMatrix(const T& v) { for (int i = 0; i < N; ++i) r_[i] = v; }
   FieldVector<T, M>& operator[](std::size_t i) { return r_[i]; }
   const FieldVector<T, M>& operator[](std::size_t i) const { return r_[i]; }
+  typedef IndexedIterator<FieldMatrix, FieldVector<T, M> > RowIterator;
+  typedef RowIterator Iterator;
+  RowIterator begin() { return RowIterator(this, 0); }
+  RowIterator end() { return RowIterator(this, N); }
   template <class X, class Y>
   void mv(const X& x, Y& y) const {                       // y = A x
     for (int i = 0; i < N; ++i) { y[i] = T(); for (int j = 0; j < M; ++j) y[i] += r_[i][j] * x[j]; }

@@ -285,3 +285,23 @@ def test_membrane_boundary_term_against_reference_operator_and_flux_class(oracle
             changed += int(np.any(P0.cell_kernel(i, j, 3, xl, u=u, weight=1.0) != mine))
     if variant == "flux_stimulation":
         assert changed == 2          # exactly the two faces above position_x = 250 um (column 2, both sides)
+
+
+def test_rownorm_against_reference_preconditioner(oracle, refop):
+    """RowNormPreconditioner<GV, 4> (rownorm_preconditioner.hh:65-155, row a15) on the assembled Jacobian of a small
+    problem incl. Dirichlet unit rows: bit-identical to the oracle's rownorm_scale (the device kernel is held
+    bit-identical to the oracle in test_spmv_and_rownorm_parity)."""
+    s = small_setup(nx=5, stimulation=True)
+    P = oracle_problem(oracle, s)
+    u0 = s["u0"]
+    P.set_time(29.0, 1.0); P.set_uold(u0); P.update_state(u0)
+    J = P.jacobian(u0)
+    rowptr, col = P.pattern()
+    rng = np.random.default_rng(9)
+    r = rng.standard_normal(P.n)
+    Jo, ro = P.rownorm(J, r)
+    Jr, rr = J.copy(), r.copy()
+    rc = refop.ax1ref_rownorm(P.nv, _ip(rowptr), _ip(col), _dp(Jr), _dp(rr))
+    assert rc == 0
+    assert np.array_equal(Jr, Jo) and np.array_equal(rr, ro)
+    assert not np.array_equal(Jo, J)
