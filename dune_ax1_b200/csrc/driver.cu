@@ -1071,6 +1071,7 @@ int drv_newton(ax1gpu_ctx* c, const ax1gpu_newton_opts* o, ax1gpu_newton_result*
           if (best_lambda == 0.0) {
             best_lambda = 1.0;
             if ((rc = step(best_lambda))) return rc;
+            if (!std::isfinite(res->defect)) break;  // NewtonDefectError outside the search's try block (:469)
           }
           if (best_lambda != lambda) {
             if ((rc = step(best_lambda))) return rc;

@@ -71,6 +71,13 @@ int ax1o_generate_y(double ymin, double ymax, double ymemb, double dmemb, double
 
 /* one GridVector primitive appended to a vector holding `start` (ops: oracle/ref_driver.cpp) */
 int ax1o_gridvector(int op, double start, int n, double a, double b, double c, double* out, int cap);
+/* The Newton line search alone, on a caller-supplied defect function (defect_cb sees the trial u and
+   returns its defect norm, NaN allowed). Writes the trial step lengths to trace (<= cap), their
+   count to *ntrace; returns the accepted defect. Used to pin the search against the reference's
+   compiled Ax1Newton::line_search (tests/test_reference_pins.py). */
+typedef double (*ax1o_defect_cb)(void* ctx, const double* u, int n);
+double ax1o_line_search(int n, double* u, const double* z, double cur_defect, double prev_defect, int maxit,
+                        ax1o_defect_cb cb, void* ctx, double* trace, int cap, int* ntrace);
 
 ax1o_problem* ax1o_create(const ax1o_config* cfg, int nx, int ny, const double* x, const double* y,
                           int left_proc_boundary, int right_proc_boundary, const double* eps_memb,

@@ -55,6 +55,16 @@ int ax1o_generate_y(double ymin, double ymax, double ymemb, double dmemb, double
   AX1O_CATCH(-1)
 }
 
+double ax1o_line_search(int n, double* u, const double* z, double cur_defect, double prev_defect, int maxit,
+                        ax1o_defect_cb cb, void* ctx, double* trace, int cap, int* ntrace) {
+  std::vector<double> prev_u(n), tr;
+  double d = ax1o::line_search((size_t)n, u, z, prev_u.data(), cur_defect, prev_defect, maxit,
+                               [&]() { return cb(ctx, u, n); }, &tr);
+  *ntrace = (int)tr.size();
+  for (int i = 0; i < (int)tr.size() && i < cap; ++i) trace[i] = tr[i];
+  return d;
+}
+
 int ax1o_gridvector(int op, double start, int n, double a, double b, double c, double* out, int cap) {
   AX1O_TRY
   std::vector<double> g = gridvector_op(op, start, n, a, b, c);

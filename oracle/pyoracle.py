@@ -102,6 +102,21 @@ def ref_operator_lib():
     return R
 
 
+DEFECT_CB = C.CFUNCTYPE(C.c_double, C.c_void_p, C.POINTER(C.c_double), C.c_int)
+
+
+def ref_newton_lib():
+    """ctypes handle of oracle/_ref/libax1refnewton.so (the reference's Ax1Newton overrides), or None."""
+    path = os.path.join(_HERE, "_ref", "libax1refnewton.so")
+    if not os.path.exists(path):
+        return None
+    R = C.CDLL(path)
+    R.ax1ref_line_search.argtypes = [C.c_int, c_double_p, c_double_p, C.c_double, C.c_double, C.c_int, C.c_double,
+                                     C.c_int, C.c_int, DEFECT_CB, C.c_void_p, c_double_p, C.c_int, c_double_p]
+    R.ax1ref_prepare_step.argtypes = [C.c_int, c_int_p, c_int_p, c_double_p, c_double_p, C.c_int]
+    return R
+
+
 def ref_lib():
     """ctypes handle of oracle/_ref/libax1ref.so, or None if it was not built."""
     if not os.path.exists(_REF_LIB):
@@ -138,6 +153,9 @@ def lib():
     L.ax1o_create.argtypes = [C.POINTER(Config), C.c_int, C.c_int, c_double_p, c_double_p, C.c_int,
                               C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]
     L.ax1o_destroy.argtypes = [C.c_void_p]
+    L.ax1o_line_search.argtypes = [C.c_int, c_double_p, c_double_p, C.c_double, C.c_double, C.c_int, DEFECT_CB,
+                                   C.c_void_p, c_double_p, C.c_int, c_int_p]
+    L.ax1o_line_search.restype = C.c_double
     L.ax1o_gridvector.argtypes = [C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, c_double_p, C.c_int]
     L.ax1o_generate_y.argtypes = [C.c_double] * 6 + [C.c_int, C.c_double, C.c_double, C.c_int,
                                                       c_double_p, C.c_int]

@@ -47,6 +47,28 @@ class BCRSMatrix {
     std::vector<Row>* r_;
     size_type i_;
   };
+  // row-wise creation (only what Ax1Newton's optional matrix reordering names; never executed by the pins)
+  class CreateIterator {
+   public:
+    CreateIterator(std::vector<Row>* r, size_type i) : r_(r), i_(i) {}
+    size_type index() const { return i_; }
+    void insert(size_type j) { (*r_)[i_].cols.push_back(j); (*r_)[i_].blocks.push_back(B()); }
+    CreateIterator& operator++() { ++i_; return *this; }
+    bool operator!=(const CreateIterator& o) const { return i_ != o.i_; }
+   private:
+    std::vector<Row>* r_;
+    size_type i_;
+  };
+  typedef Row row_type;
+  typedef B block_type;
+  enum BuildMode { row_wise, random };
+  BCRSMatrix() {}
+  BCRSMatrix(size_type n, size_type, size_type, BuildMode) : rows(n) {}
+  CreateIterator createbegin() { return CreateIterator(&rows, 0); }
+  CreateIterator createend() { return CreateIterator(&rows, rows.size()); }
+  size_type N() const { return rows.size(); }
+  size_type nonzeroes() const { size_type k = 0; for (const Row& r : rows) k += r.cols.size(); return k; }
+  Row& operator[](size_type i) { return rows[i]; }
   RowIterator begin() { return RowIterator(&rows, 0); }
   RowIterator end() { return RowIterator(&rows, rows.size()); }
   std::vector<Row> rows;

@@ -268,6 +268,41 @@ void bicgstab(const Problem& p, const BCRS& A, const Prec& M, double* x, double*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Hackbusch-Reusken line search, strategy hackbuschReuskenAcceptBestNoThrow (ax1_newton.hh:308-503).
+// `eval` recomputes the defect norm of the current u (NaN allowed: a NaN trial is simply retried
+// with a smaller lambda, :384-392); returns the defect of the accepted u. `trace` (optional)
+// receives every trial step length in evaluation order.
+double line_search(size_t n, double* u, const double* z, double* prev_u, double cur_defect, double prev_defect,
+                   int maxit, const std::function<double()>& eval, std::vector<double>* trace) {
+  auto axpy_u = [&](double lam) { for (size_t k = 0; k < n; ++k) u[k] += -lam * z[k]; };
+  auto trial = [&](double lam) { axpy_u(lam); if (trace) trace->push_back(lam); return eval(); };
+  double lambda = 1.0, best_lambda = 0.0, best_defect = cur_defect, d;
+  std::memcpy(prev_u, u, n * sizeof(double));
+  int i = 0;
+  while (true) {
+    d = trial(lambda);
+    if (d <= (1.0 - lambda / 4) * prev_defect) break;
+    if (d < best_defect) { best_defect = d; best_lambda = lambda; }
+    if (++i >= maxit) {
+      if (best_lambda == 0.0) {  // no trial improved: accept the full step anyway (:462-474)
+        best_lambda = 1.0;
+        std::memcpy(u, prev_u, n * sizeof(double));
+        d = trial(best_lambda);
+        if (!std::isfinite(d)) return d;  // outside the search's try block: NewtonDefectError ends the solve
+      }
+      if (best_lambda != lambda) {
+        std::memcpy(u, prev_u, n * sizeof(double));
+        d = trial(best_lambda);
+      }
+      break;
+    }
+    lambda *= 0.5;
+    std::memcpy(u, prev_u, n * sizeof(double));
+  }
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Newton: PDELab NewtonSolver::apply [ext] with Ax1Newton::{defect,prepare_step,line_search}
 void newton(Problem& p, double* u, const NewtonOpts& o, const Comm* comm, NewtonResult& res) {
   using clk = std::chrono::steady_clock;
@@ -345,34 +380,8 @@ void newton(Problem& p, double* u, const NewtonOpts& o, const Comm* comm, Newton
       update_state(p, u);
       if (!defect()) { res.status = NEWTON_DEFECT_NAN; break; }
     } else {
-      double lambda = 1.0, best_lambda = 0.0, best_defect = res.defect;
-      std::memcpy(prev_u.data(), u, n * sizeof(double));
-      int i = 0;
-      while (true) {
-        axpy_u(lambda);
-        update_state(p, u);
-        defect();  // NaNs are ignored and retried with a smaller lambda
-        if (res.defect <= (1.0 - lambda / 4) * prev_defect) break;
-        if (res.defect < best_defect) { best_defect = res.defect; best_lambda = lambda; }
-        if (++i >= o.line_search_maxit) {
-          if (best_lambda == 0.0) {
-            best_lambda = 1.0;
-            std::memcpy(u, prev_u.data(), n * sizeof(double));
-            axpy_u(best_lambda);
-            update_state(p, u);
-            defect();
-          }
-          if (best_lambda != lambda) {
-            std::memcpy(u, prev_u.data(), n * sizeof(double));
-            axpy_u(best_lambda);
-            update_state(p, u);
-            defect();
-          }
-          break;
-        }
-        lambda *= 0.5;
-        std::memcpy(u, prev_u.data(), n * sizeof(double));
-      }
+      res.defect = line_search(n, u, z.data(), prev_u.data(), res.defect, prev_defect, o.line_search_maxit,
+                               [&]() { update_state(p, u); defect(); return res.defect; }, nullptr);
       if (!std::isfinite(res.defect)) { res.status = NEWTON_DEFECT_NAN; break; }
     }
     res.t_assembler += secs(t2, clk::now());

@@ -305,3 +305,127 @@ def test_rownorm_against_reference_preconditioner(oracle, refop):
     assert rc == 0
     assert np.array_equal(Jr, Jo) and np.array_equal(rr, ro)
     assert not np.array_equal(Jo, J)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Ax1Newton: the reference's own line_search / prepare_step, compiled against stand-in PDELab Newton
+# bases (oracle/ref_stubs/newton_standins.hh), on synthetic defect functions
+@pytest.fixture(scope="module")
+def refnewton(oracle):
+    oracle.build_ref()
+    R = oracle.ref_newton_lib()
+    if R is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    return R
+
+
+def _line_search_case(name):
+    """(u0, z, prev_defect, defect function of the trial u). lam(u) recovers the step length of a trial."""
+    rng = np.random.default_rng(4)
+    n = 8
+    u0 = rng.standard_normal(n)
+    e = rng.standard_normal(n)
+    lam = lambda u, z: float(np.dot(u0 - u, z) / np.dot(z, z))
+    if name == "full_step":            # u0 - z is the root: lambda = 1 passes the decrease test at once
+        z = e.copy()
+        return u0, z, np.linalg.norm(e), lambda u: np.linalg.norm(u - (u0 - e))
+    if name == "overshoot":            # the root sits at lambda = 1/8: three halvings
+        z = 8.0 * e
+        return u0, z, np.linalg.norm(e), lambda u: np.linalg.norm(u - (u0 - e))
+    if name == "never_improves":       # every trial is worse than where we stand: full step accepted anyway
+        z = e.copy()
+        return u0, z, 1.0, lambda u: 1.0 + np.linalg.norm(u - u0)
+    if name == "best_in_middle":       # shallow minimum at lambda = 1/4, never a sufficient decrease
+        z = e.copy()
+        return u0, z, 1.0, lambda u: 0.99 + (lam(u, z) - 0.25) ** 2
+    if name == "best_is_last":         # decreasing towards lambda -> 0 but never enough: best == last trial
+        z = e.copy()
+        return u0, z, 1.0, lambda u: 0.9999 + 1e-5 * lam(u, z)
+    if name == "nan_then_ok":          # NaN defects for long steps are retried with a smaller lambda
+        z = e.copy()
+        return u0, z, 1.0, lambda u: float("nan") if lam(u, z) > 0.3 else 0.5 + lam(u, z)
+    if name == "nan_everywhere_but_best":   # NaN must never become "best"
+        z = e.copy()
+        return u0, z, 1.0, lambda u: 0.97 if abs(lam(u, z) - 0.125) < 1e-12 else float("nan")
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("maxit", [10, 3])
+@pytest.mark.parametrize("name", ["full_step", "overshoot", "never_improves", "best_in_middle", "best_is_last",
+                                  "nan_then_ok", "nan_everywhere_but_best"])
+def test_line_search_against_reference_newton(oracle, refnewton, name, maxit):
+    """Ax1Newton::line_search (ax1_newton.hh:308-503), strategy hackbuschReuskenAcceptBestNoThrow as
+    acme2_cyl_setup.hh:837-841 configures it: the same trial vectors in the same order, the same accepted u and
+    defect as the oracle's line_search, bit for bit."""
+    u0, z, prev, f = _line_search_case(name)
+    n = len(u0)
+
+    def run(which):
+        seen = []
+
+        def cb(ctx, up, nn):
+            u = np.ctypeslib.as_array(up, shape=(nn,)).copy()
+            seen.append(u)
+            return float(f(u))
+        cbf = oracle.DEFECT_CB(cb)
+        u = u0.copy()
+        if which == "ref":
+            out = np.zeros(4)
+            rc = refnewton.ax1ref_line_search(n, _dp(u), _dp(z.copy()), prev, prev, maxit, 0.5, 3, 0, cbf, None, None, 0,
+                                              _dp(out))
+            # a NaN defect at the finally accepted u escapes as NewtonDefectError (the oracle reports NaN and its
+            # Newton loop turns that into NEWTON_DEFECT_NAN)
+            assert rc == (3 if np.isnan(out[0]) else 0)
+            assert out[1] == len(seen) and out[2] == len(seen)      # preAssembly before every defect (:346-349)
+            assert out[3] == 1.0                                      # the solution container follows u
+            return u, out[0], seen
+        tr = np.zeros(64); ntr = C.c_int(0)
+        d = oracle.lib().ax1o_line_search(n, _dp(u), _dp(z.copy()), prev, prev, maxit, cbf, None, _dp(tr), 64,
+                                          C.byref(ntr))
+        assert ntr.value == len(seen)
+        return u, d, seen
+
+    ur, dr, sr = run("ref")
+    uo, do, so = run("oracle")
+    assert len(sr) == len(so) and all(np.array_equal(a, b) for a, b in zip(sr, so))
+    assert np.array_equal(ur, uo)
+    assert dr == do or (np.isnan(dr) and np.isnan(do))
+    # the scenario really exercises the branch it is named after
+    if maxit == 10:
+        expect = {"full_step": 1, "overshoot": 4, "never_improves": 12, "best_in_middle": 11, "best_is_last": 10,
+                  "nan_then_ok": 3, "nan_everywhere_but_best": 11}[name]
+        assert len(sr) == expect, (name, len(sr))
+
+
+def test_line_search_other_strategies_of_reference(oracle, refnewton):
+    """The strategies the product does not offer behave as documented in the reference (so that the one it does
+    offer is known to be the right one): noLineSearch takes the full step with one defect evaluation; plain
+    Hackbusch-Reusken and AcceptBest throw NewtonLineSearchError and restore u when nothing improved."""
+    u0, z, prev, f = _line_search_case("never_improves")
+    n = len(u0)
+    for strategy, rc_expect, u_expect, evals in ((0, 0, u0 - z, 1), (1, 1, u0, 11), (2, 1, u0, 11), (3, 0, u0 - z, 12)):
+        cbf = oracle.DEFECT_CB(lambda ctx, up, nn: float(f(np.ctypeslib.as_array(up, shape=(nn,)))))
+        u = u0.copy(); out = np.zeros(4)
+        rc = refnewton.ax1ref_line_search(n, _dp(u), _dp(z.copy()), prev, prev, 10, 0.5, strategy, 0, cbf, None, None, 0,
+                                          _dp(out))
+        assert rc == rc_expect and out[1] == evals
+        assert np.array_equal(u, u_expect)
+
+
+def test_prepare_step_applies_rownorm_of_reference(oracle, refnewton):
+    """Ax1Newton::prepare_step (ax1_newton.hh:216-293) with setRowPreconditioner(true): (A, r) leave it equilibrated
+    exactly as the oracle's rownorm_scale does; with it off they are untouched."""
+    s = small_setup(nx=5, stimulation=True)
+    P = oracle_problem(oracle, s)
+    u0 = s["u0"]
+    P.set_time(29.0, 1.0); P.set_uold(u0); P.update_state(u0)
+    J = P.jacobian(u0)
+    rowptr, col = P.pattern()
+    r = np.random.default_rng(9).standard_normal(P.n)
+    Jo, ro = P.rownorm(J, r)
+    Jr, rr = J.copy(), r.copy()
+    assert refnewton.ax1ref_prepare_step(P.nv, _ip(rowptr), _ip(col), _dp(Jr), _dp(rr), 1) == 0
+    assert np.array_equal(Jr, Jo) and np.array_equal(rr, ro)
+    Jr, rr = J.copy(), r.copy()
+    assert refnewton.ax1ref_prepare_step(P.nv, _ip(rowptr), _ip(col), _dp(Jr), _dp(rr), 0) == 0
+    assert np.array_equal(Jr, J) and np.array_equal(rr, r)
