@@ -133,8 +133,7 @@ __global__ void __launch_bounds__(256, 1) ilu_factor_kernel(Dev g, const double*
   double* ring = stage + 2 * (size_t)nq * AX1_ROW;                 // [3][nq][AX1_RING_ROW]
   const SlabGeom sg = slab_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(ring + 3 * (size_t)nq * AX1_RING_ROW));
   const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
-  const unsigned qmask = 0xFu << (tid & 28);
-
+  for (int k = tid; k < 3 * nq * AX1_RING_ROW; k += blockDim.x) ring[k] = 0.0;  // finite don't-care rows (see below)
   auto issue = [&](int L) {
     const LevelRow w = level_row(g, L, nlev, i0, wc, q);
     if (w.v >= 0) {
@@ -150,8 +149,10 @@ __global__ void __launch_bounds__(256, 1) ilu_factor_kernel(Dev g, const double*
     cp_async_wait<1>();
     cta_sync();  // staged row of this level and the ring rows of level L-1 are visible
     const LevelRow w = level_row(g, L, nlev, i0, wc, q);
+    const bool act = w.v >= 0;
     double row[9][4];
-    if (w.v >= 0) {
+    row[4][0] = row[4][1] = row[4][2] = row[4][3] = 0.0;
+    if (act) {
       const int il = w.il, j = w.j;
       bool ex[9];
       const double* arow = stage + ((size_t)(L & 1) * nq + q) * AX1_ROW;
@@ -168,13 +169,16 @@ __global__ void __launch_bounds__(256, 1) ilu_factor_kernel(Dev g, const double*
         row[s][2] = ex[s] ? (r == 3 ? b2.x : (r == 2 ? a.x : 0.0)) : 0.0;
         row[s][3] = ex[s] ? (r == 3 ? b2.y : a.y) : 0.0;
       }
+      // Branch-free elimination: a lower neighbour that does not exist has a zero block row (expanded above), so its
+      // L row is 0 x (any finite ring row) = 0 and every update it feeds subtracts 0; and a block U_k[tt] that points at
+      // a vertex which does not exist is zero in k's row as well, so targets outside the grid / sub-slab stay zero.
+      // Quads of a warp differ in which neighbours exist on almost every level; predication would serialise them.
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
-        if (!ex[s]) continue;
         const int dis = s % 3 - 1, djs = s / 3 - 1;
         const int Ln = L + dis + 2 * djs;
         const int qn = (j + djs) - lev_jlo(Ln, wc);
-        const double* kb = ring + ((size_t)(Ln % 3) * nq + qn) * AX1_RING_ROW;  // row k: [Dinv, U5..U8]
+        const double* kb = ex[s] ? ring + ((size_t)(Ln % 3) * nq + qn) * AX1_RING_ROW : ring;  // row k: [Dinv, U5..U8]
         double lrow[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -190,7 +194,6 @@ __global__ void __launch_bounds__(256, 1) ilu_factor_kernel(Dev g, const double*
           const int di = dis + (tt % 3 - 1), dj = djs + (tt / 3 - 1);
           if (di < -1 || di > 1 || dj < -1 || dj > 1) continue;
           const int s2 = (dj + 1) * 3 + (di + 1);
-          if (!ex[s2]) continue;
           const double* ub = kb + (tt - 4) * 16;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -201,12 +204,16 @@ __global__ void __launch_bounds__(256, 1) ilu_factor_kernel(Dev g, const double*
           }
         }
       }
-      // invert the pivot block (every lane of the quad holds one row of it)
-      double d[4][4], dinv[4][4];
+    }
+    // invert the pivot block (every lane of the quad holds one row of it). The exchange runs converged with the
+    // full mask -- quads without a row on this level shuffle don't-care values -- so it compiles to bare SHFLs
+    // instead of one collective re-convergence sequence per shuffle
+    double d[4][4], dinv[4][4];
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
+    for (int m = 0; m < 4; ++m)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) d[m][c] = __shfl_sync(qmask, row[4][c], (tid & 28) + m);
+      for (int c = 0; c < 4; ++c) d[m][c] = __shfl_sync(0xffffffffu, row[4][c], (tid & 28) + m);
+    if (act) {
       invert4(d, dinv);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
