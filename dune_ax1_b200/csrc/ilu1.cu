@@ -80,8 +80,7 @@ __global__ void __launch_bounds__(256, 1) ilu1_factor_kernel(Dev g, const double
   double* ring = stage + 2 * (size_t)nq * AX1_ROW;        // [4][nq][AX1_RING1_ROW]
   const Slab1 sg = slab1_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(ring + 4 * (size_t)nq * AX1_RING1_ROW));
   const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
-  const unsigned qmask = 0xFu << (tid & 28);
-
+  for (int k = tid; k < 4 * nq * AX1_RING1_ROW; k += blockDim.x) ring[k] = 0.0;  // finite don't-care rows (see below)
   auto issue = [&](int L) {
     const Row1 w = level_row1(g, L, nlev, i0, wc, q);
     if (w.v >= 0) {
@@ -97,8 +96,10 @@ __global__ void __launch_bounds__(256, 1) ilu1_factor_kernel(Dev g, const double
     cp_async_wait<1>();
     cta_sync();  // staged row of this level and the ring rows of level L-1 are visible
     const Row1 w = level_row1(g, L, nlev, i0, wc, q);
+    const bool act = w.v >= 0;
     double row[13][4];
-    if (w.v >= 0) {
+    row[6][0] = row[6][1] = row[6][2] = row[6][3] = 0.0;
+    if (act) {
       const int il = w.il, j = w.j;
       bool ex[13];
       const double* arow = stage + ((size_t)(L & 1) * nq + q) * AX1_ROW;
@@ -119,13 +120,14 @@ __global__ void __launch_bounds__(256, 1) ilu1_factor_kernel(Dev g, const double
           row[p][0] = row[p][1] = row[p][2] = row[p][3] = 0.0;  // level-1 fill entry
         }
       }
+      // branch-free elimination, as in ilu_factor_kernel (solver.cu): a missing lower neighbour has a zero block row,
+      // so its L row and every update it feeds are zero; a U block that points at a missing vertex is zero in k's row too
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        if (!ex[k]) continue;
         const int dik = P1_DI(k), djk = P1_DJ(k);
         const int Ln = L + dik + 3 * djk;
         const int qn = (j + djk) - lev1_jlo(Ln, wc);
-        const double* kb = ring + ((size_t)(Ln & 3) * nq + qn) * AX1_RING1_ROW;  // row k: [Dinv, U7..U12]
+        const double* kb = ex[k] ? ring + ((size_t)(Ln & 3) * nq + qn) * AX1_RING1_ROW : ring;  // row k: [Dinv, U7..U12]
         double lrow[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -140,7 +142,6 @@ __global__ void __launch_bounds__(256, 1) ilu1_factor_kernel(Dev g, const double
         for (int t = 7; t < 13; ++t) {
           const int p2 = p1_idx(dik + P1_DI(t), djk + P1_DJ(t));
           if (p2 < 0) continue;
-          if (!ex[p2]) continue;
           const double* ub = kb + (t - 6) * 16;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -151,12 +152,14 @@ __global__ void __launch_bounds__(256, 1) ilu1_factor_kernel(Dev g, const double
           }
         }
       }
-      // invert the pivot block (every lane of the quad holds one row of it)
-      double d[4][4], dinv[4][4];
+    }
+    // invert the pivot block (every lane of the quad holds one row of it); converged full-mask exchange
+    double d[4][4], dinv[4][4];
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
+    for (int m = 0; m < 4; ++m)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) d[m][c] = __shfl_sync(qmask, row[6][c], (tid & 28) + m);
+      for (int c = 0; c < 4; ++c) d[m][c] = __shfl_sync(0xffffffffu, row[6][c], (tid & 28) + m);
+    if (act) {
       invert4(d, dinv);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {

@@ -241,6 +241,131 @@ __global__ void __launch_bounds__(256, 1) ilu_factor_kernel(Dev g, const double*
 }
 
 // ------------------------------------------------------------------------------------------
+// The same factorisation for narrow sub-slabs (<= 24 vertex columns: the paper grid and the coarse multigrid
+// levels), where a level holds <= 12 rows and the sweep is bound by the dependent-instruction latency
+// of a single warp rather than by memory. Sixteen lanes share a vertex row -- lane (r, c) owns element (r, c) of
+// each of its 9 blocks -- so a level costs every thread a quarter of the multiply-adds, the pivot block is inverted
+// by its 16 owners together (Gauss-Jordan with the same compare-and-swap pivoting and the same operation order as
+// invert4, element by element, so the factor is bit-identical to ilu_factor_kernel's), and a 16-column sub-slab
+// keeps four warp schedulers busy instead of one. Rows of a block row are exchanged with full-mask shuffles; the code
+// is uniform across the CTA (rows that do not exist on a level run on zero blocks and store nothing).
+#define AX1_RING16_ROW 84  // 80 doubles + 4: the two row groups of a warp read disjoint banks
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__global__ void __launch_bounds__(256) ilu_factor16_kernel(Dev g, const double* __restrict__ A, double* LF, double* LB,
+                                                           int slab_w, int nq, const int* __restrict__ lvl_tab) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, q = tid >> 4, e = tid & 15, r = e >> 2, c = e & 3;
+  const int lane = tid & 31, rowl = lane & ~3, grp = lane & 16;  // first lane of my block row / of my vertex row
+  double* stage = reinterpret_cast<double*>(smem_raw);            // [2][nq][AX1_ROW]
+  double* ring = stage + 2 * (size_t)nq * AX1_ROW;                 // [3][nq][AX1_RING16_ROW]
+  const SlabGeom sg = slab_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(ring + 3 * (size_t)nq * AX1_RING16_ROW));
+  const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
+  for (int k = tid; k < 3 * nq * AX1_RING16_ROW; k += blockDim.x) ring[k] = 0.0;  // finite don't-care rows
+  // element (r, c) inside the 10-double arrow block (common.cuh): rows 0..2 hold (r,r), (r,3); row 3 is full
+  const bool nz = (r == 3) || (c == 3) || (r == c);
+  const int aoff = (r == 3) ? 6 + c : (c == 3 ? 2 * r + 1 : 2 * r);
+
+  auto issue = [&](int L) {
+    const LevelRow w = level_row(g, L, nlev, i0, wc, q);
+    if (w.v >= 0) {
+      const double* src = A + (size_t)w.v * AX1_ROW;
+      double* dst = stage + ((size_t)(L & 1) * nq + q) * AX1_ROW;
+      for (int k = e; k < AX1_ROW / 2; k += 16) cp_async16(dst + 2 * k, src + 2 * k);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  issue(1);
+  for (int L = 0; L < nlev; ++L) {
+    cp_async_wait<1>();
+    cta_sync();  // staged row of this level and the ring rows of level L-1 are visible
+    const LevelRow w = level_row(g, L, nlev, i0, wc, q);
+    const bool act = w.v >= 0;
+    const int il = w.il, j = w.j;
+    const double* arow = stage + ((size_t)(L & 1) * nq + q) * AX1_ROW;
+    double x[9];
+    bool ex[9];
+#pragma unroll
+    for (int s = 0; s < 9; ++s) {
+      const int di = s % 3 - 1, dj = s / 3 - 1;
+      ex[s] = act && (il + di >= 0) && (il + di < wc) && (j + dj >= 0) && (j + dj < g.nvy);
+      x[s] = (ex[s] && nz) ? arow[s * AX1_BLK + aoff] : 0.0;
+    }
+    // elimination, branch-free as in ilu_factor_kernel (missing neighbours are zero block rows)
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int dis = s % 3 - 1, djs = s / 3 - 1;
+      const int Ln = L + dis + 2 * djs;
+      const int qn = (j + djs) - lev_jlo(Ln, wc);
+      const double* kb = ex[s] ? ring + ((size_t)(Ln % 3) * nq + qn) * AX1_RING16_ROW : ring;  // [Dinv, U5..U8]
+      double xs[4], lr[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) xs[m] = shfl_d(x[s], rowl + m);
+      double sum = 0.0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) sum += xs[m] * kb[4 * m + c];
+      x[s] = sum;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) lr[m] = shfl_d(sum, rowl + m);
+#pragma unroll
+      for (int tt = 5; tt < 9; ++tt) {
+        const int di = dis + (tt % 3 - 1), dj = djs + (tt / 3 - 1);
+        if (di < -1 || di > 1 || dj < -1 || dj > 1) continue;
+        const int s2 = (dj + 1) * 3 + (di + 1);
+        const double* ub = kb + (tt - 4) * 16;
+        double su = 0.0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) su += lr[m] * ub[4 * m + c];
+        x[s2] -= su;
+      }
+    }
+    // pivot block: a = x[4]; Gauss-Jordan on [a | inv] with the compare-and-swap pivoting of invert4
+    double a = act ? x[4] : ((r == c) ? 1.0 : 0.0), inv = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      double v[4];
+      int src[4] = {0, 1, 2, 3};
+#pragma unroll
+      for (int m = 0; m < 4; ++m) v[m] = shfl_d(a, grp + 4 * m + cc);  // column cc
+#pragma unroll
+      for (int rr = cc + 1; rr < 4; ++rr) {
+        const bool sw = fabs(v[rr]) > fabs(v[cc]);
+        const double tv = v[cc];
+        v[cc] = sw ? v[rr] : v[cc];
+        v[rr] = sw ? tv : v[rr];
+        const int ts = src[cc];
+        src[cc] = sw ? src[rr] : src[cc];
+        src[rr] = sw ? ts : src[rr];
+      }
+      const int mysrc = r == 0 ? src[0] : (r == 1 ? src[1] : (r == 2 ? src[2] : src[3]));
+      const double f = r == 0 ? v[0] : (r == 1 ? v[1] : (r == 2 ? v[2] : v[3]));  // my row's entry in column cc
+      a = shfl_d(a, grp + 4 * mysrc + c);
+      inv = shfl_d(inv, grp + 4 * mysrc + c);
+      const double p = 1.0 / v[cc];
+      if (r == cc) { a *= p; inv *= p; }
+      const double apc = shfl_d(a, grp + 4 * cc + c), ipc = shfl_d(inv, grp + 4 * cc + c);
+      if (r != cc) { a -= f * apc; inv -= f * ipc; }
+    }
+    x[4] = inv;
+    if (act) {
+      const size_t p = sg.row_off + (size_t)(sg.lvl[L] + q);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) LF[p * 64 + s * 16 + e] = x[s];
+#pragma unroll
+      for (int s = 4; s < 9; ++s) LB[p * 80 + (s - 4) * 16 + e] = x[s];
+    }
+    cta_sync();  // every read of ring slot L%3 (it held level L-3) is done
+    if (act) {
+      double* kr = ring + ((size_t)(L % 3) * nq + q) * AX1_RING16_ROW;
+#pragma unroll
+      for (int s = 4; s < 9; ++s) kr[(s - 4) * 16 + e] = x[s];
+    }
+    issue(L + 2);
+  }
+  cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------
 // v = (LU)^-1 d for one sub-slab per CTA (bilu_backsolve): forward sweep with unit lower blocks,
 // backward sweep with the stored inverse diagonal; both sweeps in one launch.
 //
@@ -679,8 +804,26 @@ void ilu_level_tables(const Dev& g, int slab_w, std::vector<int>& tab) {
     tab[(size_t)t * stride + nlev] = acc;
   }
 }
+// AX1_ILU_FACTOR16=0 keeps the quad-per-row factorisation for narrow sub-slabs too (A/B)
+static bool ilu_use_factor16() {
+  static const int v = getenv("AX1_ILU_FACTOR16") ? atoi(getenv("AX1_ILU_FACTOR16")) : 1;
+  return v != 0;
+}
 void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st) {
   const int nslab = (g.nvx + slab_w - 1) / slab_w;
+  // measured (same box): 16 columns 0.74 -> 0.66 ms on the paper grid, 24 columns 0.81 -> 0.79 ms; at 32 columns
+  // (256 threads) the quad-per-row kernel is faster again (1.17 vs 1.28 ms on the myelin grid)
+  if (slab_w <= 24 && ilu_use_factor16()) {
+    const int nq = (((slab_w + 1) / 2) + 1) & ~1;  // rows per level, even: whole warps
+    const size_t smem = (size_t)nq * (2 * AX1_ROW + 3 * AX1_RING16_ROW) * sizeof(double) + (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
+    static bool attr16 = false;
+    if (!attr16) {
+      cudaFuncSetAttribute(ilu_factor16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      attr16 = true;
+    }
+    ilu_factor16_kernel<<<nslab, 16 * nq, smem, st>>>(g, A, LU, LU + (size_t)g.nv * 64, slab_w, nq, lvl_tab);
+    return;
+  }
   const int nt = slab_threads(slab_w), nq = nt / 4;
   const size_t smem = (size_t)nq * (2 * AX1_ROW + 3 * AX1_RING_ROW) * sizeof(double) + (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
   static bool attr_set = false;
