@@ -676,6 +676,40 @@ def test_ilu_apply_ragged_sizes(oracle, axlib, nx, slab_w, fill):
     dev.close()
 
 
+_FACTOR_VARIANT_SCRIPT = """
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from helpers import small_setup
+from dune_ax1_b200 import setups
+s = small_setup(nx=40, dx=100.0)
+dev = setups.make_device(s)
+u0 = s["u0"]
+dev.set_time(0.0, 1.0); dev.set_uold(u0); dev.update_state(u0)
+dev.jacobian(u0, download=False)
+out = []
+for w in (16, 24, 7):
+    dev.ilu_factor(w, fill=0)
+    out.append(dev.ilu_apply(np.random.default_rng(w).standard_normal(4 * dev.nv)))
+np.save(sys.argv[2], np.stack(out))
+dev.close()
+"""
+
+
+def test_ilu_factor_kernel_variants_bit_identical(axlib, tmp_path):
+    """Narrow sub-slabs are factorised by ilu_factor16_kernel (16 lanes per vertex row), wide ones by
+    ilu_factor_kernel (one quad per row): same operations in the same order, so the preconditioner must not change by
+    a single bit when AX1_ILU_FACTOR16=0 forces the quad kernel (compared through the sweep's output)."""
+    import os, subprocess, sys
+    root = str(__import__("pathlib").Path(__file__).resolve().parents[1])
+    outs = []
+    for v in ("1", "0"):
+        f = str(tmp_path / ("apply_%s.npy" % v))
+        env = dict(os.environ, AX1_ILU_FACTOR16=v)
+        subprocess.check_call([sys.executable, "-c", _FACTOR_VARIANT_SCRIPT, root, f], env=env, timeout=600)
+        outs.append(np.load(f))
+    assert np.all(np.isfinite(outs[0])) and np.array_equal(outs[0], outs[1])
+
+
 def test_error_behaviour(oracle, axlib):
     """Errors come back as status codes + message (never as a crash or an exception across the C boundary), and a
     Newton solve that meets NaNs reports NewtonDefectError's status like PDELab's NewtonSolver::defect."""
