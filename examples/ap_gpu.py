@@ -6,7 +6,7 @@ from dune_ax1_b200 import api, setups
 from dune_ax1_b200.timeloop import TimeLoop, DeviceTimeLoop
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 tend = float(sys.argv[2]) if len(sys.argv) > 2 else 3000.0
-slab_w = int(sys.argv[4]) if len(sys.argv) > 4 else 128
+slab_w = int(sys.argv[4]) if len(sys.argv) > 4 else 0   # 0: library default (16-column sub-slabs on this grid)
 fill = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 krylov = int(sys.argv[6]) if len(sys.argv) > 6 else 0    # 1: restarted GMRES instead of BiCGStab
 native = int(sys.argv[3]) if len(sys.argv) > 3 else 1   # 1: time loop inside the library (state resident in HBM)
