@@ -251,13 +251,18 @@ __global__ void __launch_bounds__(256, 1) ilu_factor_kernel(Dev g, const double*
 // is uniform across the CTA (rows that do not exist on a level run on zero blocks and store nothing).
 #define AX1_RING16_ROW 84  // 80 doubles + 4: the two row groups of a warp read disjoint banks
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// Levels are software-pipelined: of the four lower neighbours of a row on level L, SW and S lie on levels L-3 and
+// L-2 and only SE and W on level L-1. Rows are eliminated in increasing column order SW, S, SE, W, so the first two
+// steps of level L+1 can run while level L still does its last two steps and inverts its pivot block -- two
+// independent dependency chains per thread instead of one, and a single barrier per level (the ring slot written at
+// the end of iteration L was last read in iteration L-1). Operation order per row is unchanged.
 __global__ void __launch_bounds__(256) ilu_factor16_kernel(Dev g, const double* __restrict__ A, double* LF, double* LB,
                                                            int slab_w, int nq, const int* __restrict__ lvl_tab) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, q = tid >> 4, e = tid & 15, r = e >> 2, c = e & 3;
   const int lane = tid & 31, rowl = lane & ~3, grp = lane & 16;  // first lane of my block row / of my vertex row
-  double* stage = reinterpret_cast<double*>(smem_raw);            // [2][nq][AX1_ROW]
-  double* ring = stage + 2 * (size_t)nq * AX1_ROW;                 // [3][nq][AX1_RING16_ROW]
+  double* stage = reinterpret_cast<double*>(smem_raw);            // [3][nq][AX1_ROW]
+  double* ring = stage + 3 * (size_t)nq * AX1_ROW;                 // [3][nq][AX1_RING16_ROW]
   const SlabGeom sg = slab_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(ring + 3 * (size_t)nq * AX1_RING16_ROW));
   const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
   for (int k = tid; k < 3 * nq * AX1_RING16_ROW; k += blockDim.x) ring[k] = 0.0;  // finite don't-care rows
@@ -269,35 +274,33 @@ __global__ void __launch_bounds__(256) ilu_factor16_kernel(Dev g, const double* 
     const LevelRow w = level_row(g, L, nlev, i0, wc, q);
     if (w.v >= 0) {
       const double* src = A + (size_t)w.v * AX1_ROW;
-      double* dst = stage + ((size_t)(L & 1) * nq + q) * AX1_ROW;
+      double* dst = stage + ((size_t)(L % 3) * nq + q) * AX1_ROW;
       for (int k = e; k < AX1_ROW / 2; k += 16) cp_async16(dst + 2 * k, src + 2 * k);
     }
     cp_async_commit();
   };
-  issue(0);
-  issue(1);
-  for (int L = 0; L < nlev; ++L) {
-    cp_async_wait<1>();
-    cta_sync();  // staged row of this level and the ring rows of level L-1 are visible
-    const LevelRow w = level_row(g, L, nlev, i0, wc, q);
-    const bool act = w.v >= 0;
-    const int il = w.il, j = w.j;
-    const double* arow = stage + ((size_t)(L & 1) * nq + q) * AX1_ROW;
-    double x[9];
-    bool ex[9];
+  // which neighbours of the row this quad-of-quads holds on level L exist (bit s), 0 if it holds none
+  auto exists = [&](const LevelRow& w) {
+    unsigned m = 0;
+    if (w.v >= 0) {
 #pragma unroll
-    for (int s = 0; s < 9; ++s) {
-      const int di = s % 3 - 1, dj = s / 3 - 1;
-      ex[s] = act && (il + di >= 0) && (il + di < wc) && (j + dj >= 0) && (j + dj < g.nvy);
-      x[s] = (ex[s] && nz) ? arow[s * AX1_BLK + aoff] : 0.0;
+      for (int s = 0; s < 9; ++s) {
+        const int di = s % 3 - 1, dj = s / 3 - 1;
+        if ((w.il + di >= 0) && (w.il + di < wc) && (w.j + dj >= 0) && (w.j + dj < g.nvy)) m |= 1u << s;
+      }
     }
-    // elimination, branch-free as in ilu_factor_kernel (missing neighbours are zero block rows)
+    return m;
+  };
+  // one elimination step of row x (level L, grid row j) against its lower neighbour s; branch-free: a missing
+  // neighbour is a zero block row, so its L row and every update it feeds are zero
+  auto eliminate = [&](double (&x)[9], int s_, int L, int j, unsigned exm) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
+      if (s != s_) continue;
       const int dis = s % 3 - 1, djs = s / 3 - 1;
       const int Ln = L + dis + 2 * djs;
       const int qn = (j + djs) - lev_jlo(Ln, wc);
-      const double* kb = ex[s] ? ring + ((size_t)(Ln % 3) * nq + qn) * AX1_RING16_ROW : ring;  // [Dinv, U5..U8]
+      const double* kb = ((exm >> s) & 1u) ? ring + ((size_t)(Ln % 3) * nq + qn) * AX1_RING16_ROW : ring;  // [Dinv, U5..U8]
       double xs[4], lr[4];
 #pragma unroll
       for (int m = 0; m < 4; ++m) xs[m] = shfl_d(x[s], rowl + m);
@@ -319,7 +322,41 @@ __global__ void __launch_bounds__(256) ilu_factor16_kernel(Dev g, const double* 
         x[s2] -= su;
       }
     }
-    // pivot block: a = x[4]; Gauss-Jordan on [a | inv] with the compare-and-swap pivoting of invert4
+  };
+  auto expand = [&](double (&x)[9], int L, unsigned exm) {
+    const double* arow = stage + ((size_t)(L % 3) * nq + q) * AX1_ROW;
+#pragma unroll
+    for (int s = 0; s < 9; ++s) x[s] = (((exm >> s) & 1u) && nz) ? arow[s * AX1_BLK + aoff] : 0.0;
+  };
+
+  issue(0);
+  issue(1);
+  issue(2);
+  double xn[9];
+  LevelRow wn = level_row(g, 0, nlev, i0, wc, q);
+  unsigned exn = exists(wn);
+  cp_async_wait<2>();
+  cta_sync();  // row of level 0 staged, ring zeroed
+  expand(xn, 0, exn);
+  eliminate(xn, 0, 0, wn.j, exn);
+  eliminate(xn, 1, 0, wn.j, exn);
+  for (int L = 0; L < nlev; ++L) {
+    double x[9];
+#pragma unroll
+    for (int s = 0; s < 9; ++s) x[s] = xn[s];
+    const LevelRow w = wn;
+    const unsigned exm = exn;
+    const bool act = w.v >= 0;
+    cp_async_wait<1>();
+    cta_sync();  // row of level L+1 staged; ring row of level L-1 visible
+    wn = level_row(g, L + 1, nlev, i0, wc, q);
+    exn = exists(wn);
+    // level L: SE, W          level L+1: load, SW, S
+    eliminate(x, 2, L, w.j, exm);
+    expand(xn, L + 1, exn);
+    eliminate(x, 3, L, w.j, exm);
+    eliminate(xn, 0, L + 1, wn.j, exn);
+    // pivot block of level L: Gauss-Jordan on [a | inv] with the compare-and-swap pivoting of invert4
     double a = act ? x[4] : ((r == c) ? 1.0 : 0.0), inv = (r == c) ? 1.0 : 0.0;
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
@@ -345,6 +382,7 @@ __global__ void __launch_bounds__(256) ilu_factor16_kernel(Dev g, const double* 
       if (r == cc) { a *= p; inv *= p; }
       const double apc = shfl_d(a, grp + 4 * cc + c), ipc = shfl_d(inv, grp + 4 * cc + c);
       if (r != cc) { a -= f * apc; inv -= f * ipc; }
+      if (cc == 0) eliminate(xn, 1, L + 1, wn.j, exn);
     }
     x[4] = inv;
     if (act) {
@@ -353,14 +391,11 @@ __global__ void __launch_bounds__(256) ilu_factor16_kernel(Dev g, const double* 
       for (int s = 0; s < 4; ++s) LF[p * 64 + s * 16 + e] = x[s];
 #pragma unroll
       for (int s = 4; s < 9; ++s) LB[p * 80 + (s - 4) * 16 + e] = x[s];
-    }
-    cta_sync();  // every read of ring slot L%3 (it held level L-3) is done
-    if (act) {
-      double* kr = ring + ((size_t)(L % 3) * nq + q) * AX1_RING16_ROW;
+      double* kr = ring + ((size_t)(L % 3) * nq + q) * AX1_RING16_ROW;  // slot last read in iteration L-1
 #pragma unroll
       for (int s = 4; s < 9; ++s) kr[(s - 4) * 16 + e] = x[s];
     }
-    issue(L + 2);
+    issue(L + 3);
   }
   cp_async_wait<0>();
 }
@@ -815,7 +850,7 @@ void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, co
   // (256 threads) the quad-per-row kernel is faster again (1.17 vs 1.28 ms on the myelin grid)
   if (slab_w <= 24 && ilu_use_factor16()) {
     const int nq = (((slab_w + 1) / 2) + 1) & ~1;  // rows per level, even: whole warps
-    const size_t smem = (size_t)nq * (2 * AX1_ROW + 3 * AX1_RING16_ROW) * sizeof(double) + (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
+    const size_t smem = (size_t)nq * (3 * AX1_ROW + 3 * AX1_RING16_ROW) * sizeof(double) + (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
     static bool attr16 = false;
     if (!attr16) {
       cudaFuncSetAttribute(ilu_factor16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
