@@ -60,6 +60,55 @@ __global__ void __launch_bounds__(128) jacobian_boundary_fd_kernel(Dev g, const 
   }
 }
 
+// elec_volume_row (pnp_device.cuh) with the cell's four quadrature points precomputed and only the rows in `rows`
+// (bit r = residual row r of Na, K, Cl, pot) evaluated: same operations in the same order for those rows, so the
+// difference quotients below are bit-identical to evaluating all four rows for every perturbation.
+__device__ __forceinline__ void elec_volume_rows(const Dev& g, const CellCtx& c, const QP (&qp)[4], double fna, int k,
+                                                 double vs, double wm, bool spatial, unsigned rows, double out[4]) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const QP& q = qp[p];
+    double uCon[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) s += c.xl[4 * j + m] * q.phi[m];
+      uCon[j] = s;
+    }
+    if (spatial) {
+      double gpx = 0, gpy = 0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) { gpx += c.xl[12 + m] * q.gx[m]; gpy += c.xl[12 + m] * q.gy[m]; }
+      if (rows & 8u) {
+        const double Apx = (-g.eps_elec) * gpx, Apy = (-g.eps_elec) * gpy;
+        double chargeDensity = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) chargeDensity += g.valence[j] * uCon[j];
+        const double fPot = -chargeDensity * g.PC;
+        double val = (Apx * q.gx[k] + Apy * q.gy[k]) + (-fPot) * q.phi[k];
+        out[3] += g.dt * (val * q.factor * vs * g.S_pot);
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (!((rows >> j) & 1u)) continue;
+        double sx = 0, sy = 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { sx += c.xl[4 * j + m] * q.gx[m]; sy += c.xl[4 * j + m] * q.gy[m]; }
+        const double D = g.D[j];
+        const double Acx = D * sx, Acy = D * sy;
+        const double bx = -D * g.valence[j] * gpx, by = -D * g.valence[j] * gpy;
+        const double f = (j == NA) ? fna : 0.0;
+        double val = (Acx * q.gx[k] + Acy * q.gy[k]) - uCon[j] * (bx * q.gx[k] + by * q.gy[k]) + (-f) * q.phi[k];
+        out[j] += g.dt * (val * q.factor * vs);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if ((rows >> j) & 1u) out[j] += wm * (uCon[j] * q.phi[k] * q.factor * vs);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // PDELab NumericalJacobianVolume (formula: stuff/idefault_patch.dat:14-23) for the local operators that run
 // without an analytic jacobian_volume -- the reference's DEFAULT (use{Elec,Memb,Time}OperatorJacobianVolume
@@ -101,21 +150,28 @@ __global__ void __launch_bounds__(128) jacobian_volume_fd_kernel(Dev g, const do
         }
         continue;
       }
+      QP qp[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) make_qp(c, (p >> 1) ? AX1_GP1 : AX1_GP0, (p & 1) ? AX1_GP1 : AX1_GP0, qp[p]);
+      const double fna = source_na(g, c);
       for (int part = 0; part < 2; ++part) {     // 0: spatial operator, 1: time operator
         if (!(g.fd_mask & (part ? 4 : 1))) continue;
         const double wm = part ? 1.0 : 0.0;
         const bool spatial = part == 0;
         double down[4] = {0.0, 0.0, 0.0, 0.0};
-        elec_volume_row(g, c, k, vs, wm, spatial, down);
+        elec_volume_rows(g, c, qp, spatial ? fna : 0.0, k, vs, wm, spatial, spatial ? 15u : 7u, down);
         const int ncomp = part ? 3 : 4;           // the time operator lives on the concentrations only
-        for (int comp = 0; comp < ncomp; ++comp)
+        for (int comp = 0; comp < ncomp; ++comp) {
+          // row con_j reads c_j and (spatial part) the potential only, the potential row reads everything: the other
+          // difference quotients are exactly zero and are neither evaluated nor added
+          const unsigned rows = comp == 3 ? 15u : ((1u << comp) | (spatial ? 8u : 0u));
           for (int m = 0; m < 4; ++m) {
             const int lc = comp * 4 + m;
             const double orig = c.xl[lc];
             const double delta = fd_eps * (1.0 + fabs(orig));
             c.xl[lc] += delta;
             double up[4] = {0.0, 0.0, 0.0, 0.0};
-            elec_volume_row(g, c, k, vs, wm, spatial, up);
+            elec_volume_rows(g, c, qp, spatial ? fna : 0.0, k, vs, wm, spatial, rows, up);
             c.xl[lc] = orig;
             const int s = ((m >> 1) - kb + 1) * 3 + ((m & 1) - ka + 1);
             double* blk = Arow + s * AX1_BLK;
@@ -126,6 +182,7 @@ __global__ void __launch_bounds__(128) jacobian_volume_fd_kernel(Dev g, const do
             }
             if (spatial && !((rmask >> 3) & 1)) blk[6 + comp] += (up[3] - down[3]) / delta;
           }
+        }
       }
     }
 }
