@@ -187,6 +187,163 @@ __global__ void __launch_bounds__(256, 1) ilu1_factor_kernel(Dev g, const double
 }
 
 // ------------------------------------------------------------------------------------------
+// The same factorisation for narrow sub-slabs, 16 lanes per vertex row (lane (r, c) owns element (r, c) of each of
+// the row's 13 blocks) with the levels software-pipelined, as ilu_factor16_kernel (solver.cu) does for ILU0: of the
+// six lower neighbours, taken in ascending column order, the first three lie on levels L-4, L-3, L-2 and are
+// eliminated one iteration early, while level L-1 still runs its last three steps and inverts its pivot block.
+// Same operations in the same order per row: the factor is bit-identical to ilu1_factor_kernel's.
+#define AX1_RING1_16_ROW 116  // 7 blocks = 112 doubles + 4: the two row groups of a warp read disjoint banks
+__device__ __forceinline__ double shfl1_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__global__ void __launch_bounds__(256) ilu1_factor16_kernel(Dev g, const double* __restrict__ A, double* LF, double* LB,
+                                                            int slab_w, int nq, const int* __restrict__ lvl_tab) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, q = tid >> 4, e = tid & 15, r = e >> 2, c = e & 3;
+  const int lane = tid & 31, rowl = lane & ~3, grp = lane & 16;
+  double* stage = reinterpret_cast<double*>(smem_raw);   // [3][nq][AX1_ROW]
+  double* ring = stage + 3 * (size_t)nq * AX1_ROW;        // [4][nq][AX1_RING1_16_ROW]
+  const Slab1 sg = slab1_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(ring + 4 * (size_t)nq * AX1_RING1_16_ROW));
+  const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
+  for (int k = tid; k < 4 * nq * AX1_RING1_16_ROW; k += blockDim.x) ring[k] = 0.0;  // finite don't-care rows
+  const bool nz = (r == 3) || (c == 3) || (r == c);
+  const int aoff = (r == 3) ? 6 + c : (c == 3 ? 2 * r + 1 : 2 * r);
+
+  auto issue = [&](int L) {
+    const Row1 w = level_row1(g, L, nlev, i0, wc, q);
+    if (w.v >= 0) {
+      const double* src = A + (size_t)w.v * AX1_ROW;
+      double* dst = stage + ((size_t)(L % 3) * nq + q) * AX1_ROW;
+      for (int k = e; k < AX1_ROW / 2; k += 16) cp_async16(dst + 2 * k, src + 2 * k);
+    }
+    cp_async_commit();
+  };
+  auto exists = [&](const Row1& w) {
+    unsigned m = 0;
+    if (w.v >= 0) {
+#pragma unroll
+      for (int p = 0; p < 13; ++p) {
+        const int di = P1_DI(p), dj = P1_DJ(p);
+        if ((w.il + di >= 0) && (w.il + di < wc) && (w.j + dj >= 0) && (w.j + dj < g.nvy)) m |= 1u << p;
+      }
+    }
+    return m;
+  };
+  auto expand = [&](double (&x)[13], int L, unsigned exm) {
+    const double* arow = stage + ((size_t)(L % 3) * nq + q) * AX1_ROW;
+#pragma unroll
+    for (int p = 0; p < 13; ++p) {
+      const int di = P1_DI(p), dj = P1_DJ(p);
+      if (di >= -1 && di <= 1)   // level-0 entry: element (r, c) of the arrow block of the Jacobian row
+        x[p] = (((exm >> p) & 1u) && nz) ? arow[((dj + 1) * 3 + di + 1) * AX1_BLK + aoff] : 0.0;
+      else
+        x[p] = 0.0;              // level-1 fill entry
+    }
+  };
+  // one elimination step against lower neighbour k_; branch-free (a missing neighbour is a zero block row)
+  auto eliminate = [&](double (&x)[13], int k_, int L, int j, unsigned exm) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (k != k_) continue;
+      const int dik = P1_DI(k), djk = P1_DJ(k);
+      const int Ln = L + dik + 3 * djk;
+      const int qn = (j + djk) - lev1_jlo(Ln, wc);
+      const double* kb = ((exm >> k) & 1u) ? ring + ((size_t)(Ln & 3) * nq + qn) * AX1_RING1_16_ROW : ring;  // [Dinv, U7..U12]
+      double xs[4], lr[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) xs[m] = shfl1_d(x[k], rowl + m);
+      double sum = 0.0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) sum += xs[m] * kb[4 * m + c];
+      x[k] = sum;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) lr[m] = shfl1_d(sum, rowl + m);
+#pragma unroll
+      for (int t = 7; t < 13; ++t) {
+        const int p2 = p1_idx(dik + P1_DI(t), djk + P1_DJ(t));
+        if (p2 < 0) continue;
+        const double* ub = kb + (t - 6) * 16;
+        double su = 0.0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) su += lr[m] * ub[4 * m + c];
+        x[p2] -= su;
+      }
+    }
+  };
+
+  issue(0);
+  issue(1);
+  issue(2);
+  double xn[13];
+  Row1 wn = level_row1(g, 0, nlev, i0, wc, q);
+  unsigned exn = exists(wn);
+  cp_async_wait<2>();
+  cta_sync();  // row of level 0 staged, ring zeroed
+  expand(xn, 0, exn);
+  eliminate(xn, 0, 0, wn.j, exn);
+  eliminate(xn, 1, 0, wn.j, exn);
+  eliminate(xn, 2, 0, wn.j, exn);
+  for (int L = 0; L < nlev; ++L) {
+    double x[13];
+#pragma unroll
+    for (int p = 0; p < 13; ++p) x[p] = xn[p];
+    const Row1 w = wn;
+    const unsigned exm = exn;
+    const bool act = w.v >= 0;
+    cp_async_wait<1>();
+    cta_sync();  // row of level L+1 staged; ring row of level L-1 visible
+    wn = level_row1(g, L + 1, nlev, i0, wc, q);
+    exn = exists(wn);
+    // level L: (i+2,j-1), (i-2,j), (i-1,j)        level L+1: load, (i-1,j-1), (i,j-1), (i+1,j-1)
+    eliminate(x, 3, L, w.j, exm);
+    expand(xn, L + 1, exn);
+    eliminate(x, 4, L, w.j, exm);
+    eliminate(xn, 0, L + 1, wn.j, exn);
+    eliminate(x, 5, L, w.j, exm);
+    eliminate(xn, 1, L + 1, wn.j, exn);
+    // pivot block of level L: Gauss-Jordan on [a | inv] with the compare-and-swap pivoting of invert4
+    double a = act ? x[6] : ((r == c) ? 1.0 : 0.0), inv = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      double v[4];
+      int src[4] = {0, 1, 2, 3};
+#pragma unroll
+      for (int m = 0; m < 4; ++m) v[m] = shfl1_d(a, grp + 4 * m + cc);  // column cc
+#pragma unroll
+      for (int rr = cc + 1; rr < 4; ++rr) {
+        const bool sw = fabs(v[rr]) > fabs(v[cc]);
+        const double tv = v[cc];
+        v[cc] = sw ? v[rr] : v[cc];
+        v[rr] = sw ? tv : v[rr];
+        const int ts = src[cc];
+        src[cc] = sw ? src[rr] : src[cc];
+        src[rr] = sw ? ts : src[rr];
+      }
+      const int mysrc = r == 0 ? src[0] : (r == 1 ? src[1] : (r == 2 ? src[2] : src[3]));
+      const double f = r == 0 ? v[0] : (r == 1 ? v[1] : (r == 2 ? v[2] : v[3]));  // my row's entry in column cc
+      a = shfl1_d(a, grp + 4 * mysrc + c);
+      inv = shfl1_d(inv, grp + 4 * mysrc + c);
+      const double p = 1.0 / v[cc];
+      if (r == cc) { a *= p; inv *= p; }
+      const double apc = shfl1_d(a, grp + 4 * cc + c), ipc = shfl1_d(inv, grp + 4 * cc + c);
+      if (r != cc) { a -= f * apc; inv -= f * ipc; }
+      if (cc == 0) eliminate(xn, 2, L + 1, wn.j, exn);
+    }
+    x[6] = inv;
+    if (act) {
+      const size_t p = sg.row_off + (size_t)(sg.lvl[L] + q);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) LF[p * 96 + k * 16 + e] = x[k];
+#pragma unroll
+      for (int k = 6; k < 13; ++k) LB[p * 112 + (k - 6) * 16 + e] = x[k];
+      double* kr = ring + ((size_t)(L & 3) * nq + q) * AX1_RING1_16_ROW;  // slot last read in iteration L-1
+#pragma unroll
+      for (int k = 6; k < 13; ++k) kr[(k - 6) * 16 + e] = x[k];
+    }
+    issue(L + 3);
+  }
+  cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------
 // v = (LU)^-1 d, forward and backward sweep in one launch; same software pipeline as ilu_apply_kernel
 // (solver.cu): every lane streams its scalar row of the next D levels' blocks into a private
 // shared-memory slot with cp.async, solution values of the last levels go through a small ring.
@@ -520,6 +677,18 @@ void ilu1_level_tables(const Dev& g, int slab_w, std::vector<int>& tab) {
 }
 void launch_ilu1_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st) {
   const int nslab = (g.nvx + slab_w - 1) / slab_w;
+  static const int f16_max_w = getenv("AX1_ILU1_FACTOR16_W") ? atoi(getenv("AX1_ILU1_FACTOR16_W")) : 24;
+  if (slab_w <= f16_max_w && slab1_rows(slab_w) <= 16) {
+    const int nq = (slab1_rows(slab_w) + 1) & ~1;  // rows per level, even: whole warps
+    const size_t smem = (size_t)nq * (3 * AX1_ROW + 4 * AX1_RING1_16_ROW) * sizeof(double) + (size_t)(slab_w + 3 * g.nvy) * sizeof(int);
+    static bool attr16 = false;
+    if (!attr16) {
+      cudaFuncSetAttribute(ilu1_factor16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr16 = true;
+    }
+    ilu1_factor16_kernel<<<nslab, 16 * nq, smem, st>>>(g, A, LU, LU + (size_t)g.nv * 96, slab_w, nq, lvl_tab);
+    return;
+  }
   const int nt = slab1_threads(slab_w);
   static bool attr_set = false;
   if (!attr_set) {

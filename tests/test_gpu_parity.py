@@ -687,8 +687,8 @@ u0 = s["u0"]
 dev.set_time(0.0, 1.0); dev.set_uold(u0); dev.update_state(u0)
 dev.jacobian(u0, download=False)
 out = []
-for w in (16, 24, 7):
-    dev.ilu_factor(w, fill=0)
+for w, fill in ((16, 0), (24, 0), (7, 0), (24, 1), (12, 1), (5, 1)):
+    dev.ilu_factor(w, fill=fill)
     out.append(dev.ilu_apply(np.random.default_rng(w).standard_normal(4 * dev.nv)))
 np.save(sys.argv[2], np.stack(out))
 dev.close()
@@ -696,15 +696,16 @@ dev.close()
 
 
 def test_ilu_factor_kernel_variants_bit_identical(axlib, tmp_path):
-    """Narrow sub-slabs are factorised by ilu_factor16_kernel (16 lanes per vertex row), wide ones by
-    ilu_factor_kernel (one quad per row): same operations in the same order, so the preconditioner must not change by
-    a single bit when AX1_ILU_FACTOR16=0 forces the quad kernel (compared through the sweep's output)."""
+    """Narrow sub-slabs are factorised by ilu_factor16_kernel / ilu1_factor16_kernel (16 lanes per vertex row, levels
+    software-pipelined), wide ones by ilu_factor_kernel / ilu1_factor_kernel (one quad per row): same operations in
+    the same order, so the preconditioner must not change by a single bit when the environment forces the quad
+    kernels (compared through the sweep's output), for ILU0 and ILU(1)."""
     import os, subprocess, sys
     root = str(__import__("pathlib").Path(__file__).resolve().parents[1])
     outs = []
     for v in ("1", "0"):
         f = str(tmp_path / ("apply_%s.npy" % v))
-        env = dict(os.environ, AX1_ILU_FACTOR16=v)
+        env = dict(os.environ, AX1_ILU_FACTOR16=v, AX1_ILU1_FACTOR16_W="24" if v == "1" else "0")
         subprocess.check_call([sys.executable, "-c", _FACTOR_VARIANT_SCRIPT, root, f], env=env, timeout=600)
         outs.append(np.load(f))
     assert np.all(np.isfinite(outs[0])) and np.array_equal(outs[0], outs[1])
