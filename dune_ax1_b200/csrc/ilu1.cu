@@ -683,7 +683,7 @@ void launch_ilu1_factor(const Dev& g, const double* A, double* LU, int slab_w, c
     const size_t smem = (size_t)nq * (3 * AX1_ROW + 4 * AX1_RING1_16_ROW) * sizeof(double) + (size_t)(slab_w + 3 * g.nvy) * sizeof(int);
     static bool attr16 = false;
     if (!attr16) {
-      cudaFuncSetAttribute(ilu1_factor16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(ilu1_factor16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       attr16 = true;
     }
     ilu1_factor16_kernel<<<nslab, 16 * nq, smem, st>>>(g, A, LU, LU + (size_t)g.nv * 96, slab_w, nq, lvl_tab);

@@ -853,7 +853,7 @@ void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, co
     const size_t smem = (size_t)nq * (3 * AX1_ROW + 3 * AX1_RING16_ROW) * sizeof(double) + (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
     static bool attr16 = false;
     if (!attr16) {
-      cudaFuncSetAttribute(ilu_factor16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ilu_factor16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       attr16 = true;
     }
     ilu_factor16_kernel<<<nslab, 16 * nq, smem, st>>>(g, A, LU, LU + (size_t)g.nv * 64, slab_w, nq, lvl_tab);
