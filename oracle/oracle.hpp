@@ -5,13 +5,18 @@
 // the product: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load it. The product path (dune_ax1_b200/) never calls into oracle/.
 //
-// PARITY STATUS: "parity unpinned" at the hot-path boundary. The reference application cannot be built
-// here (needs DUNE 2.3 + MPI + autotools) and its own tests hold no golden vector for
-// residual/Jacobian/solve. What pins this oracle: (1) the shipped equilibrium state files
-// (tests/golden/, tests/test_oracle_golden.py) -- grid vector bit-exact, channel steady states,
-// steady-state residual cancellation; (2) the parts of the reference that compile without DUNE
-// (oracle/_ref from ax1_gridvector.hh, channel.hh, channelset.hh, electrolyte.hh,
-// acme2_cyl_geometrywrapper.hh; tests/test_reference_pins.py).
+// PARITY STATUS. The reference application cannot be built here (needs DUNE 2.3 + MPI + autotools, see
+// DESIGN.md) and its own tests hold no golden vector for residual / Jacobian / solve. What pins this oracle:
+// (1) the shipped equilibrium state files (tests/golden/, tests/test_oracle_golden.py) -- grid vector bit-exact,
+//     channel steady states, steady-state residual cancellation;
+// (2) the parts of the reference that compile from its own headers against the stand-ins of oracle/ref_stubs
+//     (oracle/_ref, tests/test_reference_pins.py): grid-vector primitives, HH channel classes, electrolyte,
+//     cylinder geometry wrapper, the local operators (alpha_volume, analytic jacobian_volume, alpha_boundary with
+//     the implicit membrane flux) with their parameter classes, RowNormPreconditioner, Ax1Newton::line_search and
+//     ::prepare_step.
+// Still "parity unpinned" (restated from the pinned PDELab / ISTL versions, which are not in the tree): the
+// assembler (element loop, constraints, implicit-Euler combination, scatter), the PDELab Newton loop and its
+// linear-reduction rule, BiCGStab / GMRES / ILU(n) / AMG.
 #pragma once
 #include <cmath>
 #include <cstdint>
