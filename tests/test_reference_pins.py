@@ -429,3 +429,94 @@ def test_prepare_step_applies_rownorm_of_reference(oracle, refnewton):
     Jr, rr = J.copy(), r.copy()
     assert refnewton.ax1ref_prepare_step(P.nv, _ip(rowptr), _ip(col), _dp(Jr), _dp(rr), 0) == 0
     assert np.array_equal(Jr, J) and np.array_equal(rr, r)
+
+
+def test_global_residual_is_scatter_of_reference_element_operators(oracle, refop):
+    """Row a13 as far as it can be pinned without PDELab: the oracle's GLOBAL residual of one implicit-Euler step equals
+    the reference's own compiled element operators (alpha_volume of the fully-coupled operator, the time operator and
+    the membrane Poisson operator) evaluated on every cell of the grid and scattered here in numpy as
+    r = dt * A(u) + M(u) - M(u_old), constrained rows zeroed. Checks the gather / scatter indexing, the DOF layout,
+    the implicit-Euler combination and the constraint handling of the oracle's assembler on all 4 x 180 cells; the
+    concentration rows of the two membrane-interface vertex lines also carry the boundary flux (pinned separately
+    above) and are left out."""
+    s = small_setup(nx=4, stimulation=True)
+    t, dt = 29.0, 1.0
+    run = _CellRunner(oracle, refop, s, t=t, dt=dt, stim=True)
+    P, jm, nvx = run.P, run.P.jm, s["nx"] + 1
+    rng = np.random.default_rng(12)
+    uold = s["u0"]
+    u = uold * (1.0 + 1e-3 * rng.standard_normal(uold.shape))
+    _, _, dmask = P.maps()
+    cs = np.asarray(s["cell_subdomain"]).reshape(s["ny"], s["nx"])
+    r_py = np.zeros(P.n)
+    for j in range(s["ny"]):
+        for i in range(s["nx"]):
+            vs = run.verts(i, j)
+            xl = np.array([[u[4 * v + c] for v in vs] for c in range(4)]).reshape(-1)
+            xo = np.array([[uold[4 * v + c] for v in vs] for c in range(4)]).reshape(-1)
+            if cs[j, i] == 2:                       # membrane cell: Poisson with the membrane permittivity
+                rl = dt * run.ref(2, 0, i, j, xl, 2.0)
+            else:
+                rl = dt * run.ref(0, 0, i, j, xl, 80.0) + run.ref(1, 0, i, j, xl, 80.0) - run.ref(1, 0, i, j, xo, 80.0)
+            for c in range(4):
+                for k, v in enumerate(vs):
+                    r_py[4 * v + c] += rl[4 * c + k]
+    for v in range(P.nv):
+        for c in range(4):
+            if (int(dmask[v]) >> c) & 1:
+                r_py[4 * v + c] = 0.0
+    r_or, S = P.residual(u, with_abs=True)
+    keep = np.ones((P.nv, 4), dtype=bool)
+    for jj in (jm, jm + 1):
+        keep[jj * nvx:(jj + 1) * nvx, :3] = False
+    err = (np.abs(r_py - r_or) / (S + 1e-300)).reshape(-1, 4)
+    assert err[keep].max() < 1e-13, err[keep].max()
+    assert np.abs(r_or).reshape(-1, 4)[keep].max() > 0
+    # and the rows left out really differ by the boundary flux only: they agree away from the membrane columns' flux
+    assert np.abs(r_py - r_or).reshape(-1, 4)[~keep].max() > 0
+
+
+def test_global_jacobian_is_scatter_of_reference_element_jacobians(oracle, refop):
+    """The same for the assembled matrix: the oracle's global analytic Jacobian (block CSR) equals the reference's
+    compiled jacobian_volume methods of the three local operators scattered over all cells as dt * dA + dM, on every
+    unconstrained row outside the two membrane-interface vertex lines (whose concentration rows also carry the
+    finite-difference boundary term)."""
+    s = small_setup(nx=4, stimulation=True)
+    t, dt = 29.0, 1.0
+    run = _CellRunner(oracle, refop, s, t=t, dt=dt, stim=True)
+    P, jm, nvx = run.P, run.P.jm, s["nx"] + 1
+    rng = np.random.default_rng(13)
+    u = s["u0"] * (1.0 + 1e-3 * rng.standard_normal(s["u0"].shape))
+    _, _, dmask = P.maps()
+    cs = np.asarray(s["cell_subdomain"]).reshape(s["ny"], s["nx"])
+    rowptr, col = P.pattern()
+    pos = {(int(r), int(col[k])): k for r in range(P.nv) for k in range(rowptr[r], rowptr[r + 1])}
+    J_py = np.zeros((len(col), 4, 4))
+    for j in range(s["ny"]):
+        for i in range(s["nx"]):
+            vs = run.verts(i, j)
+            xl = np.array([[u[4 * v + c] for v in vs] for c in range(4)]).reshape(-1)
+            if cs[j, i] == 2:
+                m = dt * run.ref(2, 1, i, j, xl, 2.0).reshape(16, 16)
+            else:
+                m = dt * run.ref(0, 1, i, j, xl, 80.0).reshape(16, 16) + run.ref(1, 1, i, j, xl, 80.0).reshape(16, 16)
+            for ci in range(4):
+                for vi in range(4):
+                    for cj in range(4):
+                        for vj in range(4):
+                            val = m[ci * 4 + vi, cj * 4 + vj]
+                            if val != 0.0:
+                                J_py[pos[(vs[vi], vs[vj])], ci, cj] += val
+    J_or = np.asarray(P.jacobian(u)).reshape(-1, 4, 4)
+    rowof = np.repeat(np.arange(P.nv), np.diff(rowptr))
+    scale = np.zeros((P.nv, 4)); np.maximum.at(scale, rowof, np.abs(J_or).max(axis=2))
+    keep = np.ones((P.nv, 4), dtype=bool)
+    for jj in (jm, jm + 1):
+        keep[jj * nvx:(jj + 1) * nvx, :3] = False
+    for v in range(P.nv):
+        for c in range(4):
+            if (int(dmask[v]) >> c) & 1:
+                keep[v, c] = False
+    rel = np.abs(J_py - J_or).max(axis=2) / (scale[rowof] + 1e-300)        # per (block, scalar row)
+    assert rel[keep[rowof]].max() < 1e-13, rel[keep[rowof]].max()
+    assert keep.sum() > 0.9 * keep.size
