@@ -167,6 +167,7 @@ def lib():
                                    C.POINTER(StepResult)]
     L.ax1gpu_membrane_potential_range.argtypes = [H, c_double_p, c_double_p]
     L.ax1gpu_membrane_potential_dev.argtypes = [H, c_double_p]
+    L.ax1gpu_membrane_flux_terms.argtypes = [H, c_double_p, c_double_p]
     L.ax1gpu_spmv.argtypes = [H, c_double_p, c_double_p]
     L.ax1gpu_ilu_factor.argtypes = [H, C.c_int]
     L.ax1gpu_ilu_factor_n.argtypes = [H, C.c_int, C.c_int]
@@ -574,6 +575,12 @@ class Ax1Gpu:
         res = StepResult()
         _chk(lib().ax1gpu_time_step(self.h, C.byref(tl_opts), C.byref(newton_opts), C.byref(state), C.byref(res)))
         return res
+
+    def membrane_flux_terms(self, u=None):
+        """[5 terms][3 ions][nx] output terms of the membrane flux (total, diffusion, drift, leak, voltage gated)."""
+        out = np.zeros(15 * self.nx)
+        _chk(lib().ax1gpu_membrane_flux_terms(self.h, _dp(f64(u)) if u is not None else None, _dp(out)))
+        return out.reshape(5, 3, self.nx)
 
     def membrane_potential_range(self):
         lo, hi = C.c_double(), C.c_double()

@@ -254,6 +254,55 @@ __global__ void channel_accept_kernel(int nx, ChannelDev ch) {
   for (int gt = 0; gt < 3; ++gt) ch.gate[gt][i] = ch.gate_new[gt][i];
 }
 
+// The five per-ion output terms of MembraneFluxGridFunctionImplicit::evaluate (FluxTerms: total, diffusion term,
+// drift term, leak channels, voltage-gated channels; membranefluxgridfunction_implicit.hh:42, 83-361) per membrane
+// column, seen from the cytosol side at the face centres of the two interface edges, with the NEW channel state:
+// the data behind memb_flux*.dat / the HDF5 datasets of acme2_cyl_output.hh:1215-1410. out[(term * 3 + ion) * nx + i].
+__global__ void memb_flux_terms_kernel(Dev g, const double* __restrict__ u, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nx) return;
+  double t[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) t[k] = 0.0;
+  if (g.membrane_active) {
+    const double* ua = u + 4 * (size_t)(i + g.nvx * g.jm);
+    const double* uc = u + 4 * (size_t)(i + g.nvx * (g.jm + 1));
+    double con1[3], con2[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { con1[j] = 0.5 * ua[j] + 0.5 * ua[4 + j]; con2[j] = 0.5 * uc[j] + 0.5 * uc[4 + j]; }
+    const double pot1 = 0.5 * ua[3] + 0.5 * ua[7], pot2 = 0.5 * uc[3] + 0.5 * uc[7];
+    double potJump = pot2;
+    potJump -= pot1;
+    potJump *= -1;                       // ySign: this side is the cytosol
+    const double C1 = (con_k * g.temperature) / con_e;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {        // Na, K; Cl has no channel
+      const double conRatio = con1[j] / con2[j];
+      const int valence = g.valence[j];
+      const double reversal = -log(conRatio) * (C1 / valence);
+      double total = 0.0, diff = 0.0, drift = 0.0, leakf = 0.0, vg = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int ch = j + 2 * kk;       // 0 Na_leak, 1 K_leak, 2 Nav, 3 Kv
+        const double conductance = (g.equil && kk == 1) ? 0.0 : g.geff[(size_t)ch * g.nx + i];
+        double C = (10 * conductance) / (con_e * valence * con_mol);
+        if (g.equil) C *= g.dummy_value;
+        C *= g.time_scale / g.length_scale;
+        double diffTerm = C * reversal;
+        if (fabs(conRatio - 1) < 1e-8 || isnan(conRatio)) diffTerm = 0.0;
+        const double driftTerm = C * C1 * potJump;
+        double flux = driftTerm;
+        flux -= diffTerm;
+        diff += diffTerm; drift += driftTerm; total += flux;
+        if (kk == 0) leakf += flux; else vg += flux;
+      }
+      t[0 + j] = total; t[3 + j] = diff; t[6 + j] = drift; t[9 + j] = leakf; t[12 + j] = vg;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 15; ++k) out[(size_t)k * g.nx + i] = t[k];
+}
+
 __global__ void memb_pot_kernel(Dev g, const double* u, double* vm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.nx) return;
@@ -278,6 +327,10 @@ void launch_channels(const Dev& g, const ChannelDev& ch, const double* u, int mo
 void launch_channel_accept(int nx, const ChannelDev& ch, cudaStream_t st) {
   const int bs = 128;
   channel_accept_kernel<<<(nx + bs - 1) / bs, bs, 0, st>>>(nx, ch);
+}
+void launch_memb_flux_terms(const Dev& g, const double* u, double* out, cudaStream_t st) {
+  const int bs = 128;
+  memb_flux_terms_kernel<<<(g.nx + bs - 1) / bs, bs, 0, st>>>(g, u, out);
 }
 void launch_memb_pot(const Dev& g, const double* u, double* vm, cudaStream_t st) {
   const int bs = 128;

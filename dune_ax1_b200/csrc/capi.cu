@@ -223,7 +223,7 @@ int ax1gpu_destroy(ax1gpu_handle c) {
   for (void* p : {(void*)c->d_x, (void*)c->d_y, (void*)c->d_nodevol, (void*)c->d_epsm, (void*)c->d_dmask, (void*)c->d_rowptr,
                   (void*)c->d_u, (void*)c->d_uold, (void*)c->d_r0, (void*)c->d_r, (void*)c->d_z, (void*)c->d_uprev, (void*)c->d_A,
                   (void*)c->d_LU, (void*)c->d_rt, (void*)c->d_p, (void*)c->d_v, (void*)c->d_y2, (void*)c->d_t, (void*)c->d_tmp,
-                  (void*)c->d_bcrs, (void*)c->d_gbar, (void*)c->d_chstate, (void*)c->d_geff, (void*)c->d_vrest, (void*)c->d_vm,
+                  (void*)c->d_bcrs, (void*)c->d_gbar, (void*)c->d_chstate, (void*)c->d_geff, (void*)c->d_vrest, (void*)c->d_vm, (void*)c->d_fluxterms,
                   (void*)c->d_err, (void*)c->d_partials, (void*)c->d_sums, (void*)c->d_sc, (void*)c->d_halo_send,
                   (void*)c->d_halo_recv, (void*)c->d_lvl, (void*)c->d_spartials})
     if (p) cudaFree(p);
@@ -318,6 +318,21 @@ int ax1gpu_membrane_potential(ax1gpu_handle c, const double* u, double* vm) {
   c->launches++;
   AX1_CUDA(cudaGetLastError());
   AX1_CUDA(cudaMemcpyAsync(vm, c->d_vm, c->g.nx * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  AX1_CUDA(cudaStreamSynchronize(c->stream));
+  return AX1GPU_OK;
+}
+
+int ax1gpu_membrane_flux_terms(ax1gpu_handle c, const double* u, double* terms) {
+  AX1_CHECK_H(c);
+  if (!terms) { set_error("ax1gpu_membrane_flux_terms: terms is null"); return AX1GPU_EINVAL; }
+  cudaSetDevice(c->device);
+  if (u) { int rc = up(c, c->d_u, u); if (rc) return rc; }
+  const size_t n = 15 * (size_t)c->g.nx;
+  if (!c->d_fluxterms) { int rc = dev_alloc(&c->d_fluxterms, n); if (rc) return rc; }
+  launch_memb_flux_terms(c->g, c->d_u, c->d_fluxterms, c->stream);
+  c->launches++;
+  AX1_CUDA(cudaGetLastError());
+  AX1_CUDA(cudaMemcpyAsync(terms, c->d_fluxterms, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   AX1_CUDA(cudaStreamSynchronize(c->stream));
   return AX1GPU_OK;
 }

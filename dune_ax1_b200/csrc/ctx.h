@@ -28,6 +28,7 @@ struct ax1gpu_ctx {
   // channels
   ax1::ChannelDev ch{};
   double *d_gbar = nullptr, *d_chstate = nullptr, *d_geff = nullptr, *d_vrest = nullptr, *d_vm = nullptr;
+  double* d_fluxterms = nullptr;  // 15 x nx output terms of the membrane flux (allocated on first use)
   int* d_err = nullptr;
   bool channels_initialized = false, channels_partially_initialized = false;
   // reductions / Krylov scalars

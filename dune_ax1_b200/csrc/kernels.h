@@ -21,6 +21,7 @@ void launch_channels(const Dev& g, const ChannelDev& ch, const double* u, int mo
                      double v_fixed, int* err, cudaStream_t st);
 void launch_channel_accept(int nx, const ChannelDev& ch, cudaStream_t st);
 void launch_memb_pot(const Dev& g, const double* u, double* vm, cudaStream_t st);
+void launch_memb_flux_terms(const Dev& g, const double* u, double* out, cudaStream_t st);
 // boundary_fd.cu (compiled with --fmad=false)
 void launch_jacobian_boundary_fd(const Dev& g, const double* u, double* A, cudaStream_t st);
 void launch_jacobian_volume_fd(const Dev& g, const double* u, double* A, cudaStream_t st);  // adds the g.fd_mask parts

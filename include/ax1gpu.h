@@ -200,6 +200,13 @@ int ax1gpu_membrane_potential_range(ax1gpu_handle h, double* vm_min, double* vm_
 /* membrane potential [mV] per membrane column of the device iterate */
 int ax1gpu_membrane_potential_dev(ax1gpu_handle h, double* vm_mV);
 
+/* Output terms of the trans-membrane flux per ion and membrane column of the iterate u (u == NULL: the device
+ * iterate), as MembraneFluxGridFunctionImplicit::evaluate returns them for FluxTerms TOTAL_FLUX, DIFF_TERM,
+ * DRIFT_TERM, LEAK, VOLTAGE_GATED (membranefluxgridfunction_implicit.hh:42, 83-361) on the cytosol-side interface
+ * (outer normal +y), with the new channel state: what acme2_cyl_output.hh:1215-1410 writes as memb_flux* per ion.
+ * terms[(term * 3 + ion) * nx + column], 15 * nx doubles. */
+int ax1gpu_membrane_flux_terms(ax1gpu_handle h, const double* u, double* terms);
+
 /* ---- building blocks exposed for parity tests and profiling ---- */
 int ax1gpu_spmv(ax1gpu_handle h, const double* x, double* y);
 int ax1gpu_ilu_factor(ax1gpu_handle h, int slab_w);   /* keeps the handle's current fill level (0 at creation) */

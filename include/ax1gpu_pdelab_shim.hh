@@ -96,6 +96,14 @@ class MembraneFluxShim {
     EP::library(ax1gpu_update_state(d_.handle(), VectorAccess<U>::data(u)));
   }
   void acceptTimeStep() { EP::library(ax1gpu_accept_state(d_.handle())); }  // :921-927
+  // Output side of the grid function (acme2_cyl_output.hh:1215-1410 evaluates it per membrane element and ion for
+  // FluxTerms TOTAL_FLUX .. VOLTAGE_GATED): all five terms of the device iterate in one call,
+  // terms[(fluxTerm * 3 + ion) * nx + membraneColumn]
+  enum FluxTerms { TOTAL_FLUX = 0, DIFF_TERM = 1, DRIFT_TERM = 2, LEAK = 3, VOLTAGE_GATED = 4 };
+  void evaluateTerms(std::vector<double>& terms, int nx) const {
+    terms.resize(15 * static_cast<std::size_t>(nx));
+    EP::library(ax1gpu_membrane_flux_terms(d_.handle(), nullptr, terms.data()));
+  }
 
  private:
   Device& d_;

@@ -347,6 +347,60 @@ inline bool is_interface_cell(const Problem& p, int j) { return j == p.jm - 1 ||
 
 }  // namespace
 
+// The five output terms of MembraneFluxGridFunctionImplicit::evaluate (membranefluxgridfunction_implicit.hh:83-361;
+// FluxTerms 0 total, 1 diffusion term, 2 drift term, 3 leak channels, 4 voltage-gated channels) for one membrane
+// column i, seen from the cytosol side (outer normal +y) at the face centres of the two interface edges -- what
+// acme2_cyl_output.hh:1215-1410 writes per ion. uglob = current iterate; the channel state is the NEW one.
+// out15[term * 3 + ion].
+void membrane_flux_terms(const Problem& p, int i, const double* uglob, double* out15) {
+  const Config& g = p.cfg;
+  for (int k = 0; k < 15; ++k) out15[k] = 0.0;
+  if (!g.membrane_active) return;
+  double con1[NSPEC], con2[NSPEC], pot1, pot2;
+  {
+    const double* ua = &uglob[4 * p.vid(i, p.jm)];
+    const double* ub = &uglob[4 * p.vid(i + 1, p.jm)];
+    for (int j = 0; j < NSPEC; ++j) con1[j] = 0.5 * ua[j] + 0.5 * ub[j];
+    pot1 = 0.5 * ua[POT] + 0.5 * ub[POT];
+    const double* uc = &uglob[4 * p.vid(i, p.jm + 1)];
+    const double* ud = &uglob[4 * p.vid(i + 1, p.jm + 1)];
+    for (int j = 0; j < NSPEC; ++j) con2[j] = 0.5 * uc[j] + 0.5 * ud[j];
+    pot2 = 0.5 * uc[POT] + 0.5 * ud[POT];
+  }
+  const int ySign = -1;        // this side = cytosol
+  const double n_y = 1.0;
+  const bool equil = g.do_equilibration && p.time < g.t_equilibrium;
+  static const int species_of[NCHAN] = {Na, K, Na, K};
+  double potJump = pot2;
+  potJump -= pot1;
+  potJump *= ySign;
+  for (int j = 0; j < NSPEC; ++j) {
+    double conRatio = ySign > 0 ? con2[j] / con1[j] : con1[j] / con2[j];
+    int valence = g.valence[j];
+    double C1 = (con_k * g.temperature) / con_e;
+    double reversal_potential = -std::log(conRatio) * (C1 / valence);
+    double total = 0.0, diff = 0.0, drift = 0.0, leakf = 0.0, vg = 0.0;
+    for (int k = 0; k < NCHAN; ++k) {
+      if (species_of[k] != j) continue;
+      bool leak = k < 2;
+      double conductance = (equil && !leak) ? 0.0 : eff_conductance_new(p, k, i);
+      double C = (10 * conductance) / (con_e * valence * con_mol);
+      if (equil) C *= g.dummy_value;
+      C *= g.time_scale / g.length_scale;
+      double diffTerm = C * reversal_potential;
+      if (std::fabs(conRatio - 1) < 1e-8 || std::isnan(conRatio)) diffTerm = 0.0;
+      double driftTerm = C * C1 * potJump;
+      double flux = driftTerm;
+      flux -= diffTerm;
+      diff += diffTerm; drift += driftTerm; total += flux;
+      if (leak) leakf += flux; else vg += flux;
+    }
+    out15[0 + j] = total * n_y; out15[3 + j] = diff * n_y; out15[6 + j] = drift * n_y;
+    out15[9 + j] = leakf * n_y; out15[12 + j] = vg * n_y;
+  }
+}
+
+
 // one local kernel on cell (i, j) with given local coefficients xl[16] (comp * 4 + vertex, comp = Na, K, Cl, pot):
 // which = 0 elec spatial alpha_volume, 1 time-operator alpha_volume (mass), 2 membrane Poisson alpha_volume,
 // 3 elec alpha_boundary on the membrane-interface face (uglob supplies the opposite side). weight as the

@@ -109,6 +109,9 @@ int ax1o_cell_kernel(const ax1o_problem* p, int i, int j, int which, const doubl
                      double* out16);
 /* analytic local Jacobian (16 x 16, row/column = comp*4 + vertex): which = 0 elec spatial, 1 time operator, 2 membrane */
 int ax1o_cell_jacobian(const ax1o_problem* p, int i, int j, int which, const double* xl, double weight, double* out256);
+/* output terms of the membrane flux per column: out[(term * 3 + ion) * nx + i], term = 0 total, 1 diffusion term,
+ * 2 drift term, 3 leak channels, 4 voltage-gated channels (membranefluxgridfunction_implicit.hh:42) */
+int ax1o_membrane_flux_terms(const ax1o_problem* p, const double* u, double* out);
 int ax1o_residual(const ax1o_problem* p, const double* u, double* r, double* abs_terms);
 int ax1o_jacobian(const ax1o_problem* p, const double* u, double* vals /* BCRS order */);
 void ax1o_rownorm(const ax1o_problem* p, double* vals, double* r);

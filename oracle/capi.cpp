@@ -156,6 +156,17 @@ int ax1o_cell_jacobian(const ax1o_problem* h, int i, int j, int which, const dou
   AX1O_TRY cell_jacobian(h->p, i, j, which, xl, weight, out256); return 0; AX1O_CATCH(1)
 }
 
+int ax1o_membrane_flux_terms(const ax1o_problem* h, const double* u, double* out) {
+  AX1O_TRY
+  for (int i = 0; i < h->p.nx; ++i) {
+    double t[15];
+    membrane_flux_terms(h->p, i, u, t);
+    for (int k = 0; k < 15; ++k) out[(size_t)k * h->p.nx + i] = t[k];
+  }
+  return 0;
+  AX1O_CATCH(1)
+}
+
 int ax1o_residual(const ax1o_problem* h, const double* u, double* r, double* abs_terms) {
   AX1O_TRY residual(h->p, u, r, abs_terms); return 0; AX1O_CATCH(1)
 }

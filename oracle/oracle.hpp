@@ -174,6 +174,7 @@ struct NewtonResult : ax1o_newton_result {
 };
 enum { NEWTON_OK = 0, NEWTON_NOT_CONVERGED = 1, NEWTON_LINSOLVE_FAILED = 2, NEWTON_DEFECT_NAN = 3,
        NEWTON_LINESEARCH_FAILED = 4 };
+void membrane_flux_terms(const Problem& p, int i, const double* uglob, double* out15);
 void newton(Problem& p, double* u, const NewtonOpts& o, const Comm* comm, NewtonResult& res);
 double line_search(size_t n, double* u, const double* z, double* prev_u, double cur_defect, double prev_defect,
                    int maxit, const std::function<double()>& eval, std::vector<double>* trace);

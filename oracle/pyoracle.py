@@ -96,6 +96,7 @@ def ref_operator_lib():
     R.ax1ref_local_operator.argtypes = [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p, c_double_p,
                                         C.c_int, c_double_p, c_double_p]
     R.ax1ref_rownorm.argtypes = [C.c_int, c_int_p, c_int_p, c_double_p, c_double_p]
+    R.ax1ref_membrane_flux_terms.argtypes = [C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p]
     R.ax1ref_elec_alpha_boundary.argtypes = [c_double_p, C.c_int, c_double_p, c_double_p, c_int_p, c_double_p, C.c_int,
                                              c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double,
                                              c_double_p]
@@ -153,6 +154,7 @@ def lib():
     L.ax1o_create.argtypes = [C.POINTER(Config), C.c_int, C.c_int, c_double_p, c_double_p, C.c_int,
                               C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]
     L.ax1o_destroy.argtypes = [C.c_void_p]
+    L.ax1o_membrane_flux_terms.argtypes = [C.c_void_p, c_double_p, c_double_p]
     L.ax1o_line_search.argtypes = [C.c_int, c_double_p, c_double_p, C.c_double, C.c_double, C.c_int, DEFECT_CB,
                                    C.c_void_p, c_double_p, C.c_int, c_int_p]
     L.ax1o_line_search.restype = C.c_double
@@ -331,6 +333,13 @@ class Problem:
         if lib().ax1o_cell_jacobian(self.h, int(i), int(j), int(which), _dp(f64(xl)), float(weight), _dp(out)):
             raise RuntimeError(lib().ax1o_last_error().decode())
         return out.reshape(16, 16)
+
+    def membrane_flux_terms(self, u):
+        """[5 terms][3 ions][nx]: total, diffusion term, drift term, leak, voltage gated (see ax1_oracle.h)."""
+        out = np.zeros(15 * self.nx)
+        if lib().ax1o_membrane_flux_terms(self.h, _dp(f64(u)), _dp(out)):
+            raise RuntimeError(lib().ax1o_last_error().decode())
+        return out.reshape(5, 3, self.nx)
 
     def residual(self, u, with_abs=False):
         r = np.zeros(self.n)

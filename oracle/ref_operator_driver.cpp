@@ -564,6 +564,65 @@ int ax1ref_elec_alpha_boundary(const double* cell, int from_cytosol, const doubl
   }
 }
 
+// MembraneFluxGridFunctionImplicit::evaluate (membranefluxgridfunction_implicit.hh:83-361) alone, for its five
+// output terms (FluxTerms: 0 total, 1 diffusion term, 2 drift term, 3 leak channels, 4 voltage-gated channels) --
+// what acme2_cyl_output.hh:1215-1410 writes as memb_flux / memb_flux_diff_term / ... per ion. The potential and the
+// concentrations at this side's face centre are handed in (the `implicit` overload), the opposite side through
+// `memb` as in ax1ref_elec_alpha_boundary. out15[term * 3 + ion].
+int ax1ref_membrane_flux_terms(int from_cytosol, const double* upot_ucon4, const double* memb, const double* geff,
+                               const double* equil, double temperature, double* out15) {
+  try {
+    const double cell[4] = {0.0, 1.0, 0.0, 1.0};
+    const double phys[7] = {80.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1e-6};
+    const int valence[3] = {1, 1, -1};
+    const double nodevol4[4] = {1.0, 1.0, 1.0, 1.0};
+    const double stim[7] = {0, 0, 0, 0, 0, 0, 0};
+    Setup S(cell, phys, valence, nodevol4, 0, stim, from_cytosol ? CYTOSOL : ES);
+    S.ph.electro = Electrolyte<double>(80.0, temperature, con_mol, 1e-9);
+    S.ph.prm.equil = equil[0] != 0.0;
+    S.ph.prm.general.num["dummy_value"] = equil[3];
+    typedef Physics::ChannelSet CS;
+    CS& cs = S.ph.channels;
+    cs.addChannel(Dune::shared_ptr<Channel<double, ChVec> >(new LeakChannel<double, ChVec>(Na)));
+    cs.addChannel(Dune::shared_ptr<Channel<double, ChVec> >(new LeakChannel<double, ChVec>(K)));
+    cs.addChannel(Dune::shared_ptr<Channel<double, ChVec> >(new NavChannel<double, ChVec>()));
+    cs.addChannel(Dune::shared_ptr<Channel<double, ChVec> >(new KvChannel<double, ChVec>()));
+    const int elem = 7;
+    cs.addMembraneElement(elem);
+    cs.resize();
+    for (int k = 0; k < cs.size(); ++k) cs.getChannelPtr(k)->init();
+    ChVec ones(1); ones = 1.0;
+    for (int k = 0; k < 4; ++k) {
+      cs.setConductance(k, elem, geff[k]);
+      if (k < 2) cs.setRatio(k, elem, 1.0);
+      else for (int g = 0; g < cs.getChannel(k).numGatingParticles(); ++g) cs.getChannelPtr(k)->setGatingParticle(g, ones);
+    }
+    S.flux.reset(new MembFlux(S.dgfCon, S.dgfPot, S.ph, S.sol, equil[2]));
+    S.flux->time = equil[1];
+    Intersection is;
+    is.geo.x0 = cell[0]; is.geo.x1 = cell[1]; is.geo.y = from_cytosol ? cell[3] : cell[2];
+    is.gii.eta = from_cytosol ? 1.0 : 0.0;
+    is.in = &S.e;
+    is.ny = from_cytosol ? 1.0 : -1.0;
+    is.y_opposite = memb[0]; is.pot_opposite = memb[1];
+    for (int j = 0; j < 3; ++j) is.con_opposite[j] = memb[2 + j];
+    is.ext_surface = memb[5];
+    is.index = elem;
+    Dune::FieldVector<double, 1> uPot(upot_ucon4[0]);
+    Dune::FieldVector<double, 3> uCon;
+    for (int j = 0; j < 3; ++j) uCon[j] = upot_ucon4[1 + j];
+    Dune::FieldVector<double, 1> xloc(0.5);
+    for (int term = 0; term < 5; ++term) {
+      Dune::FieldVector<double, 3> y(0.0);
+      S.flux->evaluate(is, xloc, y, term, -1, true, uPot, uCon);
+      for (int j = 0; j < 3; ++j) out15[3 * term + j] = y[j];
+    }
+    return 0;
+  } catch (std::exception&) {
+    return 1;
+  }
+}
+
 // RowNormPreconditioner<GV, 4>(A, b) (rownorm_preconditioner.hh:65-155) on a block CSR matrix with 4 x 4 blocks given
 // as rowptr / col / vals (16 doubles per block, row-major) and the right-hand side r (4 per block row); in place.
 int ax1ref_rownorm(int n, const int* rowptr, const int* col, double* vals, double* r) {

@@ -676,6 +676,25 @@ def test_ilu_apply_ragged_sizes(oracle, axlib, nx, slab_w, fill):
     dev.close()
 
 
+@pytest.mark.parametrize("name", ["paper_like", "equilibration"])
+def test_membrane_flux_output_terms_parity(oracle, axlib, name):
+    """ax1gpu_membrane_flux_terms: the five per-ion output terms of the flux grid function (total, diffusion term,
+    drift term, leak, voltage gated) of a perturbed iterate after a gating step, against the oracle's restatement
+    (itself held to the reference's compiled MembraneFluxGridFunctionImplicit in tests/test_reference_pins.py)."""
+    s = small_setup(**SETUPS[name])
+    dev, P, u0 = _both(oracle, axlib, s, t=399.0)
+    for obj in (dev, P):
+        obj.accept_state()
+        obj.update_state(u0 * (1.0 + 1e-3))
+    u = u0 * (1.0 + 1e-2 * np.random.default_rng(8).standard_normal(u0.shape))
+    tg, to = dev.membrane_flux_terms(u), P.membrane_flux_terms(u)
+    assert tg.shape == (5, 3, s["nx"]) and np.abs(to[0, :2]).min() > 0
+    scale = np.abs(to).max(axis=(0, 2), keepdims=True) + 1e-300
+    assert np.max(np.abs(tg - to) / scale) < 1e-12
+    assert np.all(tg[:, 2] == 0.0)
+    dev.close()
+
+
 _FACTOR_VARIANT_SCRIPT = """
 import sys, numpy as np
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")

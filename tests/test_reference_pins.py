@@ -555,3 +555,40 @@ def test_global_jacobian_is_scatter_of_reference_element_jacobians(oracle, refop
     rel = np.abs(J_py - J_or).max(axis=2) / (scale[rowof] + 1e-300)        # per (block, scalar row)
     assert rel[keep[rowof]].max() < 1e-13, rel[keep[rowof]].max()
     assert keep.sum() > 0.9 * keep.size
+
+
+@pytest.mark.parametrize("variant", ["hh", "equilibration"])
+def test_membrane_flux_output_terms_against_reference_flux_class(oracle, refop, variant):
+    """The five per-ion output terms of MembraneFluxGridFunctionImplicit::evaluate (total, diffusion term, drift term,
+    leak, voltage-gated; membranefluxgridfunction_implicit.hh:42, 83-361 -- the data behind memb_flux*.dat /
+    the HDF5 datasets of acme2_cyl_output.hh:1215-1410), evaluated by the reference's own class on the face-centre
+    values of both interface edges: the oracle's membrane_flux_terms agrees to rounding in every column."""
+    s = small_setup(nx=6, equilibration=(variant == "equilibration"))
+    P = oracle_problem(oracle, s)
+    u0, t, dt = s["u0"], 399.0, 1.0
+    P.set_time(t, dt); P.set_uold(u0); P.update_state(u0); P.accept_state()
+    P.update_state(u0 * (1.0 + 1e-3))                 # a gating step away from the steady state
+    rng = np.random.default_rng(5)
+    u = u0 * (1.0 + 1e-2 * rng.standard_normal(u0.shape))
+    mine = P.membrane_flux_terms(u)
+    st = P.channel_state(new=True).reshape(5, -1)
+    nvx, y, jm, p = s["nx"] + 1, s["y"], P.jm, s["params"]
+    assert np.abs(mine[0, :2]).min() > 0 and np.all(mine[:, 2] == 0.0)       # Cl has no channel
+    if variant == "equilibration":
+        assert np.all(mine[4] == 0.0)                                          # voltage-gated channels are off
+    else:
+        assert np.abs(mine[4, :2]).min() > 0
+    for i in range(s["nx"]):
+        cyt = 0.5 * u[4 * (i + nvx * jm):][:4] + 0.5 * u[4 * (i + 1 + nvx * jm):][:4]
+        es = 0.5 * u[4 * (i + nvx * (jm + 1)):][:4] + 0.5 * u[4 * (i + 1 + nvx * (jm + 1)):][:4]
+        memb = np.array([y[jm + 1], es[3], es[0], es[1], es[2], 1.0])
+        gl, gn, gk = s["g_leak"][i], s["g_nav"][i], s["g_kv"][i]
+        geff = np.array([gl * st[0, i], gl * st[1, i], gn * st[2, i] ** 3 * st[3, i], gk * st[4, i] ** 4])
+        equil = np.array([p["do_equilibration"], t, p["t_equilibrium"], p["dummy_value"]], dtype=np.float64)
+        uin = np.array([cyt[3], cyt[0], cyt[1], cyt[2]])
+        out = np.zeros(15)
+        assert refop.ax1ref_membrane_flux_terms(1, _dp(uin), _dp(memb), _dp(geff), _dp(equil), 279.45, _dp(out)) == 0
+        ref = out.reshape(5, 3)
+        scale = np.abs(ref).max(axis=0, keepdims=True) + 1e-300
+        assert np.max(np.abs(ref - mine[:, :, i]) / scale) < 1e-14, i
+        assert np.allclose(ref[0], ref[2] - ref[1], rtol=1e-12, atol=0) and np.allclose(ref[0], ref[3] + ref[4], rtol=1e-12, atol=0)
