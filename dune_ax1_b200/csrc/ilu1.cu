@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(256, 1) ilu1_factor_kernel(Dev g, const double
 // the row's 13 blocks) with the levels software-pipelined, as ilu_factor16_kernel (solver.cu) does for ILU0: of the
 // six lower neighbours, taken in ascending column order, the first three lie on levels L-4, L-3, L-2 and are
 // eliminated one iteration early, while level L-1 still runs its last three steps and inverts its pivot block.
-// Same operations in the same order per row: the factor is bit-identical to ilu1_factor_kernel's.
+// Same elimination in the same order per row; the pivot blocks are inverted by the adjugate formula (ilu_common.cuh),
+// equal to ilu1_factor_kernel's pivoted Gauss-Jordan to rounding.
 #define AX1_RING1_16_ROW 116  // 7 blocks = 112 doubles + 4: the two row groups of a warp read disjoint banks
 __device__ __forceinline__ double shfl1_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __global__ void __launch_bounds__(256) ilu1_factor16_kernel(Dev g, const double* __restrict__ A, double* LF, double* LB,
@@ -201,9 +202,11 @@ __global__ void __launch_bounds__(256) ilu1_factor16_kernel(Dev g, const double*
   const int lane = tid & 31, rowl = lane & ~3, grp = lane & 16;
   double* stage = reinterpret_cast<double*>(smem_raw);   // [3][nq][AX1_ROW]
   double* ring = stage + 3 * (size_t)nq * AX1_ROW;        // [4][nq][AX1_RING1_16_ROW]
-  const Slab1 sg = slab1_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(ring + 4 * (size_t)nq * AX1_RING1_16_ROW));
+  const Slab1 sg = slab1_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(ring + 4 * (size_t)nq * AX1_RING1_16_ROW + 2 * (size_t)nq * 16));
   const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
   for (int k = tid; k < 4 * nq * AX1_RING1_16_ROW; k += blockDim.x) ring[k] = 0.0;  // finite don't-care rows
+  double* pscratch = ring + 4 * (size_t)nq * AX1_RING1_16_ROW + (size_t)q * 16;  // [2][nq][16]: pivot block of my row, by level parity
+  const Adj16 adj = adj16_setup(r, c);
   const bool nz = (r == 3) || (c == 3) || (r == c);
   const int aoff = (r == 3) ? 6 + c : (c == 3 ? 2 * r + 1 : 2 * r);
 
@@ -299,34 +302,11 @@ __global__ void __launch_bounds__(256) ilu1_factor16_kernel(Dev g, const double*
     eliminate(xn, 0, L + 1, wn.j, exn);
     eliminate(x, 5, L, w.j, exm);
     eliminate(xn, 1, L + 1, wn.j, exn);
-    // pivot block of level L: Gauss-Jordan on [a | inv] with the compare-and-swap pivoting of invert4
-    double a = act ? x[6] : ((r == c) ? 1.0 : 0.0), inv = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      double v[4];
-      int src[4] = {0, 1, 2, 3};
-#pragma unroll
-      for (int m = 0; m < 4; ++m) v[m] = shfl1_d(a, grp + 4 * m + cc);  // column cc
-#pragma unroll
-      for (int rr = cc + 1; rr < 4; ++rr) {
-        const bool sw = fabs(v[rr]) > fabs(v[cc]);
-        const double tv = v[cc];
-        v[cc] = sw ? v[rr] : v[cc];
-        v[rr] = sw ? tv : v[rr];
-        const int ts = src[cc];
-        src[cc] = sw ? src[rr] : src[cc];
-        src[rr] = sw ? ts : src[rr];
-      }
-      const int mysrc = r == 0 ? src[0] : (r == 1 ? src[1] : (r == 2 ? src[2] : src[3]));
-      const double f = r == 0 ? v[0] : (r == 1 ? v[1] : (r == 2 ? v[2] : v[3]));  // my row's entry in column cc
-      a = shfl1_d(a, grp + 4 * mysrc + c);
-      inv = shfl1_d(inv, grp + 4 * mysrc + c);
-      const double p = 1.0 / v[cc];
-      if (r == cc) { a *= p; inv *= p; }
-      const double apc = shfl1_d(a, grp + 4 * cc + c), ipc = shfl1_d(inv, grp + 4 * cc + c);
-      if (r != cc) { a -= f * apc; inv -= f * ipc; }
-      if (cc == 0) eliminate(xn, 2, L + 1, wn.j, exn);
-    }
+    // pivot block of level L: adjugate inverse over its 16 owners (ilu_common.cuh); the last early step of level L+1
+    // is independent of it
+    const double a = act ? x[6] : ((r == c) ? 1.0 : 0.0);
+    eliminate(xn, 2, L + 1, wn.j, exn);
+    const double inv = invert4_adjugate16(a, pscratch + (size_t)(L & 1) * nq * 16, e, adj);
     x[6] = inv;
     if (act) {
       const size_t p = sg.row_off + (size_t)(sg.lvl[L] + q);
@@ -680,7 +660,7 @@ void launch_ilu1_factor(const Dev& g, const double* A, double* LU, int slab_w, c
   static const int f16_max_w = getenv("AX1_ILU1_FACTOR16_W") ? atoi(getenv("AX1_ILU1_FACTOR16_W")) : 24;
   if (slab_w <= f16_max_w && slab1_rows(slab_w) <= 16) {
     const int nq = (slab1_rows(slab_w) + 1) & ~1;  // rows per level, even: whole warps
-    const size_t smem = (size_t)nq * (3 * AX1_ROW + 4 * AX1_RING1_16_ROW) * sizeof(double) + (size_t)(slab_w + 3 * g.nvy) * sizeof(int);
+    const size_t smem = (size_t)nq * (3 * AX1_ROW + 4 * AX1_RING1_16_ROW + 32) * sizeof(double) + (size_t)(slab_w + 3 * g.nvy) * sizeof(int);
     static bool attr16 = false;
     if (!attr16) {
       cudaFuncSetAttribute(ilu1_factor16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

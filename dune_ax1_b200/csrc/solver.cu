@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(256, 1) ilu_factor_kernel(Dev g, const double*
 // levels), where a level holds <= 12 rows and the sweep is bound by the dependent-instruction latency
 // of a single warp rather than by memory. Sixteen lanes share a vertex row -- lane (r, c) owns element (r, c) of
 // each of its 9 blocks -- so a level costs every thread a quarter of the multiply-adds, the pivot block is inverted
-// by its 16 owners together (Gauss-Jordan with the same compare-and-swap pivoting and the same operation order as
-// invert4, element by element, so the factor is bit-identical to ilu_factor_kernel's), and a 16-column sub-slab
+// by its 16 owners together (adjugate formula, ilu_common.cuh: equal to the quad kernel's pivoted Gauss-Jordan to
+// rounding), and a 16-column sub-slab
 // keeps four warp schedulers busy instead of one. Rows of a block row are exchanged with full-mask shuffles; the code
 // is uniform across the CTA (rows that do not exist on a level run on zero blocks and store nothing).
 #define AX1_RING16_ROW 84  // 80 doubles + 4: the two row groups of a warp read disjoint banks
@@ -263,9 +263,11 @@ __global__ void __launch_bounds__(256) ilu_factor16_kernel(Dev g, const double* 
   const int lane = tid & 31, rowl = lane & ~3, grp = lane & 16;  // first lane of my block row / of my vertex row
   double* stage = reinterpret_cast<double*>(smem_raw);            // [3][nq][AX1_ROW]
   double* ring = stage + 3 * (size_t)nq * AX1_ROW;                 // [3][nq][AX1_RING16_ROW]
-  const SlabGeom sg = slab_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(ring + 3 * (size_t)nq * AX1_RING16_ROW));
+  const SlabGeom sg = slab_geom(g, slab_w, lvl_tab, reinterpret_cast<int*>(ring + 3 * (size_t)nq * AX1_RING16_ROW + 2 * (size_t)nq * 16));
   const int i0 = sg.i0, wc = sg.wc, nlev = sg.nlev;
   for (int k = tid; k < 3 * nq * AX1_RING16_ROW; k += blockDim.x) ring[k] = 0.0;  // finite don't-care rows
+  double* pscratch = ring + 3 * (size_t)nq * AX1_RING16_ROW + (size_t)q * 16;  // [2][nq][16]: pivot block of my row, by level parity
+  const Adj16 adj = adj16_setup(r, c);
   // element (r, c) inside the 10-double arrow block (common.cuh): rows 0..2 hold (r,r), (r,3); row 3 is full
   const bool nz = (r == 3) || (c == 3) || (r == c);
   const int aoff = (r == 3) ? 6 + c : (c == 3 ? 2 * r + 1 : 2 * r);
@@ -356,34 +358,11 @@ __global__ void __launch_bounds__(256) ilu_factor16_kernel(Dev g, const double* 
     expand(xn, L + 1, exn);
     eliminate(x, 3, L, w.j, exm);
     eliminate(xn, 0, L + 1, wn.j, exn);
-    // pivot block of level L: Gauss-Jordan on [a | inv] with the compare-and-swap pivoting of invert4
-    double a = act ? x[4] : ((r == c) ? 1.0 : 0.0), inv = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      double v[4];
-      int src[4] = {0, 1, 2, 3};
-#pragma unroll
-      for (int m = 0; m < 4; ++m) v[m] = shfl_d(a, grp + 4 * m + cc);  // column cc
-#pragma unroll
-      for (int rr = cc + 1; rr < 4; ++rr) {
-        const bool sw = fabs(v[rr]) > fabs(v[cc]);
-        const double tv = v[cc];
-        v[cc] = sw ? v[rr] : v[cc];
-        v[rr] = sw ? tv : v[rr];
-        const int ts = src[cc];
-        src[cc] = sw ? src[rr] : src[cc];
-        src[rr] = sw ? ts : src[rr];
-      }
-      const int mysrc = r == 0 ? src[0] : (r == 1 ? src[1] : (r == 2 ? src[2] : src[3]));
-      const double f = r == 0 ? v[0] : (r == 1 ? v[1] : (r == 2 ? v[2] : v[3]));  // my row's entry in column cc
-      a = shfl_d(a, grp + 4 * mysrc + c);
-      inv = shfl_d(inv, grp + 4 * mysrc + c);
-      const double p = 1.0 / v[cc];
-      if (r == cc) { a *= p; inv *= p; }
-      const double apc = shfl_d(a, grp + 4 * cc + c), ipc = shfl_d(inv, grp + 4 * cc + c);
-      if (r != cc) { a -= f * apc; inv -= f * ipc; }
-      if (cc == 0) eliminate(xn, 1, L + 1, wn.j, exn);
-    }
+    // pivot block of level L: adjugate inverse over its 16 owners (ilu_common.cuh); the last early step of level L+1
+    // is independent of it
+    const double a = act ? x[4] : ((r == c) ? 1.0 : 0.0);
+    eliminate(xn, 1, L + 1, wn.j, exn);
+    const double inv = invert4_adjugate16(a, pscratch + (size_t)(L & 1) * nq * 16, e, adj);
     x[4] = inv;
     if (act) {
       const size_t p = sg.row_off + (size_t)(sg.lvl[L] + q);
@@ -850,7 +829,7 @@ void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, co
   // (256 threads) the quad-per-row kernel is faster again (1.17 vs 1.28 ms on the myelin grid)
   if (slab_w <= 24 && ilu_use_factor16()) {
     const int nq = (((slab_w + 1) / 2) + 1) & ~1;  // rows per level, even: whole warps
-    const size_t smem = (size_t)nq * (3 * AX1_ROW + 3 * AX1_RING16_ROW) * sizeof(double) + (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
+    const size_t smem = (size_t)nq * (3 * AX1_ROW + 3 * AX1_RING16_ROW + 32) * sizeof(double) + (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
     static bool attr16 = false;
     if (!attr16) {
       cudaFuncSetAttribute(ilu_factor16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -536,8 +536,9 @@ def test_gmres_parity(oracle, axlib, restart, red):
     assert np.max(np.abs(rg - (r - P.spmv(Jo, zg)))) <= 1e-9 * np.max(np.abs(r))
     # the BiCGStab backend reaches the same solution
     zb, _, resb = dev.solve(r, 1e-12, maxit=600, slab_w=4, fill=0)
-    # (ill-conditioned system: two solvers that both reduce their residual norm by 1e-10 agree to ~1e-6)
-    assert resb.converged == 1 and np.max(np.abs(zg - zb)) <= max(1e-5, 1e3 * red) * np.max(np.abs(zb))
+    # (ill-conditioned, unequilibrated system: two solvers that both reduce their residual norm by 1e-10 agree to
+    # ~1e-5 of the largest entry: 1.06e-5 with the adjugate pivot inverse of the narrow-slab kernel, < 1e-5 before)
+    assert resb.converged == 1 and np.max(np.abs(zg - zb)) <= max(3e-5, 1e3 * red) * np.max(np.abs(zb))
     # maxit exhausted -> not converged, no error
     zq, _, resq = dev.solve_gmres(r, 1e-30, restart=restart, maxit=9, slab_w=4, fill=0)
     assert resq.converged == 0 and resq.iterations == 9
@@ -714,10 +715,11 @@ dev.close()
 """
 
 
-def test_ilu_factor_kernel_variants_bit_identical(axlib, tmp_path):
+def test_ilu_factor_kernel_variants_agree(axlib, tmp_path):
     """Narrow sub-slabs are factorised by ilu_factor16_kernel / ilu1_factor16_kernel (16 lanes per vertex row, levels
-    software-pipelined), wide ones by ilu_factor_kernel / ilu1_factor_kernel (one quad per row): same operations in
-    the same order, so the preconditioner must not change by a single bit when the environment forces the quad
+    software-pipelined, pivot blocks inverted by the adjugate formula), wide ones by ilu_factor_kernel /
+    ilu1_factor_kernel (one quad per row, pivoted Gauss-Jordan): same elimination in the same order, pivot inverses
+    equal to rounding, so the preconditioner must not change beyond 1e-10 when the environment forces the quad
     kernels (compared through the sweep's output), for ILU0 and ILU(1)."""
     import os, subprocess, sys
     root = str(__import__("pathlib").Path(__file__).resolve().parents[1])
@@ -727,7 +729,9 @@ def test_ilu_factor_kernel_variants_bit_identical(axlib, tmp_path):
         env = dict(os.environ, AX1_ILU_FACTOR16=v, AX1_ILU1_FACTOR16_W="24" if v == "1" else "0")
         subprocess.check_call([sys.executable, "-c", _FACTOR_VARIANT_SCRIPT, root, f], env=env, timeout=600)
         outs.append(np.load(f))
-    assert np.all(np.isfinite(outs[0])) and np.array_equal(outs[0], outs[1])
+    assert np.all(np.isfinite(outs[0]))
+    scale = np.abs(outs[1]).max(axis=1, keepdims=True)
+    assert np.max(np.abs(outs[0] - outs[1]) / scale) < 1e-10
 
 
 def test_error_behaviour(oracle, axlib):
