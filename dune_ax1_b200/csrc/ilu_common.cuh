@@ -51,6 +51,21 @@ __device__ __forceinline__ void invert4(double a[4][4], double inv[4][4]) {
   }
 }
 
+// shared-memory access through 32-bit shared-window addresses (no generic-pointer arithmetic on the sweeps' per-level path)
+__device__ __forceinline__ double2 lds_d2(unsigned a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ double lds_d(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_d(unsigned a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
 // Inverse of a 4 x 4 pivot block held one element per lane by 16 consecutive lanes (lane e = 4 r + c owns a[r][c]):
 // adjugate formula, inv[r][c] = (-1)^(r+c) det(minor without row c and column r) / det(a). The block goes through a
 // 16-double shared-memory scratch; every lane reads its 3 x 3 minor in cyclic row / column order (an even permutation

@@ -599,47 +599,53 @@ __global__ void __launch_bounds__(160) ilu_apply_tma_kernel(Dev g, const double*
     const bool lane0 = (tid & 31) == 0, one_warp = nt == 32;
     const bool okE = 2 * q < wc, okO = 2 * q + 1 < wc;                 // my column at even / odd levels exists
     const int capE = ((wc + 1) >> 1) - 1, capO = (wc >> 1) - 1;        // row index in the stage: min(m, cap) - q
-    const double* stage_r = stage + r * 4;
-    const double* rhs_t = stageR + tid;
-    double* ring_own = ring + (q + 1) * 4 + r;
-    const double* ring_q = ring + (q + 1) * 4;
-    double* vE = v_out + 4 * (size_t)(i0 + 2 * q) + r;               // my even column; the odd one is 4 doubles on
-    const size_t vstride = 4 * (size_t)g.nvx;
-    const size_t stage_stride = (size_t)nq * 80;
-    // ring neighbour quads (relative to my own slot q + 1) per level parity: column il + di lives in quad (il + di) >> 1
+    // Shared memory is addressed through 32-bit shared-window addresses (ld/st.shared), and what changes from level
+    // to level is kept as running byte offsets -- stage, right-hand side, barrier, ring slots, the global output
+    // element -- so the per-level address arithmetic is a handful of 32-bit adds instead of generic-pointer math.
+    const unsigned stage_u = smem_u32(stage) + (unsigned)r * 32u;      // my scalar row inside a block row
+    const unsigned rhs_u = smem_u32(stageR) + (unsigned)tid * 8u;
+    const unsigned ringq_u = smem_u32(ring) + (unsigned)(q + 1) * 32u; // my quad's 4 values inside a ring slot
+    const unsigned ringown_u = ringq_u + (unsigned)r * 8u;
+    const unsigned stage_stride_b = (unsigned)nq * 640u, rhs_stride_b = (unsigned)nt * 8u;
+    const unsigned rstride_b = (unsigned)rstride * 8u;
+    const long long vstride = 4LL * g.nvx;
+    const long long vbase = 4LL * (i0 + 2 * q) + r;                    // my even column, grid row 0
+    // ring neighbour quads (relative to my own slot) per level parity: column il + di lives in quad (il + di) >> 1
     //   forward  s = 0..3: di = -1, 0, +1, -1      backward s = 5..8: di = +1, -1, 0, +1
-    //   forward  {-4, 0, 0, -4} (even) {0, 0, 4, 0} (odd);  backward {0, -4, 0, 0} (even) {4, 0, 0, 4} (odd)
+    //   forward  {-1, 0, 0, -1} (even) {0, 0, +1, 0} (odd) quads;  backward {0, -1, 0, 0} (even) {+1, 0, 0, +1} (odd)
     int st = 0;
-    unsigned ph = 0;
-    int so0 = 0, so1 = 3 * rstride, so2 = 2 * rstride, so3 = rstride;  // ring slot offsets of levels L, L-1, L-2, L-3
+    unsigned ph = 0, st_stage = 0, st_rhs = 0, st_bar = 0;
+    unsigned so0 = 0, so1 = 3 * rstride_b, so2 = 2 * rstride_b, so3 = rstride_b;  // ring slots of levels L, L-1, L-2, L-3
+    auto advance = [&]() {
+      st_stage += stage_stride_b; st_rhs += rhs_stride_b; st_bar += 8u;
+      if (++st == D) { st = 0; st_stage = 0; st_rhs = 0; st_bar = 0; ph ^= 1u; }
+    };
 
     // ---------------- forward: y = L^-1 d ----------------
+    long long voff = vbase - vstride * q;                              // element of (column 2q + b, row m - q), L = 0
     for (int L = 0; L < nlev; ++L) {
       const int b = L & 1, m = L >> 1, j = m - q;
-      mbar_wait_a(full0 + 8u * st, ph);
+      mbar_wait_a(full0 + st_bar, ph);
       const bool act = (b ? okO : okE) && (unsigned)j < (unsigned)g.nvy;
       double2 lv[4][2], yv[4][2];
       double acc = 0.0;
       if (act) {
-        const double* lrow = stage_r + (size_t)st * stage_stride + (size_t)(min(m, b ? capO : capE) - q) * 64;
-        const double* y0 = ring_q + so3 + (b ? 0 : -4);   // (-1,-1): level L-3
-        const double* y1 = ring_q + so2;                   // ( 0,-1): level L-2
-        const double* y2 = ring_q + so1 + (b ? 4 : 0);    // (+1,-1): level L-1
-        const double* y3 = ring_q + so1 + (b ? 0 : -4);   // (-1, 0): level L-1
+        const unsigned la = stage_u + st_stage + (unsigned)(min(m, b ? capO : capE) - q) * 512u;
+        const unsigned y0 = ringq_u + so3 - (b ? 0u : 32u);   // (-1,-1): level L-3
+        const unsigned y1 = ringq_u + so2;                     // ( 0,-1): level L-2
+        const unsigned y2 = ringq_u + so1 + (b ? 32u : 0u);   // (+1,-1): level L-1
+        const unsigned y3 = ringq_u + so1 - (b ? 0u : 32u);   // (-1, 0): level L-1
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          lv[s][0] = *reinterpret_cast<const double2*>(lrow + s * 16);
-          lv[s][1] = *reinterpret_cast<const double2*>(lrow + s * 16 + 2);
-        }
-        yv[0][0] = *reinterpret_cast<const double2*>(y0); yv[0][1] = *reinterpret_cast<const double2*>(y0 + 2);
-        yv[1][0] = *reinterpret_cast<const double2*>(y1); yv[1][1] = *reinterpret_cast<const double2*>(y1 + 2);
-        yv[2][0] = *reinterpret_cast<const double2*>(y2); yv[2][1] = *reinterpret_cast<const double2*>(y2 + 2);
-        yv[3][0] = *reinterpret_cast<const double2*>(y3); yv[3][1] = *reinterpret_cast<const double2*>(y3 + 2);
-        acc = rhs_t[st * nt];
+        for (int s = 0; s < 4; ++s) { lv[s][0] = lds_d2(la + s * 128u); lv[s][1] = lds_d2(la + s * 128u + 16u); }
+        yv[0][0] = lds_d2(y0); yv[0][1] = lds_d2(y0 + 16u);
+        yv[1][0] = lds_d2(y1); yv[1][1] = lds_d2(y1 + 16u);
+        yv[2][0] = lds_d2(y2); yv[2][1] = lds_d2(y2 + 16u);
+        yv[3][0] = lds_d2(y3); yv[3][1] = lds_d2(y3 + 16u);
+        acc = lds_d(rhs_u + st_rhs);
       }
       // hand the stage back as soon as the operands are in registers (mbarrier.arrive releases the warp's reads)
       __syncwarp();
-      if (lane0) mbar_arrive_a(empty0 + 8u * st);
+      if (lane0) mbar_arrive_a(empty0 + st_bar);
       if (act) {
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
@@ -649,47 +655,47 @@ __global__ void __launch_bounds__(160) ilu_apply_tma_kernel(Dev g, const double*
           t += lv[s][1].y * yv[s][1].y;
           acc -= t;
         }
-        ring_own[so0] = acc;
-        vE[vstride * (size_t)j + 4 * b] = acc;
+        sts_d(ringown_u + so0, acc);
+        v_out[voff] = acc;
       }
       if (one_warp) __syncwarp();
       else named_bar_sync(1, nt);
-      if (++st == D) { st = 0; ph ^= 1u; }
-      { const int t = so3; so3 = so2; so2 = so1; so1 = so0; so0 = t; }
+      advance();
+      { const unsigned t = so3; so3 = so2; so2 = so1; so1 = so0; so0 = t; }
+      voff += b ? vstride - 4 : 4;
     }
     __syncthreads();
     // ---------------- backward: x = U^-1 y ----------------
-    // slot offsets now refer to levels L, L+1, L+2, L+3: before the loop so0 is the slot of level nlev (= nlev & 3)
-    int su0, su1, su2, su3;
+    // slot offsets now refer to levels L, L+1, L+2, L+3
+    unsigned su0, su1, su2, su3;
     {
       const int top = nlev - 1;
-      su0 = (top & 3) * rstride; su1 = ((top + 1) & 3) * rstride; su2 = ((top + 2) & 3) * rstride; su3 = ((top + 3) & 3) * rstride;
+      su0 = (unsigned)(top & 3) * rstride_b; su1 = (unsigned)((top + 1) & 3) * rstride_b;
+      su2 = (unsigned)((top + 2) & 3) * rstride_b; su3 = (unsigned)((top + 3) & 3) * rstride_b;
+      voff = vbase + vstride * ((top >> 1) - q) + 4 * (top & 1);
     }
     for (int L = nlev - 1; L >= 0; --L) {
       const int b = L & 1, m = L >> 1, j = m - q;
-      mbar_wait_a(full0 + 8u * st, ph);
+      mbar_wait_a(full0 + st_bar, ph);
       const bool act = (b ? okO : okE) && (unsigned)j < (unsigned)g.nvy;
       double2 uv[5][2], xv[4][2];
       double acc = 0.0;
       if (act) {
-        const double* urow = stage_r + (size_t)st * stage_stride + (size_t)(min(m, b ? capO : capE) - q) * 80;
-        const double* x0 = ring_q + su1 + (b ? 4 : 0);    // (+1, 0): level L+1
-        const double* x1 = ring_q + su1 + (b ? 0 : -4);   // (-1,+1): level L+1
-        const double* x2 = ring_q + su2;                   // ( 0,+1): level L+2
-        const double* x3 = ring_q + su3 + (b ? 4 : 0);    // (+1,+1): level L+3
+        const unsigned ua = stage_u + st_stage + (unsigned)(min(m, b ? capO : capE) - q) * 640u;
+        const unsigned x0 = ringq_u + su1 + (b ? 32u : 0u);   // (+1, 0): level L+1
+        const unsigned x1 = ringq_u + su1 - (b ? 0u : 32u);   // (-1,+1): level L+1
+        const unsigned x2 = ringq_u + su2;                     // ( 0,+1): level L+2
+        const unsigned x3 = ringq_u + su3 + (b ? 32u : 0u);   // (+1,+1): level L+3
 #pragma unroll
-        for (int s = 0; s < 5; ++s) {
-          uv[s][0] = *reinterpret_cast<const double2*>(urow + s * 16);
-          uv[s][1] = *reinterpret_cast<const double2*>(urow + s * 16 + 2);
-        }
-        xv[0][0] = *reinterpret_cast<const double2*>(x0); xv[0][1] = *reinterpret_cast<const double2*>(x0 + 2);
-        xv[1][0] = *reinterpret_cast<const double2*>(x1); xv[1][1] = *reinterpret_cast<const double2*>(x1 + 2);
-        xv[2][0] = *reinterpret_cast<const double2*>(x2); xv[2][1] = *reinterpret_cast<const double2*>(x2 + 2);
-        xv[3][0] = *reinterpret_cast<const double2*>(x3); xv[3][1] = *reinterpret_cast<const double2*>(x3 + 2);
-        acc = rhs_t[st * nt];
+        for (int s = 0; s < 5; ++s) { uv[s][0] = lds_d2(ua + s * 128u); uv[s][1] = lds_d2(ua + s * 128u + 16u); }
+        xv[0][0] = lds_d2(x0); xv[0][1] = lds_d2(x0 + 16u);
+        xv[1][0] = lds_d2(x1); xv[1][1] = lds_d2(x1 + 16u);
+        xv[2][0] = lds_d2(x2); xv[2][1] = lds_d2(x2 + 16u);
+        xv[3][0] = lds_d2(x3); xv[3][1] = lds_d2(x3 + 16u);
+        acc = lds_d(rhs_u + st_rhs);
       }
       __syncwarp();
-      if (lane0) mbar_arrive_a(empty0 + 8u * st);
+      if (lane0) mbar_arrive_a(empty0 + st_bar);
       if (act) {
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
@@ -706,14 +712,15 @@ __global__ void __launch_bounds__(160) ilu_apply_tma_kernel(Dev g, const double*
         xo += uv[0][0].y * __shfl_sync(qmask, acc, qb + 1);
         xo += uv[0][1].x * __shfl_sync(qmask, acc, qb + 2);
         xo += uv[0][1].y * __shfl_sync(qmask, acc, qb + 3);
-        ring_own[su0] = xo;
-        vE[vstride * (size_t)j + 4 * b] = xo;
+        sts_d(ringown_u + su0, xo);
+        v_out[voff] = xo;
         if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + 2 * q + b, j, r, xo);
       }
       if (one_warp) __syncwarp();
       else named_bar_sync(1, nt);
-      if (++st == D) { st = 0; ph ^= 1u; }
-      { const int t = su3; su3 = su2; su2 = su1; su1 = su0; su0 = t; }
+      advance();
+      { const unsigned t = su3; su3 = su2; su2 = su1; su1 = su0; su0 = t; }
+      voff -= b ? 4 : vstride - 4;
     }
   }
   if (P2P) halo_push_finish(hp, g.nvx, i0, wc);
