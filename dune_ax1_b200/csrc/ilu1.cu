@@ -517,99 +517,126 @@ __global__ void __launch_bounds__(288) ilu1_apply_tma_kernel(Dev g, const double
     __syncthreads();          // the consumers' forward results are in global memory
     for (int k = nlev; k < 2 * nlev; ++k) produce(k);
   } else {
+    // Quad q owns the vertex-column triple (3q, 3q+1, 3q+2): column 3q + L % 3 at level L, grid row L / 3 - q. The level
+    // loop is unrolled by three so that the column phase c3 is a compile-time constant (neighbour quads and block
+    // slots fold), shared memory is addressed through 32-bit shared-window addresses, and stage / barrier / phase
+    // are running values, as in ilu_apply_tma_kernel (solver.cu).
     const int q = tid >> 2, r = tid & 3;
-    const int rstride = (nq + 2) * 4;
-    auto release_stage = [&](int st) {
-      __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+    const unsigned full0 = smem_u32(full), empty0 = smem_u32(empty);
+    const bool lane0 = (tid & 31) == 0, one_warp = nt == 32;
+    const unsigned stage_u = smem_u32(stage) + (unsigned)r * 32u;
+    const unsigned rhs_u = smem_u32(stageR) + (unsigned)tid * 8u;
+    const unsigned rstride_b = (unsigned)(nq + 2) * 32u;
+    const unsigned ringq_u = smem_u32(ring) + (unsigned)(q + 1) * 32u;
+    const unsigned ringown_u = ringq_u + (unsigned)r * 8u;
+    const unsigned stage_stride_b = (unsigned)nq * 896u, rhs_stride_b = (unsigned)nt * 8u;
+    const long long vstride = 4LL * g.nvx;
+    const long long vbase = 4LL * (i0 + 3 * q) + r;                    // column 3q, grid row 0
+    int cap[3];
+    bool ok[3];
+#pragma unroll
+    for (int c3 = 0; c3 < 3; ++c3) { cap[c3] = (wc - c3 + 2) / 3 - 1; ok[c3] = 3 * q + c3 < wc; }  // stage row = min(L/3, cap) - q
+    int st = 0;
+    unsigned ph = 0, st_stage = 0, st_rhs = 0, st_bar = 0;
+    auto advance = [&]() {
+      st_stage += stage_stride_b; st_rhs += rhs_stride_b; st_bar += 8u;
+      if (++st == D) { st = 0; st_stage = 0; st_rhs = 0; st_bar = 0; ph ^= 1u; }
     };
     auto level_done = [&]() {
-      if (nt == 32) __syncwarp();
+      if (one_warp) __syncwarp();
       else named_bar_sync(1, nt);
     };
     // ---------------- forward: y = L^-1 d ----------------
-    for (int L = 0; L < nlev; ++L) {
-      const int st = L % D;
-      mbar_wait(&full[st], (unsigned)(L / D) & 1u);
-      const int il = 3 * q + L % 3, tj = L - il, j = tj / 3;
-      const bool act = il < wc && tj >= 0 && j < g.nvy;
-      double2 lv[6][2], yv[6][2];
-      double acc = 0.0;
-      if (act) {
-        const double* lrow = stage + ((size_t)st * nq * 112) + (size_t)(j - lev1_jlo(L, wc)) * 96 + r * 4;
+    for (int L0 = 0, m3 = 0; L0 < nlev; L0 += 3, ++m3) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          const int di = P1_DI(k), dj = P1_DJ(k);
-          const int Ln = L + di + 3 * dj;
-          const double* yp = ring + (Ln & 7) * rstride + ((il + di + 3) / 3) * 4;
-          lv[k][0] = *reinterpret_cast<const double2*>(lrow + k * 16);
-          lv[k][1] = *reinterpret_cast<const double2*>(lrow + k * 16 + 2);
-          yv[k][0] = *reinterpret_cast<const double2*>(yp);
-          yv[k][1] = *reinterpret_cast<const double2*>(yp + 2);
-        }
-        acc = stageR[st * nt + tid];
-      }
-      release_stage(st);
-      if (act) {
+      for (int c3 = 0; c3 < 3; ++c3) {
+        const int L = L0 + c3;
+        if (L >= nlev) break;
+        const int j = m3 - q;
+        mbar_wait_a(full0 + st_bar, ph);
+        const bool act = ok[c3] && (unsigned)j < (unsigned)g.nvy;
+        double2 lv[6][2], yv[6][2];
+        double acc = 0.0;
+        if (act) {
+          const unsigned la = stage_u + st_stage + (unsigned)(min(m3, cap[c3]) - q) * 768u;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          double t = lv[k][0].x * yv[k][0].x;
-          t += lv[k][0].y * yv[k][0].y;
-          t += lv[k][1].x * yv[k][1].x;
-          t += lv[k][1].y * yv[k][1].y;
-          acc -= t;
+          for (int k = 0; k < 6; ++k) {
+            const int di = P1_DI(k), dj = P1_DJ(k);
+            const int dq = (c3 + di + 3) / 3 - 1;                       // neighbour's quad relative to mine
+            const unsigned yp = ringq_u + ((unsigned)(L + di + 3 * dj) & 7u) * rstride_b + (unsigned)(dq * 32);
+            lv[k][0] = lds_d2(la + k * 128u); lv[k][1] = lds_d2(la + k * 128u + 16u);
+            yv[k][0] = lds_d2(yp); yv[k][1] = lds_d2(yp + 16u);
+          }
+          acc = lds_d(rhs_u + st_rhs);
         }
-        ring[(L & 7) * rstride + (q + 1) * 4 + r] = acc;
-        v_out[4 * (size_t)(i0 + il + g.nvx * j) + r] = acc;
+        __syncwarp();
+        if (lane0) mbar_arrive_a(empty0 + st_bar);
+        if (act) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            double t = lv[k][0].x * yv[k][0].x;
+            t += lv[k][0].y * yv[k][0].y;
+            t += lv[k][1].x * yv[k][1].x;
+            t += lv[k][1].y * yv[k][1].y;
+            acc -= t;
+          }
+          sts_d(ringown_u + ((unsigned)L & 7u) * rstride_b, acc);
+          v_out[vbase + 4 * c3 + vstride * j] = acc;
+        }
+        level_done();
+        advance();
       }
-      level_done();
     }
     __syncthreads();
     // ---------------- backward: x = U^-1 y ----------------
-    for (int L = nlev - 1; L >= 0; --L) {
-      const int k = 2 * nlev - 1 - L, st = k % D;
-      mbar_wait(&full[st], (unsigned)(k / D) & 1u);
-      const int il = 3 * q + L % 3, tj = L - il, j = tj / 3;
-      const bool act = il < wc && tj >= 0 && j < g.nvy;
-      double2 uv[7][2], xv[6][2];
-      double acc = 0.0;
-      if (act) {
-        const double* urow = stage + ((size_t)st * nq * 112) + (size_t)(j - lev1_jlo(L, wc)) * 112 + r * 4;
+    for (int m3 = (nlev - 1) / 3; m3 >= 0; --m3) {
 #pragma unroll
-        for (int p = 6; p < 13; ++p) {
-          uv[p - 6][0] = *reinterpret_cast<const double2*>(urow + (p - 6) * 16);
-          uv[p - 6][1] = *reinterpret_cast<const double2*>(urow + (p - 6) * 16 + 2);
-          if (p > 6) {
-            const int di = P1_DI(p), dj = P1_DJ(p);
-            const int Ln = L + di + 3 * dj;
-            const double* xp = ring + (Ln & 7) * rstride + ((il + di + 3) / 3) * 4;
-            xv[p - 7][0] = *reinterpret_cast<const double2*>(xp);
-            xv[p - 7][1] = *reinterpret_cast<const double2*>(xp + 2);
+      for (int c3 = 2; c3 >= 0; --c3) {
+        const int L = 3 * m3 + c3;
+        if (L >= nlev) continue;
+        const int j = m3 - q;
+        mbar_wait_a(full0 + st_bar, ph);
+        const bool act = ok[c3] && (unsigned)j < (unsigned)g.nvy;
+        double2 uv[7][2], xv[6][2];
+        double acc = 0.0;
+        if (act) {
+          const unsigned ua = stage_u + st_stage + (unsigned)(min(m3, cap[c3]) - q) * 896u;
+#pragma unroll
+          for (int p = 6; p < 13; ++p) {
+            uv[p - 6][0] = lds_d2(ua + (p - 6) * 128u); uv[p - 6][1] = lds_d2(ua + (p - 6) * 128u + 16u);
+            if (p > 6) {
+              const int di = P1_DI(p), dj = P1_DJ(p);
+              const int dq = (c3 + di + 3) / 3 - 1;
+              const unsigned xp = ringq_u + ((unsigned)(L + di + 3 * dj) & 7u) * rstride_b + (unsigned)(dq * 32);
+              xv[p - 7][0] = lds_d2(xp); xv[p - 7][1] = lds_d2(xp + 16u);
+            }
           }
+          acc = lds_d(rhs_u + st_rhs);
         }
-        acc = stageR[st * nt + tid];
-      }
-      release_stage(st);
-      if (act) {
+        __syncwarp();
+        if (lane0) mbar_arrive_a(empty0 + st_bar);
+        if (act) {
 #pragma unroll
-        for (int p = 0; p < 6; ++p) {
-          double t = uv[p + 1][0].x * xv[p][0].x;
-          t += uv[p + 1][0].y * xv[p][0].y;
-          t += uv[p + 1][1].x * xv[p][1].x;
-          t += uv[p + 1][1].y * xv[p][1].y;
-          acc -= t;
+          for (int p = 0; p < 6; ++p) {
+            double t = uv[p + 1][0].x * xv[p][0].x;
+            t += uv[p + 1][0].y * xv[p][0].y;
+            t += uv[p + 1][1].x * xv[p][1].x;
+            t += uv[p + 1][1].y * xv[p][1].y;
+            acc -= t;
+          }
+          const unsigned qmask = 0xFu << (tid & 28);
+          const int qb = tid & 28;
+          double xo = uv[0][0].x * __shfl_sync(qmask, acc, qb + 0);
+          xo += uv[0][0].y * __shfl_sync(qmask, acc, qb + 1);
+          xo += uv[0][1].x * __shfl_sync(qmask, acc, qb + 2);
+          xo += uv[0][1].y * __shfl_sync(qmask, acc, qb + 3);
+          sts_d(ringown_u + ((unsigned)L & 7u) * rstride_b, xo);
+          v_out[vbase + 4 * c3 + vstride * j] = xo;
+          if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + 3 * q + c3, j, r, xo);
         }
-        const unsigned qmask = 0xFu << (tid & 28);
-        const int qb = tid & 28;
-        double xo = uv[0][0].x * __shfl_sync(qmask, acc, qb + 0);
-        xo += uv[0][0].y * __shfl_sync(qmask, acc, qb + 1);
-        xo += uv[0][1].x * __shfl_sync(qmask, acc, qb + 2);
-        xo += uv[0][1].y * __shfl_sync(qmask, acc, qb + 3);
-        ring[(L & 7) * rstride + (q + 1) * 4 + r] = xo;
-        v_out[4 * (size_t)(i0 + il + g.nvx * j) + r] = xo;
-        if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + il, j, r, xo);
+        level_done();
+        advance();
       }
-      level_done();
     }
   }
   if (P2P) halo_push_finish(hp, g.nvx, i0, wc);
