@@ -42,6 +42,9 @@ def main():
     # ILU(1) per rank (slab_w >= local columns -> a single sub-slab per rank)
     dev.set_time(0.0, 1.0); dev.set_uold(s["u0"]); dev.update_state(s["u0"])
     ug1, rg1 = dev.newton(s["u0"], api.default_newton_opts(slab_w=64, ilu_fill=1, **kw))
+    # the same with narrow sub-slabs: the warp-specialised ILU(1) sweep with the fused halo push
+    dev.set_time(0.0, 1.0); dev.set_uold(s["u0"]); dev.update_state(s["u0"])
+    ug3, rg3 = dev.newton(s["u0"], api.default_newton_opts(slab_w=6, ilu_fill=1, **kw))
     # second backend: restarted GMRES preconditioned by the per-rank multigrid cycle + additive halo sum
     # (ISTLBackend_GMRES_AMG_ILU0, ax1_solverbackend.hh:73-302)
     dev.set_time(0.0, 1.0); dev.set_uold(s["u0"]); dev.update_state(s["u0"])
@@ -53,7 +56,8 @@ def main():
     dist.all_gather_object(gathered, dict(u2=ug2, its2=rg2.iterations, lin2=rg2.lin_iterations, status2=rg2.status,
                                           u=ug, z=zg, nrm=nrm, its=rg.iterations, lin=rg.lin_iterations,
                                           status=rg.status, lit=lres.iterations, mode=mode, u1=ug1,
-                                          its1=rg1.iterations, lin1=rg1.lin_iterations, status1=rg1.status))
+                                          its1=rg1.iterations, lin1=rg1.lin_iterations, status1=rg1.status,
+                                          u3=ug3, its3=rg3.iterations, lin3=rg3.lin_iterations, status3=rg3.status))
     ok = True
     if rank == 0:
         from oracle import pyoracle as O
@@ -85,6 +89,19 @@ def main():
             print("rank %d ILU(1): status %d its gpu/cpu %d/%d lin %d/%d field err %s"
                   % (r, g["status1"], g["its1"], res1[r].iterations, g["lin1"], res1[r].lin_iterations, err))
             ok &= g["status1"] == 0 and g["its1"] == res1[r].iterations
+            ok &= bool(np.all(err[:3] < 1e-8) and err[3] < 5e-7)
+        # ILU(1) on 6-column sub-slabs
+        for r in range(world):
+            probs[r].set_time(0.0, 1.0); probs[r].set_uold(us[r]); probs[r].update_state(us[r])
+        out3, res3, st3 = O.newton_mt(probs, us, O.default_newton_opts(ilu_fill=1, slab_w=6, **kw))
+        assert st3 == 0
+        for r in range(world):
+            g = gathered[r]
+            scale = np.max(np.abs(out3[r].reshape(-1, 4)), axis=0)
+            err = np.max(np.abs(g["u3"] - out3[r]).reshape(-1, 4) / scale, axis=0)
+            print("rank %d ILU(1) w6: status %d its gpu/cpu %d/%d lin %d/%d field err %s"
+                  % (r, g["status3"], g["its3"], res3[r].iterations, g["lin3"], res3[r].lin_iterations, err))
+            ok &= g["status3"] == 0 and g["its3"] == res3[r].iterations
             ok &= bool(np.all(err[:3] < 1e-8) and err[3] < 5e-7)
         # GMRES + multigrid
         for r in range(world):
