@@ -161,7 +161,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if myelin and args.slab_w == SLAB_W:
-        args.slab_w = 32 if world <= 2 else 16   # few columns per GPU: more, narrower sub-slabs keep the SMs busy
+        args.slab_w = 24 if args.ilu_fill == 1 else 16   # the library default on this grid: one-warp sub-slabs
 
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     nv_full = (args.nx + 1) * 181

@@ -41,6 +41,7 @@ struct ax1gpu_ctx {
   int nred_blocks = 0;
   // ILU
   int slab_w = 0;
+  bool slab_auto = false;      // slab_w was chosen by the library (re-derived when fill or multigrid change)
   int ilu_fill = 0;            // 0: block ILU0 (solver.cu), 1: block ILU(1), the reference default (ilu1.cu)
   int lvl_slab_w = 0;          // slab width / fill level the level tables were built for
   int lvl_fill = -1;

@@ -598,7 +598,9 @@ static int ensure_level_tables(ax1gpu_ctx* c) {
 
 // (re)select the preconditioner: fill 0 = block ILU0, fill 1 = block ILU(1) (SeqILUn with n = 1, the
 // reference default, acme2_cyl_setup.hh:764-765); the ILU(1) factor needs 13 instead of 9 blocks per row
-static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill) {
+static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill, int amg = -1) {
+  const bool use_amg = amg >= 0 ? amg != 0 : c->amg != 0;
+  bool picked_auto = false;
   if (fill < 0) fill = c->ilu_fill;
   if (fill > 1) { set_error("block ILU(n) is implemented on the device for n = 0 and n = 1"); return AX1GPU_EINVAL; }
   if (slab_w <= 0) {
@@ -608,7 +610,14 @@ static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill) {
     const int gran = fill == 1 ? 24 : 16;   // columns one warp sweeps: 8 rows per level = w/2 (ILU0) or w/3 (ILU(1))
     int w = (c->g.nvx + 295) / 296;
     w = ((w + gran - 1) / gran) * gran;
-    slab_w = c->slab_w > 0 ? c->slab_w : std::min(128, std::max(gran, w));
+    // up to four one-warp CTAs share an SM without slowing each other down, and the one-warp sweep (warp-level barrier
+    // only) is the fastest per level: on the myelin grid (7,252 columns) 16 instead of 32 columns gave 0.336 vs 0.373 ms
+    // per sweep and 16.8 vs 19.5 s for 20 converged time steps (ILU(1), 24 vs 48 columns: 23.3 vs 29.0 s)
+    // (not under the multigrid cycle, whose smoother gains more from wider sub-slabs: 12.1 vs 10.5 s there)
+    if (!use_amg && c->g.nvx <= gran * 4 * 148) w = gran;
+    // a width the caller chose explicitly earlier stays; an automatic one is re-derived (fill / multigrid may differ)
+    if (c->slab_w > 0 && !c->slab_auto) slab_w = c->slab_w;
+    else { slab_w = std::min(128, std::max(gran, w)); picked_auto = true; }
   }
   // one quad per wavefront row with <= 256-thread CTAs: levels are ceil(w/2) (ILU0) / ceil(w/3) (ILU(1)) rows wide
   const int wmax = fill == 1 ? ilu1_max_slab_w(c->g) : 128;
@@ -623,6 +632,7 @@ static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill) {
   }
   if (slab_w != c->slab_w || fill != c->ilu_fill) c->factored = false;
   c->slab_w = slab_w;
+  c->slab_auto = picked_auto;
   c->ilu_fill = fill;
   return ensure_level_tables(c);
 }
@@ -736,7 +746,7 @@ static int amg_vcycle(ax1gpu_ctx* c, const double* d, double* v) {
 }
 
 int drv_factor(ax1gpu_ctx* c, int slab_w, int fill, int amg) {
-  int rc = select_preconditioner(c, slab_w, fill);
+  int rc = select_preconditioner(c, slab_w, fill, amg);
   if (rc) return rc;
   if (amg >= 0) c->amg = amg ? 1 : 0;
   if (c->ilu_fill == 1) launch_ilu1_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);
