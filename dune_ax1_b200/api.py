@@ -71,7 +71,7 @@ class NewtonResult(C.Structure):
 class TimeLoopOpts(C.Structure):
     _fields_ = [("dtstart", C.c_double), ("max_dt", C.c_double), ("min_dt", C.c_double), ("max_dt_ap", C.c_double),
                 ("vm_ap_threshold", C.c_double), ("lower_limit", C.c_int), ("upper_limit", C.c_int),
-                ("max_restarts", C.c_int), ("adaptive", C.c_int)]
+                ("max_restarts", C.c_int), ("adaptive", C.c_int), ("restart_from_uold", C.c_int)]
 
 
 class TimeLoopState(C.Structure):

@@ -155,7 +155,9 @@ int ax1gpu_create(const ax1gpu_grid* grid, const unsigned char* cell_subdomain, 
   TRY(dev_alloc(&c->d_sums, 8));
   TRY(dev_alloc(&c->d_sc, 1));
   if (cudaMallocHost((void**)&c->h_sc, sizeof(Scalars)) != cudaSuccess ||
-      cudaMallocHost((void**)&c->h_pin, 8 * sizeof(double)) != cudaSuccess) { ax1gpu_destroy(c); set_error("cudaMallocHost failed"); return AX1GPU_ECUDA; }
+      cudaMallocHost((void**)&c->h_pin, 8 * sizeof(double)) != cudaSuccess ||
+      cudaMallocHost((void**)&c->h_err, 4 * sizeof(int)) != cudaSuccess) { ax1gpu_destroy(c); set_error("cudaMallocHost failed"); return AX1GPU_ECUDA; }
+  std::memset(c->h_err, 0, 4 * sizeof(int));
   for (int k = 0; k < 4; ++k)
     if (cudaEventCreate(&c->ev[k]) != cudaSuccess) { ax1gpu_destroy(c); set_error("cudaEventCreate failed"); return AX1GPU_ECUDA; }
   // constants (electrolyte.hh:61-67, default_config.hh:79-91)
@@ -229,6 +231,7 @@ int ax1gpu_destroy(ax1gpu_handle c) {
     if (p) cudaFree(p);
   if (c->h_sc) cudaFreeHost(c->h_sc);
   if (c->h_pin) cudaFreeHost(c->h_pin);
+  if (c->h_err) cudaFreeHost(c->h_err);
   for (int k = 0; k < 4; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -451,7 +454,10 @@ int ax1gpu_ilu_apply(ax1gpu_handle c, const double* d, double* v) {
   int rc = up(c, c->d_p, d);
   if (rc) return rc;
   if ((rc = drv_prec_apply(c, c->d_p, c->d_y2))) return rc;
-  return down(c, v, c->d_y2);
+  if (c->nranks > 1 && c->p2p.on)   // the halo exchange may have timed out: never hand stale columns back
+    AX1_CUDA(cudaMemcpyAsync(c->h_err, c->d_err, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = down(c, v, c->d_y2))) return rc;
+  return drv_check_p2p(c);
 }
 
 int ax1gpu_solve(ax1gpu_handle c, double* r, double reduction, int maxit, int slab_w, double* z, ax1gpu_lin_result* res) {
@@ -506,7 +512,7 @@ int ax1gpu_newton(ax1gpu_handle c, const ax1gpu_newton_opts* opts, double* u, ax
 void ax1gpu_timeloop_opts_default(ax1gpu_timeloop_opts* o) {
   // [timeStepping] defaults of acme2_cyl_parametertree.hh (seconds) over the default time_scale 1e-6
   o->dtstart = 1.0; o->max_dt = 50.0; o->min_dt = 0.05; o->max_dt_ap = 10.0; o->vm_ap_threshold = -50.0;
-  o->lower_limit = 3; o->upper_limit = 5; o->max_restarts = 3; o->adaptive = 1;
+  o->lower_limit = 3; o->upper_limit = 5; o->max_restarts = 3; o->adaptive = 1; o->restart_from_uold = 0;
 }
 
 int ax1gpu_time_step(ax1gpu_handle c, const ax1gpu_timeloop_opts* opts, const ax1gpu_newton_opts* newton,
@@ -600,6 +606,13 @@ static int p2p_setup(ax1gpu_ctx* c) {
   AX1_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(d_in); cudaFree(d_all);
   P.on = ok != 0;
+  {
+    double sec = AX1_P2P_TIMEOUT_DEFAULT_S;
+    if (const char* t = getenv("AX1_P2P_TIMEOUT_S")) { const double v = atof(t); if (v > 0.0) sec = v; }
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device) != cudaSuccess || khz <= 0) { cudaGetLastError(); khz = 1965000; }
+    P.timeout_cycles = (long long)(sec * 1e3 * (double)khz);
+  }
   return AX1GPU_OK;
 }
 

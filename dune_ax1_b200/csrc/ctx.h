@@ -38,6 +38,7 @@ struct ax1gpu_ctx {
   ax1::Scalars* d_sc = nullptr;
   ax1::Scalars* h_sc = nullptr;   // pinned
   double* h_pin = nullptr;        // pinned scratch (8 doubles)
+  int* h_err = nullptr;           // pinned copy of d_err[0..3]
   int nred_blocks = 0;
   // ILU
   int slab_w = 0;
@@ -78,6 +79,8 @@ struct ax1gpu_ctx {
     unsigned int* cnt = nullptr;           // local last-CTA counters [2]
     unsigned long long halo_seq = 0, red_seq = 0;
     size_t halo_len = 0;                   // doubles per halo slot = 3 * nvy * 4
+    long long timeout_cycles = 0;          // wait limit of one exchange in SM cycles (AX1_P2P_TIMEOUT_S, default 600 s)
+    bool broken = false;                   // an exchange timed out: sequence counters disagree, handle unusable
   } p2p;
   // accounting
   long long launches = 0;
@@ -106,4 +109,5 @@ int drv_time_step(ax1gpu_ctx* c, const ax1gpu_timeloop_opts* o, const ax1gpu_new
                   ax1gpu_step_result* out);
 int drv_norm(ax1gpu_ctx* c, const double* a, double* out_host);
 int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms);
+int drv_check_p2p(ax1gpu_ctx* c);   // after a host sync: AX1GPU_ENCCL if a peer-window exchange timed out
 }  // namespace ax1

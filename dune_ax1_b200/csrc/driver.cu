@@ -355,16 +355,25 @@ __global__ void __launch_bounds__(1024) reduce_final_p2p_kernel(const double* pa
       __threadfence_system();
       st_release_sys(reinterpret_cast<unsigned long long*>(rp.peer[lane] + slot + (size_t)rp.rank * 8 + 4), rp.seq);
       const double* q = rp.peer[rp.rank] + slot + (size_t)lane * 8;       // rank `lane`'s slot in my window
-      ok = wait_seq(reinterpret_cast<const unsigned long long*>(q + 4), rp.seq);
+      ok = wait_seq(reinterpret_cast<const unsigned long long*>(q + 4), rp.seq, rp.timeout);
       a0 = reinterpret_cast<const volatile double*>(q)[0];
       a1 = reinterpret_cast<const volatile double*>(q)[1];
     }
-    if (!ok) atomicExch(err, 1);
+    const bool all_ok = __all_sync(0xffffffffu, ok);
     double r0 = 0.0, r1 = 0.0;
     for (int k = 0; k < rp.nranks; ++k) { r0 += __shfl_sync(0xffffffffu, a0, k); r1 += __shfl_sync(0xffffffffu, a1, k); }
     if (lane == 0) {
-      sums[0] = r0; sums[1] = r1;
-      if (op != OP_NONE) scalar_step(op, sc, sums, reduction, out, aux);
+      if (!all_ok) {
+        // a peer did not arrive: its slot holds stale data. Nobody may take a convergence decision from it --
+        // NaN sums, stop the solve, flag the error for the host's next poll (check_p2p)
+        atomicExch(err, 1);
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        sums[0] = nan; sums[1] = nan;
+        sc->norm = nan; sc->converged = 0; sc->done = 1;
+      } else {
+        sums[0] = r0; sums[1] = r1;
+        if (op != OP_NONE) scalar_step(op, sc, sums, reduction, out, aux);
+      }
     }
   }
 }
@@ -372,11 +381,14 @@ __global__ void __launch_bounds__(1024) reduce_final_p2p_kernel(const double* pa
 // receiver side of the halo sum with peer windows: acquire the neighbour's sequence flag, then add the
 // three vertex columns it stored into my window (AddDataHandle)
 __global__ void halo_wait_add_kernel(Dev g, double* v, const double* slot, const unsigned long long* flag,
-                                     unsigned long long seq, int c0, int* err) {
+                                     unsigned long long seq, int c0, int* err, long long timeout, Scalars* sc) {
   __shared__ int ok_sh;
-  if (threadIdx.x == 0) ok_sh = wait_seq(flag, seq) ? 1 : 0;
+  if (threadIdx.x == 0) ok_sh = wait_seq(flag, seq, timeout) ? 1 : 0;
   __syncthreads();
-  if (!ok_sh) { if (threadIdx.x == 0) atomicExch(err, 1); return; }
+  if (!ok_sh) {   // the neighbour's columns never came: do not add stale data, stop the running solve
+    if (threadIdx.x == 0) { atomicExch(err, 1); sc->converged = 0; sc->done = 1; }
+    return;
+  }
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = 3 * g.nvy * 4;
   if (t >= n) return;
@@ -440,9 +452,11 @@ static int reduce_op_from(ax1gpu_ctx* c, const double* partials, int nblocks, in
     nblocks = AX1_RED2;
   }
   if (c->nranks > 1 && c->p2p.on) {
+    if (c->p2p.broken) return drv_check_p2p(c);
     RedP2P rp;
     for (int k = 0; k < AX1_MAX_RANKS; ++k) rp.peer[k] = c->p2p.peer[k];
     rp.rank = c->rank; rp.nranks = c->nranks; rp.seq = ++c->p2p.red_seq;
+    rp.timeout = c->p2p.timeout_cycles;
     reduce_final_p2p_kernel<<<1, 1024, 0, c->stream>>>(partials, nblocks, c->d_sums, op, c->d_sc, reduction, out, rp,
                                                        c->d_err + 2, aux);
     AX1_LAUNCH_CHECK(c);
@@ -549,9 +563,11 @@ int drv_norm(ax1gpu_ctx* c, const double* a, double* out_host) {
   int rc = reduce_op(c, c->nred_blocks, 1, OP_PLAIN_NORM, 0.0, c->d_sums + 2);
   if (rc) return rc;
   AX1_CUDA(cudaMemcpyAsync(c->h_pin, c->d_sums + 2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (c->nranks > 1 && c->p2p.on)
+    AX1_CUDA(cudaMemcpyAsync(c->h_err, c->d_err, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   AX1_CUDA(cudaStreamSynchronize(c->stream));
   *out_host = c->h_pin[0];
-  return 0;
+  return drv_check_p2p(c);
 }
 
 int drv_residual(ax1gpu_ctx* c, const double* d_u, double* d_r, double* norm_host) {
@@ -600,7 +616,9 @@ static int ensure_level_tables(ax1gpu_ctx* c) {
 // reference default, acme2_cyl_setup.hh:764-765); the ILU(1) factor needs 13 instead of 9 blocks per row
 static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill, int amg = -1) {
   const bool use_amg = amg >= 0 ? amg != 0 : c->amg != 0;
-  bool picked_auto = false;
+  // internal callers (drv_solve, drv_time_kernel) hand the handle's current width back in: that is not the caller
+  // choosing a width, an automatically derived one stays automatic
+  bool picked_auto = slab_w > 0 && slab_w == c->slab_w && c->slab_auto;
   if (fill < 0) fill = c->ilu_fill;
   if (fill > 1) { set_error("block ILU(n) is implemented on the device for n = 0 and n = 1"); return AX1GPU_EINVAL; }
   if (slab_w <= 0) {
@@ -784,12 +802,14 @@ static int halo_wait_add(ax1gpu_ctx* c, double* v, unsigned long long seq) {
   double* w = c->p2p.win;
   if (c->left_pb) {
     halo_wait_add_kernel<<<nb, bs, 0, c->stream>>>(g, v, w + AX1_P2P_HALO_OFF + (0 + par) * H,
-        reinterpret_cast<const unsigned long long*>(w + AX1_P2P_FLAG_OFF + 0), seq, 0, c->d_err + 2);
+        reinterpret_cast<const unsigned long long*>(w + AX1_P2P_FLAG_OFF + 0), seq, 0, c->d_err + 2,
+        c->p2p.timeout_cycles, c->d_sc);
     AX1_LAUNCH_CHECK(c);
   }
   if (c->right_pb) {
     halo_wait_add_kernel<<<nb, bs, 0, c->stream>>>(g, v, w + AX1_P2P_HALO_OFF + (2 + par) * H,
-        reinterpret_cast<const unsigned long long*>(w + AX1_P2P_FLAG_OFF + 1), seq, g.nvx - 3, c->d_err + 2);
+        reinterpret_cast<const unsigned long long*>(w + AX1_P2P_FLAG_OFF + 1), seq, g.nvx - 3, c->d_err + 2,
+        c->p2p.timeout_cycles, c->d_sc);
     AX1_LAUNCH_CHECK(c);
   }
   return 0;
@@ -797,6 +817,7 @@ static int halo_wait_add(ax1gpu_ctx* c, double* v, unsigned long long seq) {
 
 int drv_prec_apply(ax1gpu_ctx* c, const double* d, double* v) {
   const bool p2p = c->nranks > 1 && c->p2p.on;
+  if (p2p && c->p2p.broken) return drv_check_p2p(c);
   if (c->amg) {
     // per-rank multigrid cycle (the rank-local matrix incl. its overlap), then the additive halo sum
     int rc = amg_vcycle(c, d, v);
@@ -829,10 +850,31 @@ int drv_op_apply(ax1gpu_ctx* c, const double* x, double* y) {
   return 0;
 }
 
+// A peer-window exchange that timed out (p2p.cuh) has set d_err[2], stopped the solve (Scalars::done) and left NaN
+// sums. Report it where the host syncs anyway; afterwards the ranks' sequence counters disagree, so the handle's
+// communication is marked broken and every later exchange fails immediately instead of reading stale windows.
+static const char* P2P_TIMEOUT_MSG =
+    "peer-memory exchange timed out (a neighbour rank did not arrive within AX1_P2P_TIMEOUT_S); "
+    "the handle cannot communicate any more -- destroy it on all ranks";
+int drv_check_p2p(ax1gpu_ctx* c) {
+  if (c->nranks <= 1 || !c->p2p.on) return 0;
+  if (c->p2p.broken) { set_error(P2P_TIMEOUT_MSG); return AX1GPU_ENCCL; }
+  if (c->h_err[2]) {
+    c->h_err[2] = 0;
+    c->p2p.broken = true;
+    cudaMemsetAsync(c->d_err + 2, 0, sizeof(int), c->stream);   // reported once; `broken` keeps the handle shut
+    set_error(P2P_TIMEOUT_MSG);
+    return AX1GPU_ENCCL;
+  }
+  return 0;
+}
+
 static int poll_scalars(ax1gpu_ctx* c) {
   AX1_CUDA(cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
+  if (c->nranks > 1 && c->p2p.on)
+    AX1_CUDA(cudaMemcpyAsync(c->h_err, c->d_err, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   AX1_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  return drv_check_p2p(c);
 }
 
 // BiCGStab on A z = rhs from z = 0; rhs is overwritten with the final residual (ISTL aliases r = b)
@@ -1113,11 +1155,10 @@ int drv_newton(ax1gpu_ctx* c, const ax1gpu_newton_opts* o, ax1gpu_newton_result*
   res->t_lin_solv = t_lin_ms * 1e-3;
   res->t_elapsed = ev_ms(e3, e2) * 1e-3;
   // channel-kernel error flag (leak ratio outside [0,1], channelset.hh:298-299)
-  int herr[3] = {0, 0, 0};
-  AX1_CUDA(cudaMemcpy(herr, c->d_err, 3 * sizeof(int), cudaMemcpyDeviceToHost));
-  if (herr[0]) { set_error("Calculated leak channel ratio outside [0,1]"); return AX1GPU_ESTATE; }
-  if (herr[2]) { set_error("peer-memory exchange timed out (a neighbour rank did not arrive)"); return AX1GPU_ENCCL; }
-  return 0;
+  AX1_CUDA(cudaMemcpyAsync(c->h_err, c->d_err, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  AX1_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->h_err[0]) { set_error("Calculated leak channel ratio outside [0,1]"); return AX1GPU_ESTATE; }
+  return drv_check_p2p(c);
 }
 
 // mean device time of one kernel on resident data (roofline evidence for bench.py)

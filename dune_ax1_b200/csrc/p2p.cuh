@@ -18,7 +18,11 @@ namespace ax1 {
 #define AX1_P2P_RED_OFF 0                      // [2 parity][AX1_MAX_RANKS][8 doubles]: s0 s1 . . flag . . .
 #define AX1_P2P_FLAG_OFF (2 * AX1_MAX_RANKS * 8)  // [2 sides] u64 halo sequence flags (+6 padding)
 #define AX1_P2P_HALO_OFF (AX1_P2P_FLAG_OFF + 8)   // [2 sides][2 parity][3 * nvy * 4 doubles]
-#define AX1_P2P_TIMEOUT_CYCLES 20000000000LL   // ~10 s: a lost peer must not hang the GPU
+// A lost peer must not hang the GPU for ever, but ordinary rank skew (a rank writing output, a lazy cudaMalloc) must
+// never trip the limit: default 600 s (AX1_P2P_TIMEOUT_S), converted to SM cycles at comm_init. After a timeout the
+// exchange sets Scalars::done with NaN sums, the host reports AX1GPU_ENCCL at its next poll and the handle's
+// communication is marked broken (sequence counters of the ranks no longer agree) -- see driver.cu: check_p2p.
+#define AX1_P2P_TIMEOUT_DEFAULT_S 600.0
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -28,10 +32,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ bool wait_seq(const unsigned long long* flag, unsigned long long seq) {
+__device__ __forceinline__ bool wait_seq(const unsigned long long* flag, unsigned long long seq, long long timeout) {
   const long long t0 = clock64();
   while (ld_acquire_sys(flag) < seq)
-    if (clock64() - t0 > AX1_P2P_TIMEOUT_CYCLES) return false;
+    if (clock64() - t0 > timeout) return false;
   return true;
 }
 
@@ -76,6 +80,7 @@ struct RedP2P {
   double* peer[AX1_MAX_RANKS];  // window base of every rank (peer[rank] = own window)
   int rank, nranks;
   unsigned long long seq;
+  long long timeout;            // SM cycles a rank waits for a peer before it gives up (ctx.p2p.timeout_cycles)
 };
 
 }  // namespace ax1

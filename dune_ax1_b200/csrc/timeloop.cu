@@ -2,13 +2,20 @@
 // Acme2CylSimulation::run (dune/ax1/acme2_cyl/common/acme2_cyl_simulation.hh:236-932) with the iterate,
 // the previous step and the channel state resident in HBM:
 //   dt control   :334-343  x1.1 if the last Newton solve took < lowerLimit iterations and not more than the
-//                          one before, /1.2 if it took >= upperLimit
+//                          one before, /1.2 if it took >= upperLimit. No first-step exception: diagInfo.iterations
+//                          starts at 0 (acme2_cyl_output.hh:169), so the very first adaptive step is already 1.1 dt0
+//   equilibration :253-263 dt is held while doEquilibration && time < tEquilibrium; from the first time point
+//                          >= tEquilibrium on the `equilibrationOver` flag stays set (:241-247 only ever sets it), so
+//                          every later step runs with dt = dtstart -- restated as the reference's code does it
 //   clamps       :362-363  [minTimeStep, maxTimeStep]
 //   AP limiter   :365-383  min / max membrane potential over all membrane elements (+ comm().min / max),
 //                          dt <= maxTimeStepAP while stimulating or while max V_m > -50 mV
 //   stim start   :262-266  dt = dtstart on the step that crosses tInj_start
 //   protocol     :457, 589, 916-927  updateState(time, dt) -> solver.apply -> uold = unew -> acceptTimeStep
-//   restart      :593-638  Newton failure -> dt /= 2, iterate reset to uold, up to maxNumberNewtonRestarts
+//   restart      :593-638  Newton failure -> dt /= 2, updateState and solver.apply again on the *modified* unew
+//                          ("it might already contain better starting values", :563-566), up to
+//                          maxNumberNewtonRestarts. Deviations, both explicit: a NaN defect makes the iterate unusable,
+//                          so that one case restarts from uold; opts.restart_from_uold = 1 does so after every failure
 // Only three scalars per step (min / max V_m, the Newton result) cross PCIe.
 #include <cmath>
 #include <cstring>
@@ -72,7 +79,11 @@ int drv_time_step(ax1gpu_ctx* c, const ax1gpu_timeloop_opts* o, const ax1gpu_new
   int rc;
   std::memset(out, 0, sizeof(*out));
   // ---- choose dt (acme2_cyl_simulation.hh:255-439)
-  bool accept = !o->adaptive || s->steps == 0;
+  bool accept = !o->adaptive || (p.do_equilibration && s->time < p.t_equilibrium);
+  if (p.do_equilibration && (s->time > p.t_equilibrium || std::fabs(s->time - p.t_equilibrium) < 1e-6)) {
+    s->dt = o->dtstart;      // equilibrationOver (latched in the reference): dt reset to the start value
+    accept = true;
+  }
   if (p.do_stimulation && (s->time + s->dt > p.tinj_start && s->time < p.tinj_start)) {
     accept = true;
     s->dt = o->dtstart;
@@ -94,7 +105,8 @@ int drv_time_step(ax1gpu_ctx* c, const ax1gpu_timeloop_opts* o, const ax1gpu_new
   while (true) {
     c->time = s->time; c->dt = s->dt;
     drv_refresh_dev(c);
-    if (have_uold)   // a failed Newton solve left a wrong iterate behind: restart from the previous step
+    // the reference retries from the iterate the failed solve left behind; a NaN iterate cannot be used
+    if (have_uold && (o->restart_from_uold || nr.status == AX1GPU_NEWTON_DEFECT_NAN))
       AX1_CUDA(cudaMemcpyAsync(c->d_u, c->d_uold, bytes, cudaMemcpyDeviceToDevice, c->stream));
     if ((rc = drv_update_state(c, c->d_u))) return rc;              // gfMembFlux.updateState(time, dt)
     if (!have_uold) {

@@ -179,6 +179,8 @@ typedef struct ax1gpu_timeloop_opts {
   int lower_limit, upper_limit;   /* timeStepLowerLimitNewtonIt (3) / timeStepUpperLimitNewtonIt (5)         */
   int max_restarts;               /* maxNumberNewtonRestarts                                                 */
   int adaptive;                   /* useAdaptiveTimeStep                                                     */
+  int restart_from_uold;          /* 0 (reference, :563-566): a retry starts from the iterate the failed Newton solve
+                                     left behind, except after a NaN defect; 1: every retry starts from uold       */
 } ax1gpu_timeloop_opts;
 typedef struct ax1gpu_timeloop_state { /* carried by the caller between steps */
   double time, dt;
