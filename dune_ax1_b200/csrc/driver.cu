@@ -1171,6 +1171,13 @@ int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms) {
     if (n == "residual") { launch_residual(c->g, c->d_u, c->d_r0, c->d_r, 0, c->stream); }
     else if (n == "jacobian") { launch_jacobian_volume(c->g, c->d_u, c->d_A, c->stream); }
     else if (n == "spmv") { launch_spmv(c->g, c->d_A, c->d_y2, c->d_v, 0, c->stream); }
+    // the two variants BiCGStab launches: v = A y with <rt, v>, t = A y with <t, r> and <t, t> fused in
+    else if (n == "spmv_dot1" || n == "spmv_dot2") {
+      const Own own = own_of(c);
+      launch_spmv_dot(c->g, c->d_A, c->d_y2, c->d_v, c->nranks > 1, n == "spmv_dot1" ? 1 : 2, c->d_rt, own.lo, own.hi,
+                      own.masked, c->d_sc, c->d_spartials, c->stream);
+    }
+    else if (n == "pupdate") { pupdate_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_tmp, c->d_v, c->d_t, c->d_sc, 0); }
     else if (n == "ilu_factor") {
       if (c->ilu_fill == 1) launch_ilu1_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);
       else launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);

@@ -5,17 +5,18 @@ initial state), shared by bench.py, the tests and the examples.
   synthetic  SURVEY 8(d): same radial vector, x equidistant with dx = 100 nm, Nx cell columns,
              HH channels everywhere, deterministic perturbation of the replicated equilibrium column
 The equilibrium column is the state file the reference ships
-(src/simulation_states/equilibrium/cyl/yasp_square10mm_p0.dat, extracted to tests/golden/).
+(src/simulation_states/equilibrium/cyl/yasp_square10mm_p0.dat; input data under dune_ax1_b200/data/, read with the
+library's own state loader ax1host_state_load, as the reference's loadState does).
 """
-import json
 import os
 
 import numpy as np
 
 from . import api
 
-_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLDEN = os.path.join(_ROOT, "tests", "golden", "yasp_square10mm.json")
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+STATE_SQUARE10MM = os.path.join(_DATA, "yasp_square10mm_p0.dat")
+STATE_SQUARE1MM = os.path.join(_DATA, "yasp_square1mm_p0.dat")
 
 
 def equidistant_x(xmin, xmax, n):
@@ -28,11 +29,13 @@ def equidistant_x(xmin, xmax, n):
     return np.array(x)
 
 
-def load_equilibrium_column(path=GOLDEN):
-    g = json.load(open(path))
-    y = np.array(g["y"])
-    u = np.array(g["unew"]).reshape(len(y), 2, 4)[:, 0, :].copy()  # one vertex column [j][comp]
-    return y, u, np.array(g["channelStates"])
+def load_equilibrium_column(path=STATE_SQUARE10MM):
+    """y vector, one vertex column [j][comp] of the stored solution, serialized channel states of a shipped
+    1-column equilibrium state (Ax1SimulationState file)."""
+    g = api.load_state(path)
+    y = g["y"]
+    u = g["unew"].reshape(len(y), 2, 4)[:, 0, :].copy()
+    return y, u, g["channelStates"]
 
 
 def replicate_column(ucol, nvx):
@@ -93,7 +96,7 @@ def make_setup(nx, dx=None, xmax=None, stimulation=False, hh=True, equilibration
                 right_pb=right_pb, bc=bc, slab=(c0, c1, l0, l1))
 
 
-GOLDEN_MYELIN = os.path.join(_ROOT, "tests", "golden", "yasp_square10mm_myelin.json")
+STATE_MYELIN = os.path.join(_DATA, "yasp_square10mm_myelin_p0.dat")
 
 
 def myelin_groups(xmax=48.0e6, node_stride=1000.0e3, node_start=500.0e3, node_width=1.0e3, dx=10.0e3):
@@ -118,7 +121,7 @@ def make_myelin_setup(xmax=48.0e6, rank=0, nranks=1, stimulation=True, check_bou
     xg = mg.x_vector()
     nx = len(xg) - 1
     y, ucol_node, _ = load_equilibrium_column()
-    y2, ucol_myel, _ = load_equilibrium_column(GOLDEN_MYELIN)
+    y2, ucol_myel, _ = load_equilibrium_column(STATE_MYELIN)
     assert np.array_equal(y, y2)
     c0, c1, l0, l1 = api.slab(nx, nranks, rank) if nranks > 1 else (0, nx, 0, nx)
     if check_boundaries and nranks > 1 and rank < nranks - 1:

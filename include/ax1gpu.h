@@ -222,7 +222,8 @@ int ax1gpu_set_amg(ax1gpu_handle h, int on, int cx);
 int ax1gpu_ilu_apply(ax1gpu_handle h, const double* d, double* v);
 int ax1gpu_rownorm(ax1gpu_handle h, double* r); /* scales device Jacobian and r */
 /* run `reps` launches of one named kernel on device-resident data and return the mean device time
- * [ms] from CUDA events ("residual","jacobian","spmv","ilu_factor","ilu_apply","dot","axpy") */
+ * [ms] from CUDA events ("residual","jacobian","spmv","spmv_dot1","spmv_dot2" = the two dot-fused SpMV variants
+ * BiCGStab launches,"ilu_factor","ilu_apply","dot","axpy","pupdate") */
 int ax1gpu_time_kernel(ax1gpu_handle h, const char* name, int reps, double* ms);
 long long ax1gpu_launch_count(ax1gpu_handle h); /* kernels launched so far by this handle */
 void* ax1gpu_stream(ax1gpu_handle h);

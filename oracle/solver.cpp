@@ -362,8 +362,11 @@ void newton(Problem& p, double* u, const NewtonOpts& o, const Comm* comm, Newton
         ilu_factor(p, A, o.ilu_fill, o.slab_w, M);
         prec = [&M](const double* d, double* v) { ilu_apply(M, d, v); };
       }
-      if (o.krylov == 1) gmres(p, A, prec, z.data(), r.data(), linear_reduction, o.restart, o.lin_maxit, comm, lr);
-      else bicgstab(p, A, prec, z.data(), r.data(), linear_reduction, o.lin_maxit, comm, lr);
+      // fixed work (throughput runs): exactly lin_maxit Krylov iterations per solve, as the device driver does
+      // (reduction 0 is never reached), not "up to lin_maxit"
+      const double lin_red = o.fixed_work ? 0.0 : linear_reduction;
+      if (o.krylov == 1) gmres(p, A, prec, z.data(), r.data(), lin_red, o.restart, o.lin_maxit, comm, lr);
+      else bicgstab(p, A, prec, z.data(), r.data(), lin_red, o.lin_maxit, comm, lr);
     } catch (std::exception&) {
       res.t_lin_solv += secs(t1, clk::now());
       res.status = NEWTON_LINSOLVE_FAILED;

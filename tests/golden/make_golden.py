@@ -46,6 +46,11 @@ def main():
         with open(dst, "w") as fh:
             json.dump(d, fh, separators=(",", ":"))
         print(dst, {k: (len(v) if isinstance(v, list) else v) for k, v in d.items()})
+        # the state files themselves are input data of a run (loadState): verbatim copies for the package
+        import shutil
+        data = os.path.join(os.path.dirname(os.path.dirname(OUT)), "dune_ax1_b200", "data", f)
+        shutil.copyfile(os.path.join(REF, f), data)
+        os.chmod(data, 0o644)
 
 
 if __name__ == "__main__":

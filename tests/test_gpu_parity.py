@@ -770,3 +770,37 @@ def test_error_behaviour(oracle, axlib):
     dev.close()
     with pytest.raises(axlib.Ax1GpuError):
         dev.residual(u0)        # closed handle
+
+
+@pytest.mark.parametrize("nx,slab_w,fill", [(8, 4, 0), (20, 64, 1), (40, 16, 0)])
+def test_fields_at_rounding_floor_match_extended_precision_truth(oracle, axlib, nx, slab_w, fill):
+    """The north star's 1e-8 on converged potentials, settled with the extended-precision oracle
+    (tests/test_precision_floor.py): the potential's weakly determined mode is invisible to a defect-based stop, so
+    the comparison is made where Newton has been driven to the rounding floor of the double residual (one
+    iteration beyond `reduction 1e-8`), against the 80-bit solution of the same discrete problem. Concentrations:
+    1e-11 everywhere. Potential: the double-precision ORACLE itself -- the reference's own arithmetic -- sits
+    5e-9 (8 columns), 2.5e-8 (20), 9.5e-8 (40 columns) of max|phi| away from the 80-bit truth: that is the floor of
+    double precision for this unknown and it grows with the grid. The device must be as close to the truth as the
+    reference's arithmetic is (within 2x, or 2e-8 where the floor is lower), and device and oracle must agree with
+    each other to the same bound."""
+    from oracle import pyoracle_ld as OL
+    s = small_setup(nx=nx)
+    dev, P, u0 = _both(oracle, axlib, s)
+    Q = OL.Problem(P.cfg, P.x, P.y, eps_memb=s["eps_memb"], g_leak=s["g_leak"], g_nav=s["g_nav"], g_kv=s["g_kv"])
+    Q.set_time(0.0, 1.0); Q.set_uold(u0); Q.update_state(u0)
+    kw = dict(abs_limit=1e-14, min_lin_reduction=1e-10, maxit=8)
+    ul, _ = Q.newton(u0, oracle.default_newton_opts(reduction=1e-14, ilu_fill=fill, slab_w=slab_w if fill == 0 else 0, **kw))
+    truth = ul.astype(np.float64)
+    scale = np.max(np.abs(truth.reshape(-1, 4)), axis=0)
+    ug, ng = dev.newton(u0, axlib.default_newton_opts(reduction=1e-10, slab_w=slab_w, ilu_fill=fill, **kw))
+    uc, nc = P.newton(u0, oracle.default_newton_opts(reduction=1e-10, ilu_fill=fill, slab_w=slab_w if fill == 0 else 0, **kw))
+    assert ng.status == 0 and nc.status == 0 and ng.iterations == nc.iterations
+
+    def err(a, b):
+        return np.max(np.abs(a - b).reshape(-1, 4) / scale, axis=0)
+    e_dev, e_orc, e_do = err(ug, truth), err(uc, truth), err(ug, uc)
+    floor = max(2e-8, 2.0 * e_orc[3])
+    assert np.all(e_dev[:3] < 1e-11) and np.all(e_orc[:3] < 1e-11) and np.all(e_do[:3] < 1e-11), (e_dev, e_orc, e_do)
+    assert e_orc[3] < 2e-7, e_orc                       # the measured floor itself (see docstring)
+    assert e_dev[3] <= floor and e_do[3] <= floor, (e_dev, e_orc, e_do)
+    dev.close()
