@@ -72,6 +72,7 @@ KRYLOV_ITS = 20
 SLAB_W = 128
 PAPER_NX, PAPER_DX = 100, 100.0e3        # square10mm.config
 PAPER_CTL = dict(dtstart=1.0, lower_limit=10, upper_limit=30)   # [timeStepping] of square10mm.config
+PAPER_SPLIT = 91     # radial cut of the library-default preconditioner on the 181-point radial grid (driver.cu: auto_radial_cut)
 # algorithmic bytes per vertex. SURVEY 8(d) table for dense 4x4 blocks: jacobian 1184, spmv 1256,
 # ilu_factor 2384. The device stores the Jacobian blocks in their 10-entry "arrow" shape (80 B instead
 # of 128 B, common.cuh), so the bytes these kernels must move are smaller; roofline.achieved uses the
@@ -202,7 +203,7 @@ def cpu_synthetic(nx_sample, threads, steps, warmup, ilu_fill, slab_w):
                 t_assembler=res[0].t_assembler, t_lin_solv=res[0].t_lin_solv)
 
 
-def cpu_paper(threads, nsteps, ilu_fill, slab_w):
+def cpu_paper(threads, nsteps, ilu_fill, slab_w, ilu_split=0):
     """The paper configuration on the oracle: `threads` MPI-style x-slabs (the reference's docker default runs this
     configuration on 10 ranks, bin/run.sh:72), the restated time loop, the config's Newton tolerances."""
     from oracle import cpu_setup as CS
@@ -210,6 +211,7 @@ def cpu_paper(threads, nsteps, ilu_fill, slab_w):
     from dune_ax1_b200.timeloop import TimeLoop   # pure Python control flow, loads no native library
     O.build()
     M = CS.MultiRankProblem(PAPER_NX, PAPER_DX, threads, stimulation=True)
+    M.set_ilu_split(ilu_split)       # the radial cut of the device's default preconditioner (ax1gpu_set_ilu_split)
     tl = TimeLoop(M, M.u0, do_stimulation=True, newton_opts=O.default_newton_opts(ilu_fill=ilu_fill, slab_w=slab_w),
                   **PAPER_CTL)
     t0 = time.perf_counter()
@@ -225,7 +227,8 @@ def run_reference(args, world):
     if args.workload == "paper":
         ranks = min(threads, 10)
         cpu_paper(ranks, min(5, args.warmup), args.ilu_fill, 16)
-        r = cpu_paper(ranks, args.steps, args.ilu_fill, 16 if args.ilu_fill == 0 else 0)
+        r = cpu_paper(ranks, args.steps, args.ilu_fill, 16 if args.ilu_fill == 0 else 0,
+                      PAPER_SPLIT if args.ilu_fill == 0 else 0)
         sample = ("oracle/ restatement of the reference algorithm (not the DUNE binary), %d threads as %d x-slabs "
                   "(docker default: 10 MPI ranks), the first %d adaptive time steps of the run, %d Newton iterations in "
                   "%.2f s" % (ranks, ranks, args.steps, r["newton_iterations"], r["wall"]))
@@ -420,6 +423,7 @@ def run_paper(args, api, setups, local_rank):
     ms = ev0.elapsed_time(ev1)
     launches = dev.launch_count() - l0
     t_end = tl.time
+    split = dev.ilu_split()
     dev.close()
     # e2e: the host-side loop -- u, uold up and u down through the C ABI every step
     from dune_ax1_b200.timeloop import TimeLoop
@@ -439,7 +443,7 @@ def run_paper(args, api, setups, local_rank):
                    "h2d_bytes_per_step": 3 * n * 8, "d2h_bytes_per_step": n * 8, "timing": "host wall clock"}}
     if not args.no_cpu_baseline:
         ranks = min(os.cpu_count() or 1, 10)
-        c = cpu_paper(ranks, args.steps, args.ilu_fill, 16 if args.ilu_fill == 0 else 0)
+        c = cpu_paper(ranks, args.steps, args.ilu_fill, 16 if args.ilu_fill == 0 else 0, split)
         out["cpu_baseline"] = {"value": c["gdof"], "unit": UNIT, "cores": ranks, "kind": "port",
                                "newton_steps_per_s": c["newton_steps_per_s"],
                                "sample": "oracle/ restatement, %d threads as x-slabs, the same %d time steps (%d Newton "
@@ -695,15 +699,16 @@ def main():
             t0 = time.perf_counter()
             nits = sum(tl.step().iterations for _ in range(60))
             wallp = time.perf_counter() - t0
+            split = devp.ilu_split()
             out["paper_config"] = {"workload": "square10mm.config grid, 73,124 DOF, 60 adaptive time steps from t=0 "
                                                "(Na injection starts at 20 us), reference Newton tolerances 1e-5, "
                                                "library-default sub-slab width, time loop inside the library",
                                    "newton_steps_per_s": nits / wallp, "newton_iterations": nits, "t_end_us": tl.time,
-                                   "timing": "host wall clock"}
+                                   "ilu_radial_split_row": split, "timing": "host wall clock"}
             devp.close()
             if not args.no_cpu_baseline:
                 ranks = min(os.cpu_count() or 1, 10)
-                c = cpu_paper(ranks, 60, 0, 16)
+                c = cpu_paper(ranks, 60, 0, 16, split)
                 out["paper_config"]["cpu_baseline"] = {
                     "newton_steps_per_s": c["newton_steps_per_s"], "cores": ranks, "kind": "port",
                     "newton_iterations": c["newton_iterations"], "t_end_us": c["t_end_us"],

@@ -173,6 +173,8 @@ def lib():
     L.ax1gpu_ilu_factor_n.argtypes = [H, C.c_int, C.c_int]
     L.ax1gpu_set_amg.argtypes = [H, C.c_int, C.c_int]
     L.ax1gpu_ilu_apply.argtypes = [H, c_double_p, c_double_p]
+    L.ax1gpu_set_ilu_split.argtypes = [H, C.c_int]
+    L.ax1gpu_get_ilu_split.argtypes = [H, c_int_p]
     L.ax1gpu_rownorm.argtypes = [H, c_double_p]
     L.ax1gpu_time_kernel.argtypes = [H, C.c_char_p, C.c_int, c_double_p]
     L.ax1gpu_launch_count.argtypes = [H]
@@ -534,6 +536,16 @@ class Ax1Gpu:
     def set_amg(self, on=True, cx=0):
         """Preconditioner = one V(1,1) cycle of the x-aggregation AMG (block-ILU smoothers) instead of the ILU alone."""
         _chk(lib().ax1gpu_set_amg(self.h, int(on), int(cx)))
+
+    def set_ilu_split(self, jcut=-1):
+        """Radial split of the ILU0 sub-slabs: -1 automatic (far-field cut on latency-bound grids), 0 off, > 0 row."""
+        _chk(lib().ax1gpu_set_ilu_split(self.h, int(jcut)))
+
+    def ilu_split(self):
+        """The radial cut the last factorisation used (0: none)."""
+        v = C.c_int()
+        _chk(lib().ax1gpu_get_ilu_split(self.h, C.byref(v)))
+        return v.value
 
     def ilu_apply(self, d):
         v = np.zeros(self.n)

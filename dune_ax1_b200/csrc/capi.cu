@@ -447,6 +447,20 @@ int ax1gpu_set_amg(ax1gpu_handle c, int on, int cx) {
   return AX1GPU_OK;
 }
 
+int ax1gpu_set_ilu_split(ax1gpu_handle c, int jcut) {
+  AX1_CHECK_H(c);
+  if (jcut > 0 && (jcut < 2 || jcut > c->g.nvy - 2)) { set_error("ilu split: row out of range"); return AX1GPU_EINVAL; }
+  c->ilu_split = jcut < 0 ? -1 : jcut;
+  c->factored = false;
+  return AX1GPU_OK;
+}
+
+int ax1gpu_get_ilu_split(ax1gpu_handle c, int* active) {
+  AX1_CHECK_H(c);
+  if (active) *active = c->ilu_jc;
+  return AX1GPU_OK;
+}
+
 int ax1gpu_ilu_apply(ax1gpu_handle c, const double* d, double* v) {
   AX1_CHECK_H(c);
   cudaSetDevice(c->device);

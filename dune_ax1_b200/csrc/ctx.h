@@ -46,6 +46,9 @@ struct ax1gpu_ctx {
   int ilu_fill = 0;            // 0: block ILU0 (solver.cu), 1: block ILU(1), the reference default (ilu1.cu)
   int lvl_slab_w = 0;          // slab width / fill level the level tables were built for
   int lvl_fill = -1;
+  int lvl_jc = -1;
+  int ilu_split = -1;          // radial split of the ILU0 sub-slabs: -1 automatic, 0 off, > 0 cut at this grid row
+  int ilu_jc = 0;              // the cut in effect (0: none), chosen by select_preconditioner
   int* d_lvl = nullptr;        // level prefix tables (solver.cu / ilu1.cu)
   size_t lvl_cap = 0;          // ints allocated for d_lvl
   size_t lu_cap = 0;           // doubles allocated for d_LU (144 per vertex for ILU0, 208 for ILU(1))

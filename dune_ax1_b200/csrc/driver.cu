@@ -595,10 +595,10 @@ int drv_jacobian(ax1gpu_ctx* c, const double* d_u) {
 }
 
 static int ensure_level_tables(ax1gpu_ctx* c) {
-  if (c->d_lvl && c->lvl_slab_w == c->slab_w && c->lvl_fill == c->ilu_fill) return 0;
+  if (c->d_lvl && c->lvl_slab_w == c->slab_w && c->lvl_fill == c->ilu_fill && c->lvl_jc == c->ilu_jc) return 0;
   std::vector<int> tab;
   if (c->ilu_fill == 1) ilu1_level_tables(c->g, c->slab_w, tab);
-  else ilu_level_tables(c->g, c->slab_w, tab);
+  else ilu_level_tables(c->g, c->slab_w, tab, c->ilu_jc);
   if (tab.size() > c->lvl_cap) {
     AX1_CUDA(cudaStreamSynchronize(c->stream));
     if (c->d_lvl) { AX1_CUDA(cudaFree(c->d_lvl)); c->d_lvl = nullptr; }
@@ -609,7 +609,31 @@ static int ensure_level_tables(ax1gpu_ctx* c) {
   AX1_CUDA(cudaStreamSynchronize(c->stream));  // tab is a local
   c->lvl_slab_w = c->slab_w;
   c->lvl_fill = c->ilu_fill;
+  c->lvl_jc = c->ilu_jc;
   return 0;
+}
+
+// Where to cut the sub-slabs radially (solver.cu: ypart_select). The radial grid of the reference is refined
+// geometrically towards the membrane and uniform in the far field; a cut inside the uniform far field drops
+// couplings that are no stronger than the ones the sub-slab borders drop in x -- measured on the paper grid (oracle,
+// 40 time steps): 150 Krylov iterations without a cut, 150 with a cut at rows 86..120, 160 at row 78, 336 at 74,
+// 4728 at 60. Automatic choice: the first row of the far field (spacing >= half the largest), moved up to the
+// middle of the grid if that balances the two parts; no cut if the longer part would still hold > 70 % of the rows.
+static int auto_radial_cut(const ax1gpu_ctx* c) {
+  const int nvy = c->g.nvy;
+  if (nvy < 32) return 0;
+  double dmax = 0.0;
+  for (int j = 0; j + 1 < nvy; ++j) dmax = std::max(dmax, c->hy[j + 1] - c->hy[j]);
+  int js = -1;
+  for (int j = 0; j + 1 < nvy; ++j) {
+    if (c->hy[j + 1] - c->hy[j] >= 0.5 * dmax) { if (js < 0) js = j; }
+    else js = -1;            // the far field is the LAST run of coarse cells
+  }
+  if (js < 0) return 0;
+  const int jc = std::max(js, (nvy + 1) / 2);
+  if (jc < 8 || nvy - jc < 8) return 0;
+  if (std::max(jc, nvy - jc) > (7 * nvy) / 10) return 0;
+  return jc;
 }
 
 // (re)select the preconditioner: fill 0 = block ILU0, fill 1 = block ILU(1) (SeqILUn with n = 1, the
@@ -641,6 +665,15 @@ static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill, int amg = 
   const int wmax = fill == 1 ? ilu1_max_slab_w(c->g) : 128;
   if (slab_w > wmax) slab_w = wmax;
   if (slab_w > c->g.nvx) slab_w = c->g.nvx;
+  // radial split of the sub-slabs: block ILU0 only; automatic on latency-bound (narrow) sub-slabs without multigrid
+  int jc = 0;
+  if (fill == 0 && !use_amg) {
+    if (c->ilu_split > 0) jc = c->ilu_split;
+    // automatic only together with an automatic sub-slab width: a caller who fixes the width gets exactly the
+    // sub-slab ILU0 it asked for unless it also asks for the cut (ax1gpu_set_ilu_split)
+    else if (c->ilu_split < 0 && picked_auto && slab_w <= 64) jc = auto_radial_cut(c);
+    if (jc > 0 && (jc < 2 || c->g.nvy - jc < 2)) { set_error("ilu split row must leave two rows on either side"); return AX1GPU_EINVAL; }
+  }
   const size_t need = (size_t)c->g.nv * (fill == 1 ? 208 : 144);
   if (need > c->lu_cap) {
     AX1_CUDA(cudaStreamSynchronize(c->stream));
@@ -648,7 +681,8 @@ static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill, int amg = 
     AX1_CUDA(cudaMalloc((void**)&c->d_LU, need * sizeof(double)));
     c->lu_cap = need;
   }
-  if (slab_w != c->slab_w || fill != c->ilu_fill) c->factored = false;
+  if (slab_w != c->slab_w || fill != c->ilu_fill || jc != c->ilu_jc) c->factored = false;
+  c->ilu_jc = jc;
   c->slab_w = slab_w;
   c->slab_auto = picked_auto;
   c->ilu_fill = fill;
@@ -715,7 +749,7 @@ static int amg_setup(ax1gpu_ctx* c) {
 
 static int smoother0(ax1gpu_ctx* c, const double* d, double* v) {  // level-0 smoother: block ILU(fill)
   if (c->ilu_fill == 1) launch_ilu1_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
-  else launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
+  else launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream, nullptr, c->ilu_jc);
   AX1_LAUNCH_CHECK(c);
   return 0;
 }
@@ -768,7 +802,7 @@ int drv_factor(ax1gpu_ctx* c, int slab_w, int fill, int amg) {
   if (rc) return rc;
   if (amg >= 0) c->amg = amg ? 1 : 0;
   if (c->ilu_fill == 1) launch_ilu1_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);
-  else launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);
+  else launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream, c->ilu_jc);
   AX1_LAUNCH_CHECK(c);
   if (c->amg && (rc = amg_setup(c))) return rc;
   c->factored = true;
@@ -782,7 +816,7 @@ static HaloPush next_halo_push(ax1gpu_ctx* c) {
   hp.seq = ++c->p2p.halo_seq;
   const size_t par = (size_t)(hp.seq & 1);
   hp.cnt = c->p2p.cnt;
-  halo_contributors(c->g, c->slab_w, &hp.ncontrib[0], &hp.ncontrib[1]);
+  halo_contributors(c->g, c->slab_w, &hp.ncontrib[0], &hp.ncontrib[1], c->ilu_jc);
   if (c->left_pb) {   // my left columns -> slot "from the right neighbour" (side 1) of rank-1
     double* pw = c->p2p.peer[c->rank - 1];
     hp.dst[0] = pw + AX1_P2P_HALO_OFF + (2 + par) * H;
@@ -834,12 +868,12 @@ int drv_prec_apply(ax1gpu_ctx* c, const double* d, double* v) {
     // sweep with fused halo push into the neighbours' windows, then acquire + add what they pushed to me
     const HaloPush hp = next_halo_push(c);
     if (c->ilu_fill == 1) launch_ilu1_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream, &hp);
-    else launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream, &hp);
+    else launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream, &hp, c->ilu_jc);
     AX1_LAUNCH_CHECK(c);
     return halo_wait_add(c, v, hp.seq);
   }
   if (c->ilu_fill == 1) launch_ilu1_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
-  else launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream);
+  else launch_ilu_apply(c->g, c->d_LU, d, v, c->slab_w, c->d_lvl, c->stream, nullptr, c->ilu_jc);
   AX1_LAUNCH_CHECK(c);
   return halo_add(c, v);
 }
@@ -1180,11 +1214,11 @@ int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms) {
     else if (n == "pupdate") { pupdate_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_tmp, c->d_v, c->d_t, c->d_sc, 0); }
     else if (n == "ilu_factor") {
       if (c->ilu_fill == 1) launch_ilu1_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);
-      else launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);
+      else launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream, c->ilu_jc);
     }
     else if (n == "ilu_apply") {
       if (c->ilu_fill == 1) launch_ilu1_apply(c->g, c->d_LU, c->d_p, c->d_y2, c->slab_w, c->d_lvl, c->stream);
-      else launch_ilu_apply(c->g, c->d_LU, c->d_p, c->d_y2, c->slab_w, c->d_lvl, c->stream);
+      else launch_ilu_apply(c->g, c->d_LU, c->d_p, c->d_y2, c->slab_w, c->d_lvl, c->stream, nullptr, c->ilu_jc);
     }
     else if (n == "dot") { dot_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_rt, c->d_v, nullptr, nullptr, 0, own_of(c), nullptr, c->d_partials); }
     else if (n == "axpy") { xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_tmp, c->d_y2, c->d_t, c->d_v, c->d_rt, c->d_sc, 1, own_of(c), c->d_partials); }

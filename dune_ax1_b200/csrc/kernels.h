@@ -39,12 +39,14 @@ int spmv_blocks(const Dev& g);
 void launch_spmv_dot(const Dev& g, const double* A, const double* x, double* y, int zero_constrained, int dot_mode,
                      const double* w, int own_lo, int own_hi, int masked, const Scalars* sc, double* partials,
                      cudaStream_t st);
-void ilu_level_tables(const Dev& g, int slab_w, std::vector<int>& tab);
-void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st);
+// jc > 0 (everywhere below): radial split of the sub-slabs at grid row jc, see solver.cu: ypart_select
+void ilu_level_tables(const Dev& g, int slab_w, std::vector<int>& tab, int jc = 0);
+void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st,
+                       int jc = 0);
 // hp != null: multi-GPU with peer windows, the sweep also pushes the halo columns to the neighbours (p2p.cuh)
 void launch_ilu_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, const int* lvl_tab,
-                      cudaStream_t st, const HaloPush* hp = nullptr);
-void halo_contributors(const Dev& g, int slab_w, int* left, int* right);
+                      cudaStream_t st, const HaloPush* hp = nullptr, int jc = 0);
+void halo_contributors(const Dev& g, int slab_w, int* left, int* right, int jc = 0);
 // ilu1.cu: block ILU(1), 13 blocks per row, wavefronts il + 3 j
 int ilu1_max_slab_w(const Dev& g);
 void ilu1_level_tables(const Dev& g, int slab_w, std::vector<int>& tab);

@@ -119,6 +119,23 @@ __device__ __forceinline__ LevelRow level_row(const Dev& g, int L, int nlev, int
   return o;
 }
 
+// Radial split of the sub-slabs (jc > 0; additive Schwarz in y as well): blockIdx.y = 0 handles rows
+// [0, jc), 1 rows [jc, nvy) of its sub-slab as an independent grid -- couplings across the cut are dropped from
+// the preconditioner. The kernels below then simply see a grid of g.nvy = the part's rows: vertex-indexed arrays
+// are shifted to the part's first row, the packed factor stores all lower parts first and all upper parts after
+// them, and the level tables hold two tables (full / last sub-slab width) per part. Placed in the uniform far
+// field of the radial grid the cut costs no Krylov iterations and halves the dependency depth of a sweep
+// (w + 2 Ny wavefronts -> w + Ny).
+struct YPart { int j0, nvy_glob, lvl_off; };
+__device__ __forceinline__ YPart ypart_select(Dev& g, int jc, int slab_w) {
+  YPart yp{0, g.nvy, 0};
+  if (jc > 0) {
+    if (blockIdx.y) { yp.lvl_off = 2 * (slab_w + 2 * (jc - 1) + 1); yp.j0 = jc; g.nvy -= jc; }
+    else g.nvy = jc;
+  }
+  return yp;
+}
+
 // block ILU0 of one sub-slab per CTA (bilu0_decomposition: L_ij = A_ij * A_jj^-1, diagonal stored
 // inverted). One quad per wavefront row. The 720 B Jacobian row of level L+2 is streamed into shared
 // memory with cp.async while level L is eliminated; the finished [Dinv | U] rows of the last three
@@ -126,8 +143,13 @@ __device__ __forceinline__ LevelRow level_row(const Dev& g, int L, int nlev, int
 // the critical path of a level contains no global load.
 #define AX1_RING_ROW 82  // 80 doubles + 2 padding: 8 quads of a warp hit 8 different bank groups
 __global__ void __launch_bounds__(256, 1) ilu_factor_kernel(Dev g, const double* __restrict__ A, double* LF, double* LB,
-                                                            int slab_w, const int* __restrict__ lvl_tab) {
+                                                            int slab_w, const int* __restrict__ lvl_tab, int jc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  {
+    const YPart yp = ypart_select(g, jc, slab_w);
+    const size_t roff = (size_t)yp.j0 * g.nvx;
+    A += roff * AX1_ROW; LF += roff * 64; LB += roff * 80; lvl_tab += yp.lvl_off;
+  }
   const int tid = threadIdx.x, q = tid >> 2, r = tid & 3, nq = blockDim.x >> 2;
   double* stage = reinterpret_cast<double*>(smem_raw);            // [2][nq][AX1_ROW]
   double* ring = stage + 2 * (size_t)nq * AX1_ROW;                 // [3][nq][AX1_RING_ROW]
@@ -257,8 +279,13 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 // independent dependency chains per thread instead of one, and a single barrier per level (the ring slot written at
 // the end of iteration L was last read in iteration L-1). Operation order per row is unchanged.
 __global__ void __launch_bounds__(256) ilu_factor16_kernel(Dev g, const double* __restrict__ A, double* LF, double* LB,
-                                                           int slab_w, int nq, const int* __restrict__ lvl_tab) {
+                                                           int slab_w, int nq, const int* __restrict__ lvl_tab, int jc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  {
+    const YPart yp = ypart_select(g, jc, slab_w);
+    const size_t roff = (size_t)yp.j0 * g.nvx;
+    A += roff * AX1_ROW; LF += roff * 64; LB += roff * 80; lvl_tab += yp.lvl_off;
+  }
   const int tid = threadIdx.x, q = tid >> 4, e = tid & 15, r = e >> 2, c = e & 3;
   const int lane = tid & 31, rowl = lane & ~3, grp = lane & 16;  // first lane of my block row / of my vertex row
   double* stage = reinterpret_cast<double*>(smem_raw);            // [3][nq][AX1_ROW]
@@ -396,8 +423,13 @@ template <int D, bool P2P>
 __global__ void __launch_bounds__(256) ilu_apply_kernel(Dev g, const double* __restrict__ LF,
                                                         const double* __restrict__ LB, const double* __restrict__ d,
                                                         double* v_out, int slab_w, const int* __restrict__ lvl_tab,
-                                                        HaloPush hp) {
+                                                        HaloPush hp, int jc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const YPart yp = ypart_select(g, jc, slab_w);
+  {
+    const size_t roff = (size_t)yp.j0 * g.nvx;
+    LF += roff * 64; LB += roff * 80; d += 4 * roff; v_out += 4 * roff; lvl_tab += yp.lvl_off;
+  }
   const int nt = blockDim.x, tid = threadIdx.x;
   const int q = tid >> 2, r = tid & 3, nq = nt >> 2;
   double* stageM = reinterpret_cast<double*>(smem_raw);   // [D][5][nt][4]
@@ -517,7 +549,7 @@ __global__ void __launch_bounds__(256) ilu_apply_kernel(Dev g, const double* __r
       xo += d23.y * __shfl_sync(qmask, acc, qb + 3);
       ring[((size_t)(L & 3) * nq + q) * 4 + r] = xo;
       v_out[4 * (size_t)w.v + r] = xo;
-      if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + w.il, w.j, r, xo);
+      if (P2P) halo_push_value(hp, g.nvx, yp.nvy_glob, i0 + w.il, w.j + yp.j0, r, xo);
     }
     cta_sync();
     issue_bwd(L - D);
@@ -544,8 +576,13 @@ template <int D, bool P2P>
 __global__ void __launch_bounds__(160) ilu_apply_tma_kernel(Dev g, const double* __restrict__ LF,
                                                             const double* __restrict__ LB, const double* __restrict__ d,
                                                             double* v_out, int slab_w, const int* __restrict__ lvl_tab,
-                                                            HaloPush hp) {
+                                                            HaloPush hp, int jc) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  const YPart yp = ypart_select(g, jc, slab_w);
+  {
+    const size_t roff = (size_t)yp.j0 * g.nvx;
+    LF += roff * 64; LB += roff * 80; d += 4 * roff; v_out += 4 * roff; lvl_tab += yp.lvl_off;
+  }
   const int tid = threadIdx.x;
   const int nt = blockDim.x - 32;                                     // consumer threads; the last warp produces
   const int nq = nt >> 2;
@@ -714,7 +751,7 @@ __global__ void __launch_bounds__(160) ilu_apply_tma_kernel(Dev g, const double*
         xo += uv[0][1].y * __shfl_sync(qmask, acc, qb + 3);
         sts_d(ringown_u + su0, xo);
         v_out[voff] = xo;
-        if (P2P) halo_push_value(hp, g.nvx, g.nvy, i0 + 2 * q + b, j, r, xo);
+        if (P2P) halo_push_value(hp, g.nvx, yp.nvy_glob, i0 + 2 * q + b, j + yp.j0, r, xo);
       }
       if (one_warp) __syncwarp();
       else named_bar_sync(1, nt);
@@ -806,23 +843,34 @@ static int slab_threads(int slab_w) {
   if (t < 32) t = 32;
   return t;
 }
-// level prefix tables for full-width sub-slabs and for the (narrower) last one: 2 x (slab_w + 2 Ny + 1) ints
-void ilu_level_tables(const Dev& g, int slab_w, std::vector<int>& tab) {
-  const int stride = slab_w + 2 * (g.nvy - 1) + 1;
-  tab.assign(2 * (size_t)stride, 0);
-  const int last_wc = g.nvx - ((g.nvx - 1) / slab_w) * slab_w;
+// level prefix tables for full-width sub-slabs and for the (narrower) last one: 2 x (slab_w + 2 Ny + 1) ints;
+// with a radial split (jc > 0) one such pair per part, the lower part (rows [0, jc)) first
+static void level_tables_part(int nvx, int nvy, int slab_w, std::vector<int>& tab) {
+  const int stride = slab_w + 2 * (nvy - 1) + 1;
+  const size_t base = tab.size();
+  tab.resize(base + 2 * (size_t)stride, 0);
+  const int last_wc = nvx - ((nvx - 1) / slab_w) * slab_w;
   const int wcs[2] = {slab_w, last_wc};
   for (int t = 0; t < 2; ++t) {
-    const int wc = wcs[t], nlev = wc + 2 * (g.nvy - 1);
+    const int wc = wcs[t], nlev = wc + 2 * (nvy - 1);
     int acc = 0;
     for (int L = 0; L < nlev; ++L) {
-      tab[(size_t)t * stride + L] = acc;
+      tab[base + (size_t)t * stride + L] = acc;
       const int a = L - wc + 1;
       const int jlo = a <= 0 ? 0 : (a + 1) / 2;
-      const int jhi = std::min(g.nvy - 1, L >> 1);
+      const int jhi = std::min(nvy - 1, L >> 1);
       if (jhi >= jlo) acc += jhi - jlo + 1;
     }
-    tab[(size_t)t * stride + nlev] = acc;
+    tab[base + (size_t)t * stride + nlev] = acc;
+  }
+}
+void ilu_level_tables(const Dev& g, int slab_w, std::vector<int>& tab, int jc) {
+  tab.clear();
+  if (jc > 0) {
+    level_tables_part(g.nvx, jc, slab_w, tab);
+    level_tables_part(g.nvx, g.nvy - jc, slab_w, tab);
+  } else {
+    level_tables_part(g.nvx, g.nvy, slab_w, tab);
   }
 }
 // AX1_ILU_FACTOR16=0 keeps the quad-per-row factorisation for narrow sub-slabs too (A/B)
@@ -830,8 +878,9 @@ static bool ilu_use_factor16() {
   static const int v = getenv("AX1_ILU_FACTOR16") ? atoi(getenv("AX1_ILU_FACTOR16")) : 1;
   return v != 0;
 }
-void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st) {
-  const int nslab = (g.nvx + slab_w - 1) / slab_w;
+void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st,
+                       int jc) {
+  const dim3 nslab((g.nvx + slab_w - 1) / slab_w, jc > 0 ? 2 : 1);
   // measured (same box): 16 columns 0.74 -> 0.66 ms on the paper grid, 24 columns 0.81 -> 0.79 ms; at 32 columns
   // (256 threads) the quad-per-row kernel is faster again (1.17 vs 1.28 ms on the myelin grid)
   if (slab_w <= 24 && ilu_use_factor16()) {
@@ -842,7 +891,7 @@ void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, co
       cudaFuncSetAttribute(ilu_factor16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       attr16 = true;
     }
-    ilu_factor16_kernel<<<nslab, 16 * nq, smem, st>>>(g, A, LU, LU + (size_t)g.nv * 64, slab_w, nq, lvl_tab);
+    ilu_factor16_kernel<<<nslab, 16 * nq, smem, st>>>(g, A, LU, LU + (size_t)g.nv * 64, slab_w, nq, lvl_tab, jc);
     return;
   }
   const int nt = slab_threads(slab_w), nq = nt / 4;
@@ -852,7 +901,7 @@ void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, co
     cudaFuncSetAttribute(ilu_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  ilu_factor_kernel<<<nslab, nt, smem, st>>>(g, A, LU, LU + (size_t)g.nv * 64, slab_w, lvl_tab);
+  ilu_factor_kernel<<<nslab, nt, smem, st>>>(g, A, LU, LU + (size_t)g.nv * 64, slab_w, lvl_tab, jc);
 }
 // Depth of the cp.async pipeline of the sweeps. A level is consumed D levels after its loads were issued, so
 // the sweep advances one level per (HBM latency / D) unless bandwidth limits it first. With 256-thread CTAs
@@ -871,8 +920,8 @@ static bool ilu_use_tma() {
 }
 template <int D, bool P2P>
 static void launch_ilu_apply_t(const Dev& g, const double* LU, const double* d, double* v, int slab_w,
-                               const int* lvl_tab, const HaloPush& hp, cudaStream_t st) {
-  const int nslab = (g.nvx + slab_w - 1) / slab_w;
+                               const int* lvl_tab, const HaloPush& hp, cudaStream_t st, int jc) {
+  const dim3 nslab((g.nvx + slab_w - 1) / slab_w, jc > 0 ? 2 : 1);
   const int nt = slab_threads(slab_w);
   // Sub-slabs of up to 64 columns (small grids: the sweep is bound by per-level latency) take the warp-specialised
   // TMA pipeline; at 128 columns the sweep is bandwidth-bound, both kernels reach the same ~0.94 of the copy peak
@@ -886,7 +935,7 @@ static void launch_ilu_apply_t(const Dev& g, const double* LU, const double* d, 
       cudaFuncSetAttribute(ilu_apply_tma_kernel<D, P2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       attr_t = true;
     }
-    ilu_apply_tma_kernel<D, P2P><<<nslab, nt + 32, smem_t, st>>>(g, LU, LU + (size_t)g.nv * 64, d, v, slab_w, lvl_tab, hp);
+    ilu_apply_tma_kernel<D, P2P><<<nslab, nt + 32, smem_t, st>>>(g, LU, LU + (size_t)g.nv * 64, d, v, slab_w, lvl_tab, hp, jc);
     return;
   }
   const size_t smem = (size_t)D * nt * (5 * 32 + 8) + 4 * (size_t)(nt / 4) * 32 + (size_t)(slab_w + 2 * g.nvy) * sizeof(int);
@@ -895,27 +944,27 @@ static void launch_ilu_apply_t(const Dev& g, const double* LU, const double* d, 
     cudaFuncSetAttribute(ilu_apply_kernel<D, P2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  ilu_apply_kernel<D, P2P><<<nslab, nt, smem, st>>>(g, LU, LU + (size_t)g.nv * 64, d, v, slab_w, lvl_tab, hp);
+  ilu_apply_kernel<D, P2P><<<nslab, nt, smem, st>>>(g, LU, LU + (size_t)g.nv * 64, d, v, slab_w, lvl_tab, hp, jc);
 }
 template <bool P2P>
 static void launch_ilu_apply_d(const Dev& g, const double* LU, const double* d, double* v, int slab_w,
-                               const int* lvl_tab, const HaloPush& hp, cudaStream_t st) {
+                               const int* lvl_tab, const HaloPush& hp, cudaStream_t st, int jc) {
   switch (ilu_pick_stages(slab_threads(slab_w), 5 * 32 + 8)) {
-    case 8: launch_ilu_apply_t<8, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
-    case 6: launch_ilu_apply_t<6, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
-    case 4: launch_ilu_apply_t<4, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
-    case 3: launch_ilu_apply_t<3, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
-    default: launch_ilu_apply_t<2, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st); break;
+    case 8: launch_ilu_apply_t<8, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st, jc); break;
+    case 6: launch_ilu_apply_t<6, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st, jc); break;
+    case 4: launch_ilu_apply_t<4, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st, jc); break;
+    case 3: launch_ilu_apply_t<3, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st, jc); break;
+    default: launch_ilu_apply_t<2, P2P>(g, LU, d, v, slab_w, lvl_tab, hp, st, jc); break;
   }
 }
 void launch_ilu_apply(const Dev& g, const double* LU, const double* d, double* v, int slab_w, const int* lvl_tab,
-                      cudaStream_t st, const HaloPush* hp) {
+                      cudaStream_t st, const HaloPush* hp, int jc) {
   // the inputs of the preconditioner are already zero on constrained DOFs (see driver.cu)
-  if (hp) launch_ilu_apply_d<true>(g, LU, d, v, slab_w, lvl_tab, *hp, st);
-  else launch_ilu_apply_d<false>(g, LU, d, v, slab_w, lvl_tab, HaloPush{}, st);
+  if (hp) launch_ilu_apply_d<true>(g, LU, d, v, slab_w, lvl_tab, *hp, st, jc);
+  else launch_ilu_apply_d<false>(g, LU, d, v, slab_w, lvl_tab, HaloPush{}, st, jc);
 }
 // sub-slab CTAs that own part of the left / right three halo vertex columns
-void halo_contributors(const Dev& g, int slab_w, int* left, int* right) {
+void halo_contributors(const Dev& g, int slab_w, int* left, int* right, int jc) {
   const int nslab = (g.nvx + slab_w - 1) / slab_w;
   int l = 0, r = 0;
   for (int b = 0; b < nslab; ++b) {
@@ -923,6 +972,7 @@ void halo_contributors(const Dev& g, int slab_w, int* left, int* right) {
     if (i0 < 3) ++l;
     if (i0 + wc > g.nvx - 3) ++r;
   }
+  if (jc > 0) { l *= 2; r *= 2; }   // radial split: two CTAs per sub-slab
   *left = l; *right = r;
 }
 void launch_rownorm(const Dev& g, double* A, double* r, cudaStream_t st) {

@@ -218,6 +218,15 @@ int ax1gpu_ilu_factor_n(ax1gpu_handle h, int slab_w, int fill);
  * (on = 0) and one V(1,1) cycle of the aggregation multigrid with `cx` vertex columns per aggregate
  * (cx <= 0: keep, default 4); the hierarchy is rebuilt by the next factorisation */
 int ax1gpu_set_amg(ax1gpu_handle h, int on, int cx);
+/* Radial split of the block-ILU0 sub-slabs (additive Schwarz in y as well as in x): rows below and from grid row
+ * `jcut` on are factorised and swept separately, couplings across the cut are dropped from the preconditioner.
+ * jcut = -1 (default): automatic -- when the library also chooses the sub-slab width (slab_w <= 0) and that width is
+ * <= 64 columns (latency-bound grids), it cuts in the uniform far field of the radial grid, which costs no Krylov
+ * iterations and halves the depth of a sweep;
+ * 0: never; > 0: cut at this row. Takes effect with the next factorisation. *active (optional) returns the cut the
+ * last factorisation used. */
+int ax1gpu_set_ilu_split(ax1gpu_handle h, int jcut);
+int ax1gpu_get_ilu_split(ax1gpu_handle h, int* active);
 /* one application of the current preconditioner (ILU sweep or AMG cycle) incl. the halo sum */
 int ax1gpu_ilu_apply(ax1gpu_handle h, const double* d, double* v);
 int ax1gpu_rownorm(ax1gpu_handle h, double* r); /* scales device Jacobian and r */

@@ -85,6 +85,9 @@ ax1o_problem* ax1o_create(const ax1o_config* cfg, int nx, int ny, const double* 
 void ax1o_destroy(ax1o_problem* p);
 const char* ax1o_last_error(void);
 
+/* radial split of the ILU sub-slabs for all later factorisations of this problem: rows j < jcut and j >= jcut are
+ * factorised separately (oracle.hpp: Problem::ilu_jcut); 0 = off */
+void ax1o_set_ilu_split(ax1o_problem* p, int jcut);
 int ax1o_num_vertices(const ax1o_problem* p);
 int ax1o_membrane_row(const ax1o_problem* p);
 void ax1o_get_maps(const ax1o_problem* p, unsigned char* cell_sub, double* node_volume,

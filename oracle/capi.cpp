@@ -44,6 +44,8 @@ void ax1o_newton_opts_default(ax1o_newton_opts* o) {
 
 int ax1o_sizeof_config(void) { return (int)sizeof(ax1o_config); }
 
+void ax1o_set_ilu_split(ax1o_problem* h, int jcut) { h->p.ilu_jcut = jcut > 0 ? jcut : 0; }
+
 int ax1o_generate_y(double ymin, double ymax, double ymemb, double dmemb, double dy_cell,
                     double dy_cell_min, int n_dy_cell_min, double dy, double dy_min, int n_dy_min,
                     double* out, int cap) {

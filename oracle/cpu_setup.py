@@ -148,3 +148,7 @@ class MultiRankProblem:
         for (c0, c1, l0, l1), P, ul in zip(self.parts, self.probs, self.scatter(u)):
             vm[c0:c1] = P.membrane_potential(ul)[c0 - l0:c1 - l0]
         return vm
+
+    def set_ilu_split(self, jcut):
+        for P in self.probs:
+            P.set_ilu_split(jcut)

@@ -70,6 +70,11 @@ struct Problem {
   // time
   double time = 0, dt = 0;          // step start time and dt (flux GF); LOP time = time+dt
   std::vector<double> uold, r0;     // previous step and constant residual part -M(uold)
+  // radial split of the ILU sub-slabs (additive Schwarz in y as well): rows j < ilu_jcut and j >= ilu_jcut of a
+  // sub-slab are factorised separately, couplings across the cut are dropped from the preconditioner. 0 = off
+  // (the reference: one ILU per rank). The device places the cut in the uniform far field, where it costs no
+  // Krylov iterations and halves the dependency depth of the sweeps.
+  int ilu_jcut = 0;
 
   int vid(int i, int j) const { return i + nvx * j; }
   int cid(int i, int j) const { return i + nx * j; }
@@ -120,7 +125,7 @@ struct ILU {
 // sub-slab additive-Schwarz decomposition inside one rank: vertex columns grouped into slabs of
 // width slab_w (<=0: one slab = plain ILU on the local matrix as the reference does)
 void ilu_factor(const Problem& p, const BCRS& A, int fill_level, int slab_w, ILU& f);
-void ilu_factor_nvx(int nvx, const BCRS& A, int fill_level, int slab_w, ILU& f);  // vertex v lies in column v % nvx
+void ilu_factor_nvx(int nvx, const BCRS& A, int fill_level, int slab_w, ILU& f, int jcut = 0);  // vertex v lies in column v % nvx, row v / nvx
 void ilu_apply(const ILU& f, const double* d, double* v);
 void spmv(const BCRS& A, const double* x, double* y);
 

@@ -163,6 +163,8 @@ def lib():
                                                       c_double_p, C.c_int]
     for name in ("ax1o_num_vertices", "ax1o_membrane_row"):
         getattr(L, name).argtypes = [C.c_void_p]
+    L.ax1o_set_ilu_split.argtypes = [C.c_void_p, C.c_int]
+    L.ax1o_set_ilu_split.restype = None
     L.ax1o_get_maps.argtypes = [C.c_void_p, c_ubyte_p, c_double_p, c_ubyte_p]
     L.ax1o_pattern.argtypes = [C.c_void_p, c_int_p, c_int_p]
     L.ax1o_constants.argtypes = [C.c_void_p, c_double_p]
@@ -272,6 +274,10 @@ class Problem:
                 self.h = None
         except Exception:
             pass
+
+    def set_ilu_split(self, jcut):
+        """Factorise rows j < jcut and j >= jcut of every ILU sub-slab separately (0: off)."""
+        lib().ax1o_set_ilu_split(self.h, int(jcut))
 
     def maps(self):
         cs = np.zeros(self.nx * self.ny, dtype=np.uint8)

@@ -67,11 +67,13 @@ void mat4_invert(double* M) {  // Gauss-Jordan with partial pivoting (FieldMatri
 // then bilu0_decomposition on the enlarged pattern. slab_w > 0 first drops all blocks that couple
 // vertex columns of different sub-slabs (our many-slabs-per-rank reading of additive Schwarz).
 void ilu_factor(const Problem& p, const BCRS& A, int n_fill, int slab_w, ILU& f) {
-  ilu_factor_nvx(p.nvx, A, n_fill, slab_w, f);
+  ilu_factor_nvx(p.nvx, A, n_fill, slab_w, f, p.ilu_jcut);
 }
-void ilu_factor_nvx(int nvx, const BCRS& A, int n_fill, int slab_w, ILU& f) {
+void ilu_factor_nvx(int nvx, const BCRS& A, int n_fill, int slab_w, ILU& f, int jcut) {
   const int N = A.n;
-  auto slab_of = [&](int v) { return slab_w > 0 ? (v % nvx) / slab_w : 0; };
+  auto slab_of = [&](int v) {
+    return 2 * (slab_w > 0 ? (v % nvx) / slab_w : 0) + ((jcut > 0 && v / nvx >= jcut) ? 1 : 0);
+  };
   BCRS& LU = f.LU;
   LU.n = N;
   LU.rowptr.assign(N + 1, 0);

@@ -804,3 +804,62 @@ def test_fields_at_rounding_floor_match_extended_precision_truth(oracle, axlib, 
     assert e_orc[3] < 2e-7, e_orc                       # the measured floor itself (see docstring)
     assert e_dev[3] <= floor and e_do[3] <= floor, (e_dev, e_orc, e_do)
     dev.close()
+
+
+@pytest.mark.parametrize("nx,slab_w,jc", [(40, 16, 91), (21, 4, 100), (70, 24, 91), (150, 128, 91), (37, 16, 60)])
+def test_ilu_apply_radial_split(oracle, axlib, nx, slab_w, jc):
+    """Radial split of the sub-slabs (ax1gpu_set_ilu_split): rows below / from row jc on are factorised and swept by
+    separate CTAs, couplings across the cut dropped -- on every sweep kernel (one-warp TMA, multi-warp TMA, cp.async)
+    and factor kernel (16 lanes per row, quad per row), ragged last sub-slab included, against the oracle's ILU0 of
+    the same block structure."""
+    s = small_setup(nx=nx)
+    dev, P, u0 = _both(oracle, axlib, s)
+    Jo = P.jacobian(u0)
+    dev.set_jacobian(Jo)
+    rng = np.random.default_rng(5)
+    d = rng.standard_normal(P.n)
+    dev.set_ilu_split(jc); P.set_ilu_split(jc)
+    dev.ilu_factor(slab_w, 0)
+    assert dev.ilu_split() == jc
+    vg = dev.ilu_apply(d)
+    vo = P.ilu_apply(Jo, d, 0, slab_w)
+    assert np.max(np.abs(vg - vo)) <= 1e-9 * np.max(np.abs(vo))
+    # the split changes the preconditioner (couplings across row jc are gone) -- barely so in the far field (rows
+    # 91, 100: relative change of M^-1 d below 1e-6, which is why the cut is free), visibly at row 60
+    P.set_ilu_split(0)
+    v0 = P.ilu_apply(Jo, d, 0, slab_w)
+    assert not np.array_equal(vo, v0)
+    if jc == 60:
+        assert np.max(np.abs(vo - v0)) > 1e-6 * np.max(np.abs(v0))
+    # ... and switching it off restores the plain sub-slab ILU0
+    dev.set_ilu_split(0)
+    dev.ilu_factor(slab_w, 0)
+    assert dev.ilu_split() == 0
+    assert np.max(np.abs(dev.ilu_apply(d) - v0)) <= 1e-9 * np.max(np.abs(v0))
+    dev.close()
+
+
+def test_default_preconditioner_uses_far_field_cut_and_matches_oracle(oracle, axlib):
+    """Library defaults on a latency-bound grid (slab_w = 0): narrow sub-slabs plus the automatic cut in the uniform
+    far field of the radial grid (row 91 of the shipped 181-point vector). Newton with these defaults equals the
+    oracle running the same block structure: same Newton and (+-1) Krylov counts, fields to the usual bounds; the
+    explicit-width call keeps the unsplit ILU0."""
+    s = small_setup(nx=40)
+    dev, P, u0 = _both(oracle, axlib, s)
+    kw = dict(reduction=1e-10, abs_limit=1e-14, min_lin_reduction=1e-10, maxit=8)
+    ug, ng = dev.newton(u0, axlib.default_newton_opts(slab_w=0, **kw))
+    jc = dev.ilu_split()
+    assert jc == 91
+    P.set_ilu_split(jc)
+    uc, nc = P.newton(u0, oracle.default_newton_opts(ilu_fill=0, slab_w=16, **kw))
+    assert ng.status == 0 and nc.status == 0 and ng.iterations == nc.iterations
+    assert abs(ng.lin_iterations - nc.lin_iterations) <= ng.iterations
+    scale = np.max(np.abs(uc.reshape(-1, 4)), axis=0)
+    err = np.max(np.abs(ug - uc).reshape(-1, 4) / scale, axis=0)
+    assert np.all(err[:3] < 1e-11) and err[3] < 2e-7, err
+    # an explicit width alone does not bring the cut along
+    for obj in (dev,):
+        obj.set_time(0.0, 1.0); obj.set_uold(u0); obj.update_state(u0)
+    dev.newton(u0, axlib.default_newton_opts(slab_w=16, **kw))
+    assert dev.ilu_split() == 0
+    dev.close()
