@@ -477,7 +477,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if myelin and args.slab_w == SLAB_W:
-        args.slab_w = 24 if args.ilu_fill == 1 else 16   # the library default on this grid: one-warp sub-slabs
+        args.slab_w = 0     # library default on this grid: one-warp sub-slabs (16 / 24 columns) + far-field radial cut
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
@@ -667,6 +667,7 @@ def main():
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
            "scaling": "strong" if myelin else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": config, "comm": {0: "none", 1: "nccl", 2: "nvlink peer windows"}[dev.comm_mode()],
+           "ilu_radial_split_row": dev.ilu_split(),
            "newton_steps_per_s": newton_per_s, "newton_iterations_per_step": NEWTON_ITS,
            "krylov_iterations_per_solve": KRYLOV_ITS,
            "last_step": {"defect": last.defect, "first_defect": last.first_defect, "lin_iterations": last.lin_iterations,
