@@ -42,6 +42,7 @@ class Params(C.Structure):
         ("use_elec_jacobian_volume", C.c_int), ("use_memb_jacobian_volume", C.c_int),
         ("use_time_jacobian_volume", C.c_int),
         ("do_memb_flux_stimulation", C.c_int), ("memb_flux_ion", C.c_int), ("memb_flux_inj", C.c_double),
+        ("mori_membrane_neumann", C.c_int),
     ]
 
 
@@ -87,6 +88,15 @@ class StepResult(C.Structure):
     @property
     def iterations(self):
         return self.newton_iterations
+
+
+class MoriResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("pot_iterations", C.c_int), ("con_iterations", C.c_int),
+                ("pot_first_defect", C.c_double), ("pot_defect", C.c_double), ("con_first_defect", C.c_double),
+                ("con_defect", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class LinResult(C.Structure):
@@ -168,6 +178,10 @@ def lib():
     L.ax1gpu_membrane_potential_range.argtypes = [H, c_double_p, c_double_p]
     L.ax1gpu_membrane_potential_dev.argtypes = [H, c_double_p]
     L.ax1gpu_membrane_flux_terms.argtypes = [H, c_double_p, c_double_p]
+    L.ax1gpu_mori_step.argtypes = [H, C.POINTER(NewtonOpts), c_double_p, C.POINTER(MoriResult)]
+    L.ax1gpu_mori_assemble.argtypes = [H, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]
+    L.ax1gpu_mori_update_state.argtypes = [H, c_double_p]
+    L.ax1gpu_mori_get_gamma.argtypes = [H, c_double_p]
     L.ax1gpu_spmv.argtypes = [H, c_double_p, c_double_p]
     L.ax1gpu_ilu_factor.argtypes = [H, C.c_int]
     L.ax1gpu_ilu_factor_n.argtypes = [H, C.c_int, C.c_int]
@@ -603,6 +617,34 @@ class Ax1Gpu:
         vm = np.zeros(self.nx)
         _chk(lib().ax1gpu_membrane_potential_dev(self.h, _dp(vm)))
         return vm
+
+    # -- electroneutral (Mori) operator-split model (csrc/mori.cu)
+    def mori_step(self, u=None, opts=None):
+        """One operator-split step (potential solve, charge-layer update, concentration solve). u: host iterate
+        (returned updated) or None for the device iterate."""
+        opts = opts or default_newton_opts()
+        res = MoriResult()
+        uu = f64(u).copy() if u is not None else None
+        _chk(lib().ax1gpu_mori_step(self.h, C.byref(opts), _dp(uu), C.byref(res)))
+        return uu, res
+
+    def mori_assemble(self, which, u, ulast, jacobian=True):
+        r = np.zeros(self.n)
+        blocks = None
+        if jacobian:
+            nb = C.c_int()
+            _chk(lib().ax1gpu_pattern(self.h, None, None, C.byref(nb)))
+            blocks = np.zeros(nb.value * 16)
+        _chk(lib().ax1gpu_mori_assemble(self.h, int(which), _dp(f64(u)), _dp(f64(ulast)), _dp(r), _dp(blocks)))
+        return r, blocks
+
+    def mori_update_state(self, u=None):
+        _chk(lib().ax1gpu_mori_update_state(self.h, _dp(f64(u)) if u is not None else None))
+
+    def mori_gamma(self):
+        out = np.zeros(12 * self.nx)
+        _chk(lib().ax1gpu_mori_get_gamma(self.h, _dp(out)))
+        return out.reshape(2, 2, 3, self.nx)
 
     def upload_u(self, u):
         _chk(lib().ax1gpu_upload_u(self.h, _dp(f64(u))))

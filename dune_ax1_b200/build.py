@@ -19,6 +19,7 @@ UNITS = [
     ("amg.cu", []),
     ("driver.cu", []),
     ("timeloop.cu", []),
+    ("mori.cu", []),
     ("capi.cu", []),
     ("host_model.cpp", []),
 ]

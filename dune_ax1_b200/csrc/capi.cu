@@ -54,6 +54,7 @@ void ax1gpu_params_default(ax1gpu_params* p) {
   p->leak_ratio_na = 0.13; p->leak_ratio_k = 0.87;
   p->use_elec_jacobian_volume = p->use_memb_jacobian_volume = p->use_time_jacobian_volume = 1;
   p->do_memb_flux_stimulation = 0; p->memb_flux_ion = 2; p->memb_flux_inj = 0.0;
+  p->mori_membrane_neumann = 1;
 }
 
 void ax1gpu_newton_opts_default(ax1gpu_newton_opts* o) {
@@ -226,7 +227,7 @@ int ax1gpu_destroy(ax1gpu_handle c) {
                   (void*)c->d_u, (void*)c->d_uold, (void*)c->d_r0, (void*)c->d_r, (void*)c->d_z, (void*)c->d_uprev, (void*)c->d_A,
                   (void*)c->d_LU, (void*)c->d_rt, (void*)c->d_p, (void*)c->d_v, (void*)c->d_y2, (void*)c->d_t, (void*)c->d_tmp,
                   (void*)c->d_bcrs, (void*)c->d_gbar, (void*)c->d_chstate, (void*)c->d_geff, (void*)c->d_vrest, (void*)c->d_vm, (void*)c->d_fluxterms,
-                  (void*)c->d_err, (void*)c->d_partials, (void*)c->d_sums, (void*)c->d_sc, (void*)c->d_halo_send,
+                  (void*)c->d_mori_gamma, (void*)c->d_err, (void*)c->d_partials, (void*)c->d_sums, (void*)c->d_sc, (void*)c->d_halo_send,
                   (void*)c->d_halo_recv, (void*)c->d_lvl, (void*)c->d_spartials})
     if (p) cudaFree(p);
   if (c->h_sc) cudaFreeHost(c->h_sc);
@@ -283,7 +284,58 @@ int ax1gpu_update_state(ax1gpu_handle c, const double* u) {
   return AX1GPU_OK;
 }
 
-int ax1gpu_accept_state(ax1gpu_handle c) { AX1_CHECK_H(c); cudaSetDevice(c->device); return drv_accept_state(c); }
+int ax1gpu_accept_state(ax1gpu_handle c) {
+  AX1_CHECK_H(c);
+  cudaSetDevice(c->device);
+  int rc = drv_accept_state(c);
+  if (rc) return rc;
+  return drv_mori_accept_state(c);     // gfMoriFlux.acceptTimeStep(); no-op unless the Mori model is in use
+}
+
+int ax1gpu_mori_step(ax1gpu_handle c, const ax1gpu_newton_opts* opts, double* u, ax1gpu_mori_result* res) {
+  AX1_CHECK_H(c);
+  if (!res) { set_error("mori_step: res must not be NULL"); return AX1GPU_EINVAL; }
+  cudaSetDevice(c->device);
+  ax1gpu_newton_opts o;
+  if (opts) o = *opts; else ax1gpu_newton_opts_default(&o);
+  int rc;
+  if (u && (rc = up(c, c->d_u, u))) return rc;
+  if ((rc = drv_mori_step(c, &o, res))) return rc;
+  if (u) return down(c, u, c->d_u);
+  return AX1GPU_OK;
+}
+
+int ax1gpu_mori_assemble(ax1gpu_handle c, int which, const double* u, const double* ulast, double* r, double* blocks) {
+  AX1_CHECK_H(c);
+  if (!u || !ulast) { set_error("mori_assemble: u and ulast must not be NULL"); return AX1GPU_EINVAL; }
+  cudaSetDevice(c->device);
+  int rc;
+  if ((rc = up(c, c->d_u, u))) return rc;
+  if ((rc = up(c, c->d_uprev, ulast))) return rc;
+  if ((rc = drv_mori_assemble(c, which ? 1 : 0, c->d_u, c->d_uprev))) return rc;
+  if (r && (rc = down(c, r, c->d_r))) return rc;
+  if (blocks) return ax1gpu_get_jacobian(c, blocks);
+  AX1_CUDA(cudaStreamSynchronize(c->stream));
+  return AX1GPU_OK;
+}
+
+int ax1gpu_mori_update_state(ax1gpu_handle c, const double* u) {
+  AX1_CHECK_H(c);
+  cudaSetDevice(c->device);
+  int rc;
+  if (u && (rc = up(c, c->d_u, u))) return rc;
+  return drv_mori_update_state(c, c->d_u);
+}
+
+int ax1gpu_mori_get_gamma(ax1gpu_handle c, double* gamma) {
+  AX1_CHECK_H(c);
+  cudaSetDevice(c->device);
+  const size_t n = 12 * (size_t)c->g.nx;
+  if (!c->d_mori_gamma) { std::memset(gamma, 0, n * sizeof(double)); return AX1GPU_OK; }
+  AX1_CUDA(cudaMemcpyAsync(gamma, c->d_mori_gamma, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  AX1_CUDA(cudaStreamSynchronize(c->stream));
+  return AX1GPU_OK;
+}
 
 int ax1gpu_get_channel_state(ax1gpu_handle c, double* s, int newstate, double* v_rest) {
   AX1_CHECK_H(c);

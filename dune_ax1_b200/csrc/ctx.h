@@ -30,6 +30,9 @@ struct ax1gpu_ctx {
   double *d_gbar = nullptr, *d_chstate = nullptr, *d_geff = nullptr, *d_vrest = nullptr, *d_vm = nullptr;
   double* d_fluxterms = nullptr;  // 15 x nx output terms of the membrane flux (allocated on first use)
   int* d_err = nullptr;
+  // electroneutral (Mori) model: charge-layer states [side][old/new][ion][nx] (mori.cu), allocated on first use
+  double* d_mori_gamma = nullptr;
+  bool mori_initialized = false, mori_partially_initialized = false;
   bool channels_initialized = false, channels_partially_initialized = false;
   // reductions / Krylov scalars
   double* d_partials = nullptr;   // 2 * nred_blocks
@@ -112,5 +115,10 @@ int drv_time_step(ax1gpu_ctx* c, const ax1gpu_timeloop_opts* o, const ax1gpu_new
                   ax1gpu_step_result* out);
 int drv_norm(ax1gpu_ctx* c, const double* a, double* out_host);
 int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms);
-int drv_check_p2p(ax1gpu_ctx* c);   // after a host sync: AX1GPU_ENCCL if a peer-window exchange timed out
+int drv_check_p2p(ax1gpu_ctx* c);
+// mori.cu
+int drv_mori_update_state(ax1gpu_ctx* c, const double* d_u);
+int drv_mori_accept_state(ax1gpu_ctx* c);
+int drv_mori_assemble(ax1gpu_ctx* c, int which, const double* d_u, const double* d_ulast);   // -> d_r, d_A
+int drv_mori_step(ax1gpu_ctx* c, const ax1gpu_newton_opts* o, ax1gpu_mori_result* res);   // after a host sync: AX1GPU_ENCCL if a peer-window exchange timed out
 }  // namespace ax1

@@ -79,6 +79,9 @@ typedef struct ax1gpu_params {
    * the membrane-interface faces above stim_x (default_nernst_planck_parameters.hh:439-475)              */
   int do_memb_flux_stimulation, memb_flux_ion;
   double memb_flux_inj;
+  /* electroneutral (Mori) model only: [boundary] membrane potential Neumann (isMembraneBoundaryNeumann_Potential):
+   * the membrane interface carries the ionic + capacitive current as Neumann condition of the potential problem */
+  int mori_membrane_neumann;
 } ax1gpu_params;
 
 typedef struct ax1gpu_newton_opts {
@@ -102,6 +105,12 @@ typedef struct ax1gpu_newton_result { /* PDELab NewtonResult + ax1_newton.hh:600
   double first_defect, defect, reduction, conv_rate;
   double t_assembler, t_lin_solv, t_elapsed; /* seconds, device time from CUDA events */
 } ax1gpu_newton_result;
+
+/* result of one operator-split step of the electroneutral (Mori) model: the two Ax1LinearSubProblemSolver results */
+typedef struct ax1gpu_mori_result {
+  int status, pot_iterations, con_iterations;
+  double pot_first_defect, pot_defect, con_first_defect, con_defect;
+} ax1gpu_mori_result;
 
 typedef struct ax1gpu_lin_result { /* Dune::InverseOperatorResult */
   int converged, iterations;
@@ -208,6 +217,24 @@ int ax1gpu_membrane_potential_dev(ax1gpu_handle h, double* vm_mV);
  * (outer normal +y), with the new channel state: what acme2_cyl_output.hh:1215-1410 writes as memb_flux* per ion.
  * terms[(term * 3 + ion) * nx + column], 15 * nx doubles. */
 int ax1gpu_membrane_flux_terms(ax1gpu_handle h, const double* u, double* terms);
+
+/* ---- electroneutral (Mori) operator-split model (BASELINE configs[2]; csrc/mori.cu) -------------------------------
+ * replaces, for that model, Acme2CylMoriSimulation::run's step body (acme2_cyl_mori_simulation.hh:562-600):
+ *   solverPot.apply(unew)              Ax1LinearSubProblemSolver over Acme2CylMoriPotentialOperator
+ *   gfMoriFlux.updateState(time, dt)   ChargeLayerMoriImplicit (charge_layer_mori_implicit.hh)
+ *   solverCon.apply(time,dt,uold,unew) OneStepMethod / implicit Euler over Acme2CylMoriConcentrationOperator
+ * The caller drives it like the coupled path: ax1gpu_set_time, ax1gpu_upload_u + ax1gpu_set_uold_dev (or
+ * ax1gpu_set_uold), ax1gpu_update_state (channel gating), ax1gpu_mori_step, ax1gpu_accept_state (which also accepts
+ * the charge-layer states). Uses opts->reduction, abs_limit (min_defect), lin_maxit, slab_w, ilu_fill. u != NULL:
+ * host iterate in / out; NULL: the device iterate. Single rank. */
+int ax1gpu_mori_step(ax1gpu_handle h, const ax1gpu_newton_opts* opts, double* u, ax1gpu_mori_result* res);
+/* residual (4 per vertex; the other sub-problem's rows are 0) and optionally the Jacobian (BCRS order, identity on the
+ * other sub-problem's rows) of sub-problem `which` (0 potential, 1 concentrations) at u, with ulast = the solution of
+ * the last iteration the split lags; the device Jacobian is left in place for ax1gpu_solve */
+int ax1gpu_mori_assemble(ax1gpu_handle h, int which, const double* u, const double* ulast, double* r, double* blocks);
+int ax1gpu_mori_update_state(ax1gpu_handle h, const double* u);   /* gfMoriFlux.updateState on the host iterate u */
+/* charge-layer states gamma[((side * 2 + new) * 3 + ion) * nx + column], side 0 cytosol / 1 ES: 12 * nx doubles */
+int ax1gpu_mori_get_gamma(ax1gpu_handle h, double* gamma);
 
 /* ---- building blocks exposed for parity tests and profiling ---- */
 int ax1gpu_spmv(ax1gpu_handle h, const double* x, double* y);

@@ -34,6 +34,9 @@ typedef struct ax1o_config {
    * added to one species on the interface faces above stim_x (default_nernst_planck_parameters.hh:439-475) */
   int do_memb_flux_stimulation, memb_flux_ion;
   double memb_flux_inj;
+  /* electroneutral (Mori) model only: [boundary] membrane potential Neumann (isMembraneBoundaryNeumann_Potential) --
+   * the membrane interface carries the ionic + capacitive current as a Neumann condition of the potential problem */
+  int mori_membrane_neumann;
 } ax1o_config;
 
 typedef struct ax1o_newton_opts {
@@ -140,6 +143,23 @@ int ax1o_newton_mt(ax1o_problem** ranks, int nranks, double** u, const ax1o_newt
                    ax1o_newton_result* res /* per rank */);
 int ax1o_solve_mt(ax1o_problem** ranks, int nranks, double** vals, double** r, double** z,
                   double reduction, int maxit, int ilu_fill, int slab_w, ax1o_lin_result* res);
+
+/* ---- electroneutral (Mori) operator-split model, oracle/mori.cpp ---- */
+typedef struct ax1o_mori_result {
+  int status, pot_iterations, con_iterations;
+  double pot_first_defect, pot_defect, con_first_defect, con_defect;
+} ax1o_mori_result;
+/* which = 0: potential sub-problem, 1: concentration sub-problem. r (4 per vertex, the other sub-problem's rows 0) and,
+ * if vals != NULL, the Jacobian in BCRS order (identity on the other sub-problem's rows) at u; ulast = the solution of
+ * the last iteration the split lags (concentrations of the potential problem; drift / membrane terms of the
+ * concentration problem). uold / time / dt / channel state as set on the problem. */
+int ax1o_mori_assemble(ax1o_problem* p, int which, const double* u, const double* ulast, double* r, double* vals);
+/* charge-layer states gamma: out[((side * 2 + new) * 3 + ion) * nx + column], side 0 = cytosol (int), 1 = ES (ext) */
+void ax1o_mori_get_gamma(const ax1o_problem* p, double* out);
+void ax1o_mori_update_state(ax1o_problem* p, const double* u);   /* ChargeLayerMoriImplicit::updateState */
+/* one operator-split time step (potential solve, gamma update, concentration solve) from u = uold; uses
+ * o->reduction, abs_limit, lin_maxit, ilu_fill, slab_w. ax1o_accept_state also accepts the gamma states. */
+int ax1o_mori_step(ax1o_problem* p, double* u, const ax1o_newton_opts* o, ax1o_mori_result* res);
 
 /* external collectives (e.g. torch.distributed/gloo from Python): callbacks for one rank */
 typedef void (*ax1o_halo_add_fn)(void* ctx, int rank, double* v);

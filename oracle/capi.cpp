@@ -32,6 +32,7 @@ void ax1o_config_default(ax1o_config* c) {
   c->analytic_volume_jacobian = 7;
   c->leak_ratio_na = 0.13; c->leak_ratio_k = 0.87;
   c->do_memb_flux_stimulation = 0; c->memb_flux_ion = 2 /* Cl */; c->memb_flux_inj = 0.0;
+  c->mori_membrane_neumann = 1;
 }
 
 void ax1o_newton_opts_default(ax1o_newton_opts* o) {
@@ -123,7 +124,47 @@ void ax1o_set_uold(ax1o_problem* h, const double* uold) { set_uold(h->p, uold); 
 int ax1o_update_state(ax1o_problem* h, const double* u) {
   AX1O_TRY update_state(h->p, u); return 0; AX1O_CATCH(1)
 }
-void ax1o_accept_state(ax1o_problem* h) { accept_state(h->p); }
+void ax1o_accept_state(ax1o_problem* h) {
+  accept_state(h->p);
+  if (!h->p.mori_gamma_int_old[0].empty()) mori_accept_state(h->p);   // gfMoriFlux.acceptTimeStep()
+}
+
+int ax1o_mori_assemble(ax1o_problem* h, int which, const double* u, const double* ulast, double* r, double* vals) {
+  AX1O_TRY
+  BCRS A;
+  if (vals) build_pattern(h->p, A);
+  if (which == 0) mori_potential_assemble(h->p, u, ulast, r, vals ? &A : nullptr);
+  else mori_concentration_assemble(h->p, u, ulast, r, vals ? &A : nullptr);
+  if (vals) std::memcpy(vals, A.val.data(), A.val.size() * sizeof(double));
+  return 0;
+  AX1O_CATCH(1)
+}
+
+void ax1o_mori_get_gamma(const ax1o_problem* h, double* out) {
+  const Problem& p = h->p;
+  const int nx = p.nx;
+  if (p.mori_gamma_int_old[0].empty()) { for (int k = 0; k < 12 * nx; ++k) out[k] = 0.0; return; }
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < nx; ++i) {
+      out[((0 * 2 + 0) * 3 + j) * nx + i] = p.mori_gamma_int_old[j][i];
+      out[((0 * 2 + 1) * 3 + j) * nx + i] = p.mori_gamma_int_new[j][i];
+      out[((1 * 2 + 0) * 3 + j) * nx + i] = p.mori_gamma_ext_old[j][i];
+      out[((1 * 2 + 1) * 3 + j) * nx + i] = p.mori_gamma_ext_new[j][i];
+    }
+}
+
+void ax1o_mori_update_state(ax1o_problem* h, const double* u) { mori_update_state(h->p, u); }
+
+int ax1o_mori_step(ax1o_problem* h, double* u, const ax1o_newton_opts* o, ax1o_mori_result* res) {
+  AX1O_TRY
+  NewtonOpts no;
+  static_cast<ax1o_newton_opts&>(no) = *o;
+  MoriResult mr;
+  mori_step(h->p, u, no, mr);
+  *res = mr;
+  return 0;
+  AX1O_CATCH(-1)
+}
 
 void ax1o_get_channel_state(const ax1o_problem* h, double* s, int newstate) {
   const Problem& p = h->p;

@@ -76,6 +76,12 @@ struct Problem {
   // Krylov iterations and halves the dependency depth of the sweeps.
   int ilu_jcut = 0;
 
+  // charge layer of the electroneutral (Mori) model: gamma_j per membrane column, cytosol (int) / ES (ext) side,
+  // accepted (old) / new (charge_layer_mori_implicit.hh); empty until the first mori_update_state
+  std::vector<double> mori_gamma_int_old[NSPEC], mori_gamma_int_new[NSPEC];
+  std::vector<double> mori_gamma_ext_old[NSPEC], mori_gamma_ext_new[NSPEC];
+  bool mori_initialized = false, mori_partially_initialized = false;
+
   int vid(int i, int j) const { return i + nvx * j; }
   int cid(int i, int j) const { return i + nx * j; }
 };
@@ -129,6 +135,7 @@ void ilu_factor_nvx(int nvx, const BCRS& A, int fill_level, int slab_w, ILU& f, 
 void ilu_apply(const ILU& f, const double* d, double* v);
 void spmv(const BCRS& A, const double* x, double* y);
 
+struct MoriResult : ax1o_mori_result { MoriResult() : ax1o_mori_result{0, 0, 0, 0.0, 0.0, 0.0, 0.0} {} };
 struct LinResult : ax1o_lin_result { LinResult() : ax1o_lin_result{0, 0, 0.0, 0.0} {} };
 struct Comm {  // collectives for the overlapping multi-rank path (identity for one rank)
   void* ctx = nullptr;
@@ -181,6 +188,13 @@ enum { NEWTON_OK = 0, NEWTON_NOT_CONVERGED = 1, NEWTON_LINSOLVE_FAILED = 2, NEWT
        NEWTON_LINESEARCH_FAILED = 4 };
 void membrane_flux_terms(const Problem& p, int i, const double* uglob, double* out15);
 void newton(Problem& p, double* u, const NewtonOpts& o, const Comm* comm, NewtonResult& res);
+
+// ---- mori.cpp: electroneutral (Mori) operator-split model
+void mori_update_state(Problem& p, const double* u);
+void mori_accept_state(Problem& p);
+void mori_potential_assemble(const Problem& p, const double* u, const double* ulast, double* r, BCRS* A);
+void mori_concentration_assemble(const Problem& p, const double* u, const double* ulast, double* r, BCRS* A);
+void mori_step(Problem& p, double* u, const NewtonOpts& o, MoriResult& res);
 double line_search(size_t n, double* u, const double* z, double* prev_u, double cur_defect, double prev_defect,
                    int maxit, const std::function<double()>& eval, std::vector<double>* trace);
 

@@ -38,6 +38,7 @@ class Config(C.Structure):
         ("analytic_volume_jacobian", C.c_int), ("use_rownorm_preconditioner", C.c_int),
         ("leak_ratio_na", C.c_double), ("leak_ratio_k", C.c_double),
         ("do_memb_flux_stimulation", C.c_int), ("memb_flux_ion", C.c_int), ("memb_flux_inj", C.c_double),
+        ("mori_membrane_neumann", C.c_int),
     ]
 
 
@@ -67,6 +68,15 @@ class NewtonResult(C.Structure):
 class LinResult(C.Structure):
     _fields_ = [("converged", C.c_int), ("iterations", C.c_int), ("reduction", C.c_double),
                 ("it_half", C.c_double)]
+
+
+class MoriResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("pot_iterations", C.c_int), ("con_iterations", C.c_int),
+                ("pot_first_defect", C.c_double), ("pot_defect", C.c_double), ("con_first_defect", C.c_double),
+                ("con_defect", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 HALO_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, c_double_p)
@@ -165,6 +175,12 @@ def lib():
         getattr(L, name).argtypes = [C.c_void_p]
     L.ax1o_set_ilu_split.argtypes = [C.c_void_p, C.c_int]
     L.ax1o_set_ilu_split.restype = None
+    L.ax1o_mori_assemble.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]
+    L.ax1o_mori_get_gamma.argtypes = [C.c_void_p, c_double_p]
+    L.ax1o_mori_get_gamma.restype = None
+    L.ax1o_mori_update_state.argtypes = [C.c_void_p, c_double_p]
+    L.ax1o_mori_update_state.restype = None
+    L.ax1o_mori_step.argtypes = [C.c_void_p, c_double_p, C.POINTER(NewtonOpts), C.POINTER(MoriResult)]
     L.ax1o_get_maps.argtypes = [C.c_void_p, c_ubyte_p, c_double_p, c_ubyte_p]
     L.ax1o_pattern.argtypes = [C.c_void_p, c_int_p, c_int_p]
     L.ax1o_constants.argtypes = [C.c_void_p, c_double_p]
@@ -278,6 +294,32 @@ class Problem:
     def set_ilu_split(self, jcut):
         """Factorise rows j < jcut and j >= jcut of every ILU sub-slab separately (0: off)."""
         lib().ax1o_set_ilu_split(self.h, int(jcut))
+
+    # ---- electroneutral (Mori) operator-split model (oracle/mori.cpp)
+    def mori_assemble(self, which, u, ulast, jacobian=True):
+        """which 0: potential, 1: concentration sub-problem -> (r, BCRS values or None)"""
+        r = np.zeros(self.n)
+        vals = np.zeros(lib().ax1o_pattern(self.h, None, None) * 16) if jacobian else None
+        if lib().ax1o_mori_assemble(self.h, int(which), _dp(f64(u)), _dp(f64(ulast)), _dp(r), _dp(vals)):
+            raise RuntimeError(lib().ax1o_last_error().decode())
+        return r, vals
+
+    def mori_gamma(self):
+        """[side (0 cytosol, 1 ES)][old / new][ion][column] charge-layer states"""
+        out = np.zeros(12 * self.nx)
+        lib().ax1o_mori_get_gamma(self.h, _dp(out))
+        return out.reshape(2, 2, 3, self.nx)
+
+    def mori_update_state(self, u):
+        lib().ax1o_mori_update_state(self.h, _dp(f64(u)))
+
+    def mori_step(self, u, opts=None):
+        u = f64(u).copy()
+        opts = opts or default_newton_opts()
+        res = MoriResult()
+        if lib().ax1o_mori_step(self.h, _dp(u), C.byref(opts), C.byref(res)) < 0:
+            raise RuntimeError(lib().ax1o_last_error().decode())
+        return u, res
 
     def maps(self):
         cs = np.zeros(self.nx * self.ny, dtype=np.uint8)
