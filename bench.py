@@ -455,6 +455,101 @@ def run_paper(args, api, setups, local_rank):
     emit(out)
 
 
+def run_mori(args, api, setups, local_rank):
+    """BASELINE configs[2]: the electroneutral (Mori) operator-split model on the same synthetic grid (Nx columns,
+    dx = 100 nm, shipped radial vector). One step = one time step of Acme2CylMoriSimulation::run: channel update,
+    potential sub-problem (assemble + BiCGStab/ILU0), charge-layer update, concentration sub-problem, accept. Value =
+    DOF x steps per second; every step solves all 4 DOF per vertex once (1 + 3), both linear solves to the config's
+    reduction. A sample of the same steps runs on the oracle for parity and as CPU figure."""
+    import torch
+    workload = ("electroneutral (Mori) operator-split model, synthetic refined r-z grid Ny=180 x Nx=%d, dx=100 nm, "
+                "dt=1us: per step one potential and one concentration sub-problem solve (BiCGStab + ILU0 slab %d, "
+                "reduction 1e-5)" % (args.nx, args.slab_w))
+    config = {"workload": workload, "cells_per_gpu": args.nx * 180, "dof_total": 4 * (args.nx + 1) * 181,
+              "parallelism": "single rank", "l2": "inputs larger than L2" if args.nx >= 8192 else "reduced size"}
+    s = setups.make_setup(args.nx, dx=DX, perturbation=1e-3)
+    stream = torch.cuda.Stream(device=local_rank)
+    dev = setups.make_device(s, device=local_rank, stream=stream.cuda_stream)
+    opts = api.default_newton_opts(reduction=1e-5, abs_limit=1e-5, lin_maxit=5000, slab_w=args.slab_w, ilu_fill=0)
+    u_host_t = torch.empty(dev.n, dtype=torch.float64, pin_memory=True)
+    u_host = u_host_t.numpy()
+    u_host[:] = s["u0"]
+    dev.upload_u(u_host)
+    t = [0.0]
+
+    def step():
+        dev.set_time(t[0], 1.0)
+        dev.set_uold_dev()
+        dev.update_state()
+        _, r = dev.mori_step(None, opts)
+        dev.accept_state()
+        t[0] += 1.0
+        return r
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    l0 = dev.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    its = [0, 0]
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            r = step()
+            its[0] += r.pot_iterations; its[1] += r.con_iterations
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = dev.launch_count() - l0
+    # e2e: host buffers in and out every step
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dev.set_time(t[0], 1.0); dev.set_uold(u_host); dev.update_state(u_host)
+        un, _ = dev.mori_step(u_host, opts)
+        u_host[:] = un
+        dev.accept_state(); t[0] += 1.0
+    wall = time.perf_counter() - t0
+    n = dev.n
+    dev.close()
+    out = {"metric": "electroneutral (Mori) step throughput (DOF x time steps per second)", "value": n * args.steps / (ms * 1e-3) / 1e9,
+           "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config, "krylov_iterations_per_step": {"potential": its[0] / args.steps, "concentration": its[1] / args.steps},
+           "clocks": clocks, "gpu_launches": launches,
+           "e2e": {"value": n * args.steps / wall / 1e9, "unit": UNIT, "h2d_bytes_per_step": 3 * n * 8,
+                   "d2h_bytes_per_step": n * 8, "timing": "host wall clock"}}
+    if not args.no_cpu_baseline:
+        from oracle import cpu_setup as CS
+        from oracle import pyoracle as O
+        O.build()
+        nxs = min(args.nx, 512)
+        sg = setups.make_setup(nxs, dx=DX, perturbation=1e-3)
+        dg = setups.make_device(sg, device=local_rank)
+        P, u0 = CS.make_problem(nxs, DX, perturbation=1e-3)
+        oc = O.default_newton_opts(reduction=1e-5, abs_limit=1e-5, lin_maxit=5000, slab_w=args.slab_w, ilu_fill=0)
+        ug = uc = u0
+        tt, tcpu, itg, itc = 0.0, 0.0, [0, 0], [0, 0]
+        for _ in range(3):
+            for X, u in ((dg, ug), (P, uc)):
+                X.set_time(tt, 1.0); X.set_uold(u); X.update_state(u)
+            ug, rg = dg.mori_step(ug, opts)
+            t0 = time.perf_counter()
+            uc, rc = P.mori_step(uc, oc)
+            tcpu += time.perf_counter() - t0
+            dg.accept_state(); P.accept_state(); tt += 1.0
+            itg[0] += rg.pot_iterations; itg[1] += rg.con_iterations; itc[0] += rc.pot_iterations; itc[1] += rc.con_iterations
+        dg.close()
+        econ, epot = _field_err(ug, uc)
+        out["parity"] = {"nx": nxs, "steps": 3, "max_rel_err_con": econ, "max_rel_err_pot": epot, "krylov_its_gpu": itg,
+                         "krylov_its_cpu": itc, "green": bool(econ < 1e-8 and epot < 1e-6)}
+        out["cpu_baseline"] = {"value": 4.0 * (nxs + 1) * 181 * 3 / tcpu / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": "oracle/mori.cpp on one core, Nx=%d, 3 time steps in %.1f s" % (nxs, tcpu)}
+    emit(out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -467,10 +562,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-converged", action="store_true", help="skip the converged-tolerance step at full size")
-    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "myelin", "paper"],
+    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "myelin", "paper", "mori"],
                     help="synthetic: weak scaling, Nx columns PER GPU (headline); myelin: BASELINE config 5, the 48 mm "
                          "myelinated axon with 48 nodes of Ranvier (7,251 x 180 cells), STRONG scaling over z-slabs; "
-                         "paper: BASELINE config 2, square10mm.config action-potential run (single GPU)")
+                         "paper: BASELINE config 2, square10mm.config action-potential run (single GPU); "
+                         "mori: BASELINE config 3, the electroneutral (Mori) operator-split model on the synthetic grid")
     ap.add_argument("--ilu-fill", type=int, default=0, choices=[0, 1])
     args = ap.parse_args()
     myelin = args.workload == "myelin"
@@ -497,6 +593,10 @@ def main():
     if args.workload == "paper":
         if rank == 0:
             run_paper(args, api, setups, local_rank)
+        return
+    if args.workload == "mori":
+        if rank == 0:
+            run_mori(args, api, setups, local_rank)
         return
     if world > 1:
         dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)

@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(128) mori_assemble_kernel(Dev g, MoriDev md, c
       double rl[NR], ml[NR][4];
 #pragma unroll
       for (int q = 0; q < NR; ++q) { rl[q] = 0.0; ml[q][0] = ml[q][1] = ml[q][2] = ml[q][3] = 0.0; }
-      CellCtx co;
-      if (PHASE == 1) load_cell(g, uold, ci, cj, co);
+      CellCtx co;      // previous time step: mass term (phase 1), this side's concentration in the interface flux
+      if (PHASE == 1 || cj == g.jm - 1 || cj == g.jm + 1) load_cell(g, uold, ci, cj, co);
       const double fna = PHASE == 1 ? source_na(g, c) : 0.0;
 #pragma unroll
       for (int qa = 0; qa < 2; ++qa)
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(128) mori_assemble_kernel(Dev g, MoriDev md, c
           for (int sp = 0; sp < 3; ++sp) {
             double uc = 0.0;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) uc += (PHASE == 0 ? cl.xl[4 * sp + m] : co.xl[4 * sp + m]) * phi[m];
+            for (int m = 0; m < 4; ++m) uc += co.xl[4 * sp + m] * phi[m];   // getSolutionConOld in both operators
             double d;
             double jc = mori_interface_flux(g, md, ci, from_cytosol, sp, uPot, uc, pot2, face_centre(g, ulast, ci, jopp, sp),
                                             potJumpOld, d);

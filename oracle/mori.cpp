@@ -222,9 +222,10 @@ void mori_potential_assemble(const Problem& p, const double* u, const double* ul
     for (int i = 0; i < p.nx; ++i) {
       if (p.cell_sub[p.cid(i, j)] == MEMBRANE) continue;                // useMembraneContributions = false
       const MCell c = make_cell(p, i, j);
-      double xl[16], xc[16], rl[4] = {0, 0, 0, 0}, ml[16] = {0};
+      double xl[16], xc[16], xo[16], rl[4] = {0, 0, 0, 0}, ml[16] = {0};
       gather(c, u, xl);
       gather(c, ulast, xc);
+      gather(c, p.uold.data(), xo);
       for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b) {
           double phi[4], dxi[4], deta[4], gx[4], gy[4];
@@ -268,8 +269,8 @@ void mori_potential_assemble(const Problem& p, const double* u, const double* ul
           for (int k = 0; k < 4; ++k) uPot += xl[12 + k] * phi[k];
           double jPot = 0.0, djPot = 0.0;
           for (int sp = 0; sp < NSPEC; ++sp) {
-            double uc = 0.0;
-            for (int k = 0; k < 4; ++k) uc += xc[4 * sp + k] * phi[k];
+            double uc = 0.0;                                           // this side: getSolutionConOld (:346-350)
+            for (int k = 0; k < 4; ++k) uc += xo[4 * sp + k] * phi[k];
             double d;
             double jc = interface_flux(p, c, f, sp, uPot, uc, pot2, face_centre(p, ulast, i, f.jopp, sp), potJumpOld, &d);
             jc *= f.surfaceScale; d *= f.surfaceScale;

@@ -113,6 +113,20 @@ def ref_operator_lib():
     return R
 
 
+def ref_mori_lib():
+    """ctypes handle of oracle/_ref/libax1refmori.so (the reference's Mori operators / parameter classes / charge
+    layer on single cells), or None."""
+    path = os.path.join(_HERE, "_ref", "libax1refmori.so")
+    if not os.path.exists(path):
+        return None
+    R = C.CDLL(path)
+    R.ax1ref_mori_gamma.argtypes = [c_double_p, C.c_int, C.c_double, c_int_p, c_double_p]
+    R.ax1ref_mori_operator.argtypes = [C.c_int, C.c_int, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p,
+                                       c_double_p, c_int_p, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p,
+                                       c_double_p, c_double_p, c_double_p]
+    return R
+
+
 DEFECT_CB = C.CFUNCTYPE(C.c_double, C.c_void_p, C.POINTER(C.c_double), C.c_int)
 
 

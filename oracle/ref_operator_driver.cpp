@@ -53,6 +53,7 @@ struct Tree {
   int get(const std::string& k, int def) const { auto it = num.find(k); return it == num.end() ? def : (int)it->second; }
   std::string get(const std::string& k, const std::string& def) const { auto it = str.find(k); return it == str.end() ? def : it->second; }
   std::string get(const std::string& k, const char* def) const { return get(k, std::string(def)); }
+  std::vector<std::string> get(const std::string&, const std::vector<std::string>& def) const { return def; }
 };
 struct Acme2CylParameters {
   Tree general, boundary, stimulation, solution_ex, solution_in, equilibration, membrane;
@@ -64,7 +65,6 @@ struct Acme2CylParameters {
   AX1_BC(isLeftCytosolBoundaryDirichlet_Potential) AX1_BC(isRightCytosolBoundaryDirichlet_Potential)
   AX1_BC(isLeftDebyeBoundaryDirichlet_Potential) AX1_BC(isRightDebyeBoundaryDirichlet_Potential)
   AX1_BC(isLeftExtracellularBoundaryDirichlet_Potential) AX1_BC(isRightExtracellularBoundaryDirichlet_Potential)
-  AX1_BC(isMembraneBoundaryNeumann_Potential)
   AX1_BC(isTopBoundaryDirichlet_Concentration) AX1_BC(isBottomBoundaryDirichlet_Concentration)
   AX1_BC(isLeftCytosolBoundaryDirichlet_Concentration) AX1_BC(isRightCytosolBoundaryDirichlet_Concentration)
   AX1_BC(isLeftDebyeBoundaryDirichlet_Concentration) AX1_BC(isRightDebyeBoundaryDirichlet_Concentration)
@@ -83,7 +83,12 @@ struct Acme2CylParameters {
   double tInj_end() const { return t1; }
   double getPotentialResidualScalingFactor() const { return pot_scale; }
   bool doVolumeScaling() const { return volscale; }
-  bool useMori() const { return false; }
+  bool memb_neumann = false, use_mori = false;
+  bool isBoundaryDirichlet_Potential(const std::string&) const { return false; }
+  bool isBoundaryDirichlet_Concentration(const std::string&) const { return false; }
+  bool isMembraneBoundaryNeumann_Potential() const { return memb_neumann; }
+  bool useMori() const { return use_mori; }
+  bool useMoriCorrection() const { return false; }
   bool equil = false;
   bool doEquilibration() const { return equil; }
   std::vector<bool> isMembraneActive() const { return std::vector<bool>(1, true); }
@@ -108,6 +113,22 @@ struct Output {   // printing helper of the reference (dune/ax1/common/output.hh
 #define private public
 #include <dune/ax1/common/membranefluxgridfunction_implicit.hh>
 #undef private
+#ifdef AX1_REF_MORI
+#include <fstream>
+#include <iostream>
+#include <dune/common/ios_state.hh>
+// the electroneutral (Mori) model: charge layer (its init / timeStep are private, the driver calls them directly
+// instead of walking the grid's membrane elements in updateState), parameter classes, the two split operators
+#include <dune/ax1/common/ax1_lfs_tools.hh>
+template <typename A, typename B, typename C, typename D> class ChargeLayerMori;   // CRTP tag only (charge_layer_mori.hh)
+#define private public
+#include <dune/ax1/common/charge_layer_mori_implicit.hh>
+#undef private
+#include <dune/ax1/acme2_cyl/configurations/mori/mori_poisson_parameters.hh>
+#include <dune/ax1/acme2_cyl/configurations/mori/mori_nernst_planck_parameters.hh>
+#include <dune/ax1/acme2_cyl/operator/acme2_cyl_mori_potential_operator.hh>
+#include <dune/ax1/acme2_cyl/operator/acme2_cyl_mori_concentration_operator.hh>
+#endif
 #include <dune/ax1/acme2_cyl/operator/acme2_cyl_toperator.hh>
 #include <dune/ax1/acme2_cyl/operator/convectiondiffusionfem.hh>
 #include <istl_standins.hh>
@@ -172,7 +193,9 @@ struct Intersection {
   double ny;                          // outer normal (0, ny)
   // what the Physics look-ups return for this face (the test computes them as the grid-bound code would)
   double y_opposite, pot_opposite, con_opposite[3], ext_surface;
+  double pot_old_this = 0.0, pot_old_opposite = 0.0, memb_perm = 2.0;   // Mori charge layer: previous time step
   int index;
+  const ::Entity* outside() const { return in; }
   const FaceGeo& geometry() const { return geo; }
   const FaceInInside& geometryInInside() const { return gii; }
   const ::Entity* inside() const { return in; }
@@ -254,17 +277,36 @@ struct Physics {
     if (ySign > 0) { conRatio = con2; for (int j = 0; j < 3; ++j) conRatio[j] /= con1[j]; }
     if (ySign < 0) { conRatio = con1; for (int j = 0; j < 3; ++j) conRatio[j] /= con2[j]; }
   }
-  // the explicit-flux overloads (values of the last time step on both sides) are not reached with
-  // fullyImplicitMembraneFlux = yes
+  // the overload without the inside value (face-centre values on both sides, :603-660): the coupled path never
+  // reaches it with fullyImplicitMembraneFlux = yes; the Mori charge layer uses it for the OLD potential jump, which
+  // the test supplies on the face
   template <class DGF>
-  void getMembranePotentialJump(const Intersection&, DGF&, typename DGF::Traits::RangeType&) const {
-    DUNE_THROW(Dune::NotImplemented, "explicit membrane flux");
+  void getMembranePotentialJump(const Intersection& is, DGF&, typename DGF::Traits::RangeType& potJump) const {
+    typename DGF::Traits::RangeType pot1(is.pot_old_this), pot2(is.pot_old_opposite);
+    potJump = pot2;
+    potJump -= pot1;
+    const int ySign = Dune::sign(is.geo.y - is.y_opposite);
+    potJump *= ySign;
   }
+  double getMembranePermittivity(const Intersection& is) const { return is.memb_perm; }
+  // only named by the "boundary values loaded from a file" branches of the Mori parameter classes (not reached)
+  typedef ::Entity Element;
+  typedef const ::Entity* ElementPointer;
+  int nElements(int) const { return 1; }
+  int getSubDomainNumber(const Entity& e) const { return e.subdomain; }
+  std::string getGroupName(const Entity&) const { return std::string("default"); }
+  int getSubdomainIndex(const Entity& e) const { return e.subdomain; }
+  bool mV = false;   // convertTo_mV: identity for the coupled pins (debug output only), real for the Mori charge layer
   template <class DGF>
   void getMembraneConcentrationRatio(const Intersection&, DGF&, typename DGF::Traits::RangeType&) const {
     DUNE_THROW(Dune::NotImplemented, "explicit membrane flux");
   }
-  template <class V> V convertTo_mV(const V& v) const { return v; }   // only feeds debug output
+  template <class V> V convertTo_mV(const V& v) const {
+    if (!mV) return v;
+    V o(v);
+    o *= con_k * electro.getTemperature() / con_e * 1.0e3;
+    return o;
+  }
   Acme2CylParameters prm;
   double PC = 0, time_scale = 1e-6, length_scale = 1e-9, eps = 80.0, D[3] = {0, 0, 0};
   int z[3] = {1, 1, -1};
@@ -341,8 +383,12 @@ struct Q1FE {
   const Q1Interpolation& localInterpolation() const { return ip; }
 };
 struct FEM { struct Traits { typedef Q1FE FiniteElementType; }; };
+struct Root;
 struct Leaf {
   struct Traits { typedef Q1FE FiniteElementType; typedef std::size_t SizeType; };
+  typedef Root MultiDomainLocalFunctionSpace;          // the split (Mori) operators reach the other space through it
+  const Root* root = nullptr;
+  const Root& multiDomainLocalFunctionSpace() const { return *root; }
   int comp; Q1FE fe;
   std::size_t size() const { return 4; }
   const Q1FE& finiteElement() const { return fe; }
@@ -350,12 +396,16 @@ struct Leaf {
 struct ConSpace {
   struct Traits { typedef std::size_t SizeType; };
   template <int k> struct Child { typedef Leaf Type; };
+  typedef Root MultiDomainLocalFunctionSpace;
+  const Root* root = nullptr;
+  const Root& multiDomainLocalFunctionSpace() const { return *root; }
   Leaf c[3];
   const Leaf& child(int j) const { return c[j]; }
 };
 struct Root {
   ConSpace con; Leaf pot;
   std::size_t size() const { return 16; }
+  std::size_t maxSize() const { return 16; }
   template <int k, int dummy = 0> struct Child { typedef ConSpace Type; };
   template <int dummy> struct Child<1, dummy> { typedef Leaf Type; };
   template <int k> const typename Child<k>::Type& child() const;
@@ -364,6 +414,10 @@ template <> const ConSpace& Root::child<0>() const { return con; }
 template <> const Leaf& Root::child<1>() const { return pot; }
 struct XView {
   const double* v;
+  std::vector<double> own;                              // X xPot(multiLFS.maxSize()) of the split operators
+  XView(const double* p) : v(p) {}
+  explicit XView(std::size_t n) : v(nullptr), own(n, 0.0) { v = own.data(); }
+  XView(const XView&) = delete;
   double operator()(const Leaf& l, std::size_t i) const { return v[l.comp * 4 + i]; }
 };
 struct RView {
@@ -380,7 +434,7 @@ struct MView {   // local matrix, row = test DOF, column = trial DOF
 
 // discrete grid functions / solution container: the flux class constructs them but, in the implicit branch, only hands
 // them to the Physics look-ups above
-struct DGFBase { DGFBase(int, int) {} };
+struct DGFBase { template <class A, class B> DGFBase(const A&, const B&) {} };
 struct DGFCon {
   struct Traits { typedef GV GridViewType; typedef double RangeFieldType; typedef Dune::FieldVector<double, 3> RangeType; typedef Coord DomainType; };
   typedef DGFBase BASE_DGF;
@@ -392,16 +446,30 @@ struct DGFCon {
 struct DGFPot {
   struct Traits { typedef GV GridViewType; typedef double RangeFieldType; typedef Dune::FieldVector<double, 1> RangeType; typedef Coord DomainType; };
   DGFPot() {}
-  DGFPot(int, int) {}
+  template <class A, class B> DGFPot(const A&, const B&) {}
+};
+// the solution vectors the split operators read through SolutionContainer: on the one-cell harness a "vector" is the
+// 16 local coefficients of that cell, a local view copies them
+struct LocalVec {
+  const double* xl = nullptr;
+  template <class Cache>
+  struct ConstLocalView {
+    const LocalVec& u;
+    explicit ConstLocalView(const LocalVec& u_) : u(u_) {}
+    void bind(const Cache&) {}
+    template <class X> void read(X& x) const { for (int k = 0; k < 16; ++k) x.own[k] = u.xl[k]; }
+    void unbind() {}
+  };
 };
 struct SolutionContainer {
-  typedef int U;
-  int zero = 0;
+  typedef LocalVec U;
+  LocalVec potNew, conNew, conOld, potOld;
   int getGfsPot() const { return 0; }
   int getGfsCon() const { return 0; }
-  const int* getSolutionPotNew() const { return &zero; }
-  const int* getSolutionConNew() const { return &zero; }
-  const int* getSolutionConOld() const { return &zero; }
+  const LocalVec* getSolutionPotNew() const { return &potNew; }
+  const LocalVec* getSolutionConNew() const { return &conNew; }
+  const LocalVec* getSolutionConOld() const { return &conOld; }
+  const LocalVec* getSolutionPotOld() const { return &potOld; }
 };
 typedef MembraneFluxGridFunctionImplicit<DGFCon, DGFPot, Physics, SolutionContainer> MembFlux;
 
@@ -439,8 +507,8 @@ struct Setup {
     e.geo.x0 = cell[0]; e.geo.x1 = cell[1]; e.geo.y0 = cell[2]; e.geo.y1 = cell[3];
     e.index = 0; e.subdomain = subdomain;
     for (int i = 0; i < 4; ++i) ph.nodevol.push_back(std::make_pair(e.geo.corner(i), nodevol4[i]));
-    for (int j = 0; j < 3; ++j) lfs.con.c[j].comp = j;
-    lfs.pot.comp = 3;
+    for (int j = 0; j < 3; ++j) { lfs.con.c[j].comp = j; lfs.con.c[j].root = &lfs; }
+    lfs.pot.comp = 3; lfs.pot.root = &lfs; lfs.con.root = &lfs;
     ph.prm.boundary.num["fullyImplicitMembraneFlux"] = 1;
     flux.reset(new MembFlux(dgfCon, dgfPot, ph, sol, 0.0));
   }
@@ -470,7 +538,7 @@ int ax1ref_local_operator(int which, int jac, const double* cell, const double* 
     ParamCon paramCon;
     for (int j = 0; j < 3; ++j)
       paramCon.push_back(Dune::shared_ptr<ParamNP>(new ParamNP(j, S.gv, S.ph, S.igf, *S.flux, S.nf, 0.0)));
-    XView x{xl};
+    XView x(xl);
     ElementGeometry eg{&S.e};
     const int n = jac ? 256 : 16;
     for (int k = 0; k < n; ++k) out[k] = 0.0;
@@ -554,7 +622,7 @@ int ax1ref_elec_alpha_boundary(const double* cell, int from_cytosol, const doubl
     is.ext_surface = memb[5];
     is.index = elem;
     IntersectionGeometry ig{&is};
-    XView x{xl};
+    XView x(xl);
     for (int k = 0; k < 16; ++k) out16[k] = 0.0;
     RView r{out16};
     lop.alpha_boundary(ig, S.lfs, x, S.lfs, r);

@@ -1,5 +1,6 @@
 // stand-in (see ../../README.md): fixed-size vector / matrix with the members the reference headers touch
 #pragma once
+#include <ostream>
 #include <cmath>
 #include <cstddef>
 namespace Dune {
@@ -85,4 +86,9 @@ class FieldMatrix {
  private:
   FieldVector<T, M> r_[N];
 };
+template <class K, int n>
+std::ostream& operator<<(std::ostream& os, const FieldVector<K, n>& v) {
+  for (int i = 0; i < n; ++i) os << (i ? " " : "") << v[i];
+  return os;
+}
 }  // namespace Dune

@@ -127,3 +127,14 @@ struct ConvectionDiffusionParameterTraits {
 
 }  // namespace PDELab
 }  // namespace Dune
+
+namespace Dune { namespace PDELab {
+// index cache of a local function space (the split Mori operators build one to read the other sub-problem's
+// coefficients); nothing to cache on the one-cell harness
+template <class LFS>
+struct LFSIndexCache {
+  const LFS& lfs;
+  explicit LFSIndexCache(const LFS& l) : lfs(l) {}
+  void update() {}
+};
+} }

@@ -121,3 +121,43 @@ def test_reference_test_config_equilibration_steps(oracle, axlib):
     vm = dev.membrane_potential_dev()
     assert np.all(np.abs(vm - (-65.0)) < 2.0)
     dev.close()
+
+
+def test_paper_grid_action_potential_matches_oracle_trace(axlib):
+    """BASELINE configs[1] at full size: the square10mm.config action-potential run on the paper grid (100 x 180 cells,
+    73,124 DOF, Na injection at x = 150 um, HH channels, adaptive implicit Euler) through the library's own time
+    loop to t = 3 ms, against the oracle's trace of the same run (tests/golden/ap_trace_paper_grid.json, written by
+    tests/golden/make_ap_trace.py: ~560 time steps, ~3500 Newton iterations of the CPU oracle). Same dt sequence and
+    Newton iteration count in every step; membrane potential at the injection site / middle / far end and its
+    extrema within 1e-5 mV (1e-7 of the 110 mV excursion) over the whole trace; final concentrations 1e-8, potential
+    within its double-precision floor (test_precision_floor.py)."""
+    import json, os
+    from dune_ax1_b200 import setups
+    from dune_ax1_b200.timeloop import DeviceTimeLoop
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fx = json.load(open(os.path.join(root, "tests", "golden", "ap_trace_paper_grid.json")))
+    s = setups.make_setup(100, dx=100.0e3, stimulation=True, perturbation=0.0)
+    dev = setups.make_device(s)
+    ctl = {k: v for k, v in fx["ctl"].items() if k != "do_stimulation"}
+    tl = DeviceTimeLoop(dev, s["u0"], newton_opts=axlib.default_newton_opts(slab_w=fx["slab_w"], **fx["newton"]), **ctl)
+    sites = fx["sites"]
+    worst = 0.0
+    for k, row in enumerate(fx["steps"]):
+        r = tl.step()
+        assert abs(r.time - row[0]) <= 1e-9 * max(1.0, row[0]) and abs(r.dt - row[1]) <= 1e-12 * row[1], (k, r.time, row[:3])
+        assert r.newton_iterations == row[2], (k, r.newton_iterations, row[:4])
+        vm = dev.membrane_potential_dev()
+        dv = max(abs(vm[i] - row[4 + m]) for m, i in enumerate(sites))
+        dv = max(dv, abs(r.vm_min - row[7]), abs(r.vm_max - row[8]))
+        worst = max(worst, dv)
+    peak = max(row[4] for row in fx["steps"])
+    assert peak > 40.0                                         # the action potential fired at the injection site
+    assert worst < 1e-5, worst
+    u = tl.u.reshape(-1, 4)
+    us = np.array(fx["u_final_sample"])
+    scale = np.array(fx["u_final_absmax"])
+    err = np.max(np.abs(u[::fx["stride"]] - us) / scale, axis=0)
+    assert np.all(err[:3] < 1e-8) and err[3] < 1e-6, err
+    sg, _ = dev.channel_state()
+    assert np.max(np.abs(sg - np.array(fx["channel_state_final"]))) < 1e-8
+    dev.close()

@@ -592,3 +592,160 @@ def test_membrane_flux_output_terms_against_reference_flux_class(oracle, refop, 
         scale = np.abs(ref).max(axis=0, keepdims=True) + 1e-300
         assert np.max(np.abs(ref - mine[:, :, i]) / scale) < 1e-14, i
         assert np.allclose(ref[0], ref[2] - ref[1], rtol=1e-12, atol=0) and np.allclose(ref[0], ref[3] + ref[4], rtol=1e-12, atol=0)
+
+
+# ---- electroneutral (Mori) model: the reference's split operators, parameter classes and charge layer --------------
+@pytest.fixture(scope="module")
+def refmori(oracle):
+    oracle.build_ref()
+    R = oracle.ref_mori_lib()
+    if R is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    return R
+
+
+def test_mori_charge_layer_states_against_reference_class(oracle, refmori):
+    """ChargeLayerMoriImplicit::init / timeStep / acceptTimeStep (charge_layer_mori_implicit.hh), compiled from the
+    reference: gamma_j = z_j^2 c_j / sum z^2 c at initialisation, relaxation with tau = 1 ns afterwards. The oracle's
+    mori_update_state / accept on a one-column problem driven with the same membrane concentrations: bit-identical."""
+    s = small_setup(nx=1)
+    P = oracle_problem(oracle, s)
+    jm, nvx = P.jm, 2
+    rng = np.random.default_rng(21)
+    us = [s["u0"] * (1.0 + 5e-2 * rng.standard_normal(s["u0"].shape)) for _ in range(4)]
+    con = []
+    for u in us:
+        cc = [0.5 * u[4 * (0 + nvx * jm) + c] + 0.5 * u[4 * (1 + nvx * jm) + c] for c in range(3)]
+        ce = [0.5 * u[4 * (0 + nvx * (jm + 1)) + c] + 0.5 * u[4 * (1 + nvx * (jm + 1)) + c] for c in range(3)]
+        con += cc + ce
+    con = np.array(con)
+    dt = 0.37
+    out = np.zeros(6 * 4)
+    val = np.array([1, 1, -1], dtype=np.int32)
+    assert refmori.ax1ref_mori_gamma(_dp(con), 3, dt * 1e-6, _ip(val), _dp(out)) == 0
+    ref = out.reshape(4, 2, 3)
+    for k, u in enumerate(us):
+        P.set_time(float(k), dt)
+        P.mori_update_state(u)
+        g = P.mori_gamma()                       # [side][old/new][ion][column]
+        assert np.array_equal(g[:, 1, :, 0], ref[k]), k
+        P.accept_state()
+        assert np.array_equal(P.mori_gamma()[:, 0, :, 0], ref[k])
+    assert np.allclose(ref.sum(axis=2), 1.0, atol=1e-15)
+
+
+def _mori_scatter(oracle, refmori, which, s, P, u, ulast, uold, t, dt, gamma, active=1.0, neumann=1.0):
+    """global residual of Mori sub-problem `which` as the numpy scatter of the reference's compiled alpha_volume /
+    alpha_boundary on every electrolyte cell / membrane-interface face"""
+    cst = P.constants()
+    _, nvol, dmask = P.maps()
+    nvx, x, y, jm, p = s["nx"] + 1, s["x"], s["y"], P.jm, s["params"]
+    st = P.channel_state(new=True).reshape(5, -1)
+    cs = np.asarray(s["cell_subdomain"]).reshape(s["ny"], s["nx"])
+    val = np.array([1, 1, -1], dtype=np.int32)
+    phys = np.array([80.0, cst["D"][0], cst["D"][1], cst["D"][2], cst["PC"], 1.0, 1e-6])
+    stim = np.array([p["do_stimulation"], t + dt, p["tinj_start"], p["tinj_end"], p["stim_x"], p["stim_y"], p["I_inj"]],
+                    dtype=np.float64)
+    misc = np.array([279.45, dt, t, 5.0, neumann, active])
+    r = np.zeros(P.n)
+    loc = lambda vec, vs: np.ascontiguousarray(np.array([[vec[4 * v + c] for v in vs] for c in range(4)]).reshape(-1))
+    xnew_vec = u if which == 0 else ulast          # what getSolutionPotNew holds in this phase
+    for j in range(s["ny"]):
+        for i in range(s["nx"]):
+            if cs[j, i] == 2:
+                continue                           # no membrane contributions
+            vs = [i + nvx * j, i + 1 + nvx * j, i + nvx * (j + 1), i + 1 + nvx * (j + 1)]
+            xl = loc(u, vs)
+            # SolutionContainer on this cell: concentrations always from ulast ("ConNew"), the potential from the
+            # phase's PotNew vector
+            xnew = loc(ulast, vs)
+            xnew[12:] = loc(xnew_vec, vs)[12:]
+            xold = loc(uold, vs)
+            nv4 = np.array([nvol[v] for v in vs])
+            cell = np.array([x[i], x[i + 1], y[j], y[j + 1]])
+            gl, gn, gk = s["g_leak"][i], s["g_nav"][i], s["g_kv"][i]
+            geff = np.array([gl * st[0, i], gl * st[1, i], gn * st[2, i] ** 3 * st[3, i], gk * st[4, i] ** 4])
+            for boundary in (0, 1):
+                if boundary and j not in (jm - 1, jm + 1):
+                    continue
+                from_cyt = 1 if j == jm - 1 else 0
+                jthis, jopp = (jm, jm + 1) if from_cyt else (jm + 1, jm)
+                fc = lambda vec, row, c: 0.5 * vec[4 * (i + nvx * row) + c] + 0.5 * vec[4 * (i + 1 + nvx * row) + c]
+                memb = np.array([y[jopp], fc(xnew_vec, jopp, 3), fc(ulast, jopp, 0), fc(ulast, jopp, 1), fc(ulast, jopp, 2),
+                                 (np.pi * (y[jm + 1] + y[jm + 1])) * (x[i + 1] - x[i]), fc(uold, jthis, 3), fc(uold, jopp, 3),
+                                 s["eps_memb"][i]])
+                side = 0 if from_cyt else 1
+                gam = np.ascontiguousarray(np.concatenate([gamma[side, 0, :, i], gamma[side, 1, :, i]]))
+                out = np.zeros(16)
+                rc = refmori.ax1ref_mori_operator(which, boundary, _dp(cell), from_cyt, _dp(xl), _dp(xnew), _dp(xold),
+                                                  _dp(phys), _ip(val), _dp(nv4), 1, _dp(stim), _dp(memb), _dp(geff),
+                                                  _dp(gam), _dp(misc), _dp(out))
+                assert rc == 0
+                w = dt if which == 1 else 1.0      # OneStepMethod weights the spatial concentration operator with dt
+                for c in range(4):
+                    for k, v in enumerate(vs):
+                        r[4 * v + c] += w * out[4 * c + k]
+    for v in range(P.nv):
+        for c in range(4):
+            if (int(dmask[v]) >> c) & 1:
+                r[4 * v + c] = 0.0
+    return r
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_mori_global_residual_is_scatter_of_reference_split_operators(oracle, refop, refmori, which):
+    """Row f4: the oracle's global residual of the Mori potential (which = 0) / concentration (1) sub-problem equals the
+    reference's own Acme2CylMoriPotentialOperator / Acme2CylMoriConcentrationOperator (alpha_volume on every
+    electrolyte cell, alpha_boundary on every membrane-interface face) with its MoriPoissonParameters,
+    MoriNernstPlanckParameters (channel flux + capacitive flux, surface scaling, Na injection), ChargeLayerMoriImplicit
+    and MembraneFluxGridFunctionImplicit, compiled from /root/reference and scattered here in numpy; for the
+    concentration problem plus the (already pinned) time operator: r = dt A(c) + M(c) - M(c_old). Three different
+    vectors play the three roles (unknowns, last iteration, previous time step), the charge layer has been
+    initialised and advanced so that gamma_new != gamma_old."""
+    s = small_setup(nx=3, stimulation=True)
+    t, dt = 29.0, 0.8
+    P = oracle_problem(oracle, s)
+    u0 = s["u0"]
+    rng = np.random.default_rng(31)
+    uold = u0 * (1.0 + 1e-3 * rng.standard_normal(u0.size))
+    ulast = u0 * (1.0 + 1e-3 * rng.standard_normal(u0.size))
+    u = u0 * (1.0 + 1e-3 * rng.standard_normal(u0.size))
+    P.set_time(t - dt, dt); P.set_uold(u0); P.update_state(u0); P.accept_state()
+    P.mori_update_state(u0); P.accept_state()
+    P.set_time(t, dt); P.set_uold(uold); P.update_state(ulast)
+    P.mori_update_state(ulast)
+    gamma = P.mori_gamma()
+    assert np.max(np.abs(gamma[:, 1] - gamma[:, 0])) > 1e-6
+    r_py = _mori_scatter(oracle, refmori, which, s, P, u, ulast, uold, t, dt, gamma)
+    if which == 1:                                 # + M(c) - M(c_old): the reference's time operator (refop)
+        run = _CellRunner(oracle, refop, s, t=t, dt=dt, stim=True)
+        run.P = P
+        _, _, dmask = P.maps()
+        cs = np.asarray(s["cell_subdomain"]).reshape(s["ny"], s["nx"])
+        for j in range(s["ny"]):
+            for i in range(s["nx"]):
+                if cs[j, i] == 2:
+                    continue
+                vs = run.verts(i, j)
+                xl = np.array([[u[4 * v + c] for v in vs] for c in range(4)]).reshape(-1)
+                xo = np.array([[uold[4 * v + c] for v in vs] for c in range(4)]).reshape(-1)
+                rl = run.ref(1, 0, i, j, xl, 80.0) - run.ref(1, 0, i, j, xo, 80.0)
+                for c in range(3):
+                    for k, v in enumerate(vs):
+                        if not (int(dmask[v]) >> c) & 1:
+                            r_py[4 * v + c] += rl[4 * c + k]
+    r_or, _ = P.mori_assemble(which, u, ulast, jacobian=False)
+    # scale: sensitivity of each row to a relative perturbation of the inputs (what the row's terms add up to)
+    scale = np.zeros_like(r_or)
+    prng = np.random.default_rng(5)
+    for _ in range(3):
+        pu, pl, po = (v * (1.0 + 1e-9 * prng.standard_normal(v.size)) for v in (u, ulast, uold))
+        P.set_uold(po)
+        rp, _ = P.mori_assemble(which, pu, pl, jacobian=False)
+        scale = np.maximum(scale, np.abs(rp - r_or) / 1e-9)
+    P.set_uold(uold)
+    err = np.abs(r_py - r_or) / (scale + np.abs(r_or) + 1e-300)
+    assert err.max() < 1e-12, (which, err.max(), int(err.argmax()))
+    rows = r_or.reshape(-1, 4)
+    assert np.all(rows[:, :3] == 0.0) if which == 0 else np.all(rows[:, 3] == 0.0)
+    assert np.abs(rows).max() > 0.0
