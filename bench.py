@@ -748,6 +748,12 @@ def main():
                       "GBps": bytes_k[name] * nv / (t_ms * 1e-3) / 1e9,
                       "GBps_dense_equivalent": bytes_dense[name] * nv / (t_ms * 1e-3) / 1e9,
                       "share_of_step": counts[name] * t_ms / (ms / args.steps)}
+    # the two exchange steps of the overlapping solve (scalar reduction incl. the cross-rank sum; additive halo sum),
+    # timed in lock step on all ranks: what the weak-scaling loss is made of
+    comm = {"reduce_ms": dev.time_kernel("reduce", reps=50), "reductions_per_step": 4 * KRYLOV_ITS * NEWTON_ITS + 3 * NEWTON_ITS + 1}
+    if world > 1:
+        comm["halo_ms"] = dev.time_kernel("halo", reps=50)
+        comm["halo_sums_per_step"] = 2 * KRYLOV_ITS * NEWTON_ITS
     dom = max(kern, key=lambda k: kern[k]["share_of_step"])
     traffic, traffic_src = (None, None)
     if args.nx == NX_PER_GPU and args.slab_w == SLAB_W and not myelin and args.ilu_fill == 0:
@@ -775,7 +781,7 @@ def main():
            "clocks": clocks, "gpu_launches": launches,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * dev.n * 8,
                    "d2h_bytes_per_step": dev.n * 8, "ms_per_step": ms_e2e / args.steps},
-           "roofline": roofline}
+           "roofline": roofline, "exchange": comm}
     if conv:
         out["converged_step"] = conv
     if parity:

@@ -638,11 +638,16 @@ static int auto_radial_cut(const ax1gpu_ctx* c) {
 
 // (re)select the preconditioner: fill 0 = block ILU0, fill 1 = block ILU(1) (SeqILUn with n = 1, the
 // reference default, acme2_cyl_setup.hh:764-765); the ILU(1) factor needs 13 instead of 9 blocks per row
+#define AX1_SLAB_KEEP (-1)
 static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill, int amg = -1) {
   const bool use_amg = amg >= 0 ? amg != 0 : c->amg != 0;
-  // internal callers (drv_solve, drv_time_kernel) hand the handle's current width back in: that is not the caller
-  // choosing a width, an automatically derived one stays automatic
-  bool picked_auto = slab_w > 0 && slab_w == c->slab_w && c->slab_auto;
+  // slab_w: > 0 the caller's choice, 0 library default, AX1_SLAB_KEEP (internal callers: drv_solve, drv_time_kernel)
+  // whatever the handle currently uses -- an automatically derived width then stays automatic
+  bool picked_auto = false;
+  if (slab_w == AX1_SLAB_KEEP) {
+    if (c->slab_w > 0 && !c->slab_auto) slab_w = c->slab_w;
+    else slab_w = 0;
+  }
   if (fill < 0) fill = c->ilu_fill;
   if (fill > 1) { set_error("block ILU(n) is implemented on the device for n = 0 and n = 1"); return AX1GPU_EINVAL; }
   if (slab_w <= 0) {
@@ -918,7 +923,7 @@ int drv_solve(ax1gpu_ctx* c, double* r, double* x, double reduction, int maxit, 
   const Own own = own_of(c);
   const int G = vec_grid(c);
   int rc;
-  if (!c->factored) { rc = drv_factor(c, c->slab_w); if (rc) return rc; }
+  if (!c->factored) { rc = drv_factor(c, AX1_SLAB_KEEP); if (rc) return rc; }
   AX1_CUDA(cudaMemsetAsync(x, 0, bytes, c->stream));
   AX1_CUDA(cudaMemsetAsync(c->d_sc, 0, sizeof(Scalars), c->stream));
   // r = b - A*0 = b ; rt = r
@@ -1003,7 +1008,7 @@ int drv_solve_gmres(ax1gpu_ctx* c, double* b, double* x, double reduction, int r
     AX1_CUDA(cudaMalloc((void**)&c->d_gm, gm_len(m) * sizeof(double)));
     c->gm_cap = m;
   }
-  if (!c->factored) { rc = drv_factor(c, c->slab_w); if (rc) return rc; }
+  if (!c->factored) { rc = drv_factor(c, AX1_SLAB_KEEP); if (rc) return rc; }
   double* V = c->d_gmV;
   double* gm = c->d_gm;
   double* w = c->d_p;
@@ -1211,6 +1216,25 @@ int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms) {
       launch_spmv_dot(c->g, c->d_A, c->d_y2, c->d_v, c->nranks > 1, n == "spmv_dot1" ? 1 : 2, c->d_rt, own.lo, own.hi,
                       own.masked, c->d_sc, c->d_spartials, c->stream);
     }
+    // the two exchange steps of the overlapping Krylov solve, as the solver issues them (all ranks must call with
+    // the same reps): "reduce" = block partials -> sums over all ranks -> scalar recurrence (peer windows: one launch;
+    // NCCL: reduce + allreduce + scalar kernel); "halo" = additive halo sum of the three shared vertex columns
+    else if (n == "reduce") {
+      dot_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_rt, c->d_v, nullptr, nullptr, 0, own_of(c), nullptr, c->d_partials);
+      AX1_LAUNCH_CHECK(c);
+      int r_ = reduce_op(c, G, 1, OP_PLAIN_NORM, 0.0, c->d_sums + 2);
+      if (r_) return r_;
+      return 0;
+    }
+    else if (n == "halo") {
+      if (c->nranks > 1 && c->p2p.on) {
+        const HaloPush hp = next_halo_push(c);
+        launch_halo_push(c->g, c->d_y2, hp, c->stream);
+        AX1_LAUNCH_CHECK(c);
+        return halo_wait_add(c, c->d_y2, hp.seq);
+      }
+      return halo_add(c, c->d_y2);
+    }
     else if (n == "pupdate") { pupdate_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_tmp, c->d_v, c->d_t, c->d_sc, 0); }
     else if (n == "ilu_factor") {
       if (c->ilu_fill == 1) launch_ilu1_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream);
@@ -1226,7 +1250,7 @@ int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms) {
     AX1_LAUNCH_CHECK(c);
     return 0;
   };
-  { int rc0 = select_preconditioner(c, c->slab_w, c->ilu_fill); if (rc0) return rc0; }
+  { int rc0 = select_preconditioner(c, AX1_SLAB_KEEP, c->ilu_fill); if (rc0) return rc0; }
   AX1_CUDA(cudaMemsetAsync(c->d_sc, 0, sizeof(Scalars), c->stream));
   int rc = run();
   if (rc) return rc;

@@ -37,3 +37,35 @@ def small_setup(nx=6, **kw):
 
 def rel_err(a, b, scale):
     return float(np.max(np.abs(a - b) / (scale + 1e-300)))
+
+
+def trace_restarts(fx):
+    """Replay the time-step controller (dune_ax1_b200/timeloop.py) on a recorded trace (tests/golden/ap_trace_*.json):
+    returns, per step, how often dt was halved after a failed Newton solve in the recorded run (the controller's dt
+    divided by the recorded dt), asserting that everything else of the dt sequence follows from the controller."""
+    from dune_ax1_b200.timeloop import TimeLoop
+
+    class Replay:
+        def __init__(self, rows):
+            self.rows, self.k = rows, 0
+
+        def membrane_potential(self, u):     # the controller looks at the state before the step it chooses dt for
+            return np.array([self.rows[self.k - 1][8]]) if self.k > 0 else np.array([-65.0])
+
+    rows = fx["steps"]
+    dev = Replay(rows)
+    tl = TimeLoop(dev, np.zeros(4), newton_opts=None, do_equilibration=False, t_equilibrium=0.0, **fx["ctl"])
+    out = []
+    for k, row in enumerate(rows):
+        dev.k = k
+        tl._choose_dt()
+        n = 0
+        while tl.dt != row[1] and tl.dt > row[1] and n < 10:
+            tl.dt *= 0.5
+            n += 1
+        assert tl.dt == row[1], (k, tl.dt, row[1])
+        out.append(n)
+        tl.last_its, tl.its = tl.its, row[2]
+        tl.time += tl.dt
+        assert abs(tl.time - row[0]) <= 1e-9 * max(1.0, row[0])
+    return out
