@@ -561,6 +561,7 @@ def main():
     ap.add_argument("--cpu-nx", type=int, default=2048, help="cell columns of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-paper", action="store_true", help="skip the secondary paper-configuration figure")
     ap.add_argument("--no-converged", action="store_true", help="skip the converged-tolerance step at full size")
     ap.add_argument("--workload", default="synthetic", choices=["synthetic", "myelin", "paper", "mori"],
                     help="synthetic: weak scaling, Nx columns PER GPU (headline); myelin: BASELINE config 5, the 48 mm "
@@ -789,7 +790,7 @@ def main():
     if mg_parity:
         out["multigpu_parity"] = mg_parity
     dev.close()
-    if rank == 0 and world == 1 and not myelin:
+    if rank == 0 and world == 1 and not myelin and not args.no_paper:
         # secondary figure: the paper configuration (square10mm.config, 100 x 180 cells, 73,124 DOF), first 60
         # adaptive time steps of the stimulated run through the library's time loop (latency-bound regime), with
         # the oracle's run of the same steps beside it (10 x-slab threads = the reference's docker default)

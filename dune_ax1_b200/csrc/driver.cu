@@ -937,7 +937,7 @@ int drv_solve(ax1gpu_ctx* c, double* r, double* x, double reduction, int maxit, 
   // need 2-3 iterations per Newton step -- polling every 4th iteration ran 8 sweeps where 4 were needed.
   // Fixed-work runs (reduction = 0) never poll.
   const bool poll = reduction > 0.0;
-  const int SB = spmv_dot_blocks(c->g);
+  const int SB = spmv_blocks(c->g);
   const int zc = c->nranks > 1;
   for (k = 0; 0.5 + k < maxit; ++k) {
     // rho_new, the breakdown tests and beta were produced by OP_NORM0 / OP_NORM_B of the step before

@@ -35,7 +35,6 @@ void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int 
 void launch_spmv_residual(const Dev& g, const double* A, const double* x, const double* b, double* r,
                           int zero_constrained, cudaStream_t st);
 int spmv_blocks(const Dev& g);
-int spmv_dot_blocks(const Dev& g);   // blocks = partials per sum of launch_spmv_dot
 // SpMV with fused dot products: dot_mode 1: partial <w, y>; 2: partial <y, w> and <y, y>; one partial per block
 void launch_spmv_dot(const Dev& g, const double* A, const double* x, double* y, int zero_constrained, int dot_mode,
                      const double* w, int own_lo, int own_hi, int masked, const Scalars* sc, double* partials,

@@ -23,25 +23,15 @@ namespace ax1 {
 // DOT = 3: residual mode y = w - A x (multigrid defect), no reduction.
 // DOT = 1: also partial <w, y> (BiCGStab h = <rt, v>);  DOT = 2: partial <y, w> and <y, y>
 // (omega = <t, r> / <t, t>): the SpMV result is reduced while it is still in registers.
-// AX1_SPMV_DOT_ROWS block rows per thread in the dot-fused variants (one block reduction per AX1_SPMV_DOT_ROWS x 64
-// rows). Measured at 16.9 M vertices, round 2: 1 row 2.37 / 2.45 ms (DOT 1 / 2), 4 rows grid-strided 2.64 / 2.65 ms,
-// 4 consecutive rows 2.71 / 2.72 ms -- amortising the reduction epilogue costs more in lost memory-level
-// parallelism than it saves, so it stays at 1.
-#define AX1_SPMV_DOT_ROWS 1
 template <int DOT>
 __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restrict__ A, const double* __restrict__ x,
                                                    double* __restrict__ y, int zero_con, const double* __restrict__ w,
                                                    Own own, const Scalars* sc, double* partials) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = (int)(t >> 2), r = (int)(t & 3);
   double s[2] = {0.0, 0.0};
-  const bool fused = DOT == 1 || DOT == 2;
-  const bool skip = fused && sc && sc->done;
-  // a block owns (fused ? AX1_SPMV_DOT_ROWS : 1) x 64 CONSECUTIVE block rows: neighbouring x blocks stay in L1 / L2
-  const long long stride = blockDim.x;
-  long long t = (long long)blockIdx.x * blockDim.x * (fused ? AX1_SPMV_DOT_ROWS : 1) + threadIdx.x;
-#pragma unroll
-  for (int it = 0; it < (fused ? AX1_SPMV_DOT_ROWS : 1); ++it, t += stride) {
-    const int v = (int)(t >> 2), r = (int)(t & 3);
-    if (t >= 4LL * g.nv || skip) continue;
+  const bool active = (v < g.nv) && !(DOT && DOT != 3 && sc && sc->done);
+  if (active) {
     const int i = v % g.nvx, j = v / g.nvx;
     const double* Arow = A + (size_t)v * AX1_ROW;
     double acc = 0.0;
@@ -67,15 +57,15 @@ __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restri
     if (DOT == 3) acc = __ldg(w + 4 * (size_t)v + r) - acc;
     if (zero_con && ((g.dmask[v] >> r) & 1)) acc = 0.0;
     y[4 * (size_t)v + r] = acc;
-    if (fused) {
+    if (DOT == 1 || DOT == 2) {
       if (!own.masked || (i >= own.lo && i <= own.hi)) {
         const double wv = __ldg(w + 4 * (size_t)v + r);
-        s[0] += acc * wv;
-        if (DOT == 2) s[1] += acc * acc;
+        s[0] = acc * wv;
+        if (DOT == 2) s[1] = acc * acc;
       }
     }
   }
-  if (fused) block_reduce_store<2>(s, partials);
+  if (DOT == 1 || DOT == 2) block_reduce_store<2>(s, partials);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -829,8 +819,6 @@ __global__ void bcrs_copy_kernel(Dev g, double* A9, double* blocks, const int* _
 
 // ------------------------------------------------------------------------------------------
 int spmv_blocks(const Dev& g) { return (int)((4LL * g.nv + 255) / 256); }
-// blocks (= partials per sum) of the dot-fused variants
-int spmv_dot_blocks(const Dev& g) { return (spmv_blocks(g) + AX1_SPMV_DOT_ROWS - 1) / AX1_SPMV_DOT_ROWS; }
 void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int zero_con, cudaStream_t st) {
   spmv_kernel<0><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, nullptr, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
 }
@@ -843,8 +831,8 @@ void launch_spmv_dot(const Dev& g, const double* A, const double* x, double* y, 
                      const double* w, int own_lo, int own_hi, int masked, const Scalars* sc, double* partials,
                      cudaStream_t st) {
   const Own own{own_lo, own_hi, g.nvx, masked};
-  if (dot_mode == 1) spmv_kernel<1><<<spmv_dot_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
-  else spmv_kernel<2><<<spmv_dot_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
+  if (dot_mode == 1) spmv_kernel<1><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
+  else spmv_kernel<2><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
 }
 // one quad per wavefront row: a level of a slab of width w has at most ceil(w/2) rows
 static int slab_threads(int slab_w) {
