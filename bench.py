@@ -719,6 +719,13 @@ def main():
         lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt[0])
+        # every rank's own GPU clock under load: the ranks synchronise in every reduction, so the step runs at the
+        # pace of the slowest GPU -- under sw_power_cap the GPUs of one box do not all hold the same clock
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"rank": rank, "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons")})
+        clocks["per_rank_sm_mhz"] = [p["sm_mhz"] for p in per_rank]
+        clocks["sm_mhz_min_over_ranks"] = min(p["sm_mhz"] for p in per_rank if p["sm_mhz"] is not None)
+        clocks["reasons"] = sorted(set(r for p in per_rank for r in (p["reasons"] or [])))
     its = NEWTON_ITS * args.steps
     nv_total = nv_full * world
     if myelin:   # strong scaling: the global grid is fixed
