@@ -298,4 +298,31 @@ class TimeLoopShim {
   ax1gpu_step_result res_;
 };
 
+// The step body of the electroneutral (Mori) build, Acme2CylMoriSimulation::run (acme2_cyl_mori_simulation.hh:562-600):
+//   ulast = unew; solverPot.apply(unew); gfMoriFlux.updateState(time, dt); solverCon.apply(time, dt, uold, unew)
+// i.e. the two Ax1LinearSubProblemSolver objects of acme2_cyl_mori_setup.hh:866-893 and the charge-layer grid function
+// behind one call. The caller keeps driving gfMembFlux (MembraneFluxShim::updateState / acceptTimeStep, which also
+// accepts the charge-layer states).
+template <class U, class EP = DefaultErrorPolicy>
+class MoriStepShim {
+ public:
+  explicit MoriStepShim(Device& d) : d_(d) { ax1gpu_newton_opts_default(&lin_); lin_.ilu_fill = 0; }
+  void setReduction(double r) { lin_.reduction = r; }            // params.getReduction()
+  void setMinDefect(double m) { lin_.abs_limit = m; }            // params.getAbsLimit()
+  void setLinearSolverMaxIterations(int n) { lin_.lin_maxit = n; }
+  ax1gpu_newton_opts& options() { return lin_; }
+  // one operator-split step from unew (= uold on entry of a fresh step); time / dt / uold as set on the device
+  void apply(double time, double dt, const U& uold, U& unew) {
+    EP::library(ax1gpu_set_time(d_.handle(), time, dt));
+    EP::library(ax1gpu_set_uold(d_.handle(), VectorAccess<U>::data(uold)));
+    EP::library(ax1gpu_mori_step(d_.handle(), &lin_, VectorAccess<U>::data(unew), &res_));
+  }
+  const ax1gpu_mori_result& result() const { return res_; }     // the two StationaryLinearProblemSolverResults
+
+ private:
+  Device& d_;
+  ax1gpu_newton_opts lin_;
+  ax1gpu_mori_result res_;
+};
+
 }  // namespace ax1gpu

@@ -44,6 +44,23 @@ int main(int argc, char** argv) {
     pdesolver.setReduction(1e-9); pdesolver.setAbsoluteLimit(1e-14); pdesolver.setMinLinearReduction(1e-10);
     pdesolver.setSlabWidth(hdr[2]);
     const double time = 0.0, dt = 1.0;
+    if (hdr[3] == 3) {
+      // the Mori build's step body through MoriStepShim (acme2_cyl_mori_simulation.hh:562-600)
+      U uold = u;
+      gfMembFlux.updateState(time, dt, uold);
+      ax1gpu::MoriStepShim<U> mori(dev);
+      mori.setReduction(1e-10); mori.setMinDefect(1e-12); mori.setLinearSolverMaxIterations(500);
+      mori.options().slab_w = hdr[2];
+      mori.apply(time, dt, uold, u);
+      gfMembFlux.acceptTimeStep();
+      const ax1gpu_mori_result& mr = mori.result();
+      std::printf("mori: pot its %d defect %.3e -> %.3e, con its %d defect %.3e -> %.3e\n", mr.pot_iterations,
+                  mr.pot_first_defect, mr.pot_defect, mr.con_iterations, mr.con_first_defect, mr.con_defect);
+      FILE* o = std::fopen(argv[2], "wb");
+      std::fwrite(u.data(), sizeof(double), u.size(), o);
+      std::fclose(o);
+      return 0;
+    }
     if (hdr[3] == 2) {
       // the same step through the library's own time loop (state stays on the device)
       ax1gpu::TimeLoopShim<U> loop(dev, time, dt);

@@ -28,7 +28,7 @@ def test_shim_compiles_without_dune(axlib, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", [1, 2])   # 1: IGO / LS / PDESOLVER seam, 2: TimeLoopShim (ax1gpu_time_step)
+@pytest.mark.parametrize("mode", [1, 2, 3])   # 1: IGO / LS / PDESOLVER seam, 2: TimeLoopShim, 3: MoriStepShim
 def test_shim_time_step_matches_oracle(oracle, axlib, tmp_path, mode):
     exe = _build(tmp_path)
     s = small_setup(nx=6)
@@ -49,6 +49,14 @@ def test_shim_time_step_matches_oracle(oracle, axlib, tmp_path, mode):
     # diagInfo.iterations = 0 at the start); the IGO / PDESOLVER seam is driven with dt0 itself
     dt = 1.0 * 1.1 if mode == 2 else 1.0
     P.set_time(0.0, dt); P.update_state(s["u0"]); P.set_uold(s["u0"])
+    if mode == 3:     # the electroneutral (Mori) build: one operator-split step
+        uc, mr = P.mori_step(s["u0"], oracle.default_newton_opts(reduction=1e-10, abs_limit=1e-12, lin_maxit=500,
+                                                                 ilu_fill=0, slab_w=slab_w))
+        assert mr.status == 0
+        scale = np.max(np.abs(uc.reshape(-1, 4)), axis=0)
+        err = np.max(np.abs(ug - uc).reshape(-1, 4) / scale, axis=0)
+        assert np.all(err < 1e-9), (err, r.stdout)
+        return
     uc, rc = P.newton(s["u0"], oracle.default_newton_opts(reduction=1e-9, abs_limit=1e-14, min_lin_reduction=1e-10,
                                                         ilu_fill=0, slab_w=slab_w))
     assert rc.status == 0
