@@ -198,6 +198,8 @@ def lib():
     L.ax1gpu_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p]
     L.ax1gpu_comm_init.argtypes = [H, C.c_char_p, C.c_char_p, C.c_int, C.c_int]
     L.ax1gpu_comm_mode.argtypes = [H]
+    L.ax1gpu_p2p_export.argtypes = [H, C.c_int, C.c_int, C.c_char_p]
+    L.ax1gpu_p2p_attach.argtypes = [H, C.c_char_p]
     L.ax1host_generate_y.argtypes = [C.c_double] * 6 + [C.c_int, C.c_double, C.c_double, C.c_int, c_double_p, C.c_int]
     L.ax1host_physics_maps.argtypes = [C.POINTER(Grid), C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                        C.c_double, C.c_int, C.c_double, C.POINTER(HostBC), c_ubyte_p, c_double_p,
@@ -676,6 +678,16 @@ class Ax1Gpu:
 
     def comm_init(self, unique_id, rank, nranks, libnccl=None):
         _chk(lib().ax1gpu_comm_init(self.h, (libnccl or nccl_library_path()).encode(), unique_id, rank, nranks))
+
+    def p2p_export(self, rank, nranks):
+        """This rank's peer-window IPC handle (64 bytes); gather over all ranks, then p2p_attach."""
+        buf = C.create_string_buffer(64)
+        _chk(lib().ax1gpu_p2p_export(self.h, int(rank), int(nranks), buf))
+        return buf.raw
+
+    def p2p_attach(self, handles):
+        """handles: list of the nranks 64-byte IPC handles in rank order."""
+        _chk(lib().ax1gpu_p2p_attach(self.h, b"".join(handles)))
 
     def comm_mode(self):
         """0 single rank, 1 NCCL send/recv + allreduce, 2 NVLink peer windows (p2p.cuh)."""

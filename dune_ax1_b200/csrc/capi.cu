@@ -704,6 +704,54 @@ int ax1gpu_comm_init(ax1gpu_handle c, const char* libnccl_path, const char* id12
   return p2p_setup(c);
 }
 
+// ---- peer windows without NCCL: the caller exchanges the CUDA IPC handles itself (MPI_Allgather in a DUNE build,
+// torch.distributed / gloo in the test harness). Two calls because the exchange sits between them.
+int ax1gpu_p2p_export(ax1gpu_handle c, int rank, int nranks, char* handle64) {
+  AX1_CHECK_H(c);
+  cudaSetDevice(c->device);
+  if (nranks < 2 || nranks > AX1_MAX_RANKS || rank < 0 || rank >= nranks) { set_error("p2p_export: bad rank / nranks"); return AX1GPU_EINVAL; }
+  if ((rank > 0) != c->left_pb || (rank < nranks - 1) != c->right_pb) {
+    set_error("processor-boundary flags of the grid do not match rank/nranks"); return AX1GPU_EINVAL;
+  }
+  if (c->p2p.win) { set_error("p2p_export: communication already initialised"); return AX1GPU_ESTATE; }
+  auto& P = c->p2p;
+  P.halo_len = 3 * (size_t)c->g.nvy * 4;
+  const size_t wlen = AX1_P2P_HALO_OFF + 4 * P.halo_len;
+  AX1_CUDA(cudaMalloc((void**)&P.win, wlen * sizeof(double)));
+  AX1_CUDA(cudaMalloc((void**)&P.cnt, 2 * sizeof(unsigned int)));
+  AX1_CUDA(cudaMemsetAsync(P.win, 0, wlen * sizeof(double), c->stream));
+  AX1_CUDA(cudaMemsetAsync(P.cnt, 0, 2 * sizeof(unsigned int), c->stream));
+  AX1_CUDA(cudaStreamSynchronize(c->stream));      // zeroed before any peer can learn the handle
+  cudaIpcMemHandle_t mine;
+  AX1_CUDA(cudaIpcGetMemHandle(&mine, P.win));
+  std::memcpy(handle64, &mine, sizeof(mine));
+  c->rank = rank; c->nranks = nranks;
+  return AX1GPU_OK;
+}
+
+int ax1gpu_p2p_attach(ax1gpu_handle c, const char* all_handles) {
+  AX1_CHECK_H(c);
+  cudaSetDevice(c->device);
+  auto& P = c->p2p;
+  if (!P.win || c->nranks < 2) { set_error("p2p_attach before p2p_export"); return AX1GPU_ESTATE; }
+  for (int k = 0; k < c->nranks; ++k) {
+    if (k == c->rank) { P.peer[k] = P.win; continue; }
+    cudaIpcMemHandle_t hk;
+    std::memcpy(&hk, all_handles + (size_t)k * sizeof(hk), sizeof(hk));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, hk, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); return AX1GPU_ECUDA; }
+    P.peer[k] = (double*)ptr;
+  }
+  double sec = AX1_P2P_TIMEOUT_DEFAULT_S;
+  if (const char* t = getenv("AX1_P2P_TIMEOUT_S")) { const double v = atof(t); if (v > 0.0) sec = v; }
+  int khz = 0;
+  if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device) != cudaSuccess || khz <= 0) { cudaGetLastError(); khz = 1965000; }
+  P.timeout_cycles = (long long)(sec * 1e3 * (double)khz);
+  P.on = true;
+  return AX1GPU_OK;
+}
+
 int ax1gpu_comm_mode(ax1gpu_handle c) { return c ? (c->nranks > 1 ? (c->p2p.on ? 2 : 1) : 0) : 0; }
 
 }  // extern "C"

@@ -62,6 +62,7 @@ int drv_vm_minmax(ax1gpu_ctx* c, double* vmin, double* vmax) {
   vm_minmax_kernel<<<1, 1024, 0, c->stream>>>(c->g.nx, c->d_vm, c->d_sums + 2);
   AX1_TL_CHECK(c);
   if (c->nranks > 1) {
+    if (!c->comm) { set_error("V_m extrema over ranks need the NCCL communicator (ax1gpu_comm_init)"); return AX1GPU_ESTATE; }
     ncclResult_t r = c->nccl.AllReduce(c->d_sums + 2, c->d_sums + 2, 2, ncclDouble, ncclMax, c->comm, c->stream);
     if (r != ncclSuccess) { set_error(std::string("ncclAllReduce: ") + c->nccl.GetErrorString(r)); return AX1GPU_ENCCL; }
   }

@@ -272,6 +272,12 @@ int ax1gpu_comm_init(ax1gpu_handle h, const char* libnccl_path, const char* id12
 /* how the two exchange steps run: 0 single rank, 1 NCCL send/recv + allreduce, 2 direct stores into the
  * neighbours' memory over NVLink (CUDA IPC peer windows; default when every rank can map every peer,
  * AX1_P2P=0 forces mode 1) */
+/* Peer windows without NCCL (the data plane never needs it): ax1gpu_p2p_export allocates this rank's window and
+ * returns its CUDA IPC handle (64 bytes); the caller gathers the handles of all ranks (MPI_Allgather in a DUNE build)
+ * and hands the nranks x 64 bytes to ax1gpu_p2p_attach on every rank. Equivalent to ax1gpu_comm_init with AX1_P2P=1
+ * except that the time loop's V_m min/max over ranks (ncclMax) is not available. Ranks may share one GPU (tests). */
+int ax1gpu_p2p_export(ax1gpu_handle h, int rank, int nranks, char* handle64);
+int ax1gpu_p2p_attach(ax1gpu_handle h, const char* all_handles);
 int ax1gpu_comm_mode(ax1gpu_handle h);
 
 /* ---- host model: restatement of the reference's host-side Physics precomputations, so that the
