@@ -189,6 +189,8 @@ def lib():
     L.ax1gpu_ilu_apply.argtypes = [H, c_double_p, c_double_p]
     L.ax1gpu_set_ilu_split.argtypes = [H, C.c_int]
     L.ax1gpu_get_ilu_split.argtypes = [H, c_int_p]
+    L.ax1gpu_set_spmv_compact.argtypes = [H, C.c_int]
+    L.ax1gpu_get_spmv_compact.argtypes = [H, c_int_p]
     L.ax1gpu_rownorm.argtypes = [H, c_double_p]
     L.ax1gpu_time_kernel.argtypes = [H, C.c_char_p, C.c_int, c_double_p]
     L.ax1gpu_launch_count.argtypes = [H]
@@ -556,6 +558,16 @@ class Ax1Gpu:
     def set_ilu_split(self, jcut=-1):
         """Radial split of the ILU0 sub-slabs: -1 automatic (far-field cut on latency-bound grids), 0 off, > 0 row."""
         _chk(lib().ax1gpu_set_ilu_split(self.h, int(jcut)))
+
+    def set_spmv_compact(self, mode=-1):
+        """Solver SpMV operand in 64-byte blocks: -1 automatic (grids of >= 2^20 vertices), 0 never, 1 always."""
+        _chk(lib().ax1gpu_set_spmv_compact(self.h, int(mode)))
+
+    def spmv_compact(self):
+        """Whether the last factorisation's 64-byte-block copy of the Jacobian is what the solver multiplies with."""
+        v = C.c_int()
+        _chk(lib().ax1gpu_get_spmv_compact(self.h, C.byref(v)))
+        return bool(v.value)
 
     def ilu_split(self):
         """The radial cut the last factorisation used (0: none)."""

@@ -227,7 +227,7 @@ int ax1gpu_destroy(ax1gpu_handle c) {
                   (void*)c->d_u, (void*)c->d_uold, (void*)c->d_r0, (void*)c->d_r, (void*)c->d_z, (void*)c->d_uprev, (void*)c->d_A,
                   (void*)c->d_LU, (void*)c->d_rt, (void*)c->d_p, (void*)c->d_v, (void*)c->d_y2, (void*)c->d_t, (void*)c->d_tmp,
                   (void*)c->d_bcrs, (void*)c->d_gbar, (void*)c->d_chstate, (void*)c->d_geff, (void*)c->d_vrest, (void*)c->d_vm, (void*)c->d_fluxterms,
-                  (void*)c->d_mori_gamma, (void*)c->d_err, (void*)c->d_partials, (void*)c->d_sums, (void*)c->d_sc, (void*)c->d_halo_send,
+                  (void*)c->d_mori_gamma, (void*)c->d_Ac, (void*)c->d_err, (void*)c->d_partials, (void*)c->d_sums, (void*)c->d_sc, (void*)c->d_halo_send,
                   (void*)c->d_halo_recv, (void*)c->d_lvl, (void*)c->d_spartials})
     if (p) cudaFree(p);
   if (c->h_sc) cudaFreeHost(c->h_sc);
@@ -504,6 +504,19 @@ int ax1gpu_set_ilu_split(ax1gpu_handle c, int jcut) {
   if (jcut > 0 && (jcut < 2 || jcut > c->g.nvy - 2)) { set_error("ilu split: row out of range"); return AX1GPU_EINVAL; }
   c->ilu_split = jcut < 0 ? -1 : jcut;
   c->factored = false;
+  return AX1GPU_OK;
+}
+
+int ax1gpu_set_spmv_compact(ax1gpu_handle c, int mode) {
+  AX1_CHECK_H(c);
+  c->spmv_compact = mode < 0 ? -1 : (mode ? 1 : 0);
+  c->factored = false;
+  return AX1GPU_OK;
+}
+
+int ax1gpu_get_spmv_compact(ax1gpu_handle c, int* active) {
+  AX1_CHECK_H(c);
+  if (active) *active = c->factored && c->ac_valid;
   return AX1GPU_OK;
 }
 

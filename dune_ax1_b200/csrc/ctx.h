@@ -23,6 +23,9 @@ struct ax1gpu_ctx {
   int* d_rowptr = nullptr;
   double *d_u = nullptr, *d_uold = nullptr, *d_r0 = nullptr, *d_r = nullptr, *d_z = nullptr, *d_uprev = nullptr;
   double *d_A = nullptr, *d_LU = nullptr;
+  double* d_Ac = nullptr;      // 64-byte-block copy of d_A for the solver's SpMV (driver.cu: drv_factor), lazily allocated
+  bool ac_valid = false;
+  int spmv_compact = -1;       // -1 automatic (nv >= 2^20), 0 never, 1 always (ax1gpu_set_spmv_compact)
   double *d_rt = nullptr, *d_p = nullptr, *d_v = nullptr, *d_y2 = nullptr, *d_t = nullptr, *d_tmp = nullptr;
   double* d_bcrs = nullptr;  // staging for Jacobian up/download (allocated lazily)
   // channels

@@ -802,6 +802,14 @@ static int amg_vcycle(ax1gpu_ctx* c, const double* d, double* v) {
   return 0;
 }
 
+#define AX1_COMPACT_MIN_NV (1 << 20)
+static bool compact_enabled(const ax1gpu_ctx* c) {   // AX1_SPMV_COMPACT=0/1 overrides the automatic choice (A/B runs)
+  static const int env = getenv("AX1_SPMV_COMPACT") ? atoi(getenv("AX1_SPMV_COMPACT")) : -1;
+  const int mode = c->spmv_compact >= 0 ? c->spmv_compact : env;
+  return mode < 0 ? c->g.nv >= AX1_COMPACT_MIN_NV : mode != 0;
+}
+static inline const double* solver_Ac(const ax1gpu_ctx* c) { return (c->factored && c->ac_valid) ? c->d_Ac : nullptr; }
+
 int drv_factor(ax1gpu_ctx* c, int slab_w, int fill, int amg) {
   int rc = select_preconditioner(c, slab_w, fill, amg);
   if (rc) return rc;
@@ -810,6 +818,19 @@ int drv_factor(ax1gpu_ctx* c, int slab_w, int fill, int amg) {
   else launch_ilu_factor(c->g, c->d_A, c->d_LU, c->slab_w, c->d_lvl, c->stream, c->ilu_jc);
   AX1_LAUNCH_CHECK(c);
   if (c->amg && (rc = amg_setup(c))) return rc;
+  // The solver multiplies with A 40 times per Newton iteration: on HBM-bound grids it does so with a copy in
+  // 64-byte blocks (576 instead of 720 B per block row; solver.cu: compact_rows_kernel), built here because every
+  // change of A passes through a new factorisation. Small grids are latency-bound and skip it.
+  c->ac_valid = false;
+  if (compact_enabled(c)) {
+    if (!c->d_Ac) AX1_CUDA(cudaMalloc((void**)&c->d_Ac, (size_t)c->g.nv * AX1_CROW * sizeof(double)));
+    AX1_CUDA(cudaMemsetAsync(c->d_err + 3, 0, sizeof(int), c->stream));
+    launch_compact_rows(c->g, c->d_A, c->d_Ac, c->d_err + 3, c->stream);
+    AX1_LAUNCH_CHECK(c);
+    AX1_CUDA(cudaMemcpyAsync(c->h_err + 3, c->d_err + 3, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    AX1_CUDA(cudaStreamSynchronize(c->stream));
+    c->ac_valid = c->h_err[3] == 0;     // potential rows not exactly q x valences (FD Jacobians): multiply with A itself
+  }
   c->factored = true;
   return 0;
 }
@@ -939,13 +960,14 @@ int drv_solve(ax1gpu_ctx* c, double* r, double* x, double reduction, int maxit, 
   const bool poll = reduction > 0.0;
   const int SB = spmv_blocks(c->g);
   const int zc = c->nranks > 1;
+  const double* Ac = solver_Ac(c);
   for (k = 0; 0.5 + k < maxit; ++k) {
     // rho_new, the breakdown tests and beta were produced by OP_NORM0 / OP_NORM_B of the step before
     pupdate_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_p, c->d_v, r, c->d_sc, k == 0);
     AX1_LAUNCH_CHECK(c);
     if ((rc = drv_prec_apply(c, c->d_p, c->d_y2))) return rc;
     launch_spmv_dot(c->g, c->d_A, c->d_y2, c->d_v, zc, 1, c->d_rt, own.lo, own.hi, own.masked, c->d_sc, c->d_spartials,
-                    c->stream);                                   // v = A y, h = <rt, v>
+                    c->stream, Ac);                               // v = A y, h = <rt, v>
     AX1_LAUNCH_CHECK(c);
     if ((rc = reduce_op_from(c, c->d_spartials, SB, 1, OP_H, reduction))) return rc;
     xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, x, c->d_y2, r, c->d_v, nullptr, c->d_sc, 0, own, c->d_partials);
@@ -957,7 +979,7 @@ int drv_solve(ax1gpu_ctx* c, double* r, double* x, double reduction, int maxit, 
     }
     if ((rc = drv_prec_apply(c, r, c->d_y2))) return rc;
     launch_spmv_dot(c->g, c->d_A, c->d_y2, c->d_t, zc, 2, r, own.lo, own.hi, own.masked, c->d_sc, c->d_spartials,
-                    c->stream);                                   // t = A y, <t, r>, <t, t>
+                    c->stream, Ac);                               // t = A y, <t, r>, <t, t>
     AX1_LAUNCH_CHECK(c);
     if ((rc = reduce_op_from(c, c->d_spartials, SB, 2, OP_OMEGA, reduction))) return rc;
     xr_update_kernel<<<G, 256, 0, c->stream>>>(nv, x, c->d_y2, r, c->d_t, c->d_rt, c->d_sc, 1, own, c->d_partials);
@@ -1030,7 +1052,7 @@ int drv_solve_gmres(ax1gpu_ctx* c, double* b, double* x, double reduction, int r
     gmres_scale_kernel<<<G, 256, 0, c->stream>>>(nv, Vk(0), Vk(0), gm, c->d_sc);
     AX1_LAUNCH_CHECK(c);
     for (int i = 0; i < m && j <= maxit; ++i, ++j) {
-      launch_spmv(c->g, c->d_A, Vk(i), Vk(i + 1), zc, c->stream);      // v[i+1] as temporary
+      launch_spmv(c->g, c->d_A, Vk(i), Vk(i + 1), zc, c->stream, solver_Ac(c));      // v[i+1] as temporary
       AX1_LAUNCH_CHECK(c);
       if ((rc = drv_prec_apply(c, Vk(i + 1), w))) return rc;
       for (int k = 0; k <= i; ++k) {
@@ -1214,7 +1236,7 @@ int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms) {
     else if (n == "spmv_dot1" || n == "spmv_dot2") {
       const Own own = own_of(c);
       launch_spmv_dot(c->g, c->d_A, c->d_y2, c->d_v, c->nranks > 1, n == "spmv_dot1" ? 1 : 2, c->d_rt, own.lo, own.hi,
-                      own.masked, c->d_sc, c->d_spartials, c->stream);
+                      own.masked, c->d_sc, c->d_spartials, c->stream, solver_Ac(c));
     }
     // the two exchange steps of the overlapping Krylov solve, as the solver issues them (all ranks must call with
     // the same reps): "reduce" = block partials -> sums over all ranks -> scalar recurrence (peer windows: one launch;
@@ -1234,6 +1256,10 @@ int drv_time_kernel(ax1gpu_ctx* c, const char* name, int reps, double* ms) {
         return halo_wait_add(c, c->d_y2, hp.seq);
       }
       return halo_add(c, c->d_y2);
+    }
+    else if (n == "compact") {
+      if (!c->d_Ac) { set_error("time_kernel compact: no compact copy on this grid"); return AX1GPU_EINVAL; }
+      launch_compact_rows(c->g, c->d_A, c->d_Ac, c->d_err + 3, c->stream);
     }
     else if (n == "pupdate") { pupdate_kernel<<<G, 256, 0, c->stream>>>(nv, c->d_tmp, c->d_v, c->d_t, c->d_sc, 0); }
     else if (n == "ilu_factor") {

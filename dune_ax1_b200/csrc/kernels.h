@@ -31,14 +31,17 @@ struct Scalars {  // device-resident Krylov scalars
   double rho, rho_new, alpha, omega, beta, h, norm, norm0, tr, tt, it_half, reduction, rho_next, pad0;
   int done, converged, breakdown, pad;
 };
-void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int zero_constrained, cudaStream_t st);
+// Ac != null: multiply with the 64-byte-block copy of A (launch_compact_rows) instead of A itself
+void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int zero_constrained, cudaStream_t st,
+                 const double* Ac = nullptr);
+void launch_compact_rows(const Dev& g, const double* A, double* Ac, int* flag, cudaStream_t st);
 void launch_spmv_residual(const Dev& g, const double* A, const double* x, const double* b, double* r,
                           int zero_constrained, cudaStream_t st);
 int spmv_blocks(const Dev& g);
 // SpMV with fused dot products: dot_mode 1: partial <w, y>; 2: partial <y, w> and <y, y>; one partial per block
 void launch_spmv_dot(const Dev& g, const double* A, const double* x, double* y, int zero_constrained, int dot_mode,
                      const double* w, int own_lo, int own_hi, int masked, const Scalars* sc, double* partials,
-                     cudaStream_t st);
+                     cudaStream_t st, const double* Ac = nullptr);
 // jc > 0 (everywhere below): radial split of the sub-slabs at grid row jc, see solver.cu: ypart_select
 void ilu_level_tables(const Dev& g, int slab_w, std::vector<int>& tab, int jc = 0);
 void launch_ilu_factor(const Dev& g, const double* A, double* LU, int slab_w, const int* lvl_tab, cudaStream_t st,

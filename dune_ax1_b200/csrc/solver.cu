@@ -23,7 +23,11 @@ namespace ax1 {
 // DOT = 3: residual mode y = w - A x (multigrid defect), no reduction.
 // DOT = 1: also partial <w, y> (BiCGStab h = <rt, v>);  DOT = 2: partial <y, w> and <y, y>
 // (omega = <t, r> / <t, t>): the SpMV result is reduced while it is still in registers.
-template <int DOT>
+// COMPACT: the operand is the 64-byte-block copy of A that the solver keeps for its 40 products per Newton iteration
+// (compact_rows_kernel below): [d0 c0 | d1 c1 | d2 c2 | q p3] with the potential row's three concentration entries
+// folded into q (they are q times the valences: the charge-density term, acme2_cyl_operator_fully_coupled.hh:535) --
+// 576 B instead of 720 B per block row, one 16 B load per lane and slot, a quad reads one contiguous 64 B block.
+template <int DOT, bool COMPACT>
 __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restrict__ A, const double* __restrict__ x,
                                                    double* __restrict__ y, int zero_con, const double* __restrict__ w,
                                                    Own own, const Scalars* sc, double* partials) {
@@ -33,7 +37,8 @@ __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restri
   const bool active = (v < g.nv) && !(DOT && DOT != 3 && sc && sc->done);
   if (active) {
     const int i = v % g.nvx, j = v / g.nvx;
-    const double* Arow = A + (size_t)v * AX1_ROW;
+    const double* Arow = A + (size_t)v * (COMPACT ? AX1_CROW : AX1_ROW);
+    const double z0 = g.valence[0], z1 = g.valence[1], z2 = g.valence[2];
     double acc = 0.0;
 #pragma unroll
     for (int sl = 0; sl < 9; ++sl) {
@@ -42,6 +47,20 @@ __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restri
       if (ii < 0 || ii >= g.nvx || jj < 0 || jj >= g.nvy) continue;
       double xv[4];
       ldg4(x + 4 * (size_t)(v + di + dj * g.nvx), xv);
+      if (COMPACT) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(Arow + sl * AX1_CBLK + 2 * r));
+        if (r == 3) {
+          double cs = z0 * xv[0];
+          cs += z1 * xv[1];
+          cs += z2 * xv[2];
+          acc += a.x * cs;
+          acc += a.y * xv[3];
+        } else {
+          acc += a.x * (r == 0 ? xv[0] : (r == 1 ? xv[1] : xv[2]));
+          acc += a.y * xv[3];
+        }
+        continue;
+      }
       // branch-free arrow-row load: every lane issues two 16 B loads (lanes 0-2 read their (d,c) pair
       // twice) so that all 36 loads of the row can be in flight at once
       const double* blk = Arow + sl * AX1_BLK;
@@ -819,20 +838,55 @@ __global__ void bcrs_copy_kernel(Dev g, double* A9, double* blocks, const int* _
 
 // ------------------------------------------------------------------------------------------
 int spmv_blocks(const Dev& g) { return (int)((4LL * g.nv + 255) / 256); }
-void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int zero_con, cudaStream_t st) {
-  spmv_kernel<0><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, nullptr, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
+void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int zero_con, cudaStream_t st,
+                 const double* Ac) {
+  if (Ac) spmv_kernel<0, true><<<spmv_blocks(g), 256, 0, st>>>(g, Ac, x, y, zero_con, nullptr, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
+  else spmv_kernel<0, false><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, nullptr, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
 }
 // r = b - A x
 void launch_spmv_residual(const Dev& g, const double* A, const double* x, const double* b, double* r, int zero_con,
                           cudaStream_t st) {
-  spmv_kernel<3><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, r, zero_con, b, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
+  spmv_kernel<3, false><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, r, zero_con, b, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
 }
 void launch_spmv_dot(const Dev& g, const double* A, const double* x, double* y, int zero_con, int dot_mode,
                      const double* w, int own_lo, int own_hi, int masked, const Scalars* sc, double* partials,
-                     cudaStream_t st) {
+                     cudaStream_t st, const double* Ac) {
   const Own own{own_lo, own_hi, g.nvx, masked};
-  if (dot_mode == 1) spmv_kernel<1><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
-  else spmv_kernel<2><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
+  if (Ac) {
+    if (dot_mode == 1) spmv_kernel<1, true><<<spmv_blocks(g), 256, 0, st>>>(g, Ac, x, y, zero_con, w, own, sc, partials);
+    else spmv_kernel<2, true><<<spmv_blocks(g), 256, 0, st>>>(g, Ac, x, y, zero_con, w, own, sc, partials);
+    return;
+  }
+  if (dot_mode == 1) spmv_kernel<1, false><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
+  else spmv_kernel<2, false><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
+}
+
+// Ac = the 64-byte-block copy of the arrow rows of A for the solver's products (see spmv_kernel<., true>). One thread
+// per (vertex, slot). *flag is raised if a block's potential row is not EXACTLY q times the valences (finite-difference
+// volume Jacobians, uploaded matrices): the solver then multiplies with A itself.
+__global__ void __launch_bounds__(256) compact_rows_kernel(Dev g, const double* __restrict__ A, double* __restrict__ Ac,
+                                                           int* flag) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 9LL * g.nv) return;
+  const double* b = A + (size_t)t * AX1_BLK;
+  double v[AX1_BLK];
+#pragma unroll
+  for (int e = 0; e < AX1_BLK; e += 2) {
+    const double2 p = __ldg(reinterpret_cast<const double2*>(b + e));
+    v[e] = p.x; v[e + 1] = p.y;
+  }
+  const double z0 = g.valence[0], z1 = g.valence[1], z2 = g.valence[2];
+  const double q = v[6] / z0;
+  if (z0 * q != v[6] || z1 * q != v[7] || z2 * q != v[8]) atomicExch(flag, 1);
+  double2* o = reinterpret_cast<double2*>(Ac + (size_t)t * AX1_CBLK);
+  o[0] = make_double2(v[0], v[1]);
+  o[1] = make_double2(v[2], v[3]);
+  o[2] = make_double2(v[4], v[5]);
+  o[3] = make_double2(q, v[9]);
+}
+void launch_compact_rows(const Dev& g, const double* A, double* Ac, int* flag, cudaStream_t st) {
+  const long long nt = 9LL * g.nv;
+  compact_rows_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(g, A, Ac, flag);
 }
 // one quad per wavefront row: a level of a slab of width w has at most ceil(w/2) rows
 static int slab_threads(int slab_w) {

@@ -254,6 +254,14 @@ int ax1gpu_set_amg(ax1gpu_handle h, int on, int cx);
  * last factorisation used. */
 int ax1gpu_set_ilu_split(ax1gpu_handle h, int jcut);
 int ax1gpu_get_ilu_split(ax1gpu_handle h, int* active);
+/* Operand of the solver's matrix-vector products: mode -1 (default) automatic -- grids of >= 2^20 vertices (HBM-bound)
+ * multiply with a copy of the Jacobian in 64-byte blocks (the potential row's three concentration entries are one
+ * number times the valences, acme2_cyl_operator_fully_coupled.hh:541-547, so 8 doubles instead of 10 carry a block),
+ * built by each factorisation and bit-checked against the Jacobian: a matrix whose potential rows do not have that
+ * shape (finite-difference Jacobians) is multiplied as it is; 0: never; 1: on every grid. *active (optional) returns
+ * whether the last factorisation's copy is in use. */
+int ax1gpu_set_spmv_compact(ax1gpu_handle h, int mode);
+int ax1gpu_get_spmv_compact(ax1gpu_handle h, int* active);
 /* one application of the current preconditioner (ILU sweep or AMG cycle) incl. the halo sum */
 int ax1gpu_ilu_apply(ax1gpu_handle h, const double* d, double* v);
 int ax1gpu_rownorm(ax1gpu_handle h, double* r); /* scales device Jacobian and r */

@@ -862,3 +862,55 @@ def test_default_preconditioner_uses_far_field_cut_and_matches_oracle(oracle, ax
     dev.newton(u0, axlib.default_newton_opts(slab_w=16, **kw))
     assert dev.ilu_split() == 0
     dev.close()
+
+
+def test_solver_spmv_operand_in_64_byte_blocks(oracle, axlib):
+    """The solver's matrix-vector products on a 64-byte-block copy of the Jacobian (HBM-bound grids use it by
+    default; forced here): the potential row's concentration entries are q times the valences, so the copy holds
+    the same matrix. BiCGStab, GMRES and a Newton step follow the oracle as with the Jacobian itself; a matrix
+    without that shape is detected bit-wise and multiplied as it is."""
+    s = small_setup(nx=12)
+    dev, P, u0 = _both(oracle, axlib, s)
+    dev.set_spmv_compact(1)
+    Jo = P.jacobian(u0)
+    r = P.residual(u0)
+    dev.set_jacobian(Jo)
+    zg, rg, resg = dev.solve(r, 1e-10, maxit=500, slab_w=4)
+    assert dev.spmv_compact()
+    zo, ro, reso = P.solve(Jo, r, 1e-10, maxit=500, ilu_fill=0, slab_w=4)
+    assert resg.converged == 1 and abs(resg.iterations - reso.iterations) <= 1
+    assert np.max(np.abs(zg - zo)) <= 1e-7 * np.max(np.abs(zo))
+    assert np.linalg.norm(r - P.spmv(Jo, zg)) <= 2e-10 * np.linalg.norm(r)
+    zm, _, resm = dev.solve_gmres(r, 1e-10, restart=100, maxit=600, slab_w=4, fill=0)
+    zmo, _, resmo = P.solve_ex(Jo, r, 1e-10, maxit=600, ilu_fill=0, slab_w=4, krylov=1, restart=100)
+    assert resm.converged == 1 and abs(resm.iterations - resmo.iterations) <= 1
+    assert np.max(np.abs(zm - zmo)) <= 1e-7 * np.max(np.abs(zmo))
+    # against the same solve with the Jacobian itself: same iteration count, same solution to rounding
+    dev.set_spmv_compact(0)
+    z0, _, res0 = dev.solve(r, 1e-10, maxit=500, slab_w=4)
+    assert not dev.spmv_compact()
+    assert res0.iterations == resg.iterations and np.max(np.abs(z0 - zg)) <= 1e-9 * np.max(np.abs(z0))
+    # a potential row that is not q x valences: the copy is refused, the result is that of the plain operand
+    J2 = Jo.copy()
+    blocks = J2.reshape(-1, 4, 4)
+    b = np.flatnonzero(blocks[:, 3, 1])[7]
+    blocks[b, 3, 1] *= 1.0 + 1e-12
+    dev.set_spmv_compact(1)
+    dev.set_jacobian(J2)
+    z1, _, res1 = dev.solve(r, 1e-10, maxit=500, slab_w=4)
+    assert not dev.spmv_compact()
+    dev.set_spmv_compact(0)
+    dev.set_jacobian(J2)
+    z2, _, res2 = dev.solve(r, 1e-10, maxit=500, slab_w=4)
+    assert np.array_equal(z1, z2) and res1.iterations == res2.iterations
+    # Newton step with the compact operand
+    dev.set_spmv_compact(1)
+    og = axlib.default_newton_opts(reduction=1e-9, abs_limit=1e-14, min_lin_reduction=1e-10, slab_w=4)
+    oc = oracle.default_newton_opts(reduction=1e-9, abs_limit=1e-14, min_lin_reduction=1e-10, ilu_fill=0, slab_w=4)
+    ug, rgn = dev.newton(u0, og)
+    assert dev.spmv_compact()
+    uc, rcn = P.newton(u0, oc)
+    assert rgn.status == 0 and rgn.iterations == rcn.iterations
+    scale = np.max(np.abs(uc.reshape(-1, 4)), axis=0)
+    assert np.max(np.abs(ug - uc).reshape(-1, 4) / scale) < 1e-8
+    dev.close()
