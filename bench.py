@@ -275,10 +275,12 @@ def _field_err(ug, uc):
     return float(err[:3].max()), float(err[3])
 
 
-def sample_parity(api, setups, device, ilu_fill, slab_w, nx_fixed=512, nx_conv=256):
+def sample_parity(api, setups, device, ilu_fill, slab_w, nx_fixed=512, nx_conv=256, compact=False):
     """Device vs oracle on bounded samples of the synthetic workload with exactly the same options: (a) the
     fixed-work step the headline times (5 Newton x 20 BiCGStab, lambda = 1), (b) a step converged to tight
-    tolerances. The oracle legs run in threads beside the device legs."""
+    tolerances. The oracle legs run in threads beside the device legs. compact: the headline grid is large enough
+    for the library to multiply with the 64-byte-block copy of the Jacobian; the samples are too small for the
+    automatic rule, so the same operand is forced on them."""
     from oracle import cpu_setup as CS
     from oracle import pyoracle as O
     O.build()
@@ -303,14 +305,18 @@ def sample_parity(api, setups, device, ilu_fill, slab_w, nx_fixed=512, nx_conv=2
         dev = setups.make_device(s, device=device)
         dev.set_time(0.0, 1.0); dev.set_uold(s["u0"]); dev.update_state(s["u0"]); dev.accept_state()
         dev.set_time(1.0, 1.0); dev.set_uold(s["u0"]); dev.update_state(s["u0"])
+        if compact:
+            dev.set_spmv_compact(1)
         t0 = time.perf_counter()
         u, res = dev.newton(s["u0"], api.default_newton_opts(ilu_fill=ilu_fill, slab_w=slab_w, **kw))
         gpu[name] = (u, res, time.perf_counter() - t0)
+        operand_compact = dev.spmv_compact()
         dev.close()
     for t in th:
         t.join()
     out = {"checker": "oracle/ (CPU restatement, pinned on the reference's compiled operators)",
-           "options": "ILU%d, %d-column sub-slabs, dx = 100 nm, perturbation 1e-3, dt = 1 us" % (ilu_fill, slab_w)}
+           "options": "ILU%d, %d-column sub-slabs, dx = 100 nm, perturbation 1e-3, dt = 1 us" % (ilu_fill, slab_w),
+           "spmv_operand": "64-byte blocks (forced, as on the headline grid)" if operand_compact else "arrow blocks"}
     ok = True
     for name, (nx, kw) in cases.items():
         (ug, rg, tg), (uc, rc, tc) = gpu[name], cpu[name]
@@ -610,7 +616,7 @@ def main():
         if world > 1:
             mg_parity = multigpu_parity(api, setups, dist, rank, world, local_rank)
         elif rank == 0:
-            parity = sample_parity(api, setups, local_rank, args.ilu_fill, args.slab_w)
+            parity = sample_parity(api, setups, local_rank, args.ilu_fill, args.slab_w, compact=nv_full >= (1 << 20))
 
     if myelin:
         s = setups.make_myelin_setup(rank=rank, nranks=world)
@@ -745,6 +751,11 @@ def main():
               "dot": 3 * NEWTON_ITS + 1, "axpy": 2 * KRYLOV_ITS * NEWTON_ITS, "pupdate": KRYLOV_ITS * NEWTON_ITS}
     kern = {}
     bytes_k, bytes_dense = dict(BYTES), dict(BYTES_DENSE)
+    compact = bool(dev.spmv_compact())
+    if compact:   # the solver multiplies with the 64-byte-block copy (576 B per block row) each factorisation writes
+        bytes_k["spmv"] = 576 + 32 + 32
+        bytes_k["compact"], bytes_dense["compact"] = 720 + 576, 720 + 576
+        counts["compact"] = NEWTON_ITS
     for b in (bytes_k, bytes_dense):
         b["spmv_dot1"], b["spmv_dot2"] = b["spmv"] + 32, b["spmv"] + 32    # + the vector of the fused dot product
     if args.ilu_fill == 1:   # 13 instead of 9 blocks per factor row (ilu1.cu)
@@ -770,7 +781,7 @@ def main():
                 "frac": kern[dom]["GBps"] / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_kind": peak_kind, "algorithmic_bytes_per_launch": bytes_k[dom] * nv, "kernels": kern}
     # whole-step algorithmic traffic (SURVEY 8(d) formula, l = 1 line-search residual, k Krylov its)
-    step_bytes = NEWTON_ITS * (bytes_k["jacobian"] + bytes_k["ilu_factor"] + 2 * 104 +
+    step_bytes = NEWTON_ITS * (bytes_k["jacobian"] + bytes_k["ilu_factor"] + bytes_k.get("compact", 0) + 2 * 104 +
                                KRYLOV_ITS * (2 * bytes_k["spmv"] + 2 * bytes_k["ilu_apply"] + 416)) * nv
     step_bytes_dense = NEWTON_ITS * (1184 + bytes_dense["ilu_factor"] + 2 * 104 +
                                      KRYLOV_ITS * (2 * 1256 + 2 * bytes_dense["ilu_apply"] + 416)) * nv
@@ -782,6 +793,7 @@ def main():
            "scaling": "strong" if myelin else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": config, "comm": {0: "none", 1: "nccl", 2: "nvlink peer windows"}[dev.comm_mode()],
            "ilu_radial_split_row": dev.ilu_split(),
+           "spmv_operand": "64-byte blocks (576 B per block row)" if compact else "arrow blocks (720 B per block row)",
            "newton_steps_per_s": newton_per_s, "newton_iterations_per_step": NEWTON_ITS,
            "krylov_iterations_per_solve": KRYLOV_ITS,
            "last_step": {"defect": last.defect, "first_defect": last.first_defect, "lin_iterations": last.lin_iterations,

@@ -61,7 +61,8 @@ struct Dev {
 // Missing neighbours (domain boundary) hold zero blocks. The ILU factor blocks are dense (solver.cu).
 #define AX1_BLK 10
 #define AX1_ROW 90
-// the solver's SpMV operand: 8-double blocks [d0 c0 | d1 c1 | d2 c2 | q p3], p_j = z_j q (solver.cu: compact_rows_kernel)
+// the solver's SpMV operand: 8-double blocks [d0 c0 | d1 c1 | d2 c2 | q p3], p_j = z_j q, stored as
+// [group of 8 vertices][slot][vertex in group][8] (solver.cu: compact_rows_kernel, spmv_compact_kernel)
 #define AX1_CBLK 8
 #define AX1_CROW 72
 __host__ __device__ inline int slot_di(int s) { return s % 3 - 1; }

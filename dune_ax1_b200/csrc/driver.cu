@@ -823,7 +823,7 @@ int drv_factor(ax1gpu_ctx* c, int slab_w, int fill, int amg) {
   // change of A passes through a new factorisation. Small grids are latency-bound and skip it.
   c->ac_valid = false;
   if (compact_enabled(c)) {
-    if (!c->d_Ac) AX1_CUDA(cudaMalloc((void**)&c->d_Ac, (size_t)c->g.nv * AX1_CROW * sizeof(double)));
+    if (!c->d_Ac) AX1_CUDA(cudaMalloc((void**)&c->d_Ac, ((size_t)c->g.nv + 8) * AX1_CROW * sizeof(double)));
     AX1_CUDA(cudaMemsetAsync(c->d_err + 3, 0, sizeof(int), c->stream));
     launch_compact_rows(c->g, c->d_A, c->d_Ac, c->d_err + 3, c->stream);
     AX1_LAUNCH_CHECK(c);
@@ -905,7 +905,7 @@ int drv_prec_apply(ax1gpu_ctx* c, const double* d, double* v) {
 }
 
 int drv_op_apply(ax1gpu_ctx* c, const double* x, double* y) {
-  launch_spmv(c->g, c->d_A, x, y, c->nranks > 1, c->stream);
+  launch_spmv(c->g, c->d_A, x, y, c->nranks > 1, c->stream, solver_Ac(c));
   AX1_LAUNCH_CHECK(c);
   return 0;
 }

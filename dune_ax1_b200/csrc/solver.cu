@@ -23,11 +23,7 @@ namespace ax1 {
 // DOT = 3: residual mode y = w - A x (multigrid defect), no reduction.
 // DOT = 1: also partial <w, y> (BiCGStab h = <rt, v>);  DOT = 2: partial <y, w> and <y, y>
 // (omega = <t, r> / <t, t>): the SpMV result is reduced while it is still in registers.
-// COMPACT: the operand is the 64-byte-block copy of A that the solver keeps for its 40 products per Newton iteration
-// (compact_rows_kernel below): [d0 c0 | d1 c1 | d2 c2 | q p3] with the potential row's three concentration entries
-// folded into q (they are q times the valences: the charge-density term, acme2_cyl_operator_fully_coupled.hh:535) --
-// 576 B instead of 720 B per block row, one 16 B load per lane and slot, a quad reads one contiguous 64 B block.
-template <int DOT, bool COMPACT>
+template <int DOT>
 __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restrict__ A, const double* __restrict__ x,
                                                    double* __restrict__ y, int zero_con, const double* __restrict__ w,
                                                    Own own, const Scalars* sc, double* partials) {
@@ -37,8 +33,7 @@ __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restri
   const bool active = (v < g.nv) && !(DOT && DOT != 3 && sc && sc->done);
   if (active) {
     const int i = v % g.nvx, j = v / g.nvx;
-    const double* Arow = A + (size_t)v * (COMPACT ? AX1_CROW : AX1_ROW);
-    const double z0 = g.valence[0], z1 = g.valence[1], z2 = g.valence[2];
+    const double* Arow = A + (size_t)v * AX1_ROW;
     double acc = 0.0;
 #pragma unroll
     for (int sl = 0; sl < 9; ++sl) {
@@ -47,20 +42,6 @@ __global__ void __launch_bounds__(256) spmv_kernel(Dev g, const double* __restri
       if (ii < 0 || ii >= g.nvx || jj < 0 || jj >= g.nvy) continue;
       double xv[4];
       ldg4(x + 4 * (size_t)(v + di + dj * g.nvx), xv);
-      if (COMPACT) {
-        const double2 a = __ldg(reinterpret_cast<const double2*>(Arow + sl * AX1_CBLK + 2 * r));
-        if (r == 3) {
-          double cs = z0 * xv[0];
-          cs += z1 * xv[1];
-          cs += z2 * xv[2];
-          acc += a.x * cs;
-          acc += a.y * xv[3];
-        } else {
-          acc += a.x * (r == 0 ? xv[0] : (r == 1 ? xv[1] : xv[2]));
-          acc += a.y * xv[3];
-        }
-        continue;
-      }
       // branch-free arrow-row load: every lane issues two 16 B loads (lanes 0-2 read their (d,c) pair
       // twice) so that all 36 loads of the row can be in flight at once
       const double* blk = Arow + sl * AX1_BLK;
@@ -836,33 +817,84 @@ __global__ void bcrs_copy_kernel(Dev g, double* A9, double* blocks, const int* _
   else if (blocks[b] != 0.0) atomicExch(viol, 1);
 }
 
+// The solver's SpMV on the 64-byte-block copy of A (compact_rows_kernel below; 40 products per Newton iteration):
+// a block is [d0 c0 | d1 c1 | d2 c2 | q p3], the potential row's three concentration entries folded into q (they are
+// q times the valences: the charge-density term, acme2_cyl_operator_fully_coupled.hh:535) -- 576 B instead of 720 B
+// per block row. The copy is tiled for the load pattern of this kernel: [8 vertices][9 slots][vertex in group][8],
+// so the 16 B loads of a warp (8 vertices x 4 lanes, one slot) cover 512 contiguous bytes = 4 full cache lines
+// instead of 8 half-used ones, and each lane loads ONE component of the neighbour's x (a coalesced 256 B per warp);
+// x3 and the valence-weighted sum come from the quad by shuffles. L1 wavefronts per row: 54 instead of 108 --
+// they, not DRAM, held the row-layout variant of this kernel at 83 % of the HBM peak.
+template <int DOT>
+__global__ void __launch_bounds__(256, 8) spmv_compact_kernel(Dev g, const double* __restrict__ Ac, const double* __restrict__ x,
+                                                           double* __restrict__ y, int zero_con,
+                                                           const double* __restrict__ w, Own own, const Scalars* sc,
+                                                           double* partials) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int vt = (int)(t >> 2), r = (int)(t & 3);
+  double s[2] = {0.0, 0.0};
+  if (!(DOT && sc && sc->done)) {                  // uniform: all lanes of a warp take part in the shuffles
+    const int v = vt < g.nv ? vt : g.nv - 1;       // lanes past the end compute the last row and do not store
+    const int i = v % g.nvx, j = v / g.nvx;
+    const double* Arow = Ac + ((size_t)(v >> 3) * 9) * (8 * AX1_CBLK) + (v & 7) * AX1_CBLK + 2 * r;
+    const double zr = r < 3 ? (double)g.valence[r] : 0.0;
+    double acc = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < 9; ++sl) {
+      const int di = sl % 3 - 1, dj = sl / 3 - 1;
+      const int ii = i + di, jj = j + dj;
+      const bool ok = ii >= 0 && ii < g.nvx && jj >= 0 && jj < g.nvy;      // missing neighbours hold zero blocks
+      const double xr = ok ? __ldg(x + 4 * (size_t)(v + di + dj * g.nvx) + r) : 0.0;
+      const double2 a = __ldg(reinterpret_cast<const double2*>(Arow + sl * (8 * AX1_CBLK)));
+      const double x3 = __shfl_sync(0xffffffffu, xr, 3, 4);
+      double zx = zr * xr;
+      zx += __shfl_xor_sync(0xffffffffu, zx, 1, 4);
+      zx += __shfl_xor_sync(0xffffffffu, zx, 2, 4);
+      acc += a.x * (r == 3 ? zx : xr);
+      acc += a.y * x3;
+    }
+    if (vt < g.nv) {
+      if (zero_con && ((g.dmask[v] >> r) & 1)) acc = 0.0;
+      y[4 * (size_t)v + r] = acc;
+      if (DOT == 1 || DOT == 2) {
+        if (!own.masked || (i >= own.lo && i <= own.hi)) {
+          const double wv = __ldg(w + 4 * (size_t)v + r);
+          s[0] = acc * wv;
+          if (DOT == 2) s[1] = acc * acc;
+        }
+      }
+    }
+  }
+  if (DOT == 1 || DOT == 2) block_reduce_store<2>(s, partials);
+}
+
 // ------------------------------------------------------------------------------------------
 int spmv_blocks(const Dev& g) { return (int)((4LL * g.nv + 255) / 256); }
 void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int zero_con, cudaStream_t st,
                  const double* Ac) {
-  if (Ac) spmv_kernel<0, true><<<spmv_blocks(g), 256, 0, st>>>(g, Ac, x, y, zero_con, nullptr, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
-  else spmv_kernel<0, false><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, nullptr, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
+  if (Ac) spmv_compact_kernel<0><<<spmv_blocks(g), 256, 0, st>>>(g, Ac, x, y, zero_con, nullptr, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
+  else spmv_kernel<0><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, nullptr, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
 }
 // r = b - A x
 void launch_spmv_residual(const Dev& g, const double* A, const double* x, const double* b, double* r, int zero_con,
                           cudaStream_t st) {
-  spmv_kernel<3, false><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, r, zero_con, b, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
+  spmv_kernel<3><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, r, zero_con, b, Own{0, 0, g.nvx, 0}, nullptr, nullptr);
 }
 void launch_spmv_dot(const Dev& g, const double* A, const double* x, double* y, int zero_con, int dot_mode,
                      const double* w, int own_lo, int own_hi, int masked, const Scalars* sc, double* partials,
                      cudaStream_t st, const double* Ac) {
   const Own own{own_lo, own_hi, g.nvx, masked};
   if (Ac) {
-    if (dot_mode == 1) spmv_kernel<1, true><<<spmv_blocks(g), 256, 0, st>>>(g, Ac, x, y, zero_con, w, own, sc, partials);
-    else spmv_kernel<2, true><<<spmv_blocks(g), 256, 0, st>>>(g, Ac, x, y, zero_con, w, own, sc, partials);
+    if (dot_mode == 1) spmv_compact_kernel<1><<<spmv_blocks(g), 256, 0, st>>>(g, Ac, x, y, zero_con, w, own, sc, partials);
+    else spmv_compact_kernel<2><<<spmv_blocks(g), 256, 0, st>>>(g, Ac, x, y, zero_con, w, own, sc, partials);
     return;
   }
-  if (dot_mode == 1) spmv_kernel<1, false><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
-  else spmv_kernel<2, false><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
+  if (dot_mode == 1) spmv_kernel<1><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
+  else spmv_kernel<2><<<spmv_blocks(g), 256, 0, st>>>(g, A, x, y, zero_con, w, own, sc, partials);
 }
 
-// Ac = the 64-byte-block copy of the arrow rows of A for the solver's products (see spmv_kernel<., true>). One thread
-// per (vertex, slot). *flag is raised if a block's potential row is not EXACTLY q times the valences (finite-difference
+// Ac = the 64-byte-block copy of the arrow rows of A for the solver's products, tiled by groups of 8 vertices (see
+// spmv_compact_kernel; the caller allocates nv rounded up to a multiple of 8 rows). One thread per (vertex, slot). *flag is raised if a block's potential row is not EXACTLY q times the valences (finite-difference
 // volume Jacobians, uploaded matrices): the solver then multiplies with A itself.
 __global__ void __launch_bounds__(256) compact_rows_kernel(Dev g, const double* __restrict__ A, double* __restrict__ Ac,
                                                            int* flag) {
@@ -878,7 +910,9 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(Dev g, const double* 
   const double z0 = g.valence[0], z1 = g.valence[1], z2 = g.valence[2];
   const double q = v[6] / z0;
   if (z0 * q != v[6] || z1 * q != v[7] || z2 * q != v[8]) atomicExch(flag, 1);
-  double2* o = reinterpret_cast<double2*>(Ac + (size_t)t * AX1_CBLK);
+  const long long vv = t / 9;
+  const int sl = (int)(t - 9 * vv);
+  double2* o = reinterpret_cast<double2*>(Ac + ((size_t)(vv >> 3) * 9 + sl) * (8 * AX1_CBLK) + (vv & 7) * AX1_CBLK);
   o[0] = make_double2(v[0], v[1]);
   o[1] = make_double2(v[2], v[3]);
   o[2] = make_double2(v[4], v[5]);
