@@ -11,6 +11,8 @@ col = {n: i for i, n in enumerate(hdr)}
 want = {"gpu__time_duration.sum": "duration", "dram__bytes_read.sum": "dram_bytes_read", "dram__bytes_write.sum": "dram_bytes_write",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct", "launch__registers_per_thread": "registers",
         "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct", "sm__inst_executed.avg.per_cycle_active": "ipc_active",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed": "l1tex_throughput_pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
+        "l1tex__t_sector_hit_rate.pct": "l1_hit_rate_pct", "lts__t_sector_hit_rate.pct": "l2_hit_rate_pct",
         "launch__block_size": "block", "launch__grid_size": "grid", "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct"}
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
@@ -52,7 +54,8 @@ meta = {"capture": "ncu --set full --clock-control none, python examples/prof_ke
         "note": "means over the launches of each kernel in the capture; durations are under the profiler (cold cache, serialised) -- bench.py times with CUDA events"}
 json.dump({**meta, "kernels": out}, open(dst, "w"), indent=1)
 # what bench.py reads for roofline.traffic: bench names -> kernels
-names = {"ilu_apply": "ilu_apply_kernel<2, 0>", "spmv_dot1": "spmv_kernel<1>", "spmv_dot2": "spmv_kernel<2>", "spmv": "spmv_kernel<0>",
+names = {"ilu_apply": "ilu_apply_kernel<2, 0>", "spmv_dot1": "spmv_compact_kernel<1>", "spmv_dot2": "spmv_compact_kernel<2>", "spmv": "spmv_kernel<0>",
+         "compact": "compact_rows_kernel",
          "ilu_factor": "ilu_factor_kernel", "jacobian": "jacobian_kernel", "residual": "residual_kernel", "axpy": "xr_update_kernel"}
 tr = {}
 for b, k in names.items():

@@ -12,6 +12,6 @@ dev.jacobian(None, download=False)
 sw = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 fill = int(os.environ.get("AX1_FILL", "0"))
 dev.ilu_factor(sw, fill)
-for name in (sys.argv[3].split(",") if len(sys.argv) > 3 else ("ilu_apply", "spmv", "spmv_dot1", "spmv_dot2", "residual", "jacobian", "ilu_factor", "dot", "axpy", "pupdate")):
+for name in (sys.argv[3].split(",") if len(sys.argv) > 3 else ("ilu_apply", "spmv", "spmv_dot1", "spmv_dot2", "residual", "jacobian", "ilu_factor", "dot", "axpy", "pupdate", "compact")):
     print(name, dev.time_kernel(name, reps=2))
 dev.close()
