@@ -778,7 +778,7 @@ def main():
     if args.nx == NX_PER_GPU and args.slab_w == SLAB_W and not myelin and args.ilu_fill == 0:
         traffic, traffic_src = ncu_traffic(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["GBps"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "frac": kern[dom]["GBps"] / peak, "frac_of_nominal_8TBs": kern[dom]["GBps"] / 8000.0, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_kind": peak_kind, "algorithmic_bytes_per_launch": bytes_k[dom] * nv, "kernels": kern}
     # whole-step algorithmic traffic (SURVEY 8(d) formula, l = 1 line-search residual, k Krylov its)
     step_bytes = NEWTON_ITS * (bytes_k["jacobian"] + bytes_k["ilu_factor"] + bytes_k.get("compact", 0) + 2 * 104 +
@@ -787,6 +787,7 @@ def main():
                                      KRYLOV_ITS * (2 * 1256 + 2 * bytes_dense["ilu_apply"] + 416)) * nv
     roofline["step_frac_of_peak"] = step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak
     roofline["step_frac_of_peak_dense_equivalent"] = step_bytes_dense / (ms / args.steps * 1e-3) / 1e9 / peak
+    roofline["step_frac_of_nominal_8TBs"] = step_bytes / (ms / args.steps * 1e-3) / 1e9 / 8000.0
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

@@ -643,7 +643,7 @@ static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill, int amg = 
   const bool use_amg = amg >= 0 ? amg != 0 : c->amg != 0;
   // slab_w: > 0 the caller's choice, 0 library default, AX1_SLAB_KEEP (internal callers: drv_solve, drv_time_kernel)
   // whatever the handle currently uses -- an automatically derived width then stays automatic
-  bool picked_auto = false;
+  bool picked_auto = false, one_warp_regime = false;
   if (slab_w == AX1_SLAB_KEEP) {
     if (c->slab_w > 0 && !c->slab_auto) slab_w = c->slab_w;
     else slab_w = 0;
@@ -661,7 +661,7 @@ static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill, int amg = 
     // only) is the fastest per level: on the myelin grid (7,252 columns) 16 instead of 32 columns gave 0.336 vs 0.373 ms
     // per sweep and 16.8 vs 19.5 s for 20 converged time steps (ILU(1), 24 vs 48 columns: 23.3 vs 29.0 s)
     // (not under the multigrid cycle, whose smoother gains more from wider sub-slabs: 12.1 vs 10.5 s there)
-    if (!use_amg && c->g.nvx <= gran * 4 * 148) w = gran;
+    if (!use_amg && c->g.nvx <= gran * 4 * 148) { w = gran; one_warp_regime = true; }
     // a width the caller chose explicitly earlier stays; an automatic one is re-derived (fill / multigrid may differ)
     if (c->slab_w > 0 && !c->slab_auto) slab_w = c->slab_w;
     else { slab_w = std::min(128, std::max(gran, w)); picked_auto = true; }
@@ -676,7 +676,11 @@ static int select_preconditioner(ax1gpu_ctx* c, int slab_w, int fill, int amg = 
     if (c->ilu_split > 0) jc = c->ilu_split;
     // automatic only together with an automatic sub-slab width: a caller who fixes the width gets exactly the
     // sub-slab ILU0 it asked for unless it also asks for the cut (ax1gpu_set_ilu_split)
-    else if (c->ilu_split < 0 && picked_auto && slab_w <= 64) jc = auto_radial_cut(c);
+    // ... and only where the one-warp sub-slabs fit the GPU in one wave: there a sweep costs its dependency depth and
+    // the cut halves it. With more sub-slabs than that the SMs are busy anyway, and on the axially refined grid
+    // (dx = 100 nm, 11,648 columns, 48-column sub-slabs) the cut cost 30 instead of 25 Krylov iterations per
+    // converged step and 0.515 instead of 0.474 ms per sweep.
+    else if (c->ilu_split < 0 && picked_auto && one_warp_regime) jc = auto_radial_cut(c);
     if (jc > 0 && (jc < 2 || c->g.nvy - jc < 2)) { set_error("ilu split row must leave two rows on either side"); return AX1GPU_EINVAL; }
   }
   const size_t need = (size_t)c->g.nv * (fill == 1 ? 208 : 144);

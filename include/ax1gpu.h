@@ -248,8 +248,8 @@ int ax1gpu_set_amg(ax1gpu_handle h, int on, int cx);
 /* Radial split of the block-ILU0 sub-slabs (additive Schwarz in y as well as in x): rows below and from grid row
  * `jcut` on are factorised and swept separately, couplings across the cut are dropped from the preconditioner.
  * jcut = -1 (default): automatic -- when the library also chooses the sub-slab width (slab_w <= 0) and that width is
- * <= 64 columns (latency-bound grids), it cuts in the uniform far field of the radial grid, which costs no Krylov
- * iterations and halves the depth of a sweep;
+ * one warp's (grids of up to 9,472 vertex columns: a sweep costs its dependency depth there), it cuts in the uniform
+ * far field of the radial grid, which halves the depth of a sweep at no Krylov iterations on the paper grid;
  * 0: never; > 0: cut at this row. Takes effect with the next factorisation. *active (optional) returns the cut the
  * last factorisation used. */
 int ax1gpu_set_ilu_split(ax1gpu_handle h, int jcut);
