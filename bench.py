@@ -176,6 +176,14 @@ def workload_config(args, world):
 
 # ------------------------------------------------------------------------------------------------
 # CPU legs: oracle/ only (never the product library)
+def host_threads():
+    """The host threads this process may run on (the affinity mask, not the machine's core count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_synthetic(nx_sample, threads, steps, warmup, ilu_fill, slab_w):
     """The oracle (reference algorithm restated) on a bounded sample: `threads` overlapping x-slabs, one thread each."""
     from oracle import cpu_setup as CS
@@ -222,7 +230,7 @@ def cpu_paper(threads, nsteps, ilu_fill, slab_w, ilu_split=0):
 
 
 def run_reference(args, world):
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     workload, config = workload_config(args, world)
     if args.workload == "paper":
         ranks = min(threads, 10)
@@ -448,7 +456,7 @@ def run_paper(args, api, setups, local_rank):
            "e2e": {"value": 73124.0 * nits_h / wall_h / 1e9, "unit": UNIT, "newton_steps_per_s": nits_h / wall_h,
                    "h2d_bytes_per_step": 3 * n * 8, "d2h_bytes_per_step": n * 8, "timing": "host wall clock"}}
     if not args.no_cpu_baseline:
-        ranks = min(os.cpu_count() or 1, 10)
+        ranks = min(host_threads(), 10)
         c = cpu_paper(ranks, args.steps, args.ilu_fill, 16 if args.ilu_fill == 0 else 0, split)
         out["cpu_baseline"] = {"value": c["gdof"], "unit": UNIT, "cores": ranks, "kind": "port",
                                "newton_steps_per_s": c["newton_steps_per_s"],
@@ -769,7 +777,9 @@ def main():
                       "share_of_step": counts[name] * t_ms / (ms / args.steps)}
     # the two exchange steps of the overlapping solve (scalar reduction incl. the cross-rank sum; additive halo sum),
     # timed in lock step on all ranks: what the weak-scaling loss is made of
-    comm = {"reduce_ms": dev.time_kernel("reduce", reps=50), "reductions_per_step": 4 * KRYLOV_ITS * NEWTON_ITS + 3 * NEWTON_ITS + 1}
+    comm = {"reduce_ms": dev.time_kernel("reduce", reps=50),
+            "reduce_ms_is": "one dot kernel over two vectors + the reduction of its partials incl. the cross-rank sum",
+            "reductions_per_step": 4 * KRYLOV_ITS * NEWTON_ITS + 3 * NEWTON_ITS + 1}
     if world > 1:
         comm["halo_ms"] = dev.time_kernel("halo", reps=50)
         comm["halo_sums_per_step"] = 2 * KRYLOV_ITS * NEWTON_ITS
@@ -835,7 +845,7 @@ def main():
                                    "ilu_radial_split_row": split, "timing": "host wall clock"}
             devp.close()
             if not args.no_cpu_baseline:
-                ranks = min(os.cpu_count() or 1, 10)
+                ranks = min(host_threads(), 10)
                 c = cpu_paper(ranks, 60, 0, 16, split)
                 out["paper_config"]["cpu_baseline"] = {
                     "newton_steps_per_s": c["newton_steps_per_s"], "cores": ranks, "kind": "port",
@@ -846,7 +856,7 @@ def main():
         except Exception as e:  # never lose the headline line because of the secondary figure
             out["paper_config"] = {"error": str(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not myelin:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         r = cpu_synthetic(args.cpu_nx, threads, 1, 0, args.ilu_fill, args.slab_w)
         out["cpu_baseline"] = {
             "value": r["gdof"], "unit": UNIT, "cores": threads, "kind": "port",
