@@ -351,7 +351,7 @@ def sample_parity(api, setups, device, ilu_fill, slab_w, nx_fixed=512, nx_conv=2
     return out
 
 
-def multigpu_parity(api, setups, dist, rank, world, local_rank):
+def multigpu_parity(api, setups, dist, rank, world, local_rank, compact=False):
     """a17 where the driver sees it: a small problem on the SAME ranks / communicator kind the bench uses, device vs
     the oracle's overlapping multi-rank Newton solve on the same partition (ILU0 on narrow sub-slabs and the
     reference-default ILU(1) per rank)."""
@@ -361,6 +361,8 @@ def multigpu_parity(api, setups, dist, rank, world, local_rank):
     ids = [api.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     dev.comm_init(ids[0], rank, world)
+    if compact:     # the SpMV operand of the benchmarked grid (see sample_parity)
+        dev.set_spmv_compact(1)
     kw = dict(reduction=1e-9, abs_limit=1e-14, min_lin_reduction=1e-10)
     runs = {}
     for name, o in (("ilu0_slab4", dict(slab_w=slab_w, ilu_fill=0)), ("ilu1_per_rank", dict(slab_w=64, ilu_fill=1))):
@@ -369,6 +371,7 @@ def multigpu_parity(api, setups, dist, rank, world, local_rank):
         runs[name] = dict(u=u, its=r.iterations, lin=r.lin_iterations, status=r.status)
     _, nrm = dev.residual(s["u0"])
     mode = dev.comm_mode()
+    operand_compact = dev.spmv_compact()
     dev.close()
     gathered = [None] * world
     dist.all_gather_object(gathered, dict(runs=runs, nrm=nrm, mode=mode))
@@ -399,6 +402,7 @@ def multigpu_parity(api, setups, dist, rank, world, local_rank):
                               "krylov_its_gpu": gathered[0]["runs"][name]["lin"], "krylov_its_cpu": rc[0].lin_iterations}
         ok &= its_ok and econ < 1e-8 and epot < 5e-7     # potential: see sample_parity on its floor
     out["green"] = bool(ok)
+    out["spmv_operand"] = "64-byte blocks (forced, as on the benchmarked grid)" if operand_compact else "arrow blocks"
     return out
 
 
@@ -622,7 +626,7 @@ def main():
     parity = mg_parity = None
     if not args.no_parity and not myelin:
         if world > 1:
-            mg_parity = multigpu_parity(api, setups, dist, rank, world, local_rank)
+            mg_parity = multigpu_parity(api, setups, dist, rank, world, local_rank, compact=nv_full >= (1 << 20))
         elif rank == 0:
             parity = sample_parity(api, setups, local_rank, args.ilu_fill, args.slab_w, compact=nv_full >= (1 << 20))
 

@@ -44,6 +44,8 @@ def main():
     dev.set_time(0.0, 1.0); dev.set_uold(s["u0"]); dev.update_state(s["u0"])
     kw = dict(reduction=1e-9, abs_limit=1e-14, min_lin_reduction=1e-10)
     ug, rg = dev.newton(s["u0"], api.default_newton_opts(slab_w=slab_w, **kw))
+    if rank == 0:
+        print("spmv operand compact", dev.spmv_compact(), flush=True)
     # linear-solve building blocks on the first Jacobian
     r0, nrm = dev.residual(s["u0"])
     dev.jacobian(s["u0"], download=False)

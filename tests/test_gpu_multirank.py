@@ -23,8 +23,11 @@ def test_two_gpu_parity(p2p):
     assert out.returncode == 0 and "MULTIGPU PARITY OK" in out.stdout
 
 
-def test_two_ranks_on_one_gpu_peer_windows():
-    """The same parity script with BOTH ranks on GPU 0 (two processes, time-sliced contexts) and the peer windows
+@pytest.mark.parametrize("compact", ["auto", "1"])
+def test_two_ranks_on_one_gpu_peer_windows(compact):
+    """(compact = "1": the solver's products on the 64-byte-block operand, forced by AX1_SPMV_COMPACT -- the operand of
+    the named workload's ranks, with the constrained processor-boundary rows of the overlap.)
+    The same parity script with BOTH ranks on GPU 0 (two processes, time-sliced contexts) and the peer windows
     bootstrapped without NCCL (ax1gpu_p2p_export / ax1gpu_p2p_attach over gloo): the overlap path of row a17 -- halo sum
     pushed by the sweep kernels into the neighbour's window, owner-masked dot products summed in rank order through the
     windows, constrained processor-boundary vertices -- runs on a 1-GPU box. Skipped (not failed) if the two contexts
@@ -35,6 +38,8 @@ def test_two_ranks_on_one_gpu_peer_windows():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "run_multigpu_parity.py")]
     env = dict(os.environ, AX1_SAME_GPU="1", AX1_P2P="1", AX1_P2P_TIMEOUT_S="20")
+    if compact == "1":
+        env["AX1_SPMV_COMPACT"] = "1"
     try:
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
     except subprocess.TimeoutExpired:
@@ -44,3 +49,5 @@ def test_two_ranks_on_one_gpu_peer_windows():
     if out.returncode != 0 and ("timed out" in out.stdout or "timed out" in out.stderr):
         pytest.skip("peer-window exchange timed out with both ranks on one GPU (no time slicing between the contexts)")
     assert out.returncode == 0 and "MULTIGPU PARITY OK" in out.stdout
+    if compact == "1":
+        assert "spmv operand compact True" in out.stdout
