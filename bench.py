@@ -78,9 +78,9 @@ PAPER_SPLIT = 91     # radial cut of the library-default preconditioner on the 1
 # of 128 B, common.cuh), so the bytes these kernels must move are smaller; roofline.achieved uses the
 # bytes of the format actually stored, the dense-equivalent figure is reported beside it.
 BYTES = {"residual": 104, "jacobian": 32 + 720, "spmv": 720 + 32 + 32, "ilu_factor": 720 + 1152, "ilu_apply": 1384,
-         "dot": 64, "axpy": 224, "pupdate": 128}
+         "dot": 64, "axpy": 256, "rupdate": 96, "pupdate": 128}
 BYTES_DENSE = {"residual": 104, "jacobian": 1184, "spmv": 1256, "ilu_factor": 2384, "ilu_apply": 1384,
-               "dot": 64, "axpy": 224, "pupdate": 128}
+               "dot": 64, "axpy": 256, "rupdate": 96, "pupdate": 128}
 
 
 def measured_peak():
@@ -755,12 +755,14 @@ def main():
     # ---- roofline of the dominant kernel, measured live with CUDA events on the library stream ----
     peak, peak_kind = measured_peak()
     # launches per step: residual = 1 + 2 per Newton iteration (line search + defect), dot = norms only
-    # (the Krylov dot products are fused into the SpMV and the x,r updates), axpy = the fused x,r update;
+    # (the Krylov dot products are fused into the SpMV and the x,r updates), rupdate = r -= alpha v of the first half
+    # step, axpy = the fused x,r update of the second (x += alpha y + omega z, r -= omega t);
     # spmv_dot1 / spmv_dot2 are the two dot-fused SpMV variants BiCGStab launches (v = A y, t = A y)
     counts = {"residual": 2 * NEWTON_ITS + 1, "jacobian": NEWTON_ITS, "ilu_factor": NEWTON_ITS,
               "spmv_dot1": KRYLOV_ITS * NEWTON_ITS, "spmv_dot2": KRYLOV_ITS * NEWTON_ITS,
               "ilu_apply": 2 * KRYLOV_ITS * NEWTON_ITS,
-              "dot": 3 * NEWTON_ITS + 1, "axpy": 2 * KRYLOV_ITS * NEWTON_ITS, "pupdate": KRYLOV_ITS * NEWTON_ITS}
+              "dot": 3 * NEWTON_ITS + 1, "axpy": KRYLOV_ITS * NEWTON_ITS, "rupdate": KRYLOV_ITS * NEWTON_ITS,
+              "pupdate": KRYLOV_ITS * NEWTON_ITS}
     kern = {}
     bytes_k, bytes_dense = dict(BYTES), dict(BYTES_DENSE)
     compact = bool(dev.spmv_compact())

@@ -124,7 +124,7 @@ int ax1gpu_create(const ax1gpu_grid* grid, const unsigned char* cell_subdomain, 
   TRY(dev_upload(&c->d_dmask, (const uint8_t*)dirichlet_mask, nv, st));
   TRY(dev_upload(&c->d_epsm, memb_perm, nx, st));
   for (double** p : {&c->d_u, &c->d_uold, &c->d_r0, &c->d_r, &c->d_z, &c->d_uprev, &c->d_rt, &c->d_p, &c->d_v,
-                     &c->d_y2, &c->d_t, &c->d_tmp}) {
+                     &c->d_y2, &c->d_t, &c->d_tmp, &c->d_y1}) {
     TRY(dev_alloc(p, n4));
     if (cudaMemsetAsync(*p, 0, n4 * sizeof(double), st) != cudaSuccess) { ax1gpu_destroy(c); return AX1GPU_ECUDA; }
   }
@@ -225,7 +225,7 @@ int ax1gpu_destroy(ax1gpu_handle c) {
   if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
   for (void* p : {(void*)c->d_x, (void*)c->d_y, (void*)c->d_nodevol, (void*)c->d_epsm, (void*)c->d_dmask, (void*)c->d_rowptr,
                   (void*)c->d_u, (void*)c->d_uold, (void*)c->d_r0, (void*)c->d_r, (void*)c->d_z, (void*)c->d_uprev, (void*)c->d_A,
-                  (void*)c->d_LU, (void*)c->d_rt, (void*)c->d_p, (void*)c->d_v, (void*)c->d_y2, (void*)c->d_t, (void*)c->d_tmp,
+                  (void*)c->d_LU, (void*)c->d_rt, (void*)c->d_p, (void*)c->d_v, (void*)c->d_y2, (void*)c->d_t, (void*)c->d_tmp, (void*)c->d_y1,
                   (void*)c->d_bcrs, (void*)c->d_gbar, (void*)c->d_chstate, (void*)c->d_geff, (void*)c->d_vrest, (void*)c->d_vm, (void*)c->d_fluxterms,
                   (void*)c->d_mori_gamma, (void*)c->d_Ac, (void*)c->d_err, (void*)c->d_partials, (void*)c->d_sums, (void*)c->d_sc, (void*)c->d_halo_send,
                   (void*)c->d_halo_recv, (void*)c->d_lvl, (void*)c->d_spartials})

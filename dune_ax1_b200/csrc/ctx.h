@@ -27,6 +27,7 @@ struct ax1gpu_ctx {
   bool ac_valid = false;
   int spmv_compact = -1;       // -1 automatic (nv >= 2^20), 0 never, 1 always (ax1gpu_set_spmv_compact)
   double *d_rt = nullptr, *d_p = nullptr, *d_v = nullptr, *d_y2 = nullptr, *d_t = nullptr, *d_tmp = nullptr;
+  double* d_y1 = nullptr;      // y = M^-1 p of the current BiCGStab iteration (its x-update is applied with the second one)
   double* d_bcrs = nullptr;  // staging for Jacobian up/download (allocated lazily)
   // channels
   ax1::ChannelDev ch{};

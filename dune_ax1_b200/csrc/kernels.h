@@ -29,7 +29,7 @@ void launch_jacobian_volume_fd(const Dev& g, const double* u, double* A, cudaStr
 // solver.cu
 struct Scalars {  // device-resident Krylov scalars
   double rho, rho_new, alpha, omega, beta, h, norm, norm0, tr, tt, it_half, reduction, rho_next, pad0;
-  int done, converged, breakdown, pad;
+  int done, converged, breakdown, x_pending;   // x_pending: converged at the half step, x += alpha y still to be applied
 };
 // Ac != null: multiply with the 64-byte-block copy of A (launch_compact_rows) instead of A itself
 void launch_spmv(const Dev& g, const double* A, const double* x, double* y, int zero_constrained, cudaStream_t st,

@@ -933,3 +933,33 @@ def test_solver_spmv_operand_in_64_byte_blocks(oracle, axlib):
     # DESIGN 5), and no further from the oracle than with the Jacobian itself
     assert np.all(e_c[:3] < 1e-8) and e_c[3] < 5e-7 and e_c[3] <= 2 * e_p[3] + 1e-9, (e_c, e_p)
     dev.close()
+
+
+def test_bicgstab_half_step_exit_applies_pending_x_update(oracle, axlib):
+    """The device applies x += alpha y of a BiCGStab iteration together with x += omega z of its second half
+    (driver.cu: xr_update_kernel); a solve that converges AT the half step owes x that first update. Solves stopped by
+    a range of reductions end at whole and at half steps: each reproduces the oracle's stopping point, its solution
+    and satisfies |r - A z| <= reduction |r|."""
+    s = small_setup(nx=10)
+    dev, P, u0 = _both(oracle, axlib, s)
+    Jo = P.jacobian(u0)
+    r = P.residual(u0)
+    dev.set_jacobian(Jo)
+    halves = 0
+    for red in (1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7, 1e-8, 1e-9, 1e-10):
+        zg, _, resg = dev.solve(r, red, maxit=500, slab_w=4)
+        zo, _, reso = P.solve(Jo, r, red, maxit=500, ilu_fill=0, slab_w=4)
+        true_res = np.linalg.norm(r - P.spmv(Jo, zg)) / np.linalg.norm(r)
+        true_res_o = np.linalg.norm(r - P.spmv(Jo, zo)) / np.linalg.norm(r)
+        same_stop = resg.it_half == reso.it_half
+        err = np.max(np.abs(zg - zo)) / np.max(np.abs(zo))
+        print("red %.0e it_half gpu %.1f cpu %.1f true residual gpu %.3e cpu %.3e err %.2e" % (red, resg.it_half, reso.it_half, true_res, true_res_o, err))
+        assert resg.converged == 1 and reso.converged == 1
+        assert abs(resg.it_half - reso.it_half) <= 1.0, (red, resg.it_half, reso.it_half)
+        # the recurrence residual met the reduction; the true one follows it (a missing x += alpha y would leave it O(1))
+        assert true_res <= max(3.0 * red, 3e-10) and true_res <= 3.0 * true_res_o + 3e-10, (red, resg.it_half, true_res, true_res_o)
+        if same_stop:
+            assert err <= max(1e-7, 1e-2 * red), (red, resg.it_half, err)
+        halves += resg.it_half != np.floor(resg.it_half)
+    assert halves >= 1, halves      # the half-step exit was exercised
+    dev.close()
