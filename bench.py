@@ -171,7 +171,8 @@ def workload_config(args, world):
           % (args.nx, NEWTON_ITS, KRYLOV_ITS, args.ilu_fill, args.slab_w))
     return wl, {"workload": wl, "cells_per_gpu": args.nx * 180, "dof_total": 4 * nv_full * world,
                 "parallelism": "z-slab x%d" % world,
-                "l2": "inputs larger than L2 (working set ~46 GB per GPU)"}
+                "l2": "inputs larger than L2 (working set ~%.0f GB per GPU: Jacobian, its 64-byte-block copy, ILU factor, "
+                      "15 vectors)" % ((720 + 1152 + (576 if nv_full >= (1 << 20) else 0) + 15 * 32) * nv_full / 1e9)}
 
 
 # ------------------------------------------------------------------------------------------------
