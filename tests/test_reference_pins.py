@@ -749,3 +749,52 @@ def test_mori_global_residual_is_scatter_of_reference_split_operators(oracle, re
     rows = r_or.reshape(-1, 4)
     assert np.all(rows[:, :3] == 0.0) if which == 0 else np.all(rows[:, 3] == 0.0)
     assert np.abs(rows).max() > 0.0
+
+
+def test_potential_row_is_one_number_times_the_valences(oracle, refop):
+    """What the device's 64-byte-block SpMV operand rests on: in the analytic Jacobian the potential row
+    couples to the three concentrations through the charge density only, so its entries are z_k times one number --
+    bit for bit, because the valences are +-1. Checked (a) on the reference's own compiled element Jacobians
+    (jacobian_volume of the electrolyte operator), (b) on the oracle's assembled matrix, with and without the row-norm
+    scaling; (c) the finite-difference volume Jacobian (the reference's default mode) does NOT have that shape
+    exactly, which is why the device checks every block before it uses the operand."""
+    s = small_setup(nx=4, stimulation=True)
+    t, dt = 29.0, 1.0
+    run = _CellRunner(oracle, refop, s, t=t, dt=dt, stim=True)
+    P = run.P
+    z = np.array([1.0, 1.0, -1.0])          # Na, K, Cl (dune/ax1/common/constants.hh, default configuration)
+    assert list(np.asarray(s["params"].get("valence", [1, 1, -1]), dtype=float)) == list(z)
+    rng = np.random.default_rng(5)
+    u = s["u0"] * (1.0 + 1e-3 * rng.standard_normal(s["u0"].shape))
+    cs = np.asarray(s["cell_subdomain"]).reshape(s["ny"], s["nx"])
+    checked = 0
+    for j in range(s["ny"]):
+        for i in range(s["nx"]):
+            if cs[j, i] == 2:
+                continue
+            vs = run.verts(i, j)
+            xl = np.array([[u[4 * v + c] for v in vs] for c in range(4)]).reshape(-1)
+            m = run.ref(0, 1, i, j, xl, 80.0).reshape(4, 4, 4, 4)       # [row comp, row vertex, col comp, col vertex]
+            q = m[3, :, 0, :] / z[0]
+            for k in range(3):
+                assert np.array_equal(z[k] * q, m[3, :, k, :])
+            checked += np.count_nonzero(q)
+    assert checked > 0
+    J = np.asarray(P.jacobian(u)).reshape(-1, 4, 4)
+    r = P.residual(u)
+    Js, _ = P.rownorm(J.reshape(-1), r)
+    for M in (J, np.asarray(Js).reshape(-1, 4, 4)):
+        q = M[:, 3, 0] / z[0]
+        assert np.count_nonzero(q) > 0.5 * len(q)
+        for k in range(3):
+            assert np.array_equal(z[k] * q, M[:, 3, k])
+    # finite-difference volume Jacobians: proportional only to rounding
+    s2 = small_setup(nx=4, stimulation=True)
+    s2["params"].update(use_elec_jacobian_volume=0, use_memb_jacobian_volume=0, use_time_jacobian_volume=0)
+    P2 = oracle_problem(oracle, s2, analytic=0)
+    P2.set_time(t, dt); P2.set_uold(s2["u0"]); P2.update_state(s2["u0"])
+    F = np.asarray(P2.jacobian(u)).reshape(-1, 4, 4)
+    q = F[:, 3, 0] / z[0]
+    exact = all(np.array_equal(z[k] * q, F[:, 3, k]) for k in range(3))
+    close = all(np.allclose(z[k] * q, F[:, 3, k], rtol=1e-5, atol=1e-5 * np.abs(F[:, 3, :3]).max()) for k in range(3))
+    assert close and not exact
